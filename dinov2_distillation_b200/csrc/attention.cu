@@ -1,0 +1,550 @@
+// Flash-style attention forward / backward for the distillation path (no [B,h,N,N] tensor is ever materialised).
+//   teacher self-attention  : hub Attention.forward, head_dim 64        (via models/backbones/dinov2.py:32)
+//   ScaleKD cross-attention : losses/scalekd.py:299-314, head_dim 16/24/32/48/64/96, scale = hd^-0.5 * softmax_scale
+// v1 data path: cp.async double-buffered K/V (or Q/dO) tiles in shared memory, ldmatrix fragments,
+// mma.sync m16n8k16 bf16 -> fp32, online softmax in the exp2 domain. Token-major strided operands so q/k/v are read
+// straight out of the fused qkv / kv GEMM outputs and the output lands head-merged.
+// Backward is split in two kernels (dQ; dK+dV) so that no atomics or cross-warp transposes are needed.
+#include "common.cuh"
+#include "../../include/b200_distill.h"
+
+namespace b200 {
+
+constexpr int ATT_BQ = 64;   // rows per CTA (4 warps x 16)
+constexpr int ATT_BK = 64;   // columns per inner tile
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_PAD = 8;   // bf16 elements of row padding (16 B) -> conflict-free ldmatrix
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Load a [64][HDP] bf16 tile (row pitch HDP+PAD) of rows row0.. from a token-major strided tensor; rows >= nrows and
+// columns >= hd are zero filled (cp.async src-size 0).
+template <int HDP>
+__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, int row0, int nrows, long long ts,
+                                          int hd) {
+  constexpr int CH = HDP / 8;
+  constexpr int PITCH = HDP + ATT_PAD;
+  for (int i = threadIdx.x; i < 64 * CH; i += ATT_THREADS) {
+    const int r = i / CH, c = i - r * CH;
+    const int gr = row0 + r;
+    const bool ok = (gr < nrows) && (c * 8 < hd);
+    const __nv_bfloat16* src = ok ? g + (long long)gr * ts + c * 8 : g;
+    cp_async16(s + r * PITCH + c * 8, src, ok ? 16 : 0);
+  }
+}
+
+// A fragments (16 rows of this warp x HDP) from a row-major smem tile.
+template <int HDP>
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[HDP / 16][4], const __nv_bfloat16* s, int warp, int lane) {
+  constexpr int PITCH = HDP + ATT_PAD;
+#pragma unroll
+  for (int kb = 0; kb < HDP / 16; ++kb)
+    ldsm_x4(a[kb], s + (warp * 16 + (lane & 15)) * PITCH + kb * 16 + (lane >> 4) * 8);
+}
+
+// acc[16 x 64] (+)= A[16 x HDP] * T^T, T: smem tile [64][HDP] row-major (T rows are the output columns).
+template <int HDP>
+__device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[HDP / 16][4],
+                                         const __nv_bfloat16* t, int lane) {
+  constexpr int PITCH = HDP + ATT_PAD;
+  const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+  for (int kb = 0; kb < HDP / 16; ++kb) {
+#pragma unroll
+    for (int nb = 0; nb < 8; nb += 2) {
+      uint32_t b[4];
+      ldsm_x4(b, t + ((nb + (mi >> 1)) * 8 + rr) * PITCH + kb * 16 + (mi & 1) * 8);
+      mma_bf16(acc[nb], a[kb], b[0], b[1]);
+      mma_bf16(acc[nb + 1], a[kb], b[2], b[3]);
+    }
+  }
+}
+
+// out[16 x HDP] += P[16 x 64] * T, P given as C-layout fp32 registers (converted to bf16 A fragments), T: [64][HDP].
+template <int HDP>
+__device__ __forceinline__ void mma_p_t(float (&out)[HDP / 8][4], const float (&p)[8][4], const __nv_bfloat16* t,
+                                        int lane) {
+  constexpr int PITCH = HDP + ATT_PAD;
+  const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    uint32_t a[4];
+    a[0] = pack_bf16(p[2 * kb][0], p[2 * kb][1]);
+    a[1] = pack_bf16(p[2 * kb][2], p[2 * kb][3]);
+    a[2] = pack_bf16(p[2 * kb + 1][0], p[2 * kb + 1][1]);
+    a[3] = pack_bf16(p[2 * kb + 1][2], p[2 * kb + 1][3]);
+#pragma unroll
+    for (int nb = 0; nb < HDP / 8; nb += 2) {
+      uint32_t b[4];
+      ldsm_x4_t(b, t + (kb * 16 + (mi & 1) * 8 + rr) * PITCH + (nb + (mi >> 1)) * 8);
+      mma_bf16(out[nb], a, b[0], b[1]);
+      mma_bf16(out[nb + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+struct AttnParams {
+  const __nv_bfloat16 *q, *k, *v, *d_o;
+  const __nv_bfloat16* o_in;
+  __nv_bfloat16 *o, *dq, *dk, *dv;
+  float *lse, *delta;
+  long long q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, do_bs, do_ts, dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts;
+  int B, heads, Nq, Nk, hd;
+  float scale, scale_log2;
+};
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_kernel(const AttnParams p) {
+  constexpr int PITCH = HDP + ATT_PAD;
+  constexpr int TILE = 64 * PITCH;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sK = sQ + TILE;       // [2][TILE]
+  __nv_bfloat16* sV = sK + 2 * TILE;   // [2][TILE]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* gq = p.q + (long long)b * p.q_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gk = p.k + (long long)b * p.k_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gv = p.v + (long long)b * p.v_bs + (long long)h * p.hd;
+
+  load_tile<HDP>(sQ, gq, q0, p.Nq, p.q_ts, p.hd);
+  load_tile<HDP>(sK, gk, 0, p.Nk, p.k_ts, p.hd);
+  load_tile<HDP>(sV, gv, 0, p.Nk, p.v_ts, p.hd);
+  cp_async_commit();
+
+  const int n_tiles = (p.Nk + ATT_BK - 1) / ATT_BK;
+  uint32_t qa[HDP / 16][4];
+  float o[HDP / 8][4];
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < n_tiles) {
+      load_tile<HDP>(sK + (buf ^ 1) * TILE, gk, (it + 1) * ATT_BK, p.Nk, p.k_ts, p.hd);
+      load_tile<HDP>(sV + (buf ^ 1) * TILE, gv, (it + 1) * ATT_BK, p.Nk, p.v_ts, p.hd);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (it == 0) load_a_frags<HDP>(qa, sQ, warp, lane);
+
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+    mma_a_tT<HDP>(s, qa, sK + buf * TILE, lane);
+
+    const int kbase = it * ATT_BK;
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = kbase + nb * 8 + 2 * t4 + (e & 1);
+        float v = s[nb][e] * p.scale_log2;
+        if (col >= p.Nk) v = -INFINITY;
+        s[nb][e] = v;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float a0 = exp2f(m0 - mx0), a1 = exp2f(m1 - mx1);
+    m0 = mx0; m1 = mx1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      s[nb][0] = exp2f(s[nb][0] - mx0);
+      s[nb][1] = exp2f(s[nb][1] - mx0);
+      s[nb][2] = exp2f(s[nb][2] - mx1);
+      s[nb][3] = exp2f(s[nb][3] - mx1);
+      rs0 += s[nb][0] + s[nb][1];
+      rs1 += s[nb][2] + s[nb][3];
+    }
+    l0 = l0 * a0 + rs0;
+    l1 = l1 * a1 + rs1;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+    mma_p_t<HDP>(o, s, sV + buf * TILE, lane);
+    __syncthreads();
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  __nv_bfloat16* go = p.o + (long long)b * p.o_bs + (long long)h * p.hd;
+#pragma unroll
+  for (int nb = 0; nb < HDP / 8; ++nb) {
+    const int col = nb * 8 + 2 * t4;
+    if (col < p.hd) {
+      if (r0 < p.Nq) *reinterpret_cast<uint32_t*>(go + (long long)r0 * p.o_ts + col) = pack_bf16(o[nb][0] * inv0, o[nb][1] * inv0);
+      if (r1 < p.Nq) *reinterpret_cast<uint32_t*>(go + (long long)r1 * p.o_ts + col) = pack_bf16(o[nb][2] * inv1, o[nb][3] * inv1);
+    }
+  }
+  if (p.lse != nullptr && t4 == 0) {
+    float* lse = p.lse + ((long long)b * p.heads + h) * p.Nq;
+    const float ln2 = 0.6931471805599453f;
+    if (r0 < p.Nq) lse[r0] = (m0 + log2f(l0)) * ln2;
+    if (r1 < p.Nq) lse[r1] = (m1 + log2f(l1)) * ln2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: delta
+// delta[b, h, q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
+__global__ void attn_delta_kernel(const AttnParams p) {
+  const long long n = (long long)p.B * p.Nq * p.heads;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(i % p.heads);
+    const long long bq = i / p.heads;
+    const int q = (int)(bq % p.Nq);
+    const int b = (int)(bq / p.Nq);
+    const __nv_bfloat16* a = p.d_o + (long long)b * p.do_bs + (long long)q * p.do_ts + (long long)h * p.hd;
+    const __nv_bfloat16* c = p.o_in + (long long)b * p.o_bs + (long long)q * p.o_ts + (long long)h * p.hd;
+    float acc = 0.f;
+    for (int d = 0; d < p.hd; d += 8) {
+      const uint4 ua = *reinterpret_cast<const uint4*>(a + d);
+      const uint4 uc = *reinterpret_cast<const uint4*>(c + d);
+      const uint32_t xa[4] = {ua.x, ua.y, ua.z, ua.w}, xc[4] = {uc.x, uc.y, uc.z, uc.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = unpack_bf16(xa[e]), fc = unpack_bf16(xc[e]);
+        acc += fa.x * fc.x + fa.y * fc.y;
+      }
+    }
+    p.delta[((long long)b * p.heads + h) * p.Nq + q] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dQ
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dq_kernel(const AttnParams p) {
+  constexpr int PITCH = HDP + ATT_PAD;
+  constexpr int TILE = 64 * PITCH;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sdO = sQ + TILE;
+  __nv_bfloat16* sK = sdO + TILE;      // [2]
+  __nv_bfloat16* sV = sK + 2 * TILE;   // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* gq = p.q + (long long)b * p.q_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gdo = p.d_o + (long long)b * p.do_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gk = p.k + (long long)b * p.k_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gv = p.v + (long long)b * p.v_bs + (long long)h * p.hd;
+
+  load_tile<HDP>(sQ, gq, q0, p.Nq, p.q_ts, p.hd);
+  load_tile<HDP>(sdO, gdo, q0, p.Nq, p.do_ts, p.hd);
+  load_tile<HDP>(sK, gk, 0, p.Nk, p.k_ts, p.hd);
+  load_tile<HDP>(sV, gv, 0, p.Nk, p.v_ts, p.hd);
+  cp_async_commit();
+
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  const float* lse = p.lse + ((long long)b * p.heads + h) * p.Nq;
+  const float* dl = p.delta + ((long long)b * p.heads + h) * p.Nq;
+  const float log2e = 1.4426950408889634f;
+  const float lse0 = r0 < p.Nq ? lse[r0] * log2e : INFINITY;
+  const float lse1 = r1 < p.Nq ? lse[r1] * log2e : INFINITY;
+  const float dl0 = r0 < p.Nq ? dl[r0] : 0.f;
+  const float dl1 = r1 < p.Nq ? dl[r1] : 0.f;
+
+  const int n_tiles = (p.Nk + ATT_BK - 1) / ATT_BK;
+  uint32_t qa[HDP / 16][4], doa[HDP / 16][4];
+  float dq[HDP / 8][4];
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < n_tiles) {
+      load_tile<HDP>(sK + (buf ^ 1) * TILE, gk, (it + 1) * ATT_BK, p.Nk, p.k_ts, p.hd);
+      load_tile<HDP>(sV + (buf ^ 1) * TILE, gv, (it + 1) * ATT_BK, p.Nk, p.v_ts, p.hd);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (it == 0) {
+      load_a_frags<HDP>(qa, sQ, warp, lane);
+      load_a_frags<HDP>(doa, sdO, warp, lane);
+    }
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+    mma_a_tT<HDP>(s, qa, sK + buf * TILE, lane);
+    mma_a_tT<HDP>(dp, doa, sV + buf * TILE, lane);
+    const int kbase = it * ATT_BK;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = kbase + nb * 8 + 2 * t4 + (e & 1);
+        const float l = (e < 2) ? lse0 : lse1;
+        const float dlt = (e < 2) ? dl0 : dl1;
+        const float pv = (col < p.Nk) ? exp2f(s[nb][e] * p.scale_log2 - l) : 0.f;
+        s[nb][e] = pv * (dp[nb][e] - dlt);
+      }
+    }
+    mma_p_t<HDP>(dq, s, sK + buf * TILE, lane);
+    __syncthreads();
+  }
+  __nv_bfloat16* gdq = p.dq + (long long)b * p.dq_bs + (long long)h * p.hd;
+#pragma unroll
+  for (int nb = 0; nb < HDP / 8; ++nb) {
+    const int col = nb * 8 + 2 * t4;
+    if (col < p.hd) {
+      if (r0 < p.Nq) *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * p.dq_ts + col) = pack_bf16(dq[nb][0] * p.scale, dq[nb][1] * p.scale);
+      if (r1 < p.Nq) *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * p.dq_ts + col) = pack_bf16(dq[nb][2] * p.scale, dq[nb][3] * p.scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dK, dV
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dkv_kernel(const AttnParams p) {
+  constexpr int PITCH = HDP + ATT_PAD;
+  constexpr int TILE = 64 * PITCH;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sV = sK + TILE;
+  __nv_bfloat16* sQ = sV + TILE;        // [2]
+  __nv_bfloat16* sdO = sQ + 2 * TILE;   // [2]
+  float* sLse = reinterpret_cast<float*>(sdO + 2 * TILE);  // [2][64]
+  float* sDl = sLse + 2 * 64;                              // [2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int k0 = blockIdx.x * ATT_BK, h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* gq = p.q + (long long)b * p.q_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gdo = p.d_o + (long long)b * p.do_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gk = p.k + (long long)b * p.k_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gv = p.v + (long long)b * p.v_bs + (long long)h * p.hd;
+  const float* lse = p.lse + ((long long)b * p.heads + h) * p.Nq;
+  const float* dl = p.delta + ((long long)b * p.heads + h) * p.Nq;
+  const float log2e = 1.4426950408889634f;
+
+  auto load_q_side = [&](int buf, int qt) {
+    load_tile<HDP>(sQ + buf * TILE, gq, qt * ATT_BQ, p.Nq, p.q_ts, p.hd);
+    load_tile<HDP>(sdO + buf * TILE, gdo, qt * ATT_BQ, p.Nq, p.do_ts, p.hd);
+    if (threadIdx.x < 64) {
+      const int r = qt * ATT_BQ + threadIdx.x;
+      sLse[buf * 64 + threadIdx.x] = r < p.Nq ? lse[r] * log2e : INFINITY;
+      sDl[buf * 64 + threadIdx.x] = r < p.Nq ? dl[r] : 0.f;
+    }
+  };
+
+  load_tile<HDP>(sK, gk, k0, p.Nk, p.k_ts, p.hd);
+  load_tile<HDP>(sV, gv, k0, p.Nk, p.v_ts, p.hd);
+  load_q_side(0, 0);
+  cp_async_commit();
+
+  const int kr0 = k0 + warp * 16 + g, kr1 = kr0 + 8;
+  const bool kok0 = kr0 < p.Nk, kok1 = kr1 < p.Nk;
+  const int n_tiles = (p.Nq + ATT_BQ - 1) / ATT_BQ;
+  uint32_t ka[HDP / 16][4], va[HDP / 16][4];
+  float dk[HDP / 8][4], dv[HDP / 8][4];
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < n_tiles) {
+      load_q_side(buf ^ 1, it + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (it == 0) {
+      load_a_frags<HDP>(ka, sK, warp, lane);
+      load_a_frags<HDP>(va, sV, warp, lane);
+    }
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+    }
+    mma_a_tT<HDP>(st, ka, sQ + buf * TILE, lane);     // S^T[kv, q]
+    mma_a_tT<HDP>(dpt, va, sdO + buf * TILE, lane);   // dP^T[kv, q]
+    float pt[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qc = nb * 8 + 2 * t4 + (e & 1);
+        const float l = sLse[buf * 64 + qc];
+        const float dlt = sDl[buf * 64 + qc];
+        const bool ok = (e < 2) ? kok0 : kok1;
+        const float pv = ok ? exp2f(st[nb][e] * p.scale_log2 - l) : 0.f;
+        pt[nb][e] = pv;
+        st[nb][e] = pv * (dpt[nb][e] - dlt);
+      }
+    }
+    mma_p_t<HDP>(dv, pt, sdO + buf * TILE, lane);   // dV += P^T dO
+    mma_p_t<HDP>(dk, st, sQ + buf * TILE, lane);    // dK += dS^T Q
+    __syncthreads();
+  }
+  __nv_bfloat16* gdk = p.dk + (long long)b * p.dk_bs + (long long)h * p.hd;
+  __nv_bfloat16* gdv = p.dv + (long long)b * p.dv_bs + (long long)h * p.hd;
+#pragma unroll
+  for (int nb = 0; nb < HDP / 8; ++nb) {
+    const int col = nb * 8 + 2 * t4;
+    if (col < p.hd) {
+      if (kok0) {
+        *reinterpret_cast<uint32_t*>(gdk + (long long)kr0 * p.dk_ts + col) = pack_bf16(dk[nb][0] * p.scale, dk[nb][1] * p.scale);
+        *reinterpret_cast<uint32_t*>(gdv + (long long)kr0 * p.dv_ts + col) = pack_bf16(dv[nb][0], dv[nb][1]);
+      }
+      if (kok1) {
+        *reinterpret_cast<uint32_t*>(gdk + (long long)kr1 * p.dk_ts + col) = pack_bf16(dk[nb][2] * p.scale, dk[nb][3] * p.scale);
+        *reinterpret_cast<uint32_t*>(gdv + (long long)kr1 * p.dv_ts + col) = pack_bf16(dv[nb][2], dv[nb][3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int fill_params(const b200_attn_desc* d, AttnParams& p, bool bwd) {
+  B200_CHECK_ARG(d != nullptr, "null descriptor");
+  B200_CHECK_ARG(d->q && d->k && d->v && d->o, "null tensor");
+  B200_CHECK_ARG(d->B > 0 && d->heads > 0 && d->Nq > 0 && d->Nk > 0, "empty problem");
+  B200_CHECK_ARG(d->hd % 8 == 0 && d->hd >= 8 && d->hd <= 96, "head_dim must be a multiple of 8 in [8, 96]");
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  B200_CHECK_ARG(al(d->q) && al(d->k) && al(d->v) && al(d->o), "tensors must be 16-byte aligned");
+  B200_CHECK_ARG(d->q_ts % 8 == 0 && d->k_ts % 8 == 0 && d->v_ts % 8 == 0 && d->o_ts % 2 == 0 && d->q_bs % 8 == 0 &&
+                     d->k_bs % 8 == 0 && d->v_bs % 8 == 0 && d->o_bs % 2 == 0,
+                 "strides must keep 16-byte alignment");
+  p.q = static_cast<const __nv_bfloat16*>(d->q); p.k = static_cast<const __nv_bfloat16*>(d->k);
+  p.v = static_cast<const __nv_bfloat16*>(d->v);
+  p.o = static_cast<__nv_bfloat16*>(d->o); p.o_in = static_cast<const __nv_bfloat16*>(d->o);
+  p.lse = d->lse; p.delta = d->delta;
+  p.q_bs = d->q_bs; p.q_ts = d->q_ts; p.k_bs = d->k_bs; p.k_ts = d->k_ts; p.v_bs = d->v_bs; p.v_ts = d->v_ts;
+  p.o_bs = d->o_bs; p.o_ts = d->o_ts;
+  p.B = d->B; p.heads = d->heads; p.Nq = d->Nq; p.Nk = d->Nk; p.hd = d->hd;
+  p.scale = d->scale; p.scale_log2 = d->scale * 1.4426950408889634f;
+  if (bwd) {
+    B200_CHECK_ARG(d->d_o && d->delta && d->lse && d->dq && d->dk && d->dv, "backward needs d_o, lse, delta, dq, dk, dv");
+    B200_CHECK_ARG(al(d->d_o) && al(d->dq) && al(d->dk) && al(d->dv), "tensors must be 16-byte aligned");
+    B200_CHECK_ARG(d->do_ts % 8 == 0 && d->do_bs % 8 == 0 && d->o_ts % 8 == 0 && d->o_bs % 8 == 0, "strides");
+    B200_CHECK_ARG(d->dq_ts % 2 == 0 && d->dk_ts % 2 == 0 && d->dv_ts % 2 == 0, "strides");
+    p.d_o = static_cast<const __nv_bfloat16*>(d->d_o); p.do_bs = d->do_bs; p.do_ts = d->do_ts;
+    p.dq = static_cast<__nv_bfloat16*>(d->dq); p.dq_bs = d->dq_bs; p.dq_ts = d->dq_ts;
+    p.dk = static_cast<__nv_bfloat16*>(d->dk); p.dk_bs = d->dk_bs; p.dk_ts = d->dk_ts;
+    p.dv = static_cast<__nv_bfloat16*>(d->dv); p.dv_bs = d->dv_bs; p.dv_ts = d->dv_ts;
+  }
+  return 0;
+}
+
+template <typename K>
+static int set_smem(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <int HDP>
+static int launch_fwd(const AttnParams& p, cudaStream_t st) {
+  constexpr size_t smem = size_t(5) * 64 * (HDP + ATT_PAD) * 2;
+  static bool once = false;
+  if (!once) { B200_TRY(set_smem(attn_fwd_kernel<HDP>, smem)); once = true; }
+  dim3 grid((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
+  attn_fwd_kernel<HDP><<<grid, ATT_THREADS, smem, st>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <int HDP>
+static int launch_bwd(const AttnParams& p, cudaStream_t st) {
+  constexpr size_t smem_dq = size_t(6) * 64 * (HDP + ATT_PAD) * 2;
+  constexpr size_t smem_dkv = size_t(6) * 64 * (HDP + ATT_PAD) * 2 + 4 * 64 * sizeof(float);
+  static bool once = false;
+  if (!once) {
+    B200_TRY(set_smem(attn_bwd_dq_kernel<HDP>, smem_dq));
+    B200_TRY(set_smem(attn_bwd_dkv_kernel<HDP>, smem_dkv));
+    once = true;
+  }
+  const long long n = (long long)p.B * p.Nq * p.heads;
+  long long gd = cdiv(n, 256);
+  if (gd > (long long)sm_count() * 16) gd = (long long)sm_count() * 16;
+  attn_delta_kernel<<<(unsigned)gd, 256, 0, st>>>(p);
+  B200_LAUNCH_OK();
+  dim3 gq((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
+  attn_bwd_dq_kernel<HDP><<<gq, ATT_THREADS, smem_dq, st>>>(p);
+  B200_LAUNCH_OK();
+  dim3 gk((unsigned)cdiv(p.Nk, ATT_BK), (unsigned)p.heads, (unsigned)p.B);
+  attn_bwd_dkv_kernel<HDP><<<gk, ATT_THREADS, smem_dkv, st>>>(p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_attention_fwd(const b200_attn_desc* d, void* stream) {
+  AttnParams p{};
+  B200_TRY(fill_params(d, p, false));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p.hd <= 16) return launch_fwd<16>(p, st);
+  if (p.hd <= 32) return launch_fwd<32>(p, st);
+  if (p.hd <= 48) return launch_fwd<48>(p, st);
+  if (p.hd <= 64) return launch_fwd<64>(p, st);
+  return launch_fwd<96>(p, st);
+}
+
+extern "C" int b200_attention_bwd(const b200_attn_desc* d, void* stream) {
+  AttnParams p{};
+  B200_TRY(fill_params(d, p, true));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p.hd <= 16) return launch_bwd<16>(p, st);
+  if (p.hd <= 32) return launch_bwd<32>(p, st);
+  if (p.hd <= 48) return launch_bwd<48>(p, st);
+  if (p.hd <= 64) return launch_bwd<64>(p, st);
+  return launch_bwd<96>(p, st);
+}

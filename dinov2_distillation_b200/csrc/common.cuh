@@ -1,0 +1,89 @@
+// Shared host/device helpers for libb200distill.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace b200 {
+
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+int sm_count();
+
+#define B200_CHECK_ARG(cond, msg)                                                      \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      ::b200::set_error(std::string(__func__) + ": " + (msg) + " [" #cond "]");        \
+      return -1;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+#define B200_CUDA_OK(expr)                                                                              \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      ::b200::set_error(std::string(__func__) + ": " #expr " -> " + cudaGetErrorString(_e));            \
+      return -2;                                                                                        \
+    }                                                                                                   \
+  } while (0)
+
+#define B200_LAUNCH_OK()                                                                                \
+  do {                                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                                \
+    if (_e != cudaSuccess) {                                                                            \
+      ::b200::set_error(std::string(__func__) + ": kernel launch -> " + cudaGetErrorString(_e));        \
+      return -3;                                                                                        \
+    }                                                                                                   \
+    ::b200::count_launch();                                                                             \
+  } while (0)
+
+#define B200_TRY(expr)        \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(h);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Bump allocator over a caller-provided workspace (256-byte aligned carve-outs).
+struct Arena {
+  uint8_t* base;
+  size_t cap;
+  size_t off;
+  Arena(void* p, size_t bytes) : base(static_cast<uint8_t*>(p)), cap(bytes), off(0) {}
+  void* take(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    return base ? base + a : nullptr;
+  }
+  template <typename T>
+  T* take_n(size_t n) { return static_cast<T*>(take(n * sizeof(T))); }
+  bool ok() const { return base == nullptr || off <= cap; }
+  size_t used() const { return (off + 255) & ~size_t(255); }
+};
+
+}  // namespace b200

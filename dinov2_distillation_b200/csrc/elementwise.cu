@@ -1,0 +1,805 @@
+// Bandwidth-bound kernels of the distillation path: casts / layout changes, patch im2col, LayerNorm fwd/bwd,
+// BatchNorm(+ReLU+pos) fwd/bwd, column reductions, SwiGLU gate.  All vectorised (128-bit) and coalesced on the
+// contiguous channel dimension; reductions use warp shuffles + one atomic per block column.
+#include "common.cuh"
+#include "../../include/b200_distill.h"
+
+namespace b200 {
+
+static inline int grid_for(long long work_items, int per_block, int max_blocks_per_sm = 8) {
+  long long g = cdiv(work_items, per_block);
+  long long cap = (long long)sm_count() * max_blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------ cast
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    uint2 u;
+    u.x = pack_bf16(v.x, v.y);
+    u.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = u;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __float2bfloat16(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ transposes
+// out[c, r] = in[r, c] * row_scale[r]   (fp32 -> bf16), batch via blockIdx.z
+template <typename TOut, bool ACC>
+__global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict__ out, int rows, int cols,
+                                 const float* __restrict__ row_scale, long long in_bstride, long long out_bstride,
+                                 float* __restrict__ out2_f32, long long out_ld) {
+  __shared__ float tile[32][33];
+  in += (long long)blockIdx.z * in_bstride;
+  out += (long long)blockIdx.z * out_bstride;
+  if (out2_f32) out2_f32 += (long long)blockIdx.z * out_bstride;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = in[(long long)r * cols + c];
+      if (row_scale) v *= __ldg(row_scale + r);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) {
+      const float v = tile[threadIdx.x][j];
+      const long long o = (long long)c * out_ld + r;
+      if constexpr (sizeof(TOut) == 2) {
+        out[o] = __float2bfloat16(v);
+        if (out2_f32) out2_f32[o] = v;
+      } else {
+        if (ACC) out[o] += v; else out[o] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ patch im2col
+__global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W,
+                                    int Kp) {
+  extern __shared__ float srow[];  // [3*14][W]
+  const int Wp = W / 14, Hp = H / 14;
+  const int b = blockIdx.x / Hp, ph = blockIdx.x % Hp;
+  const int W4 = W >> 2;  // W % 14 == 0 and even; use float2 to stay safe on alignment
+  (void)W4;
+  const int W2 = W >> 1;
+  for (int idx = threadIdx.x; idx < 42 * W2; idx += blockDim.x) {
+    const int rr = idx / W2, x2 = idx - rr * W2;
+    const int c = rr / 14, i = rr - c * 14;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(img + (((long long)b * 3 + c) * H + (ph * 14 + i)) * W) + x2);
+    srow[rr * W + 2 * x2] = v.x;
+    srow[rr * W + 2 * x2 + 1] = v.y;
+  }
+  __syncthreads();
+  const int Kp2 = Kp >> 1;
+  __nv_bfloat16* obase = out + ((long long)(b * Hp + ph) * Wp) * Kp;
+  for (int idx = threadIdx.x; idx < Wp * Kp2; idx += blockDim.x) {
+    const int pw = idx / Kp2, k2 = idx - pw * Kp2;
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 2 * k2 + e;
+      if (col < 588) {
+        const int c = col / 196, rem = col - c * 196;
+        const int i = rem / 14, j = rem - i * 14;
+        v[e] = srow[(c * 14 + i) * W + pw * 14 + j];
+      } else {
+        v[e] = 0.f;
+      }
+    }
+    reinterpret_cast<uint32_t*>(obase + (long long)pw * Kp)[k2] = pack_bf16(v[0], v[1]);
+  }
+}
+
+__global__ void write_cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls,
+                                      const float* __restrict__ pos, int B, int N, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, d = i - b * D;
+  x[(long long)b * N * D + d] = cls[d] + pos[d];
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+constexpr int LN_MAX_V4 = 12;  // up to D = 1536 held in registers (one warp per row)
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float eps,
+                     float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int rows, int D, int in_period, int in_pad) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_d = 1.0f / (float)D;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    long long ir = r;
+    if (in_period > 0) ir = (long long)(r / in_period) * (in_period + in_pad) + in_pad + r % in_period;
+    const float4* xr = reinterpret_cast<const float4*>(x + ir * D);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) {
+        v[i] = xr[c4];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      } else {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) {
+        const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + bq * bq) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c4);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(b) + c4);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + be.x;
+        o.y = (v[i].y - mean) * rstd * g.y + be.y;
+        o.z = (v[i].z - mean) * rstd * g.z + be.z;
+        o.w = (v[i].w - mean) * rstd * g.w + be.w;
+        if (y32) reinterpret_cast<float4*>(y32 + (long long)r * D)[c4] = o;
+        if (y16) {
+          uint2 u;
+          u.x = pack_bf16(o.x, o.y);
+          u.y = pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(y16 + (long long)r * D)[c4] = u;
+        }
+      }
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dw,
+                     float* __restrict__ db, int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_d = 1.0f / (float)D;
+  float4 aw[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { aw[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)r * D);
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)r * D);
+    const float mu = mean[r], rs = rstd[r];
+    float4 g[NV], xh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) {
+        const float4 d4 = dyr[c4];
+        const float4 x4 = xr[c4];
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + c4);
+        xh[i] = make_float4((x4.x - mu) * rs, (x4.y - mu) * rs, (x4.z - mu) * rs, (x4.w - mu) * rs);
+        g[i] = make_float4(d4.x * w4.x, d4.y * w4.y, d4.z * w4.z, d4.w * w4.w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+        if (dw) {
+          aw[i].x += d4.x * xh[i].x; aw[i].y += d4.y * xh[i].y; aw[i].z += d4.z * xh[i].z; aw[i].w += d4.w * xh[i].w;
+          ab[i].x += d4.x; ab[i].y += d4.y; ab[i].z += d4.z; ab[i].w += d4.w;
+        }
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) {
+        float4 o;
+        o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+        if (dres) {
+          const float4 rr = reinterpret_cast<const float4*>(dres + (long long)r * D)[c4];
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        if (dx) reinterpret_cast<float4*>(dx + (long long)r * D)[c4] = o;
+        if (dx16) {
+          uint2 u;
+          u.x = pack_bf16(o.x, o.y);
+          u.y = pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(dx16 + (long long)r * D)[c4] = u;
+        }
+      }
+    }
+  }
+  if (dw) {
+    // block reduction over warps through shared memory, then one atomic per column per block
+    extern __shared__ float red[];  // [warps][2][D]  (D <= 1536, warps = 8 -> 96 KB max; sized by the launcher)
+    const int wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) {
+        reinterpret_cast<float4*>(red + (long long)(wid * 2) * D)[c4] = aw[i];
+        reinterpret_cast<float4*>(red + (long long)(wid * 2 + 1) * D)[c4] = ab[i];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float sw = 0.f, sb = 0.f;
+      for (int k = 0; k < warps_per_block; ++k) {
+        sw += red[(long long)(k * 2) * D + c];
+        sb += red[(long long)(k * 2 + 1) * D + c];
+      }
+      atomicAdd(dw + c, sw);
+      atomicAdd(db + c, sb);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column reductions
+// generic: out[c] += sum_r f(x[r,c]); MODE 0: x  (fp32/bf16) ; MODE 1: x and x^2 (out[D + c])
+// block (32, 8): threadIdx.x -> 4 consecutive columns, threadIdx.y -> row lane; blockIdx.y -> row chunk
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256)
+colreduce_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out, int rows, int cols,
+                 int rows_per_block) {
+  __shared__ float4 sh[8][32];
+  __shared__ float4 sh2[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float4 a = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+  if (c < cols) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float4 v;
+      if constexpr (sizeof(T) == 4) {
+        v = *reinterpret_cast<const float4*>(x + (long long)r * ldx + c);
+      } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(x + (long long)r * ldx + c);
+        const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+        v = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      if (SQ) { q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w; }
+    }
+  }
+  sh[threadIdx.y][threadIdx.x] = a;
+  if (SQ) sh2[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 t = sh[k][threadIdx.x];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      if (SQ) {
+        const float4 u = sh2[k][threadIdx.x];
+        q.x += u.x; q.y += u.y; q.z += u.z; q.w += u.w;
+      }
+    }
+    atomicAdd(out + c, a.x); atomicAdd(out + c + 1, a.y); atomicAdd(out + c + 2, a.z); atomicAdd(out + c + 3, a.w);
+    if (SQ) {
+      float* o2 = out + cols;
+      atomicAdd(o2 + c, q.x); atomicAdd(o2 + c + 1, q.y); atomicAdd(o2 + c + 2, q.z); atomicAdd(o2 + c + 3, q.w);
+    }
+  }
+}
+
+__global__ void zero_kernel(float* __restrict__ p, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = 0.f;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
+                                   int M, int D) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  if (sums != nullptr) {
+    const float mu = sums[c] / (float)M;
+    float var = sums[D + c] / (float)M - mu * mu;
+    var = fmaxf(var, 0.f);
+    mean[c] = mu;
+    rstd[c] = rsqrtf(var + eps);
+    if (rmean) {
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mu;
+      const float unb = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * unb;
+    }
+  } else {
+    mean[c] = rmean[c];
+    rstd[c] = rsqrtf(rvar[c] + eps);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_relu_pos_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ pos,
+                       float* __restrict__ z32, __nv_bfloat16* __restrict__ z16, long long M, int D, int HW) {
+  const int D4 = D >> 2;
+  const long long n4 = M * D4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D4;
+    const int c4 = (int)(i - r * D4);
+    const float4 v = reinterpret_cast<const float4*>(y)[i];
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
+    const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c4);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(b) + c4);
+    const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + (r % HW) * D) + c4);
+    float4 o;
+    o.x = fmaxf((v.x - mu.x) * rs.x * g.x + be.x, 0.f) + pe.x;
+    o.y = fmaxf((v.y - mu.y) * rs.y * g.y + be.y, 0.f) + pe.y;
+    o.z = fmaxf((v.z - mu.z) * rs.z * g.z + be.z, 0.f) + pe.z;
+    o.w = fmaxf((v.w - mu.w) * rs.w * g.w + be.w, 0.f) + pe.w;
+    if (z32) reinterpret_cast<float4*>(z32)[i] = o;
+    if (z16) {
+      uint2 u;
+      u.x = pack_bf16(o.x, o.y);
+      u.y = pack_bf16(o.z, o.w);
+      reinterpret_cast<uint2*>(z16)[i] = u;
+    }
+  }
+}
+
+// sums2[0:D] += sum_r dr ; sums2[D:2D] += sum_r dr * yhat ; dr = dz * (yhat*w+b > 0)
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
+                     float* __restrict__ sums2, int M, int D, int rows_per_block) {
+  __shared__ float4 sh[8][32];
+  __shared__ float4 sh2[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float4 a = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+  if (c < D) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(w + c);
+    const float4 be = *reinterpret_cast<const float4*>(b + c);
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float4 d4 = *reinterpret_cast<const float4*>(dz + (long long)r * D + c);
+      const float4 y4 = *reinterpret_cast<const float4*>(y + (long long)r * D + c);
+      float4 yh = make_float4((y4.x - mu.x) * rs.x, (y4.y - mu.y) * rs.y, (y4.z - mu.z) * rs.z, (y4.w - mu.w) * rs.w);
+      float4 dr;
+      dr.x = (yh.x * g.x + be.x > 0.f) ? d4.x : 0.f;
+      dr.y = (yh.y * g.y + be.y > 0.f) ? d4.y : 0.f;
+      dr.z = (yh.z * g.z + be.z > 0.f) ? d4.z : 0.f;
+      dr.w = (yh.w * g.w + be.w > 0.f) ? d4.w : 0.f;
+      a.x += dr.x; a.y += dr.y; a.z += dr.z; a.w += dr.w;
+      q.x += dr.x * yh.x; q.y += dr.y * yh.y; q.z += dr.z * yh.z; q.w += dr.w * yh.w;
+    }
+  }
+  sh[threadIdx.y][threadIdx.x] = a;
+  sh2[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 t = sh[k][threadIdx.x], u = sh2[k][threadIdx.x];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      q.x += u.x; q.y += u.y; q.z += u.z; q.w += u.w;
+    }
+    atomicAdd(sums2 + c, a.x); atomicAdd(sums2 + c + 1, a.y); atomicAdd(sums2 + c + 2, a.z); atomicAdd(sums2 + c + 3, a.w);
+    float* o2 = sums2 + D;
+    atomicAdd(o2 + c, q.x); atomicAdd(o2 + c + 1, q.y); atomicAdd(o2 + c + 2, q.z); atomicAdd(o2 + c + 3, q.w);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
+                    const float* __restrict__ sums2, __nv_bfloat16* __restrict__ dy16, int batch_stats, long long M,
+                    int D) {
+  const int D4 = D >> 2;
+  const long long n4 = M * D4;
+  const float invM = 1.0f / (float)M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D4;
+    const int c4 = (int)(i - r * D4);
+    const float4 d4 = reinterpret_cast<const float4*>(dz)[i];
+    const float4 y4 = reinterpret_cast<const float4*>(y)[i];
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
+    const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c4);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(b) + c4);
+    float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+    if (batch_stats) {
+      s1 = __ldg(reinterpret_cast<const float4*>(sums2) + c4);
+      s2 = __ldg(reinterpret_cast<const float4*>(sums2 + D) + c4);
+    }
+    const float yh[4] = {(y4.x - mu.x) * rs.x, (y4.y - mu.y) * rs.y, (y4.z - mu.z) * rs.z, (y4.w - mu.w) * rs.w};
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float rr[4] = {rs.x, rs.y, rs.z, rs.w};
+    const float a1[4] = {s1.x, s1.y, s1.z, s1.w}, a2[4] = {s2.x, s2.y, s2.z, s2.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float dr = (yh[e] * gg[e] + bb[e] > 0.f) ? dd[e] : 0.f;
+      o[e] = gg[e] * rr[e] * (dr - a1[e] * invM - yh[e] * a2[e] * invM);
+    }
+    uint2 u;
+    u.x = pack_bf16(o[0], o[1]);
+    u.y = pack_bf16(o[2], o[3]);
+    reinterpret_cast<uint2*>(dy16)[i] = u;
+  }
+}
+
+__global__ void batch_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int B, long long n,
+                                 int accumulate) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = make_float4(0, 0, 0, 0);
+    for (int b = 0; b < B; ++b) {
+      const float4 v = reinterpret_cast<const float4*>(x + (long long)b * n)[i];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out) + i;
+    if (accumulate) { const float4 p = *o; a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w; }
+    *o = a;
+  }
+}
+
+__global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ x12, __nv_bfloat16* __restrict__ out, long long rows,
+                              int H) {
+  const int H8 = H >> 3;
+  const long long n = rows * H8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / H8;
+    const int c8 = (int)(i - r * H8);
+    const uint4 a = *reinterpret_cast<const uint4*>(x12 + r * 2 * H + c8 * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(x12 + r * 2 * H + H + c8 * 8);
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x1 = unpack_bf16(au[e]), x2 = unpack_bf16(gu[e]);
+      const float s0 = x1.x / (1.f + __expf(-x1.x)) * x2.x;
+      const float s1 = x1.y / (1.f + __expf(-x1.y)) * x2.y;
+      o[e] = pack_bf16(s0, s1);
+    }
+    *reinterpret_cast<uint4*>(out + r * H + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void batch_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ o32,
+                                      __nv_bfloat16* __restrict__ o16, int B, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = make_float4(0, 0, 0, 0);
+    for (int b = 0; b < B; ++b) {
+      const uint2 u = reinterpret_cast<const uint2*>(x + (long long)b * n)[i];
+      const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+      a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
+    }
+    if (o32) reinterpret_cast<float4*>(o32)[i] = a;
+    if (o16) {
+      uint2 u;
+      u.x = pack_bf16(a.x, a.y);
+      u.y = pack_bf16(a.z, a.w);
+      reinterpret_cast<uint2*>(o16)[i] = u;
+    }
+  }
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float a, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, const __nv_bfloat16* __restrict__ dout,
+                                  __nv_bfloat16* __restrict__ dx12, long long rows, int H) {
+  const int H8 = H >> 3;
+  const long long n = rows * H8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / H8;
+    const int c8 = (int)(i - r * H8);
+    const uint4 a = *reinterpret_cast<const uint4*>(x12 + r * 2 * H + c8 * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(x12 + r * 2 * H + H + c8 * 8);
+    const uint4 d = *reinterpret_cast<const uint4*>(dout + r * H + c8 * 8);
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w}, du[4] = {d.x, d.y, d.z, d.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x1 = unpack_bf16(au[e]), x2 = unpack_bf16(gu[e]), dd = unpack_bf16(du[e]);
+      const float s0 = 1.f / (1.f + __expf(-x1.x)), s1 = 1.f / (1.f + __expf(-x1.y));
+      const float silu0 = x1.x * s0, silu1 = x1.y * s1;
+      const float ds0 = s0 * (1.f + x1.x * (1.f - s0)), ds1 = s1 * (1.f + x1.y * (1.f - s1));
+      o1[e] = pack_bf16(dd.x * x2.x * ds0, dd.y * x2.y * ds1);
+      o2[e] = pack_bf16(dd.x * silu0, dd.y * silu1);
+    }
+    *reinterpret_cast<uint4*>(dx12 + r * 2 * H + c8 * 8) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<uint4*>(dx12 + r * 2 * H + H + c8 * 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  }
+}
+
+template <int NV>
+static int launch_ln_fwd(const float* x, const float* w, const float* b, float eps, float* y32, void* y16, float* mean,
+                         float* rstd, int rows, int D, int in_period, int in_pad, cudaStream_t st) {
+  const int grid = grid_for(rows, 8, 8);
+  layernorm_fwd_kernel<NV><<<grid, 256, 0, st>>>(x, w, b, eps, y32, static_cast<__nv_bfloat16*>(y16), mean, rstd, rows,
+                                                 D, in_period, in_pad);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <int NV>
+static int launch_ln_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                         const float* dres, float* dx, void* dx16, float* dw, float* db, int rows, int D,
+                         cudaStream_t st) {
+  auto kern = layernorm_bwd_kernel<NV>;
+  size_t smem = dw ? size_t(8) * 2 * D * sizeof(float) : 0;
+  if (smem > 48 * 1024) {
+    static bool set = false;
+    if (!set) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
+  }
+  const int grid = grid_for(rows, 8 * 4, dw ? 2 : 8);
+  kern<<<grid, 256, smem, st>>>(dy, x, w, mean, rstd, dres, dx, static_cast<__nv_bfloat16*>(dx16), dw, db, rows, D);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <typename T, bool SQ>
+static int launch_colreduce(const T* x, long long ldx, float* out, int rows, int cols, cudaStream_t st) {
+  const int gx = (int)cdiv(cols, 128);
+  int gy = (int)cdiv((long long)sm_count() * 4, gx);
+  int rpb = (int)cdiv(rows, gy);
+  if (rpb < 64) rpb = 64;
+  gy = (int)cdiv(rows, rpb);
+  colreduce_kernel<T, SQ><<<dim3(gx, gy), dim3(32, 8), 0, st>>>(x, ldx, out, rows, cols, rpb);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_cast_f32_bf16(const float* x, void* y, long long n, void* stream) {
+  B200_CHECK_ARG(x && y && n >= 0, "bad args");
+  if (n == 0) return 0;
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "alignment");
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_transpose_f32_bf16(const float* in, void* out, int rows, int cols, const float* row_scale,
+                                       void* stream) {
+  B200_CHECK_ARG(in && out && rows > 0 && cols > 0, "bad args");
+  dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), 1);
+  transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, rows);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_transpose_f32_bf16_ld(const float* in, void* out, int rows, int cols, long long out_ld,
+                                          const float* row_scale, void* stream) {
+  B200_CHECK_ARG(in && out && rows > 0 && cols > 0 && out_ld >= rows, "bad args");
+  dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), 1);
+  transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, out_ld);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_nchw_to_tokens(const float* x, void* tok_bf16, float* tok_f32, int B, int C, int HW,
+                                   void* stream) {
+  B200_CHECK_ARG(x && (tok_bf16 || tok_f32) && B > 0 && C > 0 && HW > 0, "bad args");
+  dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(C, 32), (unsigned)B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tok_bf16) {
+    transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, st>>>(
+        x, static_cast<__nv_bfloat16*>(tok_bf16), C, HW, nullptr, (long long)C * HW, (long long)C * HW, tok_f32, C);
+  } else {
+    transpose_kernel<float, false><<<grid, dim3(32, 8), 0, st>>>(x, tok_f32, C, HW, nullptr, (long long)C * HW,
+                                                                  (long long)C * HW, nullptr, C);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_tokens_to_nchw(const float* tok, float* x, int B, int C, int HW, int accumulate, void* stream) {
+  B200_CHECK_ARG(tok && x && B > 0 && C > 0 && HW > 0, "bad args");
+  dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(HW, 32), (unsigned)B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (accumulate) {
+    transpose_kernel<float, true><<<grid, dim3(32, 8), 0, st>>>(tok, x, HW, C, nullptr, (long long)C * HW,
+                                                                 (long long)C * HW, nullptr, HW);
+  } else {
+    transpose_kernel<float, false><<<grid, dim3(32, 8), 0, st>>>(tok, x, HW, C, nullptr, (long long)C * HW,
+                                                                  (long long)C * HW, nullptr, HW);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_patch_im2col(const float* img, void* out, int B, int H, int W, int Kp, void* stream) {
+  B200_CHECK_ARG(img && out && B > 0, "bad args");
+  B200_CHECK_ARG(H % 14 == 0 && W % 14 == 0 && H > 0 && W > 0, "image size must be a multiple of the 14-pixel patch");
+  B200_CHECK_ARG(Kp >= 588 && Kp % 8 == 0, "Kp must be >= 588 and a multiple of 8");
+  const size_t smem = size_t(42) * W * sizeof(float);
+  B200_CHECK_ARG(smem <= 200 * 1024, "image too wide");
+  if (smem > 48 * 1024) {
+    static size_t set_to = 0;
+    if (set_to < smem) {
+      B200_CUDA_OK(cudaFuncSetAttribute(patch_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set_to = smem;
+    }
+  }
+  patch_im2col_kernel<<<B * (H / 14), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      img, static_cast<__nv_bfloat16*>(out), H, W, Kp);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_write_cls_rows(float* x, const float* cls, const float* pos, int B, int N, int D, void* stream) {
+  B200_CHECK_ARG(x && cls && pos && B > 0 && N > 0 && D > 0, "bad args");
+  write_cls_rows_kernel<<<(unsigned)cdiv((long long)B * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, cls, pos, B, N, D);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_layernorm_fwd(const float* x, const float* w, const float* b, float eps, float* y_f32,
+                                  void* y_bf16, float* mean, float* rstd, int rows, int D, int in_period, int in_pad,
+                                  void* stream) {
+  B200_CHECK_ARG(x && w && b && rows > 0, "bad args");
+  B200_CHECK_ARG(D % 4 == 0 && D > 0 && D <= LN_MAX_V4 * 128, "D must be a multiple of 4 and <= 1536");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nv = (int)cdiv(D, 128);
+  if (nv <= 3) return launch_ln_fwd<3>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, st);
+  if (nv <= 6) return launch_ln_fwd<6>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, st);
+  if (nv <= 8) return launch_ln_fwd<8>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, st);
+  return launch_ln_fwd<12>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, st);
+}
+
+extern "C" int b200_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean,
+                                  const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dw, float* db,
+                                  int rows, int D, void* stream) {
+  B200_CHECK_ARG(dy && x && w && mean && rstd && rows > 0, "bad args");
+  B200_CHECK_ARG((dw == nullptr) == (db == nullptr), "dw and db go together");
+  B200_CHECK_ARG(D % 4 == 0 && D > 0 && D <= LN_MAX_V4 * 128, "D must be a multiple of 4 and <= 1536");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nv = (int)cdiv(D, 128);
+  if (nv <= 3) return launch_ln_bwd<3>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, rows, D, st);
+  if (nv <= 6) return launch_ln_bwd<6>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, rows, D, st);
+  if (nv <= 8) return launch_ln_bwd<8>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, rows, D, st);
+  return launch_ln_bwd<12>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, rows, D, st);
+}
+
+extern "C" int b200_bn_stats(const float* y, float* sums, int M, int D, void* stream) {
+  B200_CHECK_ARG(y && sums && M > 0 && D > 0 && D % 4 == 0, "bad args");
+  return launch_colreduce<float, true>(y, D, sums, M, D, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_bn_finalize(const float* sums, float* mean, float* rstd, float* running_mean, float* running_var,
+                                float momentum, float eps, int M, int D, void* stream) {
+  B200_CHECK_ARG(mean && rstd && D > 0, "bad args");
+  B200_CHECK_ARG(sums || (running_mean && running_var), "need batch sums or running statistics");
+  bn_finalize_kernel<<<(unsigned)cdiv(D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, mean, rstd, running_mean, running_var, momentum, eps, M, D);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_bn_relu_pos_fwd(const float* y, const float* mean, const float* rstd, const float* w,
+                                    const float* b, const float* pos, float* z_f32, void* z_bf16, int M, int D, int HW,
+                                    void* stream) {
+  B200_CHECK_ARG(y && mean && rstd && w && b && pos && (z_f32 || z_bf16) && M > 0 && D % 4 == 0 && HW > 0, "bad args");
+  bn_relu_pos_fwd_kernel<<<grid_for((long long)M * D / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, mean, rstd, w, b, pos, z_f32, static_cast<__nv_bfloat16*>(z_bf16), M, D, HW);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_bn_relu_pos_bwd_reduce(const float* dz, const float* y, const float* mean, const float* rstd,
+                                           const float* w, const float* b, float* sums2, float* dpos, int M, int D,
+                                           int HW, void* stream) {
+  B200_CHECK_ARG(dz && y && mean && rstd && w && b && sums2 && M > 0 && D % 4 == 0, "bad args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int gx = (int)cdiv(D, 128);
+  int gy = (int)cdiv((long long)sm_count() * 4, gx);
+  int rpb = (int)cdiv(M, gy);
+  if (rpb < 64) rpb = 64;
+  gy = (int)cdiv(M, rpb);
+  bn_bwd_reduce_kernel<<<dim3(gx, gy), dim3(32, 8), 0, st>>>(dz, y, mean, rstd, w, b, sums2, M, D, rpb);
+  B200_LAUNCH_OK();
+  if (dpos) {
+    B200_CHECK_ARG(M % HW == 0 && ((long long)HW * D) % 4 == 0, "M must be a multiple of HW");
+    return b200_batch_sum(dz, dpos, M / HW, (long long)HW * D, stream);
+  }
+  return 0;
+}
+
+extern "C" int b200_bn_relu_pos_bwd_apply(const float* dz, const float* y, const float* mean, const float* rstd,
+                                          const float* w, const float* b, const float* sums2, void* dy_bf16,
+                                          int use_batch_stats, int M, int D, void* stream) {
+  B200_CHECK_ARG(dz && y && mean && rstd && w && b && dy_bf16 && M > 0 && D % 4 == 0, "bad args");
+  B200_CHECK_ARG(!use_batch_stats || sums2, "batch statistics need sums2");
+  bn_bwd_apply_kernel<<<grid_for((long long)M * D / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dz, y, mean, rstd, w, b, sums2, static_cast<__nv_bfloat16*>(dy_bf16), use_batch_stats, M, D);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_colsum(const void* x, int x_is_bf16, long long ldx, float* out, int rows, int cols, void* stream) {
+  B200_CHECK_ARG(x && out && rows > 0 && cols > 0 && cols % 4 == 0 && ldx % 4 == 0, "bad args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_is_bf16) return launch_colreduce<__nv_bfloat16, false>(static_cast<const __nv_bfloat16*>(x), ldx, out, rows, cols, st);
+  return launch_colreduce<float, false>(static_cast<const float*>(x), ldx, out, rows, cols, st);
+}
+
+extern "C" int b200_batch_sum(const float* x, float* out, int B, long long n, void* stream) {
+  B200_CHECK_ARG(x && out && B > 0 && n > 0 && n % 4 == 0, "bad args");
+  batch_sum_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, B, n, 1);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_swiglu(const void* x12, void* out, int rows, int H, void* stream) {
+  B200_CHECK_ARG(x12 && out && rows > 0 && H > 0 && H % 8 == 0, "bad args");
+  swiglu_kernel<<<grid_for((long long)rows * H / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x12), static_cast<__nv_bfloat16*>(out), rows, H);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_batch_sum_bf16(const void* x, float* out_f32, void* out_bf16, int B, long long n, void* stream) {
+  B200_CHECK_ARG(x && (out_f32 || out_bf16) && B > 0 && n > 0 && n % 4 == 0, "bad args");
+  batch_sum_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), out_f32, static_cast<__nv_bfloat16*>(out_bf16), B, n);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_axpy(const float* x, float* y, float a, long long n, void* stream) {
+  B200_CHECK_ARG(x && y && n > 0, "bad args");
+  axpy_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, a, n);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_swiglu_bwd(const void* x12, const void* d_out, void* d_x12, int rows, int H, void* stream) {
+  B200_CHECK_ARG(x12 && d_out && d_x12 && rows > 0 && H > 0 && H % 8 == 0, "bad args");
+  swiglu_bwd_kernel<<<grid_for((long long)rows * H / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x12), static_cast<const __nv_bfloat16*>(d_out),
+      static_cast<__nv_bfloat16*>(d_x12), rows, H);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+namespace b200 {
+int zero_f32(float* p, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  zero_kernel<<<grid_for(n, 1024, 4), 256, 0, st>>>(p, n);
+  B200_LAUNCH_OK();
+  return 0;
+}
+}  // namespace b200

@@ -1,0 +1,540 @@
+// Composite entry points: one C call runs a whole teacher forward, one teacher block (forward / input-gradient), or a
+// whole ScaleKD AttentionProjector forward / backward.  Only kernel sequencing lives here; every kernel is in
+// gemm_tcgen05.cu / attention.cu / elementwise.cu / kd_loss.cu.
+#include "common.cuh"
+#include "../../include/b200_distill.h"
+
+#include <math.h>
+#include <string.h>
+
+namespace b200 {
+
+int zero_f32(float* p, long long n, cudaStream_t st);
+
+typedef __nv_bfloat16 bf16;
+
+static int auto_split(int M, int N, int K) {
+  const long long tiles = cdiv(M, 128) * cdiv(N, 128);
+  const long long kb = cdiv(K, 64);
+  long long s = cdiv((long long)sm_count(), tiles);
+  if (s > kb / 4) s = kb / 4;  // at least 4 k-blocks per split
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+struct Gemm {
+  b200_gemm_desc d;
+  Gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K) {
+    memset(&d, 0, sizeof d);
+    d.A = A; d.lda = lda; d.B = B; d.ldb = ldb; d.M = M; d.N = N; d.K = K; d.split_k = 1;
+  }
+  Gemm& bias(const float* b) { d.bias = b; return *this; }
+  Gemm& act(int a) { d.act = a; return *this; }
+  Gemm& aux(const void* a, long long ld, int mode) { d.aux = a; d.ldaux = ld; d.aux_mode = mode; return *this; }
+  Gemm& col_scale(const float* g) { d.col_scale = g; return *this; }
+  Gemm& residual(const float* r, long long ld, int period = 0) { d.residual = r; d.ldres = ld; d.res_row_period = period; return *this; }
+  Gemm& out32(float* o, long long ld) { d.out_f32 = o; d.ldo32 = ld; return *this; }
+  Gemm& out16(void* o, long long ld) { d.out_bf16 = o; d.ldo16 = ld; return *this; }
+  Gemm& out16_pre(void* o, long long ld) { d.out_bf16_pre = o; d.ldo16_pre = ld; return *this; }
+  Gemm& row_map(int period, int pad) { d.out_row_period = period; d.out_row_pad = pad; return *this; }
+  // wgrad form: both operands token-major (contraction over rows), fp32 atomic accumulate, split over the contraction
+  Gemm& wgrad() {
+    d.a_mn_major = 1; d.b_mn_major = 1; d.atomic_add = 1;
+    d.split_k = auto_split(d.M, d.N, d.K);
+    return *this;
+  }
+  int run(void* stream) { return b200_gemm_bf16(&d, stream); }
+};
+
+// ================================================================================================ teacher
+struct VitWs {
+  bf16 *xn, *qkv, *attn, *h, *h12, *d16, *dh, *dqkv, *dattn, *dh12;
+  float *t32, *dmid, *delta, *lse;
+};
+
+static void carve_block_ws(Arena& a, const b200_vit_config* c, long long M, int B, int N, bool bwd, VitWs& w) {
+  const int D = c->D, F = c->F;
+  memset(&w, 0, sizeof w);
+  if (!bwd) {
+    w.xn = a.take_n<bf16>(M * D);
+    w.qkv = a.take_n<bf16>(M * 3 * D);
+    w.attn = a.take_n<bf16>(M * D);
+    w.h = a.take_n<bf16>(M * F);
+    if (c->swiglu) w.h12 = a.take_n<bf16>(M * 2 * F);
+    w.lse = a.take_n<float>((long long)B * c->heads * N);
+  } else {
+    w.d16 = a.take_n<bf16>(M * D);
+    w.dh = a.take_n<bf16>(M * F);
+    if (c->swiglu) w.dh12 = a.take_n<bf16>(M * 2 * F);
+    w.t32 = a.take_n<float>(M * D);
+    w.dmid = a.take_n<float>(M * D);
+    w.dattn = a.take_n<bf16>(M * D);
+    w.dqkv = a.take_n<bf16>(M * 3 * D);
+    w.delta = a.take_n<float>((long long)B * c->heads * N);
+    if (c->swiglu) w.h = a.take_n<bf16>(M * F);
+  }
+}
+
+struct VitSave {
+  float *mean1, *rstd1, *mean2, *rstd2, *lse, *x_mid;
+  bf16 *qkv, *attn, *h_pre;  // h_pre: [M, F] pre-GELU, or [M, 2F] w12 output for SwiGLU
+};
+
+static void carve_block_save(Arena& a, const b200_vit_config* c, long long M, int B, int N, VitSave& s) {
+  const int D = c->D, F = c->F;
+  s.mean1 = a.take_n<float>(M); s.rstd1 = a.take_n<float>(M);
+  s.mean2 = a.take_n<float>(M); s.rstd2 = a.take_n<float>(M);
+  s.lse = a.take_n<float>((long long)B * c->heads * N);
+  s.x_mid = a.take_n<float>(M * D);
+  s.qkv = a.take_n<bf16>(M * 3 * D);
+  s.attn = a.take_n<bf16>(M * D);
+  s.h_pre = a.take_n<bf16>(M * (c->swiglu ? 2 * F : F));
+}
+
+static int attn_desc_self(b200_attn_desc& ad, const b200_vit_config* c, const bf16* qkv, bf16* o, float* lse, int B,
+                          int N) {
+  const int D = c->D;
+  memset(&ad, 0, sizeof ad);
+  ad.q = qkv; ad.k = qkv + D; ad.v = qkv + 2 * D;
+  ad.q_bs = ad.k_bs = ad.v_bs = (long long)N * 3 * D;
+  ad.q_ts = ad.k_ts = ad.v_ts = 3 * D;
+  ad.o = o; ad.o_bs = (long long)N * D; ad.o_ts = D;
+  ad.lse = lse;
+  ad.B = B; ad.heads = c->heads; ad.Nq = N; ad.Nk = N; ad.hd = D / c->heads;
+  ad.scale = 1.0f / sqrtf((float)ad.hd);
+  return 0;
+}
+
+static int vit_block_fwd_impl(const b200_vit_config* c, const b200_vit_block* k, const float* x, float* y, int B, int N,
+                              VitSave* sv, VitWs& w, void* stream) {
+  const int D = c->D, F = c->F;
+  const long long M = (long long)B * N;
+  const int Mi = (int)M;
+  bf16* qkv = sv ? sv->qkv : w.qkv;
+  bf16* attn = sv ? sv->attn : w.attn;
+  float* lse = sv ? sv->lse : w.lse;
+  float* x_mid = sv ? sv->x_mid : y;
+  // attention half
+  B200_TRY(b200_layernorm_fwd(x, k->ln1_w, k->ln1_b, c->ln_eps, nullptr, w.xn, sv ? sv->mean1 : nullptr,
+                              sv ? sv->rstd1 : nullptr, Mi, D, 0, 0, stream));
+  B200_TRY(Gemm(w.xn, D, k->qkv_w, D, Mi, 3 * D, D).bias(k->qkv_b).out16(qkv, 3 * D).run(stream));
+  b200_attn_desc ad;
+  attn_desc_self(ad, c, qkv, attn, lse, B, N);
+  B200_TRY(b200_attention_fwd(&ad, stream));
+  B200_TRY(Gemm(attn, D, k->proj_w, D, Mi, D, D).bias(k->proj_b).col_scale(k->ls1).residual(x, D).out32(x_mid, D).run(stream));
+  // MLP half
+  B200_TRY(b200_layernorm_fwd(x_mid, k->ln2_w, k->ln2_b, c->ln_eps, nullptr, w.xn, sv ? sv->mean2 : nullptr,
+                              sv ? sv->rstd2 : nullptr, Mi, D, 0, 0, stream));
+  if (!c->swiglu) {
+    Gemm g1(w.xn, D, k->fc1_w, D, Mi, F, D);
+    g1.bias(k->fc1_b).act(B200_ACT_GELU).out16(w.h, F);
+    if (sv) g1.out16_pre(sv->h_pre, F);
+    B200_TRY(g1.run(stream));
+  } else {
+    bf16* h12 = sv ? sv->h_pre : w.h12;
+    B200_TRY(Gemm(w.xn, D, k->fc1_w, D, Mi, 2 * F, D).bias(k->fc1_b).out16(h12, 2 * F).run(stream));
+    B200_TRY(b200_swiglu(h12, w.h, Mi, F, stream));
+  }
+  B200_TRY(Gemm(w.h, F, k->fc2_w, F, Mi, D, F).bias(k->fc2_b).col_scale(k->ls2).residual(x_mid, D).out32(y, D).run(stream));
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" size_t b200_vit_block_ws_bytes(const b200_vit_config* c, int B, int N) {
+  if (!c) return 0;
+  Arena f(nullptr, 0), b(nullptr, 0);
+  VitWs w;
+  carve_block_ws(f, c, (long long)B * N, B, N, false, w);
+  carve_block_ws(b, c, (long long)B * N, B, N, true, w);
+  return (f.used() > b.used() ? f.used() : b.used()) + 256;
+}
+
+extern "C" size_t b200_vit_block_save_bytes(const b200_vit_config* c, int B, int N) {
+  if (!c) return 0;
+  Arena a(nullptr, 0);
+  VitSave s;
+  carve_block_save(a, c, (long long)B * N, B, N, s);
+  return a.used() + 256;
+}
+
+extern "C" int b200_vit_block_fwd(const b200_vit_config* c, const b200_vit_block* blk, const float* x, float* y, int B,
+                                  int N, void* save, void* ws, size_t ws_bytes, void* stream) {
+  B200_CHECK_ARG(c && blk && x && y && ws && B > 0 && N > 0, "bad args");
+  B200_CHECK_ARG(c->D % c->heads == 0, "D must be divisible by heads");
+  B200_CHECK_ARG(save == nullptr || x != y, "in-place forward cannot save activations");
+  Arena a(ws, ws_bytes);
+  VitWs w;
+  carve_block_ws(a, c, (long long)B * N, B, N, false, w);
+  B200_CHECK_ARG(a.ok(), "workspace too small");
+  VitSave sv;
+  if (save) {
+    Arena s(save, size_t(-1) >> 1);
+    carve_block_save(s, c, (long long)B * N, B, N, sv);
+  }
+  return vit_block_fwd_impl(c, blk, x, y, B, N, save ? &sv : nullptr, w, stream);
+}
+
+extern "C" int b200_vit_block_bwd_input(const b200_vit_config* c, const b200_vit_block* k, const float* x,
+                                        const float* dy, float* dx, int B, int N, const void* save, void* ws,
+                                        size_t ws_bytes, void* stream) {
+  B200_CHECK_ARG(c && k && x && dy && dx && save && ws && B > 0 && N > 0, "bad args");
+  B200_CHECK_ARG(k->qkv_wT && k->proj_wT && k->fc1_wT && k->fc2_wT,
+                 "block has no transposed weights (not in the re-used stage range)");
+  const int D = c->D, F = c->F;
+  const long long M = (long long)B * N;
+  const int Mi = (int)M;
+  Arena a(ws, ws_bytes);
+  VitWs w;
+  carve_block_ws(a, c, M, B, N, true, w);
+  B200_CHECK_ARG(a.ok(), "workspace too small");
+  VitSave sv;
+  Arena s(const_cast<void*>(save), size_t(-1) >> 1);
+  carve_block_save(s, c, M, B, N, sv);
+
+  // MLP half: y = x_mid + ls2 * fc2(act(fc1(LN2(x_mid))))     (ls2 is folded into fc2_wT)
+  B200_TRY(b200_cast_f32_bf16(dy, w.d16, M * D, stream));
+  if (!c->swiglu) {
+    B200_TRY(Gemm(w.d16, D, k->fc2_wT, D, Mi, F, D).aux(sv.h_pre, F, B200_AUX_DGELU).out16(w.dh, F).run(stream));
+    B200_TRY(Gemm(w.dh, F, k->fc1_wT, F, Mi, D, F).out32(w.t32, D).run(stream));
+  } else {
+    B200_TRY(Gemm(w.d16, D, k->fc2_wT, D, Mi, F, D).out16(w.dh, F).run(stream));
+    B200_TRY(b200_swiglu_bwd(sv.h_pre, w.dh, w.dh12, Mi, F, stream));
+    B200_TRY(Gemm(w.dh12, 2 * F, k->fc1_wT, 2 * F, Mi, D, 2 * F).out32(w.t32, D).run(stream));
+  }
+  B200_TRY(b200_layernorm_bwd(w.t32, sv.x_mid, k->ln2_w, sv.mean2, sv.rstd2, dy, w.dmid, w.d16, nullptr, nullptr, Mi, D,
+                              stream));
+  // attention half: x_mid = x + ls1 * proj(attn(qkv(LN1(x))))  (ls1 is folded into proj_wT)
+  B200_TRY(Gemm(w.d16, D, k->proj_wT, D, Mi, D, D).out16(w.dattn, D).run(stream));
+  b200_attn_desc ad;
+  attn_desc_self(ad, c, sv.qkv, sv.attn, sv.lse, B, N);
+  ad.d_o = w.dattn; ad.do_bs = (long long)N * D; ad.do_ts = D;
+  ad.delta = w.delta;
+  ad.dq = w.dqkv; ad.dk = w.dqkv + D; ad.dv = w.dqkv + 2 * D;
+  ad.dq_bs = ad.dk_bs = ad.dv_bs = (long long)N * 3 * D;
+  ad.dq_ts = ad.dk_ts = ad.dv_ts = 3 * D;
+  B200_TRY(b200_attention_bwd(&ad, stream));
+  B200_TRY(Gemm(w.dqkv, 3 * D, k->qkv_wT, 3 * D, Mi, D, 3 * D).out32(w.t32, D).run(stream));
+  B200_TRY(b200_layernorm_bwd(w.t32, x, k->ln1_w, sv.mean1, sv.rstd1, w.dmid, dx, nullptr, nullptr, nullptr, Mi, D,
+                              stream));
+  return 0;
+}
+
+extern "C" size_t b200_vit_forward_ws_bytes(const b200_vit_config* c, int B, int H, int W) {
+  if (!c) return 0;
+  const int HW = (H / 14) * (W / 14), N = HW + 1;
+  Arena a(nullptr, 0);
+  a.take_n<bf16>((long long)B * HW * 592);
+  a.take_n<float>((long long)B * N * c->D);
+  VitWs w;
+  carve_block_ws(a, c, (long long)B * N, B, N, false, w);
+  return a.used() + 256;
+}
+
+extern "C" int b200_vit_forward(const b200_vit_config* c, const b200_vit_block* blocks, const void* patch_w, int Kp,
+                                const float* patch_b, const float* cls, const float* pos, const float* norm_w,
+                                const float* norm_b, const float* img, int B, int H, int W, float* out_tokens,
+                                void* ws, size_t ws_bytes, void* stream) {
+  B200_CHECK_ARG(c && blocks && patch_w && patch_b && cls && pos && norm_w && norm_b && img && out_tokens && ws,
+                 "null argument");
+  B200_CHECK_ARG(B > 0 && H % 14 == 0 && W % 14 == 0 && H > 0 && W > 0, "image size must be a multiple of 14");
+  B200_CHECK_ARG(Kp == 592, "patch weight must be padded to 592 columns");
+  const int D = c->D;
+  const int HW = (H / 14) * (W / 14), N = HW + 1;
+  const long long M = (long long)B * N;
+  Arena a(ws, ws_bytes);
+  bf16* patches = a.take_n<bf16>((long long)B * HW * Kp);
+  float* x = a.take_n<float>(M * D);
+  VitWs w;
+  carve_block_ws(a, c, M, B, N, false, w);
+  B200_CHECK_ARG(a.ok(), "workspace too small");
+
+  B200_TRY(b200_patch_im2col(img, patches, B, H, W, Kp, stream));
+  // x[b*N + 1 + p, :] = patches . Wp^T + bias + pos[1 + p, :]
+  B200_TRY(Gemm(patches, Kp, patch_w, Kp, B * HW, D, Kp).bias(patch_b).residual(pos + D, D, HW).out32(x, D).row_map(HW, 1).run(stream));
+  B200_TRY(b200_write_cls_rows(x, cls, pos, B, N, D, stream));
+  for (int l = 0; l < c->L; ++l) B200_TRY(vit_block_fwd_impl(c, &blocks[l], x, x, B, N, nullptr, w, stream));
+  B200_TRY(b200_layernorm_fwd(x, norm_w, norm_b, c->ln_eps, out_tokens, nullptr, nullptr, nullptr, (int)M, D, 0, 0,
+                              stream));
+  return 0;
+}
+
+// ================================================================================================ ScaleKD projector
+namespace b200 {
+
+struct ProjSave {
+  bf16 *xt16, *z16, *qsrc16, *q16, *kv16, *o16, *g16, *h16;
+  float *y, *bn_mean, *bn_rstd, *lse, *f32, *mean1, *rstd1, *u32, *mean2, *rstd2;
+};
+
+static void carve_proj_save(Arena& a, const b200_projector_config* c, int B, ProjSave& s) {
+  const long long M = (long long)B * c->HW;
+  const int D = c->D;
+  s.xt16 = a.take_n<bf16>(M * c->Cs);
+  s.y = a.take_n<float>(M * D);
+  s.bn_mean = a.take_n<float>(D);
+  s.bn_rstd = a.take_n<float>(D);
+  s.z16 = a.take_n<bf16>(M * D);
+  s.qsrc16 = a.take_n<bf16>(M * D);
+  s.q16 = a.take_n<bf16>(M * D);
+  s.kv16 = a.take_n<bf16>(M * 2 * D);
+  s.o16 = a.take_n<bf16>(M * D);
+  s.lse = a.take_n<float>((long long)B * c->heads * c->HW);
+  s.f32 = a.take_n<float>(M * D);
+  s.mean1 = a.take_n<float>(M); s.rstd1 = a.take_n<float>(M);
+  s.g16 = a.take_n<bf16>(M * D);
+  s.h16 = a.take_n<bf16>(M * 4 * D);
+  s.u32 = a.take_n<float>(M * D);
+  s.mean2 = a.take_n<float>(M); s.rstd2 = a.take_n<float>(M);
+}
+
+struct ProjFwdWs {
+  bf16 *wc16, *wq16, *wkv16, *wp16, *w1_16, *w2_16;
+  float *bkv, *sums, *pos_t, *z32, *g32;
+};
+static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, ProjFwdWs& w) {
+  const long long M = (long long)B * c->HW;
+  const long long D = c->D;
+  w.wc16 = a.take_n<bf16>(D * c->Cs);
+  w.wq16 = a.take_n<bf16>(D * D);
+  w.wkv16 = a.take_n<bf16>(2 * D * D);
+  w.wp16 = a.take_n<bf16>(D * D);
+  w.w1_16 = a.take_n<bf16>(4 * D * D);
+  w.w2_16 = a.take_n<bf16>(4 * D * D);
+  w.bkv = a.take_n<float>(2 * D);
+  w.sums = a.take_n<float>(2 * D);
+  w.pos_t = a.take_n<float>((long long)c->HW * D);
+  w.z32 = a.take_n<float>(M * D);
+  w.g32 = a.take_n<float>(M * D);
+}
+
+struct ProjBwdWs {
+  bf16 *w2T, *w1T, *wpT, *wkvT, *wqT, *wcT;
+  bf16 *du16, *dh16, *df16, *do16, *dq16, *dkv16, *dqs16, *dy16;
+  float *du32, *dg32, *df32, *dz32, *dqs32, *sums2, *dpos_t, *delta, *dxt32;
+};
+static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, ProjBwdWs& w) {
+  const long long M = (long long)B * c->HW;
+  const long long D = c->D;
+  w.w2T = a.take_n<bf16>(4 * D * D);
+  w.w1T = a.take_n<bf16>(4 * D * D);
+  w.wpT = a.take_n<bf16>(D * D);
+  w.wkvT = a.take_n<bf16>(2 * D * D);
+  w.wqT = a.take_n<bf16>(D * D);
+  w.wcT = a.take_n<bf16>(D * c->Cs);
+  w.du16 = a.take_n<bf16>(M * D);
+  w.dh16 = a.take_n<bf16>(M * 4 * D);
+  w.df16 = a.take_n<bf16>(M * D);
+  w.do16 = a.take_n<bf16>(M * D);
+  w.dq16 = a.take_n<bf16>(M * D);
+  w.dkv16 = a.take_n<bf16>(M * 2 * D);
+  w.dqs16 = a.take_n<bf16>((long long)c->HW * D);
+  w.dy16 = a.take_n<bf16>(M * D);
+  w.du32 = a.take_n<float>(M * D);
+  w.dg32 = a.take_n<float>(M * D);
+  w.df32 = a.take_n<float>(M * D);
+  w.dz32 = a.take_n<float>(M * D);
+  w.dqs32 = a.take_n<float>((long long)c->HW * D);
+  w.sums2 = a.take_n<float>(2 * D);
+  w.dpos_t = a.take_n<float>((long long)c->HW * D);
+  w.delta = a.take_n<float>((long long)B * c->heads * c->HW);
+  w.dxt32 = a.take_n<float>(M * c->Cs);
+}
+
+static int check_proj_cfg(const b200_projector_config* c, int B) {
+  B200_CHECK_ARG(c != nullptr && B > 0, "bad args");
+  B200_CHECK_ARG(c->D > 0 && c->Cs > 0 && c->HW > 0 && c->heads > 0, "bad config");
+  B200_CHECK_ARG(c->D % c->heads == 0, "teacher_dims must be divisible by num_heads");
+  const int hd = c->D / c->heads;
+  B200_CHECK_ARG(hd % 8 == 0 && hd <= 96, "head_dim (teacher_dims / num_heads) must be a multiple of 8 and <= 96");
+  B200_CHECK_ARG(c->D % 8 == 0 && c->Cs % 8 == 0, "channel counts must be multiples of 8");
+  return 0;
+}
+
+static void proj_attn_desc(b200_attn_desc& ad, const b200_projector_config* c, const ProjSave& s, bool ext_query,
+                           int B) {
+  const int D = c->D, HW = c->HW;
+  memset(&ad, 0, sizeof ad);
+  ad.q = s.q16; ad.q_bs = ext_query ? (long long)HW * D : 0; ad.q_ts = D;
+  ad.k = s.kv16; ad.v = s.kv16 + D;
+  ad.k_bs = ad.v_bs = (long long)HW * 2 * D; ad.k_ts = ad.v_ts = 2 * D;
+  ad.o = s.o16; ad.o_bs = (long long)HW * D; ad.o_ts = D;
+  ad.lse = s.lse;
+  ad.B = B; ad.heads = c->heads; ad.Nq = HW; ad.Nk = HW; ad.hd = D / c->heads;
+  ad.scale = c->softmax_scale / sqrtf((float)ad.hd);
+}
+
+}  // namespace b200
+
+extern "C" size_t b200_projector_ws_bytes(const b200_projector_config* c, int B) {
+  if (!c || B <= 0) return 0;
+  Arena f(nullptr, 0), b(nullptr, 0);
+  ProjFwdWs wf;
+  ProjBwdWs wb;
+  carve_proj_fwd_ws(f, c, B, wf);
+  carve_proj_bwd_ws(b, c, B, wb);
+  return (f.used() > b.used() ? f.used() : b.used()) + 256;
+}
+
+extern "C" size_t b200_projector_save_bytes(const b200_projector_config* c, int B) {
+  if (!c || B <= 0) return 0;
+  Arena a(nullptr, 0);
+  ProjSave s;
+  carve_proj_save(a, c, B, s);
+  return a.used() + 256;
+}
+
+extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_projector_params* p, const float* x,
+                                  const float* query, int B, float* out, void* save, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  B200_TRY(check_proj_cfg(c, B));
+  B200_CHECK_ARG(p && x && out && save && ws, "null argument");
+  B200_CHECK_ARG(query != nullptr || p->query_w != nullptr, "There is no query!");
+  const int D = c->D, Cs = c->Cs, HW = c->HW;
+  const long long M = (long long)B * HW;
+  const int Mi = (int)M;
+  const bool ext = query != nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena sa(save, size_t(-1) >> 1);
+  ProjSave s;
+  carve_proj_save(sa, c, B, s);
+  Arena wa(ws, ws_bytes);
+  ProjFwdWs w;
+  carve_proj_fwd_ws(wa, c, B, w);
+  B200_CHECK_ARG(wa.ok(), "workspace too small");
+
+  // bf16 working copies of the fp32 master weights
+  B200_TRY(b200_cast_f32_bf16(p->conv_w, w.wc16, (long long)D * Cs, stream));
+  B200_TRY(b200_cast_f32_bf16(p->q_w, w.wq16, (long long)D * D, stream));
+  B200_TRY(b200_cast_f32_bf16(p->k_w, w.wkv16, (long long)D * D, stream));
+  B200_TRY(b200_cast_f32_bf16(p->v_w, w.wkv16 + (long long)D * D, (long long)D * D, stream));
+  B200_TRY(b200_cast_f32_bf16(p->p_w, w.wp16, (long long)D * D, stream));
+  B200_TRY(b200_cast_f32_bf16(p->ffn1_w, w.w1_16, 4LL * D * D, stream));
+  B200_TRY(b200_cast_f32_bf16(p->ffn2_w, w.w2_16, 4LL * D * D, stream));
+  B200_CUDA_OK(cudaMemcpyAsync(w.bkv, p->k_b, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  B200_CUDA_OK(cudaMemcpyAsync(w.bkv + D, p->v_b, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  // proj_student: conv1x1 -> BN -> ReLU, + pos_embed            (losses/scalekd.py:199-201, :238)
+  B200_TRY(b200_nchw_to_tokens(x, s.xt16, nullptr, B, Cs, HW, stream));
+  B200_TRY(Gemm(s.xt16, Cs, w.wc16, Cs, Mi, D, Cs).bias(p->conv_b).out32(s.y, D).run(stream));
+  if (c->training) {
+    B200_TRY(zero_f32(w.sums, 2 * D, st));
+    B200_TRY(b200_bn_stats(s.y, w.sums, Mi, D, stream));
+    B200_TRY(b200_bn_finalize(w.sums, s.bn_mean, s.bn_rstd, p->bn_running_mean, p->bn_running_var, c->bn_momentum,
+                              c->bn_eps, Mi, D, stream));
+  } else {
+    B200_TRY(b200_bn_finalize(nullptr, s.bn_mean, s.bn_rstd, p->bn_running_mean, p->bn_running_var, c->bn_momentum,
+                              c->bn_eps, Mi, D, stream));
+  }
+  B200_TRY(b200_nchw_to_tokens(p->pos_embed, nullptr, w.pos_t, 1, D, HW, stream));
+  B200_TRY(b200_bn_relu_pos_fwd(s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.pos_t, w.z32, s.z16, Mi, D, HW, stream));
+
+  // cross attention: q from the query tokens, k/v from the student tokens      (losses/scalekd.py:299-316)
+  const int Mq = ext ? Mi : HW;
+  B200_TRY(b200_cast_f32_bf16(ext ? query : p->query_w, s.qsrc16, (long long)Mq * D, stream));
+  B200_TRY(Gemm(s.qsrc16, D, w.wq16, D, Mq, D, D).bias(p->q_b).out16(s.q16, D).run(stream));
+  B200_TRY(Gemm(s.z16, D, w.wkv16, D, Mi, 2 * D, D).bias(w.bkv).out16(s.kv16, 2 * D).run(stream));
+  b200_attn_desc ad;
+  proj_attn_desc(ad, c, s, ext, B);
+  B200_TRY(b200_attention_fwd(&ad, stream));
+  B200_TRY(Gemm(s.o16, D, w.wp16, D, Mi, D, D).bias(p->p_b).residual(w.z32, D).out32(s.f32, D).run(stream));
+
+  // norm -> FFN(ReLU) + residual -> norm_2                                      (losses/scalekd.py:243-245)
+  B200_TRY(b200_layernorm_fwd(s.f32, p->ln1_w, p->ln1_b, c->ln_eps, w.g32, s.g16, s.mean1, s.rstd1, Mi, D, 0, 0, stream));
+  B200_TRY(Gemm(s.g16, D, w.w1_16, D, Mi, 4 * D, D).bias(p->ffn1_b).act(B200_ACT_RELU).out16(s.h16, 4 * D).run(stream));
+  B200_TRY(Gemm(s.h16, 4 * D, w.w2_16, 4 * D, Mi, D, 4 * D).bias(p->ffn2_b).residual(w.g32, D).out32(s.u32, D).run(stream));
+  B200_TRY(b200_layernorm_fwd(s.u32, p->ln2_w, p->ln2_b, c->ln_eps, out, nullptr, s.mean2, s.rstd2, Mi, D, 0, 0, stream));
+  return 0;
+}
+
+extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_projector_params* p,
+                                  const b200_projector_grads* g, const float* x, const float* query, const float* dout,
+                                  int B, float* dx, int dx_accumulate, float* dquery, const void* save, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  B200_TRY(check_proj_cfg(c, B));
+  B200_CHECK_ARG(p && g && dout && save && ws, "null argument");
+  (void)x;
+  const int D = c->D, Cs = c->Cs, HW = c->HW;
+  const long long M = (long long)B * HW;
+  const int Mi = (int)M;
+  const bool ext = query != nullptr;
+  B200_CHECK_ARG(!ext || dquery != nullptr || true, "");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena sa(const_cast<void*>(save), size_t(-1) >> 1);
+  ProjSave s;
+  carve_proj_save(sa, c, B, s);
+  Arena wa(ws, ws_bytes);
+  ProjBwdWs w;
+  carve_proj_bwd_ws(wa, c, B, w);
+  B200_CHECK_ARG(wa.ok(), "workspace too small");
+
+  // transposed bf16 weights for the dgrad GEMMs
+  B200_TRY(b200_transpose_f32_bf16(p->ffn2_w, w.w2T, D, 4 * D, nullptr, stream));   // [D,4D] -> [4D, D]
+  B200_TRY(b200_transpose_f32_bf16(p->ffn1_w, w.w1T, 4 * D, D, nullptr, stream));   // [4D,D] -> [D, 4D]
+  B200_TRY(b200_transpose_f32_bf16(p->p_w, w.wpT, D, D, nullptr, stream));
+  B200_TRY(b200_transpose_f32_bf16_ld(p->k_w, w.wkvT, D, D, 2 * D, nullptr, stream));      // [D, 2D]: [Wk^T | Wv^T]
+  B200_TRY(b200_transpose_f32_bf16_ld(p->v_w, w.wkvT + D, D, D, 2 * D, nullptr, stream));
+  B200_TRY(b200_transpose_f32_bf16(p->q_w, w.wqT, D, D, nullptr, stream));
+  B200_TRY(b200_transpose_f32_bf16(p->conv_w, w.wcT, D, Cs, nullptr, stream));       // [D,Cs] -> [Cs, D]
+
+  // norm_2
+  B200_TRY(b200_layernorm_bwd(dout, s.u32, p->ln2_w, s.mean2, s.rstd2, nullptr, w.du32, w.du16, g->ln2_w, g->ln2_b, Mi, D, stream));
+  // FFN: u = g + W2 relu(W1 g + b1) + b2
+  B200_TRY(b200_colsum(w.du32, 0, D, g->ffn2_b, Mi, D, stream));
+  B200_TRY(Gemm(w.du16, D, s.h16, 4 * D, D, 4 * D, Mi).out32(g->ffn2_w, 4 * D).wgrad().run(stream));
+  B200_TRY(Gemm(w.du16, D, w.w2T, D, Mi, 4 * D, D).aux(s.h16, 4 * D, B200_AUX_DRELU).out16(w.dh16, 4 * D).run(stream));
+  B200_TRY(b200_colsum(w.dh16, 1, 4 * D, g->ffn1_b, Mi, 4 * D, stream));
+  B200_TRY(Gemm(w.dh16, 4 * D, s.g16, D, 4 * D, D, Mi).out32(g->ffn1_w, D).wgrad().run(stream));
+  B200_TRY(Gemm(w.dh16, 4 * D, w.w1T, 4 * D, Mi, D, 4 * D).residual(w.du32, D).out32(w.dg32, D).run(stream));
+  // norm
+  B200_TRY(b200_layernorm_bwd(w.dg32, s.f32, p->ln1_w, s.mean1, s.rstd1, nullptr, w.df32, w.df16, g->ln1_w, g->ln1_b, Mi, D, stream));
+  // attention output projection: f = Wp o + bp + z
+  B200_TRY(b200_colsum(w.df32, 0, D, g->p_b, Mi, D, stream));
+  B200_TRY(Gemm(w.df16, D, s.o16, D, D, D, Mi).out32(g->p_w, D).wgrad().run(stream));
+  B200_TRY(Gemm(w.df16, D, w.wpT, D, Mi, D, D).out16(w.do16, D).run(stream));
+  // attention core
+  b200_attn_desc ad;
+  proj_attn_desc(ad, c, s, ext, B);
+  ad.d_o = w.do16; ad.do_bs = (long long)HW * D; ad.do_ts = D;
+  ad.delta = w.delta;
+  ad.dq = w.dq16; ad.dq_bs = (long long)HW * D; ad.dq_ts = D;
+  ad.dk = w.dkv16; ad.dv = w.dkv16 + D;
+  ad.dk_bs = ad.dv_bs = (long long)HW * 2 * D; ad.dk_ts = ad.dv_ts = 2 * D;
+  B200_TRY(b200_attention_bwd(&ad, stream));
+  // q path
+  if (ext) {
+    B200_TRY(b200_colsum(w.dq16, 1, D, g->q_b, Mi, D, stream));
+    B200_TRY(Gemm(w.dq16, D, s.qsrc16, D, D, D, Mi).out32(g->q_w, D).wgrad().run(stream));
+    if (dquery) B200_TRY(Gemm(w.dq16, D, w.wqT, D, Mi, D, D).out32(dquery, D).run(stream));
+  } else {
+    B200_TRY(b200_batch_sum_bf16(w.dq16, w.dqs32, w.dqs16, B, (long long)HW * D, stream));
+    B200_TRY(b200_colsum(w.dqs32, 0, D, g->q_b, HW, D, stream));
+    B200_TRY(Gemm(w.dqs16, D, s.qsrc16, D, D, D, HW).out32(g->q_w, D).wgrad().run(stream));
+    if (g->query_w)
+      B200_TRY(Gemm(w.dqs16, D, w.wqT, D, HW, D, D).residual(g->query_w, D).out32(g->query_w, D).run(stream));
+  }
+  // k / v path
+  B200_TRY(b200_colsum(w.dkv16, 1, 2 * D, g->k_b, Mi, D, stream));
+  B200_TRY(b200_colsum(w.dkv16 + D, 1, 2 * D, g->v_b, Mi, D, stream));
+  B200_TRY(Gemm(w.dkv16, 2 * D, s.z16, D, D, D, Mi).out32(g->k_w, D).wgrad().run(stream));
+  B200_TRY(Gemm(w.dkv16 + D, 2 * D, s.z16, D, D, D, Mi).out32(g->v_w, D).wgrad().run(stream));
+  B200_TRY(Gemm(w.dkv16, 2 * D, w.wkvT, 2 * D, Mi, D, 2 * D).residual(w.df32, D).out32(w.dz32, D).run(stream));
+  // BN + ReLU + pos_embed
+  B200_TRY(zero_f32(w.sums2, 2 * D, st));
+  B200_TRY(zero_f32(w.dpos_t, (long long)HW * D, st));
+  B200_TRY(b200_bn_relu_pos_bwd_reduce(w.dz32, s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.sums2, w.dpos_t, Mi, D, HW, stream));
+  B200_TRY(b200_tokens_to_nchw(w.dpos_t, g->pos_embed, 1, D, HW, 1, stream));
+  B200_TRY(b200_axpy(w.sums2, g->bn_b, 1.0f, D, stream));
+  B200_TRY(b200_axpy(w.sums2 + D, g->bn_w, 1.0f, D, stream));
+  B200_TRY(b200_bn_relu_pos_bwd_apply(w.dz32, s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.sums2, w.dy16, c->training ? 1 : 0, Mi, D, stream));
+  // conv1x1
+  B200_TRY(b200_colsum(w.dy16, 1, D, g->conv_b, Mi, D, stream));
+  B200_TRY(Gemm(w.dy16, D, s.xt16, Cs, D, Cs, Mi).out32(g->conv_w, Cs).wgrad().run(stream));
+  if (dx) {
+    B200_TRY(Gemm(w.dy16, D, w.wcT, D, Mi, Cs, D).out32(w.dxt32, Cs).run(stream));
+    B200_TRY(b200_tokens_to_nchw(w.dxt32, dx, B, Cs, HW, dx_accumulate, stream));
+  }
+  return 0;
+}

@@ -1,0 +1,507 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA (128B swizzle) -> smem ring -> tcgen05.mma -> TMEM
+// (double-buffered accumulators) -> tcgen05.ld epilogue with fused bias / activation / LayerScale / residual.
+//
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : MMA issuer   (one elected lane; tcgen05.commit releases smem slots / publishes accumulators)
+//   warp 2      : TMEM allocate / free
+//   warps 4..7  : epilogue (warp w reads TMEM lanes 32*(w%4) .. +31, one output row per thread)
+//
+// C[M,N] = A * B^T.  Operands may be K-major (contraction contiguous; the nn.Linear layout) or MN-major (output dim
+// contiguous; used by wgrad dW = dY^T X where both operands are token-major).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/b200_distill.h"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace b200 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, num_kb, kb_per_split, split_k, total_tiles;
+  const float* bias;
+  int act;
+  const __nv_bfloat16* aux;
+  long long ldaux;
+  int aux_mode;
+  const float* col_scale;
+  const float* residual;
+  long long ldres;
+  int res_row_period;
+  float* out_f32;
+  long long ldo32;
+  int atomic_add;
+  __nv_bfloat16* out_bf16;
+  long long ldo16;
+  __nv_bfloat16* out_bf16_pre;
+  long long ldo16_pre;
+  int out_row_period, out_row_pad;
+  int vec_ok;  // all leading dims / pointers allow 16-byte vector access
+};
+
+template <int BN>
+struct TileCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 6 : (BN == 192 ? 5 : 4);
+  static constexpr int TMEM_STRIDE = (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * TMEM_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok, int row, int n0, float (&v)[32],
+                                               bool first_split) {
+  if (!row_ok || n0 >= p.N) return;
+  const bool full = (n0 + 32 <= p.N) && p.vec_ok;
+  if (p.bias != nullptr && first_split) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+    }
+  }
+  long long orow = row;
+  if (p.out_row_period > 0) {
+    orow = (long long)(row / p.out_row_period) * (p.out_row_period + p.out_row_pad) + p.out_row_pad +
+           row % p.out_row_period;
+  }
+  if (p.out_bf16_pre != nullptr) {
+    __nv_bfloat16* dst = p.out_bf16_pre + orow * p.ldo16_pre + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
+        u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(dst + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+    }
+  }
+  if (p.act == B200_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == B200_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (p.aux_mode != B200_AUX_NONE) {
+    const __nv_bfloat16* ax = p.aux + (long long)row * p.ldaux + n0;
+    float a[32];
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(ax + j));
+        float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+        a[j] = f0.x; a[j + 1] = f0.y; a[j + 2] = f1.x; a[j + 3] = f1.y;
+        a[j + 4] = f2.x; a[j + 5] = f2.y; a[j + 6] = f3.x; a[j + 7] = f3.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? __bfloat162float(ax[j]) : 0.0f;
+    }
+    if (p.aux_mode == B200_AUX_DGELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(a[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
+    }
+  }
+  if (p.col_scale != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0 + j));
+        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] *= __ldg(p.col_scale + n0 + j);
+    }
+  }
+  if (p.residual != nullptr && first_split) {
+    const long long rr = p.res_row_period > 0 ? (row % p.res_row_period) : orow;
+    const float* rs = p.residual + rr * p.ldres + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 r = *reinterpret_cast<const float4*>(rs + j);
+        v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] += rs[j];
+    }
+  }
+  if (p.out_f32 != nullptr) {
+    float* dst = p.out_f32 + orow * p.ldo32 + n0;
+    if (p.atomic_add) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) atomicAdd(dst + j, v[j]);
+    } else if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = v[j];
+    }
+  }
+  if (p.out_bf16 != nullptr) {
+    __nv_bfloat16* dst = p.out_bf16 + orow * p.ldo16 + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
+        u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(dst + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int ks = t / tiles_mn;
+        const int r = t - ks * tiles_mn;
+        const int m0 = (r / p.n_tiles) * BM;
+        const int n0 = (r % p.n_tiles) * BN;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + A_TILE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int ks = t / tiles_mn;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::TMEM_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 elements = 32 bytes inside the 128B swizzle row; SBO = 8 rows * 128B.
+            // MN-major: 16 contraction rows = 2 swizzle atoms of 1024B; LBO = next 64-wide column block (64 rows*128B).
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int ks = t / tiles_mn;
+      const int r = t - ks * tiles_mn;
+      const int m0 = (r / p.n_tiles) * BM;
+      const int n0 = (r % p.n_tiles) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + c * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        epilogue_chunk(p, row_ok, row, n0 + c * 32, v, ks == 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, ld;
+  uint32_t b0, b1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= k.d0 * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.d1 * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= k.ld * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    h ^= (uint64_t(k.b0) << 32 | k.b1) + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// 2-D bf16 tensor map: dim0 (contiguous) x dim1 rows with row pitch ld elements; box b0 x b1; 128B swizzle.
+int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
+                       uint32_t b1) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, d0, d1, ld, b0, b1};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -4; }
+  cuuint64_t gdim[2] = {d0, d1};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) ptr=%p dims=(%llu,%llu) ld=%llu box=(%u,%u)", (int)r,
+             ptr, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
+    set_error(buf);
+    return -4;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using Cfg = TileCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                          cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, p, st);
+  if (a_mn && b_mn) return launch_gemm<BN, true, true>(ta, tb, p, st);
+  if (a_mn) return launch_gemm<BN, true, false>(ta, tb, p, st);
+  return launch_gemm<BN, false, true>(ta, tb, p, st);
+}
+
+static int pick_bn(int N, int m_tiles) {
+  // fewest wasted columns first; among equals prefer the widest tile (less smem traffic per MMA).
+  const int cands[3] = {256, 192, 128};
+  int best = 128;
+  double best_cost = 1e30;
+  const int sms = sm_count();
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long long nt = cdiv(N, bn);
+    const long long tiles = nt * m_tiles;
+    const long long waves = cdiv(tiles, sms);
+    // cost ~ waves * per-tile time (proportional to bn) ; small penalty for narrow tiles
+    double cost = double(waves) * bn * (bn == 128 ? 1.06 : 1.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
+  B200_CHECK_ARG(d != nullptr, "null descriptor");
+  B200_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "empty problem");
+  B200_CHECK_ARG(d->A && d->B, "null operand");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(d->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->B) & 15) == 0,
+                 "operands must be 16-byte aligned");
+  B200_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0, "operand leading dims must be multiples of 8 elements");
+  B200_CHECK_ARG(d->out_f32 || d->out_bf16, "no output");
+  const int split = d->split_k < 1 ? 1 : d->split_k;
+  if (split > 1) {
+    B200_CHECK_ARG(d->out_f32 && d->atomic_add && !d->out_bf16 && !d->out_bf16_pre && d->act == 0 &&
+                       d->aux_mode == 0 && d->col_scale == nullptr,
+                   "split_k > 1 needs a plain atomic fp32 epilogue");
+  }
+  GemmParams p{};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.m_tiles = (int)cdiv(d->M, BM);
+  p.num_kb = (int)cdiv(d->K, BK);
+  int sk = split > p.num_kb ? p.num_kb : split;
+  p.kb_per_split = (int)cdiv(p.num_kb, sk);
+  p.split_k = (int)cdiv(p.num_kb, p.kb_per_split);
+  const int bn = pick_bn(d->N, p.m_tiles * p.split_k);
+  p.n_tiles = (int)cdiv(d->N, bn);
+  p.total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+  p.bias = d->bias; p.act = d->act;
+  p.aux = static_cast<const __nv_bfloat16*>(d->aux); p.ldaux = d->ldaux; p.aux_mode = d->aux ? d->aux_mode : 0;
+  p.col_scale = d->col_scale;
+  p.residual = d->residual; p.ldres = d->ldres; p.res_row_period = d->res_row_period;
+  p.out_f32 = d->out_f32; p.ldo32 = d->ldo32; p.atomic_add = d->atomic_add;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16); p.ldo16 = d->ldo16;
+  p.out_bf16_pre = static_cast<__nv_bfloat16*>(d->out_bf16_pre); p.ldo16_pre = d->ldo16_pre;
+  p.out_row_period = d->out_row_period; p.out_row_pad = d->out_row_pad;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  bool vec = true;
+  if (p.bias) vec = vec && al16(p.bias);
+  if (p.aux_mode) vec = vec && al16(p.aux) && p.ldaux % 8 == 0;
+  if (p.col_scale) vec = vec && al16(p.col_scale);
+  if (p.residual) vec = vec && al16(p.residual) && p.ldres % 4 == 0;
+  if (p.out_f32) vec = vec && al16(p.out_f32) && p.ldo32 % 4 == 0;
+  if (p.out_bf16) vec = vec && al16(p.out_bf16) && p.ldo16 % 8 == 0;
+  if (p.out_bf16_pre) vec = vec && al16(p.out_bf16_pre) && p.ldo16_pre % 8 == 0;
+  p.vec_ok = vec ? 1 : 0;
+
+  CUtensorMap ta, tb;
+  if (!d->a_mn_major) {
+    B200_TRY(make_tensor_map_2d(&ta, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM));
+  } else {
+    B200_TRY(make_tensor_map_2d(&ta, d->A, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, 64, BK));
+  }
+  if (!d->b_mn_major) {
+    B200_TRY(make_tensor_map_2d(&tb, d->B, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, (uint32_t)bn));
+  } else {
+    B200_TRY(make_tensor_map_2d(&tb, d->B, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, BK));
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool amn = d->a_mn_major != 0, bmn = d->b_mn_major != 0;
+  if (bn == 256) return dispatch_major<256>(amn, bmn, ta, tb, p, st);
+  if (bn == 192) return dispatch_major<192>(amn, bmn, ta, tb, p, st);
+  return dispatch_major<128>(amn, bmn, ta, tb, p, st);
+}

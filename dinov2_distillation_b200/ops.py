@@ -1,0 +1,235 @@
+"""Tensor-level wrappers over the C ABI (PyTorch is only used for device memory and streams).
+
+Every function requires CUDA tensors and launches hand-written kernels from libb200distill.so on the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+ACT = {"none": 0, "gelu": 1, "relu": 2}
+AUX = {"none": 0, "dgelu": 1, "drelu": 2}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.B200Error("b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+def launch_count() -> int:
+    return int(L.load().b200_launch_count())
+
+
+def reset_launch_count() -> None:
+    L.load().b200_reset_launch_count()
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False,
+         bias: Optional[torch.Tensor] = None, act: str = "none", aux: Optional[torch.Tensor] = None,
+         aux_mode: str = "none", col_scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         res_row_period: int = 0, out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None,
+         atomic_add: bool = False, split_k: int = 1, out_pre: bool = False, out_row_period: int = 0,
+         out_row_pad: int = 0):
+    """C = epilogue(A @ B^T). K-major: a [M,K], b [N,K]. MN-major: a [K,M], b [K,N] (contraction over rows)."""
+    _need_cuda(a, b, bias, aux, col_scale, residual, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.stride(-1) == 1 and b.stride(-1) == 1
+    if a_mn_major:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn_major:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape)
+    d = L.GemmDesc()
+    d.A, d.lda, d.a_mn_major = a.data_ptr(), a.stride(0), int(a_mn_major)
+    d.B, d.ldb, d.b_mn_major = b.data_ptr(), b.stride(0), int(b_mn_major)
+    d.M, d.N, d.K, d.split_k = M, N, K, split_k
+    d.bias = _p(bias)
+    d.act = ACT[act]
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16
+        d.aux, d.ldaux, d.aux_mode = aux.data_ptr(), aux.stride(0), AUX[aux_mode]
+    d.col_scale = _p(col_scale)
+    if residual is not None:
+        assert residual.dtype == torch.float32
+        d.residual, d.ldres, d.res_row_period = residual.data_ptr(), residual.stride(0), res_row_period
+    out_rows = M if out_row_period <= 0 else (M // out_row_period) * (out_row_period + out_row_pad)
+    if out is None:
+        out = torch.empty(out_rows, N, device=a.device, dtype=out_dtype)
+    pre = None
+    if out.dtype == torch.float32:
+        d.out_f32, d.ldo32, d.atomic_add = out.data_ptr(), out.stride(0), int(atomic_add)
+    else:
+        assert out.dtype == torch.bfloat16
+        d.out_bf16, d.ldo16 = out.data_ptr(), out.stride(0)
+    if out_pre:
+        pre = torch.empty(out_rows, N, device=a.device, dtype=torch.bfloat16)
+        d.out_bf16_pre, d.ldo16_pre = pre.data_ptr(), pre.stride(0)
+    d.out_row_period, d.out_row_pad = out_row_period, out_row_pad
+    L.check(L.load().b200_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
+    return (out, pre) if out_pre else out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x, dtype=torch.bfloat16)
+    L.check(L.load().b200_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "cast")
+    return y
+
+
+def transpose_bf16(w: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [R, C] -> bf16 [C, R] (optionally rows scaled first)."""
+    _need_cuda(w, row_scale)
+    w = w.contiguous()
+    R, Cc = w.shape
+    out = torch.empty(Cc, R, device=w.device, dtype=torch.bfloat16)
+    L.check(L.load().b200_transpose_f32_bf16(w.data_ptr(), out.data_ptr(), R, Cc, _p(row_scale), _stream()), "transpose")
+    return out
+
+
+def nchw_to_tokens(x: torch.Tensor, want_f32: bool = False):
+    _need_cuda(x)
+    x = x.contiguous()
+    B, Cc = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel()
+    t16 = torch.empty(B * HW, Cc, device=x.device, dtype=torch.bfloat16)
+    t32 = torch.empty(B * HW, Cc, device=x.device, dtype=torch.float32) if want_f32 else None
+    L.check(L.load().b200_nchw_to_tokens(x.data_ptr(), t16.data_ptr(), _p(t32), B, Cc, HW, _stream()), "nchw_to_tokens")
+    return (t16, t32) if want_f32 else t16
+
+
+def tokens_to_nchw(tok: torch.Tensor, B: int, HW: int) -> torch.Tensor:
+    _need_cuda(tok)
+    Cc = tok.shape[-1]
+    out = torch.empty(B, Cc, HW, device=tok.device, dtype=torch.float32)
+    L.check(L.load().b200_tokens_to_nchw(tok.data_ptr(), out.data_ptr(), B, Cc, HW, 0, _stream()), "tokens_to_nchw")
+    return out
+
+
+def patch_im2col(img: torch.Tensor, Kp: int = 592) -> torch.Tensor:
+    _need_cuda(img)
+    img = img.contiguous()
+    B, _, H, W = img.shape
+    out = torch.empty(B * (H // 14) * (W // 14), Kp, device=img.device, dtype=torch.bfloat16)
+    L.check(L.load().b200_patch_im2col(img.data_ptr(), out.data_ptr(), B, H, W, Kp, _stream()), "patch_im2col")
+    return out
+
+
+def layernorm_fwd(x, w, b, eps, want_f32=True, want_bf16=False, want_stats=False, in_period=0, in_pad=0, rows=None):
+    _need_cuda(x, w, b)
+    D = x.shape[-1]
+    if rows is None:
+        rows = x.numel() // D
+    y32 = torch.empty(rows, D, device=x.device, dtype=torch.float32) if want_f32 else None
+    y16 = torch.empty(rows, D, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    L.check(L.load().b200_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps), _p(y32), _p(y16), _p(mean),
+                                        _p(rstd), rows, D, in_period, in_pad, _stream()), "layernorm_fwd")
+    return y32, y16, mean, rstd
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dres=None, want_wgrad=True, want_bf16=False):
+    _need_cuda(dy, x, w, mean, rstd, dres)
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dx = torch.empty(rows, D, device=x.device, dtype=torch.float32)
+    dx16 = torch.empty(rows, D, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    dw = torch.zeros(D, device=x.device, dtype=torch.float32) if want_wgrad else None
+    db = torch.zeros(D, device=x.device, dtype=torch.float32) if want_wgrad else None
+    L.check(L.load().b200_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                        _p(dres), dx.data_ptr(), _p(dx16), _p(dw), _p(db), rows, D, _stream()),
+            "layernorm_bwd")
+    return dx, dx16, dw, db
+
+
+def _attn_desc(q, k, v, o, lse, heads, scale):
+    # q: [B, Nq, heads*hd] view (possibly expanded over batch), k/v: [B, Nk, heads*hd] views
+    B, Nq, Dm = q.shape
+    Nk = k.shape[1]
+    d = L.AttnDesc()
+    d.q, d.q_bs, d.q_ts = q.data_ptr(), q.stride(0), q.stride(1)
+    d.k, d.k_bs, d.k_ts = k.data_ptr(), k.stride(0), k.stride(1)
+    d.v, d.v_bs, d.v_ts = v.data_ptr(), v.stride(0), v.stride(1)
+    d.o, d.o_bs, d.o_ts = o.data_ptr(), o.stride(0), o.stride(1)
+    d.lse = _p(lse)
+    d.B, d.heads, d.Nq, d.Nk, d.hd = B, heads, Nq, Nk, Dm // heads
+    d.scale = float(scale)
+    return d
+
+
+def attention_fwd(q, k, v, heads: int, scale: float):
+    """q [B,Nq,D], k/v [B,Nk,D] bf16 (last dim contiguous, any batch/token strides) -> o [B,Nq,D] bf16, lse [B,h,Nq]."""
+    _need_cuda(q, k, v)
+    B, Nq, Dm = q.shape
+    o = torch.empty(B, Nq, Dm, device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, Nq, device=q.device, dtype=torch.float32)
+    d = _attn_desc(q, k, v, o, lse, heads, scale)
+    L.check(L.load().b200_attention_fwd(C.byref(d), _stream()), "attention_fwd")
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float):
+    _need_cuda(q, k, v, o, lse, d_o)
+    B, Nq, Dm = q.shape
+    Nk = k.shape[1]
+    dq = torch.empty(B, Nq, Dm, device=q.device, dtype=torch.bfloat16)
+    dk = torch.empty(B, Nk, Dm, device=q.device, dtype=torch.bfloat16)
+    dv = torch.empty(B, Nk, Dm, device=q.device, dtype=torch.bfloat16)
+    delta = torch.empty(B, heads, Nq, device=q.device, dtype=torch.float32)
+    d = _attn_desc(q, k, v, o, lse, heads, scale)
+    d.d_o, d.do_bs, d.do_ts = d_o.data_ptr(), d_o.stride(0), d_o.stride(1)
+    d.delta = delta.data_ptr()
+    d.dq, d.dq_bs, d.dq_ts = dq.data_ptr(), dq.stride(0), dq.stride(1)
+    d.dk, d.dk_bs, d.dk_ts = dk.data_ptr(), dk.stride(0), dk.stride(1)
+    d.dv, d.dv_bs, d.dv_ts = dv.data_ptr(), dv.stride(0), dv.stride(1)
+    L.check(L.load().b200_attention_bwd(C.byref(d), _stream()), "attention_bwd")
+    return dq, dk, dv
+
+
+def kd_loss_fwd(S: torch.Tensor, T_tokens: torch.Tensor, t_skip: int, freq: bool, alpha: float):
+    """S fp32 [B,HW,D]; T_tokens fp32 [B,Nt,D] (contiguous). Returns (out[2] = (loss, similarity), ws)."""
+    _need_cuda(S, T_tokens)
+    B, HW, D = S.shape
+    Nt = T_tokens.shape[1]
+    ws = torch.empty(int(L.load().b200_kd_loss_ws_floats(B, HW, D)), device=S.device, dtype=torch.float32)
+    out = torch.empty(2, device=S.device, dtype=torch.float32)
+    L.check(L.load().b200_kd_loss_fwd(S.data_ptr(), T_tokens.data_ptr(), B, HW, D, Nt, t_skip, int(freq), float(alpha),
+                                      out.data_ptr(), ws.data_ptr(), _stream()), "kd_loss_fwd")
+    return out, ws
+
+
+def kd_loss_bwd(S, T_tokens, t_skip, freq, alpha, g_out, ws):
+    _need_cuda(S, T_tokens, g_out, ws)
+    B, HW, D = S.shape
+    Nt = T_tokens.shape[1]
+    dS = torch.empty_like(S)
+    L.check(L.load().b200_kd_loss_bwd(S.data_ptr(), T_tokens.data_ptr(), B, HW, D, Nt, t_skip, int(freq), float(alpha),
+                                      g_out.data_ptr(), dS.data_ptr(), 0, ws.data_ptr(), _stream()), "kd_loss_bwd")
+    return dS
+
+
+def dct_zero_dc_idct(x_tokens: torch.Tensor, R: int) -> torch.Tensor:
+    """Explicit DCT cross-check: x [B, R*R, D] fp32 contiguous -> same shape."""
+    _need_cuda(x_tokens)
+    B, HW, D = x_tokens.shape
+    y = torch.empty_like(x_tokens)
+    L.check(L.load().b200_dct_zero_dc_idct(x_tokens.data_ptr(), y.data_ptr(), B, R, D, HW * D, D, _stream()), "dct")
+    return y

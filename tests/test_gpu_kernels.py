@@ -1,0 +1,266 @@
+"""Kernel-level parity on the GPU: each hand-written kernel against a plain PyTorch fp32 statement of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from dinov2_distillation_b200 import ops
+    return ops
+
+
+def rel_err(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(0)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 384), (514, 1152, 384), (1000, 256, 592),
+                                   (16448, 384, 1536), (300, 192, 128), (77, 1536, 384), (2048, 2048, 1024)])
+def test_gemm_kmajor_plain(M, N, K):
+    ops = _ops()
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a, b)
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+    out16 = ops.gemm(a, b, out_dtype=torch.bfloat16)
+    assert rel_err(out16, ref) < 6e-3
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("M,N,K", [(384, 384, 4096), (128, 256, 128), (1024, 200, 333 * 8), (384, 1536, 1000)])
+def test_gemm_mn_major(a_mn, b_mn, M, N, K):
+    ops = _ops()
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    ref = a.float() @ b.float().t()
+    aa = a.t().contiguous() if a_mn else a
+    bb = b.t().contiguous() if b_mn else b
+    out = ops.gemm(aa, bb, a_mn_major=a_mn, b_mn_major=b_mn)
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+
+
+def test_gemm_split_k_atomic():
+    ops = _ops()
+    M, N, K = 384, 1536, 16384
+    a = bf(torch.randn(K, M, device="cuda"))
+    b = bf(torch.randn(K, N, device="cuda") / math.sqrt(K))
+    ref = a.float().t() @ b.float()
+    base = torch.randn(M, N, device="cuda")
+    out = base.clone()
+    ops.gemm(a, b, a_mn_major=True, b_mn_major=True, out=out, atomic_add=True, split_k=16)
+    assert rel_err(out - base, ref) < 2e-3
+
+
+def test_gemm_epilogues():
+    ops = _ops()
+    M, N, K = 1030, 768, 384
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    bias = torch.randn(N, device="cuda")
+    gamma = torch.rand(N, device="cuda") + 0.1
+    res = torch.randn(M, N, device="cuda")
+    acc = a.float() @ b.float().t() + bias
+    # bias + gelu, with pre-activation copy
+    out, pre = ops.gemm(a, b, bias=bias, act="gelu", out_dtype=torch.bfloat16, out_pre=True)
+    assert rel_err(out, torch.nn.functional.gelu(acc)) < 6e-3
+    assert rel_err(pre, acc) < 6e-3
+    # bias + relu
+    out = ops.gemm(a, b, bias=bias, act="relu", out_dtype=torch.bfloat16)
+    assert rel_err(out, torch.relu(acc)) < 6e-3
+    # LayerScale + residual, in place on the residual stream
+    x = res.clone()
+    ops.gemm(a, b, bias=bias, col_scale=gamma, residual=x, out=x)
+    assert rel_err(x, res + gamma * acc) < 2e-3
+    # aux: multiply by gelu'(aux) / relu mask
+    aux = bf(torch.randn(M, N, device="cuda"))
+    out = ops.gemm(a, b, aux=aux, aux_mode="dgelu")
+    xa = aux.float()
+    dg = 0.5 * (1 + torch.erf(xa / math.sqrt(2))) + xa * torch.exp(-0.5 * xa * xa) / math.sqrt(2 * math.pi)
+    assert rel_err(out, (a.float() @ b.float().t()) * dg) < 2e-3
+    out = ops.gemm(a, b, aux=aux, aux_mode="drelu")
+    assert rel_err(out, (a.float() @ b.float().t()) * (xa > 0)) < 2e-3
+    # periodic residual + row remap (patch-embed form)
+    period, pad = 103, 1
+    pos = torch.randn(period, N, device="cuda")
+    out = torch.zeros((M // period) * (period + pad), N, device="cuda")
+    ops.gemm(a, b, bias=bias, residual=pos, res_row_period=period, out=out, out_row_period=period, out_row_pad=pad)
+    ref = (acc.view(M // period, period, N) + pos).reshape(M // period, period, N)
+    got = out.view(M // period, period + pad, N)[:, pad:, :]
+    assert rel_err(got, ref) < 2e-3
+    assert out.view(M // period, period + pad, N)[:, 0, :].abs().max().item() == 0.0
+
+
+def test_gemm_odd_n_tail():
+    ops = _ops()
+    M, N, K = 200, 72, 64
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda"))
+    bias = torch.randn(N, device="cuda")
+    out = ops.gemm(a, b, bias=bias)
+    assert rel_err(out, a.float() @ b.float().t() + bias) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("D", [384, 768, 1024, 1536])
+def test_layernorm_fwd_bwd(D):
+    ops = _ops()
+    rows = 1031
+    x = torch.randn(rows, D, device="cuda") * 2 + 0.5
+    w = torch.randn(D, device="cuda")
+    b = torch.randn(D, device="cuda")
+    y32, y16, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6, want_bf16=True, want_stats=True)
+    ref = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-6)
+    assert (y32 - ref).abs().max().item() < 1e-4
+    assert rel_err(y16, ref) < 5e-3
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    dy = torch.randn(rows, D, device="cuda")
+    dres = torch.randn(rows, D, device="cuda")
+    torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-6).backward(dy)
+    dx, dx16, dw, db = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres, want_bf16=True)
+    assert rel_err(dx, xr.grad + dres) < 1e-5
+    assert rel_err(dw, wr.grad) < 1e-4
+    assert rel_err(db, br.grad) < 1e-4
+    assert rel_err(dx16, xr.grad + dres) < 5e-3
+
+
+def test_layernorm_drop_cls_rows():
+    ops = _ops()
+    B, N, D = 3, 17, 384
+    x = torch.randn(B, N, D, device="cuda")
+    w = torch.ones(D, device="cuda")
+    b = torch.zeros(D, device="cuda")
+    y32, _, _, _ = ops.layernorm_fwd(x, w, b, 1e-6, in_period=N - 1, in_pad=1, rows=B * (N - 1))
+    ref = torch.nn.functional.layer_norm(x[:, 1:], (D,), w, b, 1e-6).reshape(-1, D)
+    assert (y32 - ref).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, heads, scale):
+    B, Nq, D = q.shape
+    Nk = k.shape[1]
+    hd = D // heads
+    qh = q.float().view(B, Nq, heads, hd).transpose(1, 2)
+    kh = k.float().view(B, Nk, heads, hd).transpose(1, 2)
+    vh = v.float().view(B, Nk, heads, hd).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(B, Nq, D)
+
+
+@pytest.mark.parametrize("hd,heads,Nq,Nk", [(64, 6, 257, 257), (16, 24, 256, 256), (24, 16, 256, 256), (32, 24, 100, 77),
+                                            (48, 16, 64, 200), (96, 16, 130, 130), (64, 16, 1370, 1370)])
+def test_attention_fwd_bwd(hd, heads, Nq, Nk):
+    ops = _ops()
+    B = 2
+    D = hd * heads
+    scale = 5.0 / math.sqrt(hd) if hd != 64 else 1.0 / math.sqrt(hd)
+    q = bf(torch.randn(B, Nq, D, device="cuda") * 0.5)
+    k = bf(torch.randn(B, Nk, D, device="cuda") * 0.5)
+    v = bf(torch.randn(B, Nk, D, device="cuda"))
+    o, lse = ops.attention_fwd(q, k, v, heads, scale)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qr, kr, vr, heads, scale)
+    assert rel_err(o, ref) < 1e-2, rel_err(o, ref)
+    d_o = bf(torch.randn(B, Nq, D, device="cuda"))
+    ref.backward(d_o.float())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale)
+    assert rel_err(dv, vr.grad) < 2e-2, rel_err(dv, vr.grad)
+    assert rel_err(dk, kr.grad) < 2e-2, rel_err(dk, kr.grad)
+    assert rel_err(dq, qr.grad) < 2e-2, rel_err(dq, qr.grad)
+
+
+def test_attention_strided_qkv_and_shared_query():
+    ops = _ops()
+    B, N, heads, hd = 3, 70, 6, 64
+    D = heads * hd
+    qkv = bf(torch.randn(B, N, 3 * D, device="cuda") * 0.5)
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    o, _ = ops.attention_fwd(q, k, v, heads, hd ** -0.5)
+    assert rel_err(o, _attn_ref(q, k, v, heads, hd ** -0.5)) < 1e-2
+    qs = bf(torch.randn(1, N, D, device="cuda") * 0.5).expand(B, N, D)   # batch stride 0
+    o, _ = ops.attention_fwd(qs, k, v, heads, hd ** -0.5)
+    assert rel_err(o, _attn_ref(qs, k, v, heads, hd ** -0.5)) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ loss terms
+def _ref_loss(S, T_map, alpha, freq):
+    import torch.nn.functional as F
+    N, C, H, W = T_map.shape
+    s = S.permute(0, 2, 1).contiguous().view(N, C, H, W)
+    t = T_map
+    if freq:
+        s = s - s.mean(dim=(2, 3), keepdim=True)
+        t = t - t.mean(dim=(2, 3), keepdim=True)
+    s = F.normalize(s, dim=1)
+    t = F.normalize(t, dim=1)
+    loss = ((s - t) ** 2).sum() / N * alpha
+    sim = F.cosine_similarity(s, t, dim=1).mean()
+    return loss, sim
+
+
+@pytest.mark.parametrize("freq", [False, True])
+@pytest.mark.parametrize("B,R,D", [(2, 16, 384), (3, 37, 1024)])
+def test_kd_loss_fwd_bwd(freq, B, R, D):
+    ops = _ops()
+    HW = R * R
+    S = torch.randn(B, HW, D, device="cuda")
+    T = torch.randn(B, HW + 1, D, device="cuda") + 0.3
+    T_map = T[:, 1:].reshape(B, R, R, D).permute(0, 3, 1, 2)
+    out, ws = ops.kd_loss_fwd(S, T, 1, freq, 0.08)
+    Sr = S.clone().requires_grad_(True)
+    loss, sim = _ref_loss(Sr, T_map, 0.08, freq)
+    assert abs(out[0].item() - loss.item()) / abs(loss.item()) < 1e-4
+    assert abs(out[1].item() - sim.item()) < 1e-4
+    g = torch.tensor([1.7, 0.0], device="cuda")
+    (loss * 1.7).backward()
+    dS = ops.kd_loss_bwd(S, T, 1, freq, 0.08, g, ws)
+    assert rel_err(dS, Sr.grad) < 1e-3, rel_err(dS, Sr.grad)
+
+
+def test_dct_identity_matches_mean_subtraction():
+    ops = _ops()
+    for R in (16, 37):
+        x = torch.randn(2, R * R, 40, device="cuda")
+        y = ops.dct_zero_dc_idct(x, R)
+        ref = x - x.mean(dim=1, keepdim=True)
+        assert (y - ref).abs().max().item() < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ layout kernels
+def test_im2col_matches_unfold():
+    ops = _ops()
+    img = torch.randn(2, 3, 56, 70, device="cuda")
+    got = ops.patch_im2col(img).float()
+    ref = torch.nn.functional.unfold(img, 14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert (got[:, :588] - ref).abs().max().item() < 2e-2
+    assert got[:, 588:].abs().max().item() == 0
+
+
+def test_token_layout_roundtrip():
+    ops = _ops()
+    x = torch.randn(3, 72, 5, 7, device="cuda")
+    t16, t32 = ops.nchw_to_tokens(x, want_f32=True)
+    ref = x.flatten(2).transpose(1, 2).reshape(-1, 72)
+    assert (t32 - ref).abs().max().item() == 0
+    assert rel_err(t16, ref) < 5e-3
+    back = ops.tokens_to_nchw(t32, 3, 35)
+    assert (back.view_as(x) - x).abs().max().item() == 0
+    w = torch.randn(96, 40, device="cuda")
+    s = torch.rand(96, device="cuda")
+    assert rel_err(ops.transpose_bf16(w, s), (w * s[:, None]).t()) < 5e-3
