@@ -31,6 +31,7 @@ class GemmDesc(C.Structure):
         ("out_bf16", c_vp), ("ldo16", c_ll),
         ("out_bf16_pre", c_vp), ("ldo16_pre", c_ll),
         ("out_row_period", C.c_int), ("out_row_pad", C.c_int),
+        ("a_is_fp16", C.c_int), ("b_is_fp16", C.c_int), ("out16_is_fp16", C.c_int), ("aux_is_fp16", C.c_int),
     ]
 
 
@@ -48,6 +49,7 @@ class AttnDesc(C.Structure):
         ("dq", c_vp), ("dq_bs", c_ll), ("dq_ts", c_ll),
         ("dk", c_vp), ("dk_bs", c_ll), ("dk_ts", c_ll),
         ("dv", c_vp), ("dv_bs", c_ll), ("dv_ts", c_ll),
+        ("qkvo_is_fp16", C.c_int),
     ]
 
 
@@ -101,17 +103,20 @@ SIGNATURES = {
     "b200_reset_launch_count": (None, []),
     "b200_gemm_bf16": (_i, [C.POINTER(GemmDesc), c_vp]),
     "b200_cast_f32_bf16": (_i, [c_fp, c_vp, c_ll, c_vp]),
+    "b200_split3_16": (_i, [c_fp, c_vp, c_ll, _i, _i, _i, c_vp]),
+    "b200_cast_f32_f16": (_i, [c_fp, c_vp, c_ll, c_vp]),
+    "b200_cast_f16_bf16": (_i, [c_vp, c_vp, c_ll, c_vp]),
     "b200_transpose_f32_bf16": (_i, [c_fp, c_vp, _i, _i, c_fp, c_vp]),
     "b200_transpose_f32_bf16_ld": (_i, [c_fp, c_vp, _i, _i, c_ll, c_fp, c_vp]),
-    "b200_nchw_to_tokens": (_i, [c_fp, c_vp, c_fp, _i, _i, _i, c_vp]),
+    "b200_nchw_to_tokens": (_i, [c_fp, c_vp, c_fp, _i, _i, _i, _i, c_vp]),
     "b200_tokens_to_nchw": (_i, [c_fp, c_fp, _i, _i, _i, _i, c_vp]),
     "b200_patch_im2col": (_i, [c_fp, c_vp, _i, _i, _i, _i, c_vp]),
     "b200_write_cls_rows": (_i, [c_fp, c_fp, c_fp, _i, _i, _i, c_vp]),
-    "b200_layernorm_fwd": (_i, [c_fp, c_fp, c_fp, _f, c_fp, c_vp, c_fp, c_fp, _i, _i, _i, _i, c_vp]),
+    "b200_layernorm_fwd": (_i, [c_fp, c_fp, c_fp, _f, c_fp, c_vp, c_fp, c_fp, _i, _i, _i, _i, _i, c_vp]),
     "b200_layernorm_bwd": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, c_fp, c_fp, _i, _i, c_vp]),
     "b200_bn_stats": (_i, [c_fp, c_fp, _i, _i, c_vp]),
     "b200_bn_finalize": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, _f, _f, _i, _i, c_vp]),
-    "b200_bn_relu_pos_fwd": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, _i, _i, _i, c_vp]),
+    "b200_bn_relu_pos_fwd": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, _i, _i, _i, _i, c_vp]),
     "b200_bn_relu_pos_bwd_reduce": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, c_vp]),
     "b200_bn_relu_pos_bwd_apply": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, _i, _i, _i, c_vp]),
     "b200_colsum": (_i, [c_vp, _i, c_ll, c_fp, _i, _i, c_vp]),

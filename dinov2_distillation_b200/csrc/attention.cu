@@ -41,6 +41,30 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool F16>
+__device__ __forceinline__ void mma_16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (F16) mma_f16(c, a, b0, b1); else mma_bf16(c, a, b0, b1);
+}
+__device__ __forceinline__ uint32_t pack_half(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_16(float a, float b) {
+  if constexpr (F16) return pack_half(a, b); else return pack_bf16(a, b);
+}
+// packed fp16x2 -> packed bf16x2 (saved forward activations are fp16; gradient MMAs run in bf16 for range)
+__device__ __forceinline__ uint32_t h2_to_bf2(uint32_t u) {
+  const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+  return pack_bf16(f.x, f.y);
+}
+
 // Load a [64][HDP] bf16 tile (row pitch HDP+PAD) of rows row0.. from a token-major strided tensor; rows >= nrows and
 // columns >= hd are zero filled (cp.async src-size 0).
 template <int HDP>
@@ -66,8 +90,17 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&a)[HDP / 16][4], const _
     ldsm_x4(a[kb], s + (warp * 16 + (lane & 15)) * PITCH + kb * 16 + (lane >> 4) * 8);
 }
 
-// acc[16 x 64] (+)= A[16 x HDP] * T^T, T: smem tile [64][HDP] row-major (T rows are the output columns).
 template <int HDP>
+__device__ __forceinline__ void cvt_frags_h2b(uint32_t (&a)[HDP / 16][4]) {
+#pragma unroll
+  for (int kb = 0; kb < HDP / 16; ++kb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a[kb][e] = h2_to_bf2(a[kb][e]);
+}
+
+// acc[16 x 64] (+)= A[16 x HDP] * T^T, T: smem tile [64][HDP] row-major (T rows are the output columns).
+// F16: fp16 MMA (A and T fp16). CVT: T holds fp16 but the MMA is bf16 (A is a bf16 gradient) -> convert fragments.
+template <int HDP, bool F16, bool CVT>
 __device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[HDP / 16][4],
                                          const __nv_bfloat16* t, int lane) {
   constexpr int PITCH = HDP + ATT_PAD;
@@ -78,14 +111,18 @@ __device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)
     for (int nb = 0; nb < 8; nb += 2) {
       uint32_t b[4];
       ldsm_x4(b, t + ((nb + (mi >> 1)) * 8 + rr) * PITCH + kb * 16 + (mi & 1) * 8);
-      mma_bf16(acc[nb], a[kb], b[0], b[1]);
-      mma_bf16(acc[nb + 1], a[kb], b[2], b[3]);
+      if constexpr (CVT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b[e] = h2_to_bf2(b[e]);
+      }
+      mma_16<F16>(acc[nb], a[kb], b[0], b[1]);
+      mma_16<F16>(acc[nb + 1], a[kb], b[2], b[3]);
     }
   }
 }
 
-// out[16 x HDP] += P[16 x 64] * T, P given as C-layout fp32 registers (converted to bf16 A fragments), T: [64][HDP].
-template <int HDP>
+// out[16 x HDP] += P[16 x 64] * T, P given as C-layout fp32 registers (converted to 16-bit A fragments), T: [64][HDP].
+template <int HDP, bool F16, bool CVT>
 __device__ __forceinline__ void mma_p_t(float (&out)[HDP / 8][4], const float (&p)[8][4], const __nv_bfloat16* t,
                                         int lane) {
   constexpr int PITCH = HDP + ATT_PAD;
@@ -93,16 +130,20 @@ __device__ __forceinline__ void mma_p_t(float (&out)[HDP / 8][4], const float (&
 #pragma unroll
   for (int kb = 0; kb < 4; ++kb) {
     uint32_t a[4];
-    a[0] = pack_bf16(p[2 * kb][0], p[2 * kb][1]);
-    a[1] = pack_bf16(p[2 * kb][2], p[2 * kb][3]);
-    a[2] = pack_bf16(p[2 * kb + 1][0], p[2 * kb + 1][1]);
-    a[3] = pack_bf16(p[2 * kb + 1][2], p[2 * kb + 1][3]);
+    a[0] = pack_16<F16>(p[2 * kb][0], p[2 * kb][1]);
+    a[1] = pack_16<F16>(p[2 * kb][2], p[2 * kb][3]);
+    a[2] = pack_16<F16>(p[2 * kb + 1][0], p[2 * kb + 1][1]);
+    a[3] = pack_16<F16>(p[2 * kb + 1][2], p[2 * kb + 1][3]);
 #pragma unroll
     for (int nb = 0; nb < HDP / 8; nb += 2) {
       uint32_t b[4];
       ldsm_x4_t(b, t + (kb * 16 + (mi & 1) * 8 + rr) * PITCH + (nb + (mi >> 1)) * 8);
-      mma_bf16(out[nb], a, b[0], b[1]);
-      mma_bf16(out[nb + 1], a, b[2], b[3]);
+      if constexpr (CVT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b[e] = h2_to_bf2(b[e]);
+      }
+      mma_16<F16>(out[nb], a, b[0], b[1]);
+      mma_16<F16>(out[nb + 1], a, b[2], b[3]);
     }
   }
 }
@@ -115,10 +156,11 @@ struct AttnParams {
   long long q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, do_bs, do_ts, dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts;
   int B, heads, Nq, Nk, hd;
   float scale, scale_log2;
+  int half;
 };
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int HDP>
+template <int HDP, bool HALF>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const AttnParams p) {
   constexpr int PITCH = HDP + ATT_PAD;
@@ -163,7 +205,7 @@ attn_fwd_kernel(const AttnParams p) {
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-    mma_a_tT<HDP>(s, qa, sK + buf * TILE, lane);
+    mma_a_tT<HDP, HALF, false>(s, qa, sK + buf * TILE, lane);
 
     const int kbase = it * ATT_BK;
     float mx0 = m0, mx1 = m1;
@@ -199,7 +241,7 @@ attn_fwd_kernel(const AttnParams p) {
     l1 = l1 * a1 + rs1;
 #pragma unroll
     for (int i = 0; i < HDP / 8; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
-    mma_p_t<HDP>(o, s, sV + buf * TILE, lane);
+    mma_p_t<HDP, HALF, false>(o, s, sV + buf * TILE, lane);
     __syncthreads();
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
@@ -213,8 +255,8 @@ attn_fwd_kernel(const AttnParams p) {
   for (int nb = 0; nb < HDP / 8; ++nb) {
     const int col = nb * 8 + 2 * t4;
     if (col < p.hd) {
-      if (r0 < p.Nq) *reinterpret_cast<uint32_t*>(go + (long long)r0 * p.o_ts + col) = pack_bf16(o[nb][0] * inv0, o[nb][1] * inv0);
-      if (r1 < p.Nq) *reinterpret_cast<uint32_t*>(go + (long long)r1 * p.o_ts + col) = pack_bf16(o[nb][2] * inv1, o[nb][3] * inv1);
+      if (r0 < p.Nq) *reinterpret_cast<uint32_t*>(go + (long long)r0 * p.o_ts + col) = pack_16<HALF>(o[nb][0] * inv0, o[nb][1] * inv0);
+      if (r1 < p.Nq) *reinterpret_cast<uint32_t*>(go + (long long)r1 * p.o_ts + col) = pack_16<HALF>(o[nb][2] * inv1, o[nb][3] * inv1);
     }
   }
   if (p.lse != nullptr && t4 == 0) {
@@ -227,6 +269,7 @@ attn_fwd_kernel(const AttnParams p) {
 
 // ------------------------------------------------------------------------------------------------ backward: delta
 // delta[b, h, q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
+template <bool HALF>
 __global__ void attn_delta_kernel(const AttnParams p) {
   const long long n = (long long)p.B * p.Nq * p.heads;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -243,7 +286,8 @@ __global__ void attn_delta_kernel(const AttnParams p) {
       const uint32_t xa[4] = {ua.x, ua.y, ua.z, ua.w}, xc[4] = {uc.x, uc.y, uc.z, uc.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 fa = unpack_bf16(xa[e]), fc = unpack_bf16(xc[e]);
+        const float2 fa = unpack_bf16(xa[e]);
+        const float2 fc = HALF ? __half22float2(*reinterpret_cast<const __half2*>(&xc[e])) : unpack_bf16(xc[e]);
         acc += fa.x * fc.x + fa.y * fc.y;
       }
     }
@@ -252,7 +296,7 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
-template <int HDP>
+template <int HDP, bool HALF>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const AttnParams p) {
   constexpr int PITCH = HDP + ATT_PAD;
@@ -313,8 +357,8 @@ attn_bwd_dq_kernel(const AttnParams p) {
       s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
       dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
     }
-    mma_a_tT<HDP>(s, qa, sK + buf * TILE, lane);
-    mma_a_tT<HDP>(dp, doa, sV + buf * TILE, lane);
+    mma_a_tT<HDP, HALF, false>(s, qa, sK + buf * TILE, lane);
+    mma_a_tT<HDP, false, HALF>(dp, doa, sV + buf * TILE, lane);
     const int kbase = it * ATT_BK;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
@@ -327,7 +371,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
         s[nb][e] = pv * (dp[nb][e] - dlt);
       }
     }
-    mma_p_t<HDP>(dq, s, sK + buf * TILE, lane);
+    mma_p_t<HDP, false, HALF>(dq, s, sK + buf * TILE, lane);
     __syncthreads();
   }
   __nv_bfloat16* gdq = p.dq + (long long)b * p.dq_bs + (long long)h * p.hd;
@@ -342,7 +386,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
-template <int HDP>
+template <int HDP, bool HALF>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const AttnParams p) {
   constexpr int PITCH = HDP + ATT_PAD;
@@ -405,6 +449,7 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     if (it == 0) {
       load_a_frags<HDP>(ka, sK, warp, lane);
       load_a_frags<HDP>(va, sV, warp, lane);
+      if constexpr (HALF) cvt_frags_h2b<HDP>(va);  // V meets the bf16 gradient dO
     }
     float st[8][4], dpt[8][4];
 #pragma unroll
@@ -412,8 +457,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
       st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
       dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
     }
-    mma_a_tT<HDP>(st, ka, sQ + buf * TILE, lane);     // S^T[kv, q]
-    mma_a_tT<HDP>(dpt, va, sdO + buf * TILE, lane);   // dP^T[kv, q]
+    mma_a_tT<HDP, HALF, false>(st, ka, sQ + buf * TILE, lane);     // S^T[kv, q]
+    mma_a_tT<HDP, false, false>(dpt, va, sdO + buf * TILE, lane);  // dP^T[kv, q]
     float pt[8][4];
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
@@ -428,8 +473,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
         st[nb][e] = pv * (dpt[nb][e] - dlt);
       }
     }
-    mma_p_t<HDP>(dv, pt, sdO + buf * TILE, lane);   // dV += P^T dO
-    mma_p_t<HDP>(dk, st, sQ + buf * TILE, lane);    // dK += dS^T Q
+    mma_p_t<HDP, false, false>(dv, pt, sdO + buf * TILE, lane);  // dV += P^T dO
+    mma_p_t<HDP, false, HALF>(dk, st, sQ + buf * TILE, lane);    // dK += dS^T Q
     __syncthreads();
   }
   __nv_bfloat16* gdk = p.dk + (long long)b * p.dk_bs + (long long)h * p.hd;
@@ -469,6 +514,7 @@ static int fill_params(const b200_attn_desc* d, AttnParams& p, bool bwd) {
   p.o_bs = d->o_bs; p.o_ts = d->o_ts;
   p.B = d->B; p.heads = d->heads; p.Nq = d->Nq; p.Nk = d->Nk; p.hd = d->hd;
   p.scale = d->scale; p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.half = d->qkvo_is_fp16 ? 1 : 0;
   if (bwd) {
     B200_CHECK_ARG(d->d_o && d->delta && d->lse && d->dq && d->dk && d->dv, "backward needs d_o, lse, delta, dq, dk, dv");
     B200_CHECK_ARG(al(d->d_o) && al(d->dq) && al(d->dk) && al(d->dv), "tensors must be 16-byte aligned");
@@ -488,39 +534,47 @@ static int set_smem(K kern, size_t bytes) {
   return 0;
 }
 
-template <int HDP>
-static int launch_fwd(const AttnParams& p, cudaStream_t st) {
+template <int HDP, bool HALF>
+static int launch_fwd_t(const AttnParams& p, cudaStream_t st) {
   constexpr size_t smem = size_t(5) * 64 * (HDP + ATT_PAD) * 2;
   static bool once = false;
-  if (!once) { B200_TRY(set_smem(attn_fwd_kernel<HDP>, smem)); once = true; }
+  if (!once) { B200_TRY(set_smem(attn_fwd_kernel<HDP, HALF>, smem)); once = true; }
   dim3 grid((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
-  attn_fwd_kernel<HDP><<<grid, ATT_THREADS, smem, st>>>(p);
+  attn_fwd_kernel<HDP, HALF><<<grid, ATT_THREADS, smem, st>>>(p);
   B200_LAUNCH_OK();
   return 0;
 }
-
 template <int HDP>
-static int launch_bwd(const AttnParams& p, cudaStream_t st) {
+static int launch_fwd(const AttnParams& p, cudaStream_t st) {
+  return p.half ? launch_fwd_t<HDP, true>(p, st) : launch_fwd_t<HDP, false>(p, st);
+}
+
+template <int HDP, bool HALF>
+static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
   constexpr size_t smem_dq = size_t(6) * 64 * (HDP + ATT_PAD) * 2;
   constexpr size_t smem_dkv = size_t(6) * 64 * (HDP + ATT_PAD) * 2 + 4 * 64 * sizeof(float);
   static bool once = false;
   if (!once) {
-    B200_TRY(set_smem(attn_bwd_dq_kernel<HDP>, smem_dq));
-    B200_TRY(set_smem(attn_bwd_dkv_kernel<HDP>, smem_dkv));
+    B200_TRY(set_smem(attn_bwd_dq_kernel<HDP, HALF>, smem_dq));
+    B200_TRY(set_smem(attn_bwd_dkv_kernel<HDP, HALF>, smem_dkv));
     once = true;
   }
   const long long n = (long long)p.B * p.Nq * p.heads;
   long long gd = cdiv(n, 256);
   if (gd > (long long)sm_count() * 16) gd = (long long)sm_count() * 16;
-  attn_delta_kernel<<<(unsigned)gd, 256, 0, st>>>(p);
+  attn_delta_kernel<HALF><<<(unsigned)gd, 256, 0, st>>>(p);
   B200_LAUNCH_OK();
   dim3 gq((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
-  attn_bwd_dq_kernel<HDP><<<gq, ATT_THREADS, smem_dq, st>>>(p);
+  attn_bwd_dq_kernel<HDP, HALF><<<gq, ATT_THREADS, smem_dq, st>>>(p);
   B200_LAUNCH_OK();
   dim3 gk((unsigned)cdiv(p.Nk, ATT_BK), (unsigned)p.heads, (unsigned)p.B);
-  attn_bwd_dkv_kernel<HDP><<<gk, ATT_THREADS, smem_dkv, st>>>(p);
+  attn_bwd_dkv_kernel<HDP, HALF><<<gk, ATT_THREADS, smem_dkv, st>>>(p);
   B200_LAUNCH_OK();
   return 0;
+}
+template <int HDP>
+static int launch_bwd(const AttnParams& p, cudaStream_t st) {
+  return p.half ? launch_bwd_t<HDP, true>(p, st) : launch_bwd_t<HDP, false>(p, st);
 }
 
 }  // namespace b200

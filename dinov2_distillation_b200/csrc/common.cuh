@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -60,6 +61,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
+}
+
+// 16-bit packing with a runtime element type: fp16 (ScaleKD projector forward operands) or bf16 (everything else)
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
+  if (fp16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16(a, b);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return unpack_bf16(u);
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* dst, float v, int fp16) {
+  if (fp16) *reinterpret_cast<__half*>(dst) = __float2half_rn(v);
+  else *dst = __float2bfloat16(v);
+}
+__device__ __forceinline__ float load16(const __nv_bfloat16* src, int fp16) {
+  if (fp16) return __half2float(*reinterpret_cast<const __half*>(src));
+  return __bfloat162float(*src);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -15,18 +15,66 @@ static inline int grid_for(long long work_items, int per_block, int max_blocks_p
 }
 
 // ------------------------------------------------------------------------------------------------ cast
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n,
+                                     int fp16) {
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     uint2 u;
-    u.x = pack_bf16(v.x, v.y);
-    u.y = pack_bf16(v.z, v.w);
+    u.x = pack16(v.x, v.y, fp16);
+    u.y = pack16(v.z, v.w, fp16);
     reinterpret_cast<uint2*>(y)[i] = u;
   }
   for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    y[i] = __float2bfloat16(x[i]);
+    store16(y + i, x[i], fp16);
+}
+
+__global__ void cast_f16_bf16_kernel(const __half* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[e]));
+      o[e] = pack_bf16(f.x, f.y);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __float2bfloat16(__half2float(x[i]));
+}
+
+// 3-term split cast: x = hi + lo with hi = r16(x), lo = r16(x - hi) (r16 = round to fp16 or bf16).
+// out row = [hi | hi | lo] (left operand) or [hi | lo | hi] (right operand): a plain 16-bit GEMM over the 3K-long
+// contraction then yields hi*hi + hi*lo + lo*hi, i.e. ~2x the mantissa bits. Used for the one GEMM whose result feeds
+// BatchNorm -> ReLU with no residual around it (conv1x1 of proj_student), where mask flips dominate the gradient error.
+__global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K,
+                              int right, int fp16) {
+  const int K4 = K >> 2;
+  const long long n4 = rows * K4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / K4;
+    const int c4 = (int)(i - r * K4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = fp16 ? __half2float(__float2half_rn(f[e])) : __bfloat162float(__float2bfloat16(f[e]));
+      lo[e] = f[e] - hi[e];
+    }
+    uint2 uh, ul;
+    uh.x = pack16(hi[0], hi[1], fp16); uh.y = pack16(hi[2], hi[3], fp16);
+    ul.x = pack16(lo[0], lo[1], fp16); ul.y = pack16(lo[2], lo[3], fp16);
+    __nv_bfloat16* o = out + r * 3 * K + c4 * 4;
+    *reinterpret_cast<uint2*>(o) = uh;
+    *reinterpret_cast<uint2*>(o + K) = right ? ul : uh;
+    *reinterpret_cast<uint2*>(o + 2 * K) = right ? uh : ul;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ transposes
@@ -34,7 +82,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 template <typename TOut, bool ACC>
 __global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict__ out, int rows, int cols,
                                  const float* __restrict__ row_scale, long long in_bstride, long long out_bstride,
-                                 float* __restrict__ out2_f32, long long out_ld) {
+                                 float* __restrict__ out2_f32, long long out_ld, int fp16) {
   __shared__ float tile[32][33];
   in += (long long)blockIdx.z * in_bstride;
   out += (long long)blockIdx.z * out_bstride;
@@ -56,7 +104,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict_
       const float v = tile[threadIdx.x][j];
       const long long o = (long long)c * out_ld + r;
       if constexpr (sizeof(TOut) == 2) {
-        out[o] = __float2bfloat16(v);
+        store16(reinterpret_cast<__nv_bfloat16*>(out) + o, v, fp16);
         if (out2_f32) out2_f32[o] = v;
       } else {
         if (ACC) out[o] += v; else out[o] = v;
@@ -117,7 +165,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float eps,
                      float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int rows, int D, int in_period, int in_pad) {
+                     float* __restrict__ rstd_out, int rows, int D, int in_period, int in_pad, int fp16) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_d = 1.0f / (float)D;
@@ -166,8 +214,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
         if (y32) reinterpret_cast<float4*>(y32 + (long long)r * D)[c4] = o;
         if (y16) {
           uint2 u;
-          u.x = pack_bf16(o.x, o.y);
-          u.y = pack_bf16(o.z, o.w);
+          u.x = pack16(o.x, o.y, fp16);
+          u.y = pack16(o.z, o.w, fp16);
           reinterpret_cast<uint2*>(y16 + (long long)r * D)[c4] = u;
         }
       }
@@ -338,7 +386,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __rest
 __global__ void __launch_bounds__(256)
 bn_relu_pos_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ pos,
-                       float* __restrict__ z32, __nv_bfloat16* __restrict__ z16, long long M, int D, int HW) {
+                       float* __restrict__ z32, __nv_bfloat16* __restrict__ z16, long long M, int D, int HW,
+                       int fp16) {
   const int D4 = D >> 2;
   const long long n4 = M * D4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -358,8 +407,8 @@ bn_relu_pos_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
     if (z32) reinterpret_cast<float4*>(z32)[i] = o;
     if (z16) {
       uint2 u;
-      u.x = pack_bf16(o.x, o.y);
-      u.y = pack_bf16(o.z, o.w);
+      u.x = pack16(o.x, o.y, fp16);
+      u.y = pack16(o.z, o.w, fp16);
       reinterpret_cast<uint2*>(z16)[i] = u;
     }
   }
@@ -539,10 +588,10 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, const _
 
 template <int NV>
 static int launch_ln_fwd(const float* x, const float* w, const float* b, float eps, float* y32, void* y16, float* mean,
-                         float* rstd, int rows, int D, int in_period, int in_pad, cudaStream_t st) {
+                         float* rstd, int rows, int D, int in_period, int in_pad, int fp16, cudaStream_t st) {
   const int grid = grid_for(rows, 8, 8);
   layernorm_fwd_kernel<NV><<<grid, 256, 0, st>>>(x, w, b, eps, y32, static_cast<__nv_bfloat16*>(y16), mean, rstd, rows,
-                                                 D, in_period, in_pad);
+                                                 D, in_period, in_pad, fp16);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -584,7 +633,36 @@ extern "C" int b200_cast_f32_bf16(const float* x, void* y, long long n, void* st
   if (n == 0) return 0;
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "alignment");
   cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<__nv_bfloat16*>(y), n);
+      x, static_cast<__nv_bfloat16*>(y), n, 0);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_cast_f32_f16(const float* x, void* y, long long n, void* stream) {
+  B200_CHECK_ARG(x && y && n >= 0, "bad args");
+  if (n == 0) return 0;
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "alignment");
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n, 1);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_cast_f16_bf16(const void* x, void* y, long long n, void* stream) {
+  B200_CHECK_ARG(x && y && n >= 0, "bad args");
+  if (n == 0) return 0;
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "alignment");
+  cast_f16_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__nv_bfloat16*>(y), n);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_split3_16(const float* x, void* out, long long rows, int K, int right_operand, int out_is_fp16,
+                              void* stream) {
+  B200_CHECK_ARG(x && out && rows > 0 && K > 0 && K % 4 == 0, "bad args");
+  split3_kernel<<<grid_for(rows * K / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(out), rows, K, right_operand ? 1 : 0, out_is_fp16 ? 1 : 0);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -594,7 +672,7 @@ extern "C" int b200_transpose_f32_bf16(const float* in, void* out, int rows, int
   B200_CHECK_ARG(in && out && rows > 0 && cols > 0, "bad args");
   dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), 1);
   transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, rows);
+      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, rows, 0);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -604,22 +682,22 @@ extern "C" int b200_transpose_f32_bf16_ld(const float* in, void* out, int rows, 
   B200_CHECK_ARG(in && out && rows > 0 && cols > 0 && out_ld >= rows, "bad args");
   dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), 1);
   transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, out_ld);
+      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, out_ld, 0);
   B200_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200_nchw_to_tokens(const float* x, void* tok_bf16, float* tok_f32, int B, int C, int HW,
-                                   void* stream) {
+                                   int tok16_is_fp16, void* stream) {
   B200_CHECK_ARG(x && (tok_bf16 || tok_f32) && B > 0 && C > 0 && HW > 0, "bad args");
   dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(C, 32), (unsigned)B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tok_bf16) {
     transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, st>>>(
-        x, static_cast<__nv_bfloat16*>(tok_bf16), C, HW, nullptr, (long long)C * HW, (long long)C * HW, tok_f32, C);
+        x, static_cast<__nv_bfloat16*>(tok_bf16), C, HW, nullptr, (long long)C * HW, (long long)C * HW, tok_f32, C, tok16_is_fp16);
   } else {
     transpose_kernel<float, false><<<grid, dim3(32, 8), 0, st>>>(x, tok_f32, C, HW, nullptr, (long long)C * HW,
-                                                                  (long long)C * HW, nullptr, C);
+                                                                  (long long)C * HW, nullptr, C, 0);
   }
   B200_LAUNCH_OK();
   return 0;
@@ -631,10 +709,10 @@ extern "C" int b200_tokens_to_nchw(const float* tok, float* x, int B, int C, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (accumulate) {
     transpose_kernel<float, true><<<grid, dim3(32, 8), 0, st>>>(tok, x, HW, C, nullptr, (long long)C * HW,
-                                                                 (long long)C * HW, nullptr, HW);
+                                                                 (long long)C * HW, nullptr, HW, 0);
   } else {
     transpose_kernel<float, false><<<grid, dim3(32, 8), 0, st>>>(tok, x, HW, C, nullptr, (long long)C * HW,
-                                                                  (long long)C * HW, nullptr, HW);
+                                                                  (long long)C * HW, nullptr, HW, 0);
   }
   B200_LAUNCH_OK();
   return 0;
@@ -669,15 +747,15 @@ extern "C" int b200_write_cls_rows(float* x, const float* cls, const float* pos,
 
 extern "C" int b200_layernorm_fwd(const float* x, const float* w, const float* b, float eps, float* y_f32,
                                   void* y_bf16, float* mean, float* rstd, int rows, int D, int in_period, int in_pad,
-                                  void* stream) {
+                                  int y16_is_fp16, void* stream) {
   B200_CHECK_ARG(x && w && b && rows > 0, "bad args");
   B200_CHECK_ARG(D % 4 == 0 && D > 0 && D <= LN_MAX_V4 * 128, "D must be a multiple of 4 and <= 1536");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nv = (int)cdiv(D, 128);
-  if (nv <= 3) return launch_ln_fwd<3>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, st);
-  if (nv <= 6) return launch_ln_fwd<6>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, st);
-  if (nv <= 8) return launch_ln_fwd<8>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, st);
-  return launch_ln_fwd<12>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, st);
+  if (nv <= 3) return launch_ln_fwd<3>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
+  if (nv <= 6) return launch_ln_fwd<6>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
+  if (nv <= 8) return launch_ln_fwd<8>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
+  return launch_ln_fwd<12>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
 }
 
 extern "C" int b200_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean,
@@ -711,10 +789,10 @@ extern "C" int b200_bn_finalize(const float* sums, float* mean, float* rstd, flo
 
 extern "C" int b200_bn_relu_pos_fwd(const float* y, const float* mean, const float* rstd, const float* w,
                                     const float* b, const float* pos, float* z_f32, void* z_bf16, int M, int D, int HW,
-                                    void* stream) {
+                                    int z16_is_fp16, void* stream) {
   B200_CHECK_ARG(y && mean && rstd && w && b && pos && (z_f32 || z_bf16) && M > 0 && D % 4 == 0 && HW > 0, "bad args");
   bn_relu_pos_fwd_kernel<<<grid_for((long long)M * D / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      y, mean, rstd, w, b, pos, z_f32, static_cast<__nv_bfloat16*>(z_bf16), M, D, HW);
+      y, mean, rstd, w, b, pos, z_f32, static_cast<__nv_bfloat16*>(z_bf16), M, D, HW, z16_is_fp16);
   B200_LAUNCH_OK();
   return 0;
 }

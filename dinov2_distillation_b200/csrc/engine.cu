@@ -37,6 +37,9 @@ struct Gemm {
   Gemm& out16(void* o, long long ld) { d.out_bf16 = o; d.ldo16 = ld; return *this; }
   Gemm& out16_pre(void* o, long long ld) { d.out_bf16_pre = o; d.ldo16_pre = ld; return *this; }
   Gemm& row_map(int period, int pad) { d.out_row_period = period; d.out_row_pad = pad; return *this; }
+  Gemm& fp16_operands() { d.a_is_fp16 = 1; d.b_is_fp16 = 1; return *this; }
+  Gemm& out16_fp16() { d.out16_is_fp16 = 1; return *this; }
+  Gemm& aux_fp16() { d.aux_is_fp16 = 1; return *this; }
   // wgrad form: both operands token-major (contraction over rows), fp32 atomic accumulate, split over the contraction
   Gemm& wgrad() {
     d.a_mn_major = 1; d.b_mn_major = 1; d.atomic_add = 1;
@@ -116,7 +119,7 @@ static int vit_block_fwd_impl(const b200_vit_config* c, const b200_vit_block* k,
   float* x_mid = sv ? sv->x_mid : y;
   // attention half
   B200_TRY(b200_layernorm_fwd(x, k->ln1_w, k->ln1_b, c->ln_eps, nullptr, w.xn, sv ? sv->mean1 : nullptr,
-                              sv ? sv->rstd1 : nullptr, Mi, D, 0, 0, stream));
+                              sv ? sv->rstd1 : nullptr, Mi, D, 0, 0, 0, stream));
   B200_TRY(Gemm(w.xn, D, k->qkv_w, D, Mi, 3 * D, D).bias(k->qkv_b).out16(qkv, 3 * D).run(stream));
   b200_attn_desc ad;
   attn_desc_self(ad, c, qkv, attn, lse, B, N);
@@ -124,7 +127,7 @@ static int vit_block_fwd_impl(const b200_vit_config* c, const b200_vit_block* k,
   B200_TRY(Gemm(attn, D, k->proj_w, D, Mi, D, D).bias(k->proj_b).col_scale(k->ls1).residual(x, D).out32(x_mid, D).run(stream));
   // MLP half
   B200_TRY(b200_layernorm_fwd(x_mid, k->ln2_w, k->ln2_b, c->ln_eps, nullptr, w.xn, sv ? sv->mean2 : nullptr,
-                              sv ? sv->rstd2 : nullptr, Mi, D, 0, 0, stream));
+                              sv ? sv->rstd2 : nullptr, Mi, D, 0, 0, 0, stream));
   if (!c->swiglu) {
     Gemm g1(w.xn, D, k->fc1_w, D, Mi, F, D);
     g1.bias(k->fc1_b).act(B200_ACT_GELU).out16(w.h, F);
@@ -256,53 +259,63 @@ extern "C" int b200_vit_forward(const b200_vit_config* c, const b200_vit_block* 
   B200_TRY(Gemm(patches, Kp, patch_w, Kp, B * HW, D, Kp).bias(patch_b).residual(pos + D, D, HW).out32(x, D).row_map(HW, 1).run(stream));
   B200_TRY(b200_write_cls_rows(x, cls, pos, B, N, D, stream));
   for (int l = 0; l < c->L; ++l) B200_TRY(vit_block_fwd_impl(c, &blocks[l], x, x, B, N, nullptr, w, stream));
-  B200_TRY(b200_layernorm_fwd(x, norm_w, norm_b, c->ln_eps, out_tokens, nullptr, nullptr, nullptr, (int)M, D, 0, 0,
+  B200_TRY(b200_layernorm_fwd(x, norm_w, norm_b, c->ln_eps, out_tokens, nullptr, nullptr, nullptr, (int)M, D, 0, 0, 0,
                               stream));
   return 0;
 }
 
 // ================================================================================================ ScaleKD projector
+// Precision policy: the projector FORWARD runs fp16 operands with fp32 accumulation -- the reference's own
+// default is fp16 autocast (train.py:263) and fp16's 11-bit mantissa keeps the ReLU masks (BN->ReLU, FFN) in step with
+// the fp32 oracle, which bf16's 8 bits do not. Gradients have a wide dynamic range, so every BACKWARD operand is bf16:
+// saved fp16 activations are converted on the fly (cast_f16_bf16) right before the wgrad GEMM that consumes them.
 namespace b200 {
 
+typedef __nv_bfloat16 h16;  // storage type for fp16 buffers (2 bytes; the kernels are told which format it holds)
+
 struct ProjSave {
-  bf16 *xt16, *z16, *qsrc16, *q16, *kv16, *o16, *g16, *h16;
+  h16 *z, *qsrc, *q, *kv, *o, *g, *h;   // fp16
+  bf16* xt;                             // bf16 student tokens (only the conv wgrad reads them)
   float *y, *bn_mean, *bn_rstd, *lse, *f32, *mean1, *rstd1, *u32, *mean2, *rstd2;
 };
 
 static void carve_proj_save(Arena& a, const b200_projector_config* c, int B, ProjSave& s) {
   const long long M = (long long)B * c->HW;
   const int D = c->D;
-  s.xt16 = a.take_n<bf16>(M * c->Cs);
+  s.xt = a.take_n<bf16>(M * c->Cs);
   s.y = a.take_n<float>(M * D);
   s.bn_mean = a.take_n<float>(D);
   s.bn_rstd = a.take_n<float>(D);
-  s.z16 = a.take_n<bf16>(M * D);
-  s.qsrc16 = a.take_n<bf16>(M * D);
-  s.q16 = a.take_n<bf16>(M * D);
-  s.kv16 = a.take_n<bf16>(M * 2 * D);
-  s.o16 = a.take_n<bf16>(M * D);
+  s.z = a.take_n<h16>(M * D);
+  s.qsrc = a.take_n<h16>(M * D);
+  s.q = a.take_n<h16>(M * D);
+  s.kv = a.take_n<h16>(M * 2 * D);
+  s.o = a.take_n<h16>(M * D);
   s.lse = a.take_n<float>((long long)B * c->heads * c->HW);
   s.f32 = a.take_n<float>(M * D);
   s.mean1 = a.take_n<float>(M); s.rstd1 = a.take_n<float>(M);
-  s.g16 = a.take_n<bf16>(M * D);
-  s.h16 = a.take_n<bf16>(M * 4 * D);
+  s.g = a.take_n<h16>(M * D);
+  s.h = a.take_n<h16>(M * 4 * D);
   s.u32 = a.take_n<float>(M * D);
   s.mean2 = a.take_n<float>(M); s.rstd2 = a.take_n<float>(M);
 }
 
 struct ProjFwdWs {
-  bf16 *wc16, *wq16, *wkv16, *wp16, *w1_16, *w2_16;
-  float *bkv, *sums, *pos_t, *z32, *g32;
+  h16 *wc3, *wq, *wkv, *wp, *w1, *w2;   // fp16 working copies of the fp32 master weights (wc3: 3-term split)
+  h16* xt3;                             // 3-term split of the student tokens [M, 3Cs]
+  float *bkv, *sums, *pos_t, *z32, *g32, *xt32;
 };
 static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, ProjFwdWs& w) {
   const long long M = (long long)B * c->HW;
   const long long D = c->D;
-  w.wc16 = a.take_n<bf16>(D * c->Cs);
-  w.wq16 = a.take_n<bf16>(D * D);
-  w.wkv16 = a.take_n<bf16>(2 * D * D);
-  w.wp16 = a.take_n<bf16>(D * D);
-  w.w1_16 = a.take_n<bf16>(4 * D * D);
-  w.w2_16 = a.take_n<bf16>(4 * D * D);
+  w.wc3 = a.take_n<h16>(3 * D * c->Cs);
+  w.xt3 = a.take_n<h16>(M * 3 * c->Cs);
+  w.xt32 = a.take_n<float>(M * c->Cs);
+  w.wq = a.take_n<h16>(D * D);
+  w.wkv = a.take_n<h16>(2 * D * D);
+  w.wp = a.take_n<h16>(D * D);
+  w.w1 = a.take_n<h16>(4 * D * D);
+  w.w2 = a.take_n<h16>(4 * D * D);
   w.bkv = a.take_n<float>(2 * D);
   w.sums = a.take_n<float>(2 * D);
   w.pos_t = a.take_n<float>((long long)c->HW * D);
@@ -312,7 +325,7 @@ static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, P
 
 struct ProjBwdWs {
   bf16 *w2T, *w1T, *wpT, *wkvT, *wqT, *wcT;
-  bf16 *du16, *dh16, *df16, *do16, *dq16, *dkv16, *dqs16, *dy16;
+  bf16 *du16, *dh16, *df16, *do16, *dq16, *dkv16, *dqs16, *dy16, *act16;
   float *du32, *dg32, *df32, *dz32, *dqs32, *sums2, *dpos_t, *delta, *dxt32;
 };
 static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, ProjBwdWs& w) {
@@ -332,6 +345,7 @@ static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, P
   w.dkv16 = a.take_n<bf16>(M * 2 * D);
   w.dqs16 = a.take_n<bf16>((long long)c->HW * D);
   w.dy16 = a.take_n<bf16>(M * D);
+  w.act16 = a.take_n<bf16>(M * (4 * D > c->Cs ? 4 * D : c->Cs));
   w.du32 = a.take_n<float>(M * D);
   w.dg32 = a.take_n<float>(M * D);
   w.df32 = a.take_n<float>(M * D);
@@ -357,13 +371,21 @@ static void proj_attn_desc(b200_attn_desc& ad, const b200_projector_config* c, c
                            int B) {
   const int D = c->D, HW = c->HW;
   memset(&ad, 0, sizeof ad);
-  ad.q = s.q16; ad.q_bs = ext_query ? (long long)HW * D : 0; ad.q_ts = D;
-  ad.k = s.kv16; ad.v = s.kv16 + D;
+  ad.q = s.q; ad.q_bs = ext_query ? (long long)HW * D : 0; ad.q_ts = D;
+  ad.k = s.kv; ad.v = s.kv + D;
   ad.k_bs = ad.v_bs = (long long)HW * 2 * D; ad.k_ts = ad.v_ts = 2 * D;
-  ad.o = s.o16; ad.o_bs = (long long)HW * D; ad.o_ts = D;
+  ad.o = s.o; ad.o_bs = (long long)HW * D; ad.o_ts = D;
   ad.lse = s.lse;
   ad.B = B; ad.heads = c->heads; ad.Nq = HW; ad.Nk = HW; ad.hd = D / c->heads;
   ad.scale = c->softmax_scale / sqrtf((float)ad.hd);
+  ad.qkvo_is_fp16 = 1;
+}
+
+// dW[N_, K_] += dY^T X with X a saved fp16 activation: convert X to bf16 into scratch, then the token-major wgrad GEMM.
+static int wgrad_from_fp16(const bf16* dY, long long ld_dy, const h16* X, long long rows, int x_cols, bf16* scratch,
+                           float* dW, int n_out, void* stream) {
+  B200_TRY(b200_cast_f16_bf16(X, scratch, rows * x_cols, stream));
+  return Gemm(dY, ld_dy, scratch, x_cols, n_out, x_cols, (int)rows).out32(dW, x_cols).wgrad().run(stream);
 }
 
 }  // namespace b200
@@ -405,20 +427,22 @@ extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_pro
   carve_proj_fwd_ws(wa, c, B, w);
   B200_CHECK_ARG(wa.ok(), "workspace too small");
 
-  // bf16 working copies of the fp32 master weights
-  B200_TRY(b200_cast_f32_bf16(p->conv_w, w.wc16, (long long)D * Cs, stream));
-  B200_TRY(b200_cast_f32_bf16(p->q_w, w.wq16, (long long)D * D, stream));
-  B200_TRY(b200_cast_f32_bf16(p->k_w, w.wkv16, (long long)D * D, stream));
-  B200_TRY(b200_cast_f32_bf16(p->v_w, w.wkv16 + (long long)D * D, (long long)D * D, stream));
-  B200_TRY(b200_cast_f32_bf16(p->p_w, w.wp16, (long long)D * D, stream));
-  B200_TRY(b200_cast_f32_bf16(p->ffn1_w, w.w1_16, 4LL * D * D, stream));
-  B200_TRY(b200_cast_f32_bf16(p->ffn2_w, w.w2_16, 4LL * D * D, stream));
+  // fp16 working copies of the fp32 master weights
+  B200_TRY(b200_split3_16(p->conv_w, w.wc3, D, Cs, 1, 1, stream));
+  B200_TRY(b200_cast_f32_f16(p->q_w, w.wq, (long long)D * D, stream));
+  B200_TRY(b200_cast_f32_f16(p->k_w, w.wkv, (long long)D * D, stream));
+  B200_TRY(b200_cast_f32_f16(p->v_w, w.wkv + (long long)D * D, (long long)D * D, stream));
+  B200_TRY(b200_cast_f32_f16(p->p_w, w.wp, (long long)D * D, stream));
+  B200_TRY(b200_cast_f32_f16(p->ffn1_w, w.w1, 4LL * D * D, stream));
+  B200_TRY(b200_cast_f32_f16(p->ffn2_w, w.w2, 4LL * D * D, stream));
   B200_CUDA_OK(cudaMemcpyAsync(w.bkv, p->k_b, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   B200_CUDA_OK(cudaMemcpyAsync(w.bkv + D, p->v_b, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   // proj_student: conv1x1 -> BN -> ReLU, + pos_embed            (losses/scalekd.py:199-201, :238)
-  B200_TRY(b200_nchw_to_tokens(x, s.xt16, nullptr, B, Cs, HW, stream));
-  B200_TRY(Gemm(s.xt16, Cs, w.wc16, Cs, Mi, D, Cs).bias(p->conv_b).out32(s.y, D).run(stream));
+  // the conv feeds BN -> ReLU with no residual around it: run it as a 3-term split fp16 product (K -> 3K)
+  B200_TRY(b200_nchw_to_tokens(x, s.xt, w.xt32, B, Cs, HW, 0, stream));
+  B200_TRY(b200_split3_16(w.xt32, w.xt3, M, Cs, 0, 1, stream));
+  B200_TRY(Gemm(w.xt3, 3 * Cs, w.wc3, 3 * Cs, Mi, D, 3 * Cs).fp16_operands().bias(p->conv_b).out32(s.y, D).run(stream));
   if (c->training) {
     B200_TRY(zero_f32(w.sums, 2 * D, st));
     B200_TRY(b200_bn_stats(s.y, w.sums, Mi, D, stream));
@@ -428,24 +452,24 @@ extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_pro
     B200_TRY(b200_bn_finalize(nullptr, s.bn_mean, s.bn_rstd, p->bn_running_mean, p->bn_running_var, c->bn_momentum,
                               c->bn_eps, Mi, D, stream));
   }
-  B200_TRY(b200_nchw_to_tokens(p->pos_embed, nullptr, w.pos_t, 1, D, HW, stream));
-  B200_TRY(b200_bn_relu_pos_fwd(s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.pos_t, w.z32, s.z16, Mi, D, HW, stream));
+  B200_TRY(b200_nchw_to_tokens(p->pos_embed, nullptr, w.pos_t, 1, D, HW, 0, stream));
+  B200_TRY(b200_bn_relu_pos_fwd(s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.pos_t, w.z32, s.z, Mi, D, HW, 1, stream));
 
   // cross attention: q from the query tokens, k/v from the student tokens      (losses/scalekd.py:299-316)
   const int Mq = ext ? Mi : HW;
-  B200_TRY(b200_cast_f32_bf16(ext ? query : p->query_w, s.qsrc16, (long long)Mq * D, stream));
-  B200_TRY(Gemm(s.qsrc16, D, w.wq16, D, Mq, D, D).bias(p->q_b).out16(s.q16, D).run(stream));
-  B200_TRY(Gemm(s.z16, D, w.wkv16, D, Mi, 2 * D, D).bias(w.bkv).out16(s.kv16, 2 * D).run(stream));
+  B200_TRY(b200_cast_f32_f16(ext ? query : p->query_w, s.qsrc, (long long)Mq * D, stream));
+  B200_TRY(Gemm(s.qsrc, D, w.wq, D, Mq, D, D).fp16_operands().bias(p->q_b).out16(s.q, D).out16_fp16().run(stream));
+  B200_TRY(Gemm(s.z, D, w.wkv, D, Mi, 2 * D, D).fp16_operands().bias(w.bkv).out16(s.kv, 2 * D).out16_fp16().run(stream));
   b200_attn_desc ad;
   proj_attn_desc(ad, c, s, ext, B);
   B200_TRY(b200_attention_fwd(&ad, stream));
-  B200_TRY(Gemm(s.o16, D, w.wp16, D, Mi, D, D).bias(p->p_b).residual(w.z32, D).out32(s.f32, D).run(stream));
+  B200_TRY(Gemm(s.o, D, w.wp, D, Mi, D, D).fp16_operands().bias(p->p_b).residual(w.z32, D).out32(s.f32, D).run(stream));
 
   // norm -> FFN(ReLU) + residual -> norm_2                                      (losses/scalekd.py:243-245)
-  B200_TRY(b200_layernorm_fwd(s.f32, p->ln1_w, p->ln1_b, c->ln_eps, w.g32, s.g16, s.mean1, s.rstd1, Mi, D, 0, 0, stream));
-  B200_TRY(Gemm(s.g16, D, w.w1_16, D, Mi, 4 * D, D).bias(p->ffn1_b).act(B200_ACT_RELU).out16(s.h16, 4 * D).run(stream));
-  B200_TRY(Gemm(s.h16, 4 * D, w.w2_16, 4 * D, Mi, D, 4 * D).bias(p->ffn2_b).residual(w.g32, D).out32(s.u32, D).run(stream));
-  B200_TRY(b200_layernorm_fwd(s.u32, p->ln2_w, p->ln2_b, c->ln_eps, out, nullptr, s.mean2, s.rstd2, Mi, D, 0, 0, stream));
+  B200_TRY(b200_layernorm_fwd(s.f32, p->ln1_w, p->ln1_b, c->ln_eps, w.g32, s.g, s.mean1, s.rstd1, Mi, D, 0, 0, 1, stream));
+  B200_TRY(Gemm(s.g, D, w.w1, D, Mi, 4 * D, D).fp16_operands().bias(p->ffn1_b).act(B200_ACT_RELU).out16(s.h, 4 * D).out16_fp16().run(stream));
+  B200_TRY(Gemm(s.h, 4 * D, w.w2, 4 * D, Mi, D, 4 * D).fp16_operands().bias(p->ffn2_b).residual(w.g32, D).out32(s.u32, D).run(stream));
+  B200_TRY(b200_layernorm_fwd(s.u32, p->ln2_w, p->ln2_b, c->ln_eps, out, nullptr, s.mean2, s.rstd2, Mi, D, 0, 0, 0, stream));
   return 0;
 }
 
@@ -460,7 +484,6 @@ extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_pro
   const long long M = (long long)B * HW;
   const int Mi = (int)M;
   const bool ext = query != nullptr;
-  B200_CHECK_ARG(!ext || dquery != nullptr || true, "");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena sa(const_cast<void*>(save), size_t(-1) >> 1);
   ProjSave s;
@@ -483,18 +506,18 @@ extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_pro
   B200_TRY(b200_layernorm_bwd(dout, s.u32, p->ln2_w, s.mean2, s.rstd2, nullptr, w.du32, w.du16, g->ln2_w, g->ln2_b, Mi, D, stream));
   // FFN: u = g + W2 relu(W1 g + b1) + b2
   B200_TRY(b200_colsum(w.du32, 0, D, g->ffn2_b, Mi, D, stream));
-  B200_TRY(Gemm(w.du16, D, s.h16, 4 * D, D, 4 * D, Mi).out32(g->ffn2_w, 4 * D).wgrad().run(stream));
-  B200_TRY(Gemm(w.du16, D, w.w2T, D, Mi, 4 * D, D).aux(s.h16, 4 * D, B200_AUX_DRELU).out16(w.dh16, 4 * D).run(stream));
+  B200_TRY(wgrad_from_fp16(w.du16, D, s.h, M, 4 * D, w.act16, g->ffn2_w, D, stream));
+  B200_TRY(Gemm(w.du16, D, w.w2T, D, Mi, 4 * D, D).aux(s.h, 4 * D, B200_AUX_DRELU).aux_fp16().out16(w.dh16, 4 * D).run(stream));
   B200_TRY(b200_colsum(w.dh16, 1, 4 * D, g->ffn1_b, Mi, 4 * D, stream));
-  B200_TRY(Gemm(w.dh16, 4 * D, s.g16, D, 4 * D, D, Mi).out32(g->ffn1_w, D).wgrad().run(stream));
+  B200_TRY(wgrad_from_fp16(w.dh16, 4 * D, s.g, M, D, w.act16, g->ffn1_w, 4 * D, stream));
   B200_TRY(Gemm(w.dh16, 4 * D, w.w1T, 4 * D, Mi, D, 4 * D).residual(w.du32, D).out32(w.dg32, D).run(stream));
   // norm
   B200_TRY(b200_layernorm_bwd(w.dg32, s.f32, p->ln1_w, s.mean1, s.rstd1, nullptr, w.df32, w.df16, g->ln1_w, g->ln1_b, Mi, D, stream));
   // attention output projection: f = Wp o + bp + z
   B200_TRY(b200_colsum(w.df32, 0, D, g->p_b, Mi, D, stream));
-  B200_TRY(Gemm(w.df16, D, s.o16, D, D, D, Mi).out32(g->p_w, D).wgrad().run(stream));
+  B200_TRY(wgrad_from_fp16(w.df16, D, s.o, M, D, w.act16, g->p_w, D, stream));
   B200_TRY(Gemm(w.df16, D, w.wpT, D, Mi, D, D).out16(w.do16, D).run(stream));
-  // attention core
+  // attention core (q/k/v/o fp16 from the forward; gradients bf16)
   b200_attn_desc ad;
   proj_attn_desc(ad, c, s, ext, B);
   ad.d_o = w.do16; ad.do_bs = (long long)HW * D; ad.do_ts = D;
@@ -506,20 +529,20 @@ extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_pro
   // q path
   if (ext) {
     B200_TRY(b200_colsum(w.dq16, 1, D, g->q_b, Mi, D, stream));
-    B200_TRY(Gemm(w.dq16, D, s.qsrc16, D, D, D, Mi).out32(g->q_w, D).wgrad().run(stream));
+    B200_TRY(wgrad_from_fp16(w.dq16, D, s.qsrc, M, D, w.act16, g->q_w, D, stream));
     if (dquery) B200_TRY(Gemm(w.dq16, D, w.wqT, D, Mi, D, D).out32(dquery, D).run(stream));
   } else {
     B200_TRY(b200_batch_sum_bf16(w.dq16, w.dqs32, w.dqs16, B, (long long)HW * D, stream));
     B200_TRY(b200_colsum(w.dqs32, 0, D, g->q_b, HW, D, stream));
-    B200_TRY(Gemm(w.dqs16, D, s.qsrc16, D, D, D, HW).out32(g->q_w, D).wgrad().run(stream));
+    B200_TRY(wgrad_from_fp16(w.dqs16, D, s.qsrc, HW, D, w.act16, g->q_w, D, stream));
     if (g->query_w)
       B200_TRY(Gemm(w.dqs16, D, w.wqT, D, HW, D, D).residual(g->query_w, D).out32(g->query_w, D).run(stream));
   }
   // k / v path
   B200_TRY(b200_colsum(w.dkv16, 1, 2 * D, g->k_b, Mi, D, stream));
   B200_TRY(b200_colsum(w.dkv16 + D, 1, 2 * D, g->v_b, Mi, D, stream));
-  B200_TRY(Gemm(w.dkv16, 2 * D, s.z16, D, D, D, Mi).out32(g->k_w, D).wgrad().run(stream));
-  B200_TRY(Gemm(w.dkv16 + D, 2 * D, s.z16, D, D, D, Mi).out32(g->v_w, D).wgrad().run(stream));
+  B200_TRY(wgrad_from_fp16(w.dkv16, 2 * D, s.z, M, D, w.act16, g->k_w, D, stream));
+  B200_TRY(Gemm(w.dkv16 + D, 2 * D, w.act16, D, D, D, Mi).out32(g->v_w, D).wgrad().run(stream));  // act16 still holds z
   B200_TRY(Gemm(w.dkv16, 2 * D, w.wkvT, 2 * D, Mi, D, 2 * D).residual(w.df32, D).out32(w.dz32, D).run(stream));
   // BN + ReLU + pos_embed
   B200_TRY(zero_f32(w.sums2, 2 * D, st));
@@ -531,7 +554,7 @@ extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_pro
   B200_TRY(b200_bn_relu_pos_bwd_apply(w.dz32, s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.sums2, w.dy16, c->training ? 1 : 0, Mi, D, stream));
   // conv1x1
   B200_TRY(b200_colsum(w.dy16, 1, D, g->conv_b, Mi, D, stream));
-  B200_TRY(Gemm(w.dy16, D, s.xt16, Cs, D, Cs, Mi).out32(g->conv_w, Cs).wgrad().run(stream));
+  B200_TRY(Gemm(w.dy16, D, s.xt, Cs, D, Cs, Mi).out32(g->conv_w, Cs).wgrad().run(stream));
   if (dx) {
     B200_TRY(Gemm(w.dy16, D, w.wcT, D, Mi, Cs, D).out32(w.dxt32, Cs).run(stream));
     B200_TRY(b200_tokens_to_nchw(w.dxt32, dx, B, Cs, HW, dx_accumulate, stream));

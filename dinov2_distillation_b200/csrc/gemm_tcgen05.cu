@@ -42,6 +42,8 @@ struct GemmParams {
   long long ldo16_pre;
   int out_row_period, out_row_pad;
   int vec_ok;  // all leading dims / pointers allow 16-byte vector access
+  int out16_fp16, aux_fp16;  // 16-bit output / aux element type: 0 = bf16, 1 = fp16
+  uint32_t idesc;            // tcgen05 instruction descriptor (operand formats, majors, tile shape)
 };
 
 template <int BN>
@@ -82,14 +84,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint4 u;
-        u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
-        u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+        u.x = pack16(v[j], v[j + 1], p.out16_fp16); u.y = pack16(v[j + 2], v[j + 3], p.out16_fp16);
+        u.z = pack16(v[j + 4], v[j + 5], p.out16_fp16); u.w = pack16(v[j + 6], v[j + 7], p.out16_fp16);
         *reinterpret_cast<uint4*>(dst + j) = u;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+        if (n0 + j < p.N) store16(dst + j, v[j], p.out16_fp16);
     }
   }
   if (p.act == B200_ACT_GELU) {
@@ -106,13 +108,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint4 u = __ldg(reinterpret_cast<const uint4*>(ax + j));
-        float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+        float2 f0 = unpack16(u.x, p.aux_fp16), f1 = unpack16(u.y, p.aux_fp16), f2 = unpack16(u.z, p.aux_fp16), f3 = unpack16(u.w, p.aux_fp16);
         a[j] = f0.x; a[j + 1] = f0.y; a[j + 2] = f1.x; a[j + 3] = f1.y;
         a[j + 4] = f2.x; a[j + 5] = f2.y; a[j + 6] = f3.x; a[j + 7] = f3.y;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? __bfloat162float(ax[j]) : 0.0f;
+      for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? load16(ax + j, p.aux_fp16) : 0.0f;
     }
     if (p.aux_mode == B200_AUX_DGELU) {
 #pragma unroll
@@ -172,14 +174,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint4 u;
-        u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
-        u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+        u.x = pack16(v[j], v[j + 1], p.out16_fp16); u.y = pack16(v[j + 2], v[j + 3], p.out16_fp16);
+        u.z = pack16(v[j + 4], v[j + 5], p.out16_fp16); u.w = pack16(v[j + 6], v[j + 7], p.out16_fp16);
         *reinterpret_cast<uint4*>(dst + j) = u;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
+        if (n0 + j < p.N) store16(dst + j, v[j], p.out16_fp16);
     }
   }
 }
@@ -258,7 +260,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      const uint32_t idesc = p.idesc;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -487,6 +489,12 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   if (p.out_bf16) vec = vec && al16(p.out_bf16) && p.ldo16 % 8 == 0;
   if (p.out_bf16_pre) vec = vec && al16(p.out_bf16_pre) && p.ldo16_pre % 8 == 0;
   p.vec_ok = vec ? 1 : 0;
+  p.out16_fp16 = d->out16_is_fp16 ? 1 : 0;
+  p.aux_fp16 = d->aux_is_fp16 ? 1 : 0;
+  // a_format / b_format: 0 = F16, 1 = BF16 (bits 7-9 / 10-12)
+  p.idesc = make_idesc_bf16(BM, bn, d->a_mn_major != 0, d->b_mn_major != 0);
+  if (d->a_is_fp16) p.idesc &= ~(7u << 7);
+  if (d->b_is_fp16) p.idesc &= ~(7u << 10);
 
   CUtensorMap ta, tb;
   if (!d->a_mn_major) {

@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's `DistillationModule` hot methods (train/distillation_module.py):
+`_initialize_loss` (:112-137), `_forward_specific_stage` (:139-178), `_compute_losses` (:180-246),
+`_extract_features` (:311-337) and `training_step` (:247-276) -- same names, same dict keys, same quirks -- for users
+who run the distillation step without Lightning (bench.py, smoke(), the parity tests). With the real reference, use
+`plugin.install()` instead and keep its own DistillationModule.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .scalekd import LOSS_REGISTRY
+
+_STAGE_FRACTION = {"res2": 0.25, "res3": 0.50, "res4": 0.75}
+
+
+class DistillationStep(nn.Module):
+    """student: callable images -> {'res4': [B,C,H,W], ...} (already resized to the teacher grid, as ModelWrapper does,
+    models/model_zoo.py:118-128) or None when features are supplied directly; teacher: DINOv2ViT-like;
+    loss_specs: the `loss.losses` list of the config (type / weight / kwargs)."""
+
+    def __init__(self, student: Optional[nn.Module], teacher: nn.Module, loss_specs: List[dict],
+                 teacher_key: str = "feature_map"):
+        super().__init__()
+        self.student = student
+        self.teacher = teacher
+        self.teacher_key = teacher_key
+        self.teacher.eval()
+        for p in self.teacher.parameters():
+            p.requires_grad = False
+        self.losses = nn.ModuleDict()
+        self.loss_weights: Dict[str, float] = {}
+        for spec in loss_specs:
+            kwargs = dict(spec["kwargs"])
+            name = kwargs.get("name", spec["type"])
+            self.losses[name] = LOSS_REGISTRY[spec["type"]](**kwargs)
+            self.loss_weights[name] = spec["weight"]
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self.teacher.eval()  # frozen (distillation_module.py:104-108)
+        return self
+
+    def _forward_specific_stage(self, feat, layer):
+        n_total = len(self.teacher.model.blocks)
+        start = int(n_total * _STAGE_FRACTION[layer])
+        end = n_total - 1 if layer == "res4" else int(n_total / 4) - 1
+        for i in range(start, end):
+            feat = self.teacher.model.blocks[i](feat)
+        return feat
+
+    def _compute_losses(self, features):
+        total_loss = 0
+        loss_dict = {}
+        spatial_query = frequency_query = None
+        for name in sorted(self.losses.keys()):
+            layer = name.split("_")[1]
+            loss_fn, weight = self.losses[name], self.loss_weights[name]
+            s_feat = features["student"][layer]
+            if "res5" in name:
+                loss = loss_fn(s_feat, features["teacher"], query_s=spatial_query, query_f=frequency_query)
+                loss_dict[f"{name}_total_loss"] = loss["loss"] * weight
+                loss_dict[f"{name}_frequency_loss"] = loss["frequency_loss"] * weight
+                loss_dict[f"{name}_spatial_loss"] = loss["spatial_loss"] * weight
+                loss_dict[f"{name}_spatial_similarity"] = loss["spatial_similarity"]
+                loss_dict[f"{name}_frequency_similarity"] = loss["frequency_similarity"]
+                total_loss = total_loss + loss["loss"] * weight
+                break
+            feat_spat = loss_fn.project_feat_spat(s_feat, query=spatial_query)
+            feat_freq = loss_fn.project_feat_freq(s_feat, query=frequency_query)
+            feat_spat = self._forward_specific_stage(feat_spat, layer)
+            feat_freq = self._forward_specific_stage(feat_freq, layer)
+            spatial_query, frequency_query = feat_spat, feat_freq
+            spatial_loss, spatial_similarity = loss_fn.get_spat_loss(feat_spat, features["teacher"])
+            # sic: the reference scores the "frequency" branch of non-res5 stages with the SPATIAL loss (:236-237)
+            frequency_loss, frequency_similarity = loss_fn.get_spat_loss(feat_freq, features["teacher"])
+            loss_dict[f"{name}_total_loss"] = (spatial_loss + frequency_loss) * weight
+            loss_dict[f"{name}_frequency_loss"] = frequency_loss * weight
+            loss_dict[f"{name}_spatial_loss"] = spatial_loss * weight
+            loss_dict[f"{name}_spatial_similarity"] = spatial_similarity
+            loss_dict[f"{name}_frequency_similarity"] = frequency_similarity
+            total_loss = total_loss + (spatial_loss + frequency_loss) * weight
+        loss_dict["loss"] = total_loss
+        return loss_dict
+
+    def _extract_features(self, batch):
+        with torch.no_grad():
+            teacher_features = self.teacher(batch)[self.teacher_key]
+        return {"student": self.student(batch), "teacher": teacher_features}
+
+    def training_step(self, batch, batch_idx=0):
+        losses = self._compute_losses(self._extract_features(batch))
+        self.last_losses = losses
+        return losses["loss"]
+
+    forward = training_step

@@ -45,7 +45,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
          out_row_pad: int = 0):
     """C = epilogue(A @ B^T). K-major: a [M,K], b [N,K]. MN-major: a [K,M], b [K,N] (contraction over rows)."""
     _need_cuda(a, b, bias, aux, col_scale, residual, out)
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dtype in (torch.bfloat16, torch.float16) and b.dtype in (torch.bfloat16, torch.float16)
     assert a.stride(-1) == 1 and b.stride(-1) == 1
     if a_mn_major:
         K, M = a.shape
@@ -60,11 +60,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     d.A, d.lda, d.a_mn_major = a.data_ptr(), a.stride(0), int(a_mn_major)
     d.B, d.ldb, d.b_mn_major = b.data_ptr(), b.stride(0), int(b_mn_major)
     d.M, d.N, d.K, d.split_k = M, N, K, split_k
+    d.a_is_fp16, d.b_is_fp16 = int(a.dtype == torch.float16), int(b.dtype == torch.float16)
     d.bias = _p(bias)
     d.act = ACT[act]
     if aux is not None:
-        assert aux.dtype == torch.bfloat16
+        assert aux.dtype in (torch.bfloat16, torch.float16)
         d.aux, d.ldaux, d.aux_mode = aux.data_ptr(), aux.stride(0), AUX[aux_mode]
+        d.aux_is_fp16 = int(aux.dtype == torch.float16)
     d.col_scale = _p(col_scale)
     if residual is not None:
         assert residual.dtype == torch.float32
@@ -76,10 +78,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if out.dtype == torch.float32:
         d.out_f32, d.ldo32, d.atomic_add = out.data_ptr(), out.stride(0), int(atomic_add)
     else:
-        assert out.dtype == torch.bfloat16
+        assert out.dtype in (torch.bfloat16, torch.float16)
         d.out_bf16, d.ldo16 = out.data_ptr(), out.stride(0)
+        d.out16_is_fp16 = int(out.dtype == torch.float16)
     if out_pre:
-        pre = torch.empty(out_rows, N, device=a.device, dtype=torch.bfloat16)
+        pre = torch.empty(out_rows, N, device=a.device, dtype=out.dtype if out.dtype != torch.float32 else torch.bfloat16)
         d.out_bf16_pre, d.ldo16_pre = pre.data_ptr(), pre.stride(0)
     d.out_row_period, d.out_row_pad = out_row_period, out_row_pad
     L.check(L.load().b200_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
@@ -111,7 +114,7 @@ def nchw_to_tokens(x: torch.Tensor, want_f32: bool = False):
     HW = x[0, 0].numel()
     t16 = torch.empty(B * HW, Cc, device=x.device, dtype=torch.bfloat16)
     t32 = torch.empty(B * HW, Cc, device=x.device, dtype=torch.float32) if want_f32 else None
-    L.check(L.load().b200_nchw_to_tokens(x.data_ptr(), t16.data_ptr(), _p(t32), B, Cc, HW, _stream()), "nchw_to_tokens")
+    L.check(L.load().b200_nchw_to_tokens(x.data_ptr(), t16.data_ptr(), _p(t32), B, Cc, HW, 0, _stream()), "nchw_to_tokens")
     return (t16, t32) if want_f32 else t16
 
 
@@ -142,7 +145,7 @@ def layernorm_fwd(x, w, b, eps, want_f32=True, want_bf16=False, want_stats=False
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
     L.check(L.load().b200_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps), _p(y32), _p(y16), _p(mean),
-                                        _p(rstd), rows, D, in_period, in_pad, _stream()), "layernorm_fwd")
+                                        _p(rstd), rows, D, in_period, in_pad, 0, _stream()), "layernorm_fwd")
     return y32, y16, mean, rstd
 
 
@@ -172,6 +175,7 @@ def _attn_desc(q, k, v, o, lse, heads, scale):
     d.lse = _p(lse)
     d.B, d.heads, d.Nq, d.Nk, d.hd = B, heads, Nq, Nk, Dm // heads
     d.scale = float(scale)
+    d.qkvo_is_fp16 = int(q.dtype == torch.float16)
     return d
 
 
@@ -179,7 +183,7 @@ def attention_fwd(q, k, v, heads: int, scale: float):
     """q [B,Nq,D], k/v [B,Nk,D] bf16 (last dim contiguous, any batch/token strides) -> o [B,Nq,D] bf16, lse [B,h,Nq]."""
     _need_cuda(q, k, v)
     B, Nq, Dm = q.shape
-    o = torch.empty(B, Nq, Dm, device=q.device, dtype=torch.bfloat16)
+    o = torch.empty(B, Nq, Dm, device=q.device, dtype=q.dtype)
     lse = torch.empty(B, heads, Nq, device=q.device, dtype=torch.float32)
     d = _attn_desc(q, k, v, o, lse, heads, scale)
     L.check(L.load().b200_attention_fwd(C.byref(d), _stream()), "attention_fwd")

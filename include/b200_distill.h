@@ -62,20 +62,31 @@ typedef struct b200_gemm_desc {
   void* out_bf16; long long ldo16;
   void* out_bf16_pre; long long ldo16_pre; /* optional bf16 copy of (acc+bias) before act */
   int out_row_period, out_row_pad; /* period>0: out row = (r/period)*(period+pad) + pad + r%period */
+  /* 16-bit element types: 0 = bf16 (default), 1 = fp16. The ScaleKD projector FORWARD runs fp16 operands (the
+   * reference's own default is fp16 AMP, train.py:263); gradients stay bf16 for range. A and B may differ. */
+  int a_is_fp16, b_is_fp16, out16_is_fp16, aux_is_fp16;
 } b200_gemm_desc;
 
 int b200_gemm_bf16(const b200_gemm_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ bandwidth kernels */
-/* fp32 -> bf16 cast (n elements). */
+/* fp32 -> bf16 / fp16 casts and fp16 -> bf16 (n elements). */
 int b200_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+int b200_cast_f32_f16(const float* x, void* y, long long n, void* stream);
+int b200_cast_f16_bf16(const void* x, void* y, long long n, void* stream);
+/* 3-term split cast, fp32 [rows, K] -> 16-bit [rows, 3K] = [hi | hi | lo] (left operand) or [hi | lo | hi] (right
+ * operand), hi = r16(x), lo = r16(x - hi). A plain GEMM over the 3K contraction then carries ~2x the mantissa bits.
+ * Used for proj_student's conv1x1, whose output feeds BatchNorm -> ReLU with no residual around it: there a flipped
+ * ReLU mask is a first-order gradient error (precision policy). */
+int b200_split3_16(const float* x, void* out, long long rows, int K, int right_operand, int out_is_fp16, void* stream);
 /* out[c, r] = in[r, c] for in [rows, cols] fp32 -> bf16 (weight transposes for dgrad); optional per-row scale. */
 int b200_transpose_f32_bf16(const float* in, void* out, int rows, int cols, const float* row_scale, void* stream);
 /* same with an explicit output row pitch (elements), to write side-by-side blocks of a concatenated matrix. */
 int b200_transpose_f32_bf16_ld(const float* in, void* out, int rows, int cols, long long out_ld,
                                const float* row_scale, void* stream);
 /* NCHW fp32 [B,C,HW] <-> token-major [B*HW, C]. to_tokens: fp32 -> bf16 (+ optional fp32 copy); from_tokens: fp32 -> fp32. */
-int b200_nchw_to_tokens(const float* x, void* tok_bf16, float* tok_f32, int B, int C, int HW, void* stream);
+int b200_nchw_to_tokens(const float* x, void* tok_bf16, float* tok_f32, int B, int C, int HW, int tok16_is_fp16,
+                        void* stream);
 int b200_tokens_to_nchw(const float* tok, float* x, int B, int C, int HW, int accumulate, void* stream);
 
 /* patch-embed im2col: images fp32 [B,3,H,W] -> bf16 [B*(H/14)*(W/14), Kp], column = c*196 + i*14 + j, zero padded to
@@ -88,7 +99,8 @@ int b200_write_cls_rows(float* x, const float* cls, const float* pos, int B, int
  * row mapping: in row = (r/in_period)*(in_period+in_pad)+in_pad + r%in_period when in_period>0 (drop cls rows).
  * (hub Block.norm1/norm2/norm eps 1e-6; losses/scalekd.py:215-216 eps 1e-5) */
 int b200_layernorm_fwd(const float* x, const float* w, const float* b, float eps, float* y_f32, void* y_bf16,
-                       float* mean, float* rstd, int rows, int D, int in_period, int in_pad, void* stream);
+                       float* mean, float* rstd, int rows, int D, int in_period, int in_pad, int y16_is_fp16,
+                       void* stream);
 /* dx = LNbwd(dy) (+ dres if given). dw/db (fp32 [D]) accumulate with atomics when non-NULL. dx_bf16 optional copy. */
 int b200_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                        const float* dres, float* dx, void* dx_bf16, float* dw, float* db, int rows, int D,
@@ -102,7 +114,8 @@ int b200_bn_finalize(const float* sums, float* mean, float* rstd, float* running
                      float momentum, float eps, int M, int D, void* stream);
 /* z = relu((y-mean)*rstd*w + b) + pos[r % HW, :] ; z_f32 and z_bf16 outputs. */
 int b200_bn_relu_pos_fwd(const float* y, const float* mean, const float* rstd, const float* w, const float* b,
-                         const float* pos, float* z_f32, void* z_bf16, int M, int D, int HW, void* stream);
+                         const float* pos, float* z_f32, void* z_bf16, int M, int D, int HW, int z16_is_fp16,
+                         void* stream);
 /* backward of the above, pass 1: dr = dz * (z_pre > 0); sums2[0:D] += sum dr, sums2[D:2D] += sum dr*yhat;
  * dpos[r%HW,:] += dz (atomics).  pass 2: dy = w*rstd*(dr - sum_dr/M - yhat*sum_dr_yhat/M). */
 int b200_bn_relu_pos_bwd_reduce(const float* dz, const float* y, const float* mean, const float* rstd, const float* w,
@@ -144,6 +157,8 @@ typedef struct b200_attn_desc {
   void* dq; long long dq_bs, dq_ts;       /* bf16 (per-batch, even if q is batch invariant) */
   void* dk; long long dk_bs, dk_ts;       /* bf16 */
   void* dv; long long dv_bs, dv_ts;       /* bf16 */
+  /* 1: q, k, v, o are fp16 (ScaleKD projector forward precision); gradients d_o/dq/dk/dv are always bf16 */
+  int qkvo_is_fp16;
 } b200_attn_desc;
 int b200_attention_fwd(const b200_attn_desc* d, void* stream);
 int b200_attention_bwd(const b200_attn_desc* d, void* stream);

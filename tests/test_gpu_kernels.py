@@ -185,6 +185,30 @@ def test_attention_fwd_bwd(hd, heads, Nq, Nk):
     assert rel_err(dq, qr.grad) < 2e-2, rel_err(dq, qr.grad)
 
 
+@pytest.mark.parametrize("hd,heads,N", [(16, 24, 256), (24, 16, 256), (64, 4, 150), (96, 2, 70)])
+def test_attention_fp16_forward_bf16_grads(hd, heads, N):
+    """ScaleKD projector precision policy: q/k/v/o fp16, gradients bf16."""
+    ops = _ops()
+    B = 2
+    D = hd * heads
+    scale = 5.0 / math.sqrt(hd)
+    q = (torch.randn(B, N, D, device="cuda") * 0.5).half()
+    k = (torch.randn(B, N, D, device="cuda") * 0.5).half()
+    v = torch.randn(B, N, D, device="cuda").half()
+    o, lse = ops.attention_fwd(q, k, v, heads, scale)
+    assert o.dtype == torch.float16
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qr, kr, vr, heads, scale)
+    assert rel_err(o, ref) < 2e-3, rel_err(o, ref)
+    d_o = bf(torch.randn(B, N, D, device="cuda") * 1e-4)   # tiny gradients: would underflow in fp16
+    ref.backward(d_o.float())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale)
+    assert dq.dtype == torch.bfloat16
+    assert rel_err(dv, vr.grad) < 1e-2, rel_err(dv, vr.grad)
+    assert rel_err(dk, kr.grad) < 1e-2, rel_err(dk, kr.grad)
+    assert rel_err(dq, qr.grad) < 1e-2, rel_err(dq, qr.grad)
+
+
 def test_attention_strided_qkv_and_shared_query():
     ops = _ops()
     B, N, heads, hd = 3, 70, 6, 64
@@ -264,3 +288,21 @@ def test_token_layout_roundtrip():
     w = torch.randn(96, 40, device="cuda")
     s = torch.rand(96, device="cuda")
     assert rel_err(ops.transpose_bf16(w, s), (w * s[:, None]).t()) < 5e-3
+
+
+@pytest.mark.parametrize("adt,bdt", [(torch.float16, torch.float16)])
+@pytest.mark.parametrize("mn", [False, True])
+def test_gemm_fp16_operands(adt, bdt, mn):
+    """Projector forward runs fp16 operands (A and B must share the format: tcgen05 kind::f16 traps on a mix)."""
+    ops = _ops()
+    M, N, K = 384, 512, 2048
+    a = torch.randn(M, K, device="cuda").to(adt)
+    b = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(bdt)
+    ref = a.float() @ b.float().t()
+    aa = a.t().contiguous() if mn else a
+    bb = b.t().contiguous() if mn else b
+    out = ops.gemm(aa, bb, a_mn_major=mn, b_mn_major=mn)
+    assert rel_err(out, ref) < 1e-3, rel_err(out, ref)
+    out16 = ops.gemm(aa, bb, a_mn_major=mn, b_mn_major=mn, out_dtype=torch.float16, act="relu")
+    assert out16.dtype == torch.float16
+    assert rel_err(out16, torch.relu(ref)) < 2e-3

@@ -1,0 +1,311 @@
+"""Module-level parity on the GPU, through the C ABI: the drop-in DINOv2ViT / ScaleKD / DistillationStep against the
+oracle (oracle/*.py, CPU fp32) and against the golden vectors produced by the unmodified reference
+(tests/golden/*.pt, see oracle/make_golden.py).
+
+Tolerances (BASELINE.json north_star): teacher features cosine >= 0.9999; ScaleKD loss rel err <= 1e-3
+(similarities: abs 1e-3); projector gradients rel err <= 1e-2.
+"""
+import os
+import warnings
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+LOSS_RTOL = 1e-3
+SIM_ATOL = 1e-3
+GRAD_RTOL = 1e-2
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def flat_rel(pairs):
+    """Relative error of the concatenated gradient vector: sqrt(sum |g - g*|^2) / sqrt(sum |g*|^2)."""
+    num = sum(((a.detach().float().cpu() - b.detach().float().cpu()) ** 2).sum().item() for a, b in pairs)
+    den = sum((b.detach().float().cpu() ** 2).sum().item() for a, b in pairs)
+    return (num / max(den, 1e-60)) ** 0.5
+
+
+# Per-tensor bound for the few ill-conditioned reductions (bias gradients of the frequency branch are column sums of a
+# token-mean-free signal: they cancel to a small number, so their RELATIVE error is amplified). The north-star gate
+# (<= 1e-2) is applied to the student-feature gradient, to every weight matrix and to the flat projector gradient.
+PER_TENSOR_LOOSE = 5e-2
+
+
+def _mods():
+    warnings.simplefilter("ignore")
+    from dinov2_distillation_b200 import scalekd, teacher, distill
+    return scalekd, teacher, distill
+
+
+def _check_out(out, ref):
+    for k in ("spatial_loss", "frequency_loss", "loss"):
+        r = abs(out[k].item() - ref[k].item()) / abs(ref[k].item())
+        assert r <= LOSS_RTOL, (k, out[k].item(), ref[k].item())
+    for k in ("spatial_similarity", "frequency_similarity"):
+        assert abs(out[k].item() - ref[k].item()) <= SIM_ATOL, (k, out[k].item(), ref[k].item())
+
+
+def test_scalekd_golden_tiny():
+    scalekd, _, _ = _mods()
+    g = torch.load(os.path.join(GOLDEN, "scalekd_tiny.pt"))
+    m = scalekd.ScaleKD(**g["kwargs"])
+    m.load_state_dict(g["state_dict"])
+    m = m.cuda().train()
+    S = g["preds_S"].cuda().requires_grad_(True)
+    out = m(S, g["preds_T"].cuda())
+    _check_out(out, g["out"])
+    out["loss"].backward()
+    worst = {"dS": rel(S.grad, g["grad_S"])}
+    for k, p in m.named_parameters():
+        ref = g["grads"][k]
+        if ref.norm() < 1e-6 * max(1.0, ref.numel() ** 0.5):  # conv bias: BN cancels it (gradient ~ 0)
+            assert p.grad.norm().item() < 1e-3
+            continue
+        worst[k] = rel(p.grad, ref)
+    flat = flat_rel([(p.grad, g["grads"][k]) for k, p in m.named_parameters()])
+    print("flat", flat, "worst", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+    assert worst["dS"] <= GRAD_RTOL and flat <= GRAD_RTOL, (flat, worst)
+    bad = {k: v for k, v in worst.items() if v > (GRAD_RTOL if k.endswith("weight") else PER_TENSOR_LOOSE)}
+    assert not bad, (bad, worst)
+    # BatchNorm running statistics follow the reference's update
+    sd = m.state_dict()
+    for k in ("projector_0.proj_student.1.running_mean", "projector_0.proj_student.1.running_var"):
+        assert rel(sd[k], g["state_dict_after"][k]) < 1e-3
+    assert int(sd["projector_0.proj_student.1.num_batches_tracked"]) == 1
+
+
+def test_scalekd_golden_cfg1():
+    """BASELINE.json configs[0] loss shapes (vits14 + resnet_18 res5, B=2)."""
+    scalekd, _, _ = _mods()
+    g = torch.load(os.path.join(GOLDEN, "scalekd_cfg1.pt"))
+    torch.manual_seed(g["seed_model"])
+    m = scalekd.ScaleKD(**g["kwargs"]).cuda().train()
+    gen = torch.Generator().manual_seed(g["seed_data"])
+    S = torch.randn(2, 512, 16, 16, generator=gen).cuda().requires_grad_(True)
+    T = torch.randn(2, 384, 16, 16, generator=gen).cuda()
+    out = m(S, T)
+    _check_out(out, g["out"])
+    out["loss"].backward()
+    errs = {"dS_norm": abs(S.grad.norm().item() - g["grad_S_norm"].item()) / g["grad_S_norm"].item(),
+            "dS_sample": rel(S.grad.flatten()[::997], g["grad_S_sample"])}
+    for k, p in m.named_parameters():
+        n_ref = g["grad_norms"][k].item()
+        if n_ref < 1e-4:
+            continue
+        errs[k + ":norm"] = abs(p.grad.norm().item() - n_ref) / n_ref
+        smp = p.grad.flatten()[::max(1, p.numel() // 64)][:64]
+        errs[k + ":sample"] = rel(smp, g["grad_samples"][k])
+    print("worst", sorted(errs.items(), key=lambda kv: -kv[1])[:8])
+    bad = {k: v for k, v in errs.items()
+           if v > (GRAD_RTOL if (k.startswith("dS") or "weight:norm" in k) else PER_TENSOR_LOOSE)}
+    assert not bad, (bad, errs)
+
+
+def test_scalekd_eval_mode_and_external_query():
+    """validation_step path: BN uses running statistics; query supplied by the previous stage."""
+    scalekd, _, _ = _mods()
+    from oracle import scalekd_ref
+    kw = dict(name="scalekd_res5", alpha=[0.08, 0.06], student_dims=48, teacher_dims=64, query_hw=[4, 4], pos_hw=[4, 4],
+              pos_dims=64, window_shapes=[1, 1], self_query=False, softmax_scale=[5.0, 2.0], num_heads=8)
+    torch.manual_seed(5)
+    m = scalekd.ScaleKD(**kw)
+    with torch.no_grad():
+        for n, b in m.named_buffers():
+            if n.endswith("running_mean"):
+                b.normal_(0, 0.3)
+            if n.endswith("running_var"):
+                b.uniform_(0.5, 1.5)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(6)
+    S = torch.randn(3, 48, 4, 4, generator=g)
+    T = torch.randn(3, 64, 4, 4, generator=g)
+    qs = torch.randn(3, 16, 64, generator=g)
+    qf = torch.randn(3, 16, 64, generator=g)
+    ref = scalekd_ref.scalekd_forward(sd, S, T, qs, qf, alpha=kw["alpha"], hw=(4, 4), num_heads=8,
+                                      softmax_scale=kw["softmax_scale"], training=False)
+    with torch.no_grad():
+        out = m(S.cuda(), T.cuda(), query_s=qs.cuda(), query_f=qf.cuda())
+    _check_out(out, ref)
+    with pytest.raises(NotImplementedError):
+        m(S.cuda(), T.cuda())
+
+
+def _teacher_pair(name_or_cfg, seed, pos_grid=37):
+    _, teacher, _ = _mods()
+    from oracle import dinov2_ref
+    if isinstance(name_or_cfg, str):
+        cfg = dinov2_ref.TEACHER_CFGS[name_or_cfg]
+        sd = dinov2_ref.make_state_dict(cfg, seed=seed)
+        t = teacher.DINOv2ViT(name_or_cfg)
+        t.model.load_state_dict(sd)
+    else:
+        cfg = name_or_cfg
+        sd = dinov2_ref.make_state_dict(cfg, seed=seed, pos_grid=pos_grid)
+        t = teacher.DINOv2ViT.__new__(teacher.DINOv2ViT)
+        torch.nn.Module.__init__(t)
+        t.model = teacher.DinoVisionTransformerB200(cfg.dim, cfg.depth, cfg.heads, cfg.ffn_hidden, cfg.swiglu)
+        t.model.pos_embed = torch.nn.Parameter(torch.zeros(1, 1 + pos_grid * pos_grid, cfg.dim))
+        t.model.load_state_dict(sd)
+        t.H = t.W = None
+    return t.cuda().eval(), cfg, sd
+
+
+@pytest.mark.parametrize("name,size,B", [("dinov2_vits14", 224, 2), ("dinov2_vits14", 518, 1), ("dinov2_vitb14", 224, 2)])
+def test_teacher_features_vs_oracle(name, size, B):
+    from oracle import dinov2_ref
+    t, cfg, sd = _teacher_pair(name, seed=1)
+    x = torch.randn(B, 3, size, size, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ref = dinov2_ref.teacher_feature_map(sd, cfg, x)
+    got = t(x.cuda())["feature_map"]
+    assert got.shape == ref.shape
+    assert got.stride() == ref.stride()  # same strided view as the reference (dinov2.py:40)
+    g, r = got.float().cpu(), ref
+    cos = torch.nn.functional.cosine_similarity(g.flatten(1), r.flatten(1), dim=1)
+    assert cos.min().item() >= 0.9999, cos
+    tok_cos = torch.nn.functional.cosine_similarity(g, r, dim=1)
+    assert tok_cos.min().item() >= 0.999, tok_cos.min()
+    assert (g - r).abs().max().item() < 0.25  # bf16 operands vs fp32 oracle, unit-variance features
+
+
+def test_teacher_swiglu_small():
+    """vitg14's SwiGLU FFN path at a reduced width/depth (full vitg14 is covered by bench configs)."""
+    from oracle import dinov2_ref
+    cfg = dinov2_ref.VitCfg(256, 3, 4, 344 * 2, True)
+    t, cfg, sd = _teacher_pair(cfg, seed=7, pos_grid=5)
+    x = torch.randn(2, 3, 70, 70, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ref = dinov2_ref.teacher_feature_map(sd, cfg, x)
+    got = t(x.cuda())["feature_map"].float().cpu()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(1), ref.flatten(1), dim=1)
+    assert cos.min().item() >= 0.9999, cos
+
+
+@pytest.mark.parametrize("swiglu", [False, True])
+def test_teacher_block_input_gradient(swiglu):
+    """_forward_specific_stage path: blocks[i](feat) differentiable w.r.t. feat (distillation_module.py:176-177)."""
+    from oracle import dinov2_ref
+    cfg = dinov2_ref.VitCfg(128, 2, 2, 512 if not swiglu else 344, swiglu)
+    t, cfg, sd = _teacher_pair(cfg, seed=9, pos_grid=5)
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(2, 25, 128, generator=g)
+    dy = torch.randn(2, 25, 128, generator=g)
+    fr = feat.clone().requires_grad_(True)
+    ref = dinov2_ref.block(sd, 1, dinov2_ref.block(sd, 0, fr, cfg), cfg)
+    ref.backward(dy)
+    fc = feat.cuda().requires_grad_(True)
+    out = t.model.blocks[1](t.model.blocks[0](fc))
+    out.backward(dy.cuda())
+    assert rel(out, ref) < 1e-2, rel(out, ref)
+    assert rel(fc.grad, fr.grad) < 2e-2, rel(fc.grad, fr.grad)
+    with torch.no_grad():
+        out2 = t.model.blocks[1](t.model.blocks[0](feat.cuda()))
+    assert rel(out2, ref) < 1e-2
+
+
+def test_pipeline_golden_tiny():
+    """res4 -> re-used teacher blocks -> res5 chaining, against the reference's own _compute_losses."""
+    _, teacher, distill = _mods()
+    from oracle import dinov2_ref
+    g = torch.load(os.path.join(GOLDEN, "pipeline_tiny.pt"))
+    cfg = dinov2_ref.VitCfg(*g["teacher_cfg"])
+    t, _, _ = _teacher_pair(cfg, seed=21, pos_grid=4)
+    t.model.load_state_dict(g["teacher_sd"])
+    step = distill.DistillationStep(None, t, g["specs"])
+    step.losses.load_state_dict(g["losses_sd"])
+    step = step.cuda().train()
+    # teacher features from OUR teacher on the fixture's images (also checks the teacher against the oracle's map)
+    T = t(g["img"].cuda())["feature_map"]
+    cos = torch.nn.functional.cosine_similarity(T.float().cpu().flatten(1), g["teacher_map"].flatten(1), dim=1)
+    assert cos.min().item() >= 0.9999
+    feats = {k: v.cuda().requires_grad_(True) for k, v in g["feats"].items()}
+    out = step._compute_losses({"student": feats, "teacher": g["teacher_map"].cuda()})
+    assert sorted(out.keys()) == sorted(g["out"].keys())
+    for k, v in g["out"].items():
+        if k.endswith("similarity"):
+            assert abs(out[k].item() - v.item()) <= 2 * SIM_ATOL, (k, out[k].item(), v.item())
+        else:
+            assert abs(out[k].item() - v.item()) / abs(v.item()) <= 2 * LOSS_RTOL, (k, out[k].item(), v.item())
+    out["loss"].backward()
+    errs = {"d_" + k: rel(feats[k].grad, g["grad_feats"][k]) for k in feats}
+    for k, p in step.losses.named_parameters():
+        ref = g["grads"].get(k)
+        if ref is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0, k
+            continue
+        if ref.norm() < 1e-5:
+            continue
+        errs[k] = rel(p.grad, ref)
+    flat = flat_rel([(p.grad, g["grads"][k]) for k, p in step.losses.named_parameters() if k in g["grads"]])
+    print("flat", flat, "worst", sorted(errs.items(), key=lambda kv: -kv[1])[:8])
+    assert flat <= GRAD_RTOL, flat
+    bad = {k: v for k, v in errs.items()
+           if v > (GRAD_RTOL if (k.startswith("d_") or k.endswith("weight")) else PER_TENSOR_LOOSE)}
+    assert not bad, (bad, errs)
+
+
+def test_cfg2_shapes_vs_oracle_port():
+    """config.yaml losses (res4 heads 16 self-query + res5 heads 24) on vits14 dims, B=4, against the oracle port."""
+    _, teacher, distill = _mods()
+    from oracle import dinov2_ref, scalekd_ref
+    t, cfg, tsd = _teacher_pair("dinov2_vits14", seed=1)
+    common = dict(alpha=[0.08, 0.06], teacher_dims=384, query_hw=[16, 16], pos_hw=[16, 16], pos_dims=384,
+                  window_shapes=[1, 1], softmax_scale=[5.0, 5.0])
+    specs = [
+        {"type": "scalekd", "weight": 1, "kwargs": dict(common, name="scalekd_res4", student_dims=512, self_query=True, num_heads=16)},
+        {"type": "scalekd", "weight": 1.0, "kwargs": dict(common, name="scalekd_res5", student_dims=1024, self_query=False, num_heads=24)},
+    ]
+    torch.manual_seed(3)
+    step = distill.DistillationStep(None, t, specs)
+    sds = {n: {k: v.detach().clone() for k, v in m.state_dict().items()} for n, m in step.losses.items()}
+    step = step.cuda().train()
+    gen = torch.Generator().manual_seed(2)
+    B = 4
+    img = torch.randn(B, 3, 224, 224, generator=gen)
+    f4 = torch.randn(B, 512, 16, 16, generator=gen)
+    f5 = torch.randn(B, 1024, 16, 16, generator=gen)
+    # oracle (CPU fp32)
+    with torch.no_grad():
+        T_ref = dinov2_ref.teacher_feature_map(tsd, cfg, img)
+    for sd in sds.values():
+        for v in sd.values():
+            if v.is_floating_point():
+                v.requires_grad_(True)
+    losses = {n: dict(sd=sds[n], weight=s["weight"], alpha=common["alpha"], hw=(16, 16),
+                      num_heads=s["kwargs"]["num_heads"], softmax_scale=common["softmax_scale"])
+              for n, s in zip(["scalekd_res4", "scalekd_res5"], specs)}
+    blocks = [lambda x, i=i: dinov2_ref.block(tsd, i, x, cfg) for i in range(cfg.depth)]
+    r4, r5 = f4.clone().requires_grad_(True), f5.clone().requires_grad_(True)
+    ref = scalekd_ref.compute_losses(losses, {"res4": r4, "res5": r5}, T_ref, blocks)
+    ref["loss"].backward()
+    # ours
+    c4, c5 = f4.cuda().requires_grad_(True), f5.cuda().requires_grad_(True)
+    T = t(img.cuda())["feature_map"]
+    out = step._compute_losses({"student": {"res4": c4, "res5": c5}, "teacher": T})
+    out["loss"].backward()
+    for k, v in ref.items():
+        if k.endswith("similarity"):
+            assert abs(out[k].item() - v.item()) <= 2 * SIM_ATOL, (k, out[k].item(), v.item())
+        else:
+            assert abs(out[k].item() - v.item()) / abs(v.item()) <= 2 * LOSS_RTOL, (k, out[k].item(), v.item())
+    errs = {"d_res4": rel(c4.grad, r4.grad), "d_res5": rel(c5.grad, r5.grad)}
+    for n, m in step.losses.items():
+        for k, p in m.named_parameters():
+            rg = sds[n][k].grad
+            if rg is None or rg.norm() < 1e-5:
+                continue
+            errs[f"{n}.{k}"] = rel(p.grad, rg)
+    flat = flat_rel([(p.grad, sds[n][k].grad) for n, m in step.losses.items() for k, p in m.named_parameters()
+                     if sds[n][k].grad is not None])
+    print("flat", flat, "worst", sorted(errs.items(), key=lambda kv: -kv[1])[:10])
+    assert flat <= GRAD_RTOL, flat
+    bad = {k: v for k, v in errs.items()
+           if v > (GRAD_RTOL if (k.startswith("d_") or k.endswith("weight")) else PER_TENSOR_LOOSE)}
+    assert not bad, (bad, errs)
