@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- distillation hot-path throughput (teacher fwd + ScaleKD fwd/bwd) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+Prints ONE JSON line (rank 0). A "step" is one pass of the hot path over one synthetic batch:
+frozen DINOv2 teacher forward -> ScaleKD projectors / re-used teacher blocks / loss terms forward -> backward to the
+student features and the projector parameters (-> one NCCL mean-allreduce of the flat gradient arena when N > 1).
+The student network itself is out of scope (stock PyTorch in the reference): its tapped features are synthetic tensors
+of the shapes ModelWrapper hands to the losses.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "distill images/sec (teacher fwd+ScaleKD fwd/bwd)"
+UNIT = "images/s"
+
+# BASELINE.json configs. per-GPU batch is fixed as N grows (weak scaling, like `batch_size ... #per gpu`, config.yaml:75)
+WORKLOADS = {
+    "cfg1": dict(desc="dinov2_vits14 + resnet_18, ScaleKD res5 only, B=2 @224", teacher="dinov2_vits14", size=224, batch=2,
+                 losses=[("scalekd_res5", 512, 24, True)]),
+    "cfg2": dict(desc="dinov2_vits14 -> stdc_2, config.yaml ScaleKD res4+res5, B=64/GPU @224", teacher="dinov2_vits14",
+                 size=224, batch=64, losses=[("scalekd_res4", 512, 16, True), ("scalekd_res5", 1024, 24, False)]),
+    "cfg3": dict(desc="dinov2_vitb14 -> convnext_tiny, ScaleKD res4+res5, B=32/GPU @224", teacher="dinov2_vitb14",
+                 size=224, batch=32, losses=[("scalekd_res4", 384, 16, True), ("scalekd_res5", 768, 24, False)]),
+    "cfg4": dict(desc="dinov2_vitl14 -> swin_tiny, ScaleKD res4+res5 (heads 16), B=32/GPU @518", teacher="dinov2_vitl14",
+                 size=518, batch=32, losses=[("scalekd_res4", 384, 16, True), ("scalekd_res5", 768, 16, False)]),
+    "cfg5": dict(desc="dinov2_vitg14 teacher forward only, B=64/GPU @224", teacher="dinov2_vitg14", size=224, batch=64,
+                 losses=[]),
+}
+TEACHER_DIMS = {"dinov2_vits14": (384, 12, 6, 1536, False), "dinov2_vitb14": (768, 12, 12, 3072, False),
+                "dinov2_vitl14": (1024, 24, 16, 4096, False), "dinov2_vitg14": (1536, 40, 24, 4096, True)}
+
+
+def loss_specs(wl):
+    D = TEACHER_DIMS[wl["teacher"]][0]
+    g = wl["size"] // 14
+    specs = []
+    for name, cs, heads, self_query in wl["losses"]:
+        specs.append({"type": "scalekd", "weight": 1.0, "kwargs": dict(
+            name=name, alpha=[0.08, 0.06], student_dims=cs, teacher_dims=D, query_hw=[g, g], pos_hw=[g, g], pos_dims=D,
+            window_shapes=[1, 1], self_query=self_query, softmax_scale=[5.0, 5.0], num_heads=heads)})
+    return specs
+
+
+def algorithmic_gflop_per_image(wl):
+    """SURVEY.md section 8(d) formulas (GEMM 2MNK, attention 4 N^2 D fwd / 8 N^2 D bwd; elementwise not counted)."""
+    D, L, h, F, swiglu = TEACHER_DIMS[wl["teacher"]]
+    hw = (wl["size"] // 14) ** 2
+    n = hw + 1
+
+    def block(ntok):
+        ffn = 6 * ntok * D * F if swiglu else 4 * ntok * D * F
+        return 8 * ntok * D * D + ffn + 4 * ntok * ntok * D
+
+    teacher = 2 * hw * 588 * D + L * block(n)
+    proj_f = sum(2 * hw * cs * D + 24 * hw * D * D + 4 * hw * hw * D for _, cs, _, _ in wl["losses"]) * 2
+    stage_f = 0
+    if any("res4" in nm for nm, *_ in wl["losses"]):
+        stage_f = 2 * sum(block(hw) for _ in range(int(L * 0.75), L - 1))
+    stage_b = 0
+    if stage_f:
+        per = (8 * hw * D * D + (6 if swiglu else 4) * hw * D * F) + 8 * hw * hw * D
+        stage_b = 2 * per * len(range(int(L * 0.75), L - 1))
+    total = teacher + proj_f + stage_f + 2 * proj_f + stage_b
+    return dict(teacher=teacher / 1e9, projector_fwd=proj_f / 1e9, stage_fwd=stage_f / 1e9,
+                backward=(2 * proj_f + stage_b) / 1e9, total=total / 1e9)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_step_factory(wl, batch, seed=0):
+    """The reference's CPU path for this workload: oracle teacher restatement + oracle ScaleKD/_compute_losses port
+    (oracle/*.py; /root/reference itself cannot travel to the GPU box). Returns a callable running one fwd+bwd step."""
+    from oracle import dinov2_ref, scalekd_ref
+    cfg = dinov2_ref.TEACHER_CFGS[wl["teacher"]]
+    tsd = dinov2_ref.make_state_dict(cfg, seed=1)
+    g = wl["size"] // 14
+    gen = torch.Generator().manual_seed(seed)
+    img = torch.randn(batch, 3, wl["size"], wl["size"], generator=gen)
+    feats, losses = {}, {}
+    for i, (name, cs, heads, self_query) in enumerate(wl["losses"]):
+        layer = name.split("_")[1]
+        feats[layer] = torch.randn(batch, cs, g, g, generator=gen, requires_grad=True)
+        sd = scalekd_ref.make_scalekd_state(cs, cfg.dim, (g, g), self_query, seed=3 + i)
+        for v in sd.values():
+            if v.is_floating_point():
+                v.requires_grad_(True)
+        losses[name] = dict(sd=sd, weight=1.0, alpha=[0.08, 0.06], hw=(g, g), num_heads=heads, softmax_scale=[5.0, 5.0])
+    blocks = [lambda x, i=i: dinov2_ref.block(tsd, i, x, cfg) for i in range(cfg.depth)]
+
+    def step():
+        with torch.no_grad():
+            T = dinov2_ref.teacher_feature_map(tsd, cfg, img)
+        if not losses:
+            return float(T.float().mean())
+        out = scalekd_ref.compute_losses(losses, feats, T, blocks)
+        out["loss"].backward()
+        return float(out["loss"])
+
+    return step
+
+
+def time_cpu_reference(wl, batch, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_reference_step_factory(wl, batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch / dt, dt
+
+
+def run_reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    b = min(wl["batch"], args.cpu_batch)
+    steps = max(1, min(args.steps, 3))
+    ips, dt = time_cpu_reference(wl, b, steps, max(1, min(args.warmup, 1)))
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "bounded_sample": f"B={b} images per step on the host CPU"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} step(s) of B={b} images, oracle port of the reference (teacher restatement "
+                                   f"+ ScaleKD/_compute_losses), torch CPU fp32, {cores} threads"},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def build_gpu_step(wl, device):
+    warnings.simplefilter("ignore")
+    from dinov2_distillation_b200 import distributed as D
+    from dinov2_distillation_b200.distill import DistillationStep
+    from dinov2_distillation_b200.teacher import DINOv2ViT
+    torch.manual_seed(3)
+    teacher = DINOv2ViT(wl["teacher"])
+    step = DistillationStep(None, teacher, loss_specs(wl)).to(device).train()
+    g = wl["size"] // 14
+    gen = torch.Generator().manual_seed(0)
+    B = wl["batch"]
+    host = {"img": torch.randn(B, 3, wl["size"], wl["size"], generator=gen).pin_memory()}
+    for name, cs, _, _ in wl["losses"]:
+        host[name.split("_")[1]] = torch.randn(B, cs, g, g, generator=gen).pin_memory()
+    params = [p for p in step.losses.parameters()]
+    arena = D.FlatGradArena(params) if params else None
+    return step, host, arena
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="images per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback); use --impl reference")
+    from dinov2_distillation_b200 import _lib as L
+    from dinov2_distillation_b200 import distributed as D
+    import torch.distributed as dist
+    rank, world, local = D.init_from_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    lib = L.load()
+
+    step, host, arena = build_gpu_step(wl, device)
+    dev = {k: v.to(device) for k, v in host.items()}
+    layers = [n.split("_")[1] for n, *_ in wl["losses"]]
+    feats = {k: dev[k].clone().requires_grad_(True) for k in layers}
+
+    def hot_path(img, feats):
+        """One step with inputs resident in HBM."""
+        if arena is not None:
+            arena.zero()
+        for f in feats.values():
+            f.grad = None
+        T = step.teacher(img)["feature_map"]
+        if not layers:
+            return T
+        out = step._compute_losses({"student": feats, "teacher": T})
+        out["loss"].backward()
+        if arena is not None and world > 1:
+            w = arena.allreduce_mean()
+            if w is not None:
+                w.wait()
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        hot_path(dev["img"], feats)
+    sync_all()
+
+    # ---- timed region: device-resident inputs, CUDA events, max over ranks
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.b200_reset_launch_count()
+    with ClockSampler(local) as clocks:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            hot_path(dev["img"], feats)
+        e1.record()
+        sync_all()
+    launches = int(lib.b200_launch_count())
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = wl["batch"] * world * args.steps / (ms / 1e3)
+
+    # ---- end to end: pinned host inputs -> H2D every step, loss metrics -> D2H every step
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    metrics_host = torch.empty(16, dtype=torch.float32).pin_memory()
+    d2h = 0
+
+    def e2e_step():
+        nonlocal d2h
+        img = host["img"].to(device, non_blocking=True)
+        f = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in layers}
+        out = hot_path(img, f)
+        if layers:
+            vals = torch.stack([v.detach().float().reshape(()) for _, v in sorted(out.items())])
+        else:
+            vals = out.float().mean().reshape(1)
+        metrics_host[:vals.numel()].copy_(vals, non_blocking=True)
+        d2h = vals.numel() * 4
+        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+        return float(metrics_host[0])
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = wl["batch"] * world * args.steps / (float(t.item()) / 1e3)
+
+    # ---- roofline leg: per-launch CUDA-event timing of the dense kernels over the same steps (rank 0 reports)
+    roofline, extra = None, {}
+    if not args.no_roofline:
+        import ctypes as C
+        lib.b200_profile_enable(1)
+        nprof = max(2, min(args.steps, 5))
+        for _ in range(nprof):
+            hot_path(dev["img"], feats)
+        torch.cuda.synchronize()
+        ms_c, fl_c, n_c = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
+        L.check(lib.b200_profile_read(3, ms_c, fl_c, n_c), "profile_read")
+        lib.b200_profile_enable(0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        if n_c[0] > 0 and ms_c[0] > 0:
+            ach = fl_c[0] / (ms_c[0] * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                        "launches_per_step": n_c[0] / nprof, "avg_launch_us": ms_c[0] * 1e3 / n_c[0],
+                        "algorithmic_gflop_per_launch": fl_c[0] / n_c[0] / 1e9,
+                        "share_of_step": (ms_c[0] / nprof) / ms_per_step}
+        for i, nm in ((1, "attention_fwd"), (2, "attention_bwd")):
+            if n_c[i] > 0 and ms_c[i] > 0:
+                extra[nm] = {"tflops": fl_c[i] / (ms_c[i] * 1e-3) / 1e12, "ms_per_step": ms_c[i] / nprof,
+                             "launches_per_step": n_c[i] / nprof}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        b = min(wl["batch"], args.cpu_batch)
+        ips, dt = time_cpu_reference(wl, b, 1, 1)
+        cpu = {"value": ips, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 timed step (after 1 warm-up) of B={b} images of {args.workload} through the oracle port "
+                         f"(torch CPU fp32), {dt:.2f} s/step"}
+
+    if rank == 0:
+        gf = algorithmic_gflop_per_image(wl)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": wl["batch"],
+                       "global_batch": wl["batch"] * world, "image_size": wl["size"],
+                       "student_features": "synthetic (student network out of scope)", "parallelism": f"dp{world}",
+                       "precision": "teacher bf16 operands / fp32 accum+residual; projector fwd fp16 operands, bwd bf16",
+                       "l2": "per-step working set (activations >> 126 MB L2) ; no explicit flush",
+                       "algorithmic_gflop_per_image": gf},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "model_tflops": value * gf["total"] / 1e3 / world,
+            "kernels": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

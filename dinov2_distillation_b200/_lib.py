@@ -32,6 +32,7 @@ class GemmDesc(C.Structure):
         ("out_bf16_pre", c_vp), ("ldo16_pre", c_ll),
         ("out_row_period", C.c_int), ("out_row_pad", C.c_int),
         ("a_is_fp16", C.c_int), ("b_is_fp16", C.c_int), ("out16_is_fp16", C.c_int), ("aux_is_fp16", C.c_int),
+        ("algo_flops_scale", C.c_float),
     ]
 
 
@@ -101,6 +102,8 @@ SIGNATURES = {
     "b200_abi_version": (_i, []),
     "b200_launch_count": (c_ll, []),
     "b200_reset_launch_count": (None, []),
+    "b200_profile_enable": (None, [_i]),
+    "b200_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll)]),
     "b200_gemm_bf16": (_i, [C.POINTER(GemmDesc), c_vp]),
     "b200_cast_f32_bf16": (_i, [c_fp, c_vp, c_ll, c_vp]),
     "b200_split3_16": (_i, [c_fp, c_vp, c_ll, _i, _i, _i, c_vp]),

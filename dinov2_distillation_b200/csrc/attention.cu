@@ -540,7 +540,9 @@ static int launch_fwd_t(const AttnParams& p, cudaStream_t st) {
   static bool once = false;
   if (!once) { B200_TRY(set_smem(attn_fwd_kernel<HDP, HALF>, smem)); once = true; }
   dim3 grid((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
+  const int prof = prof_begin(st);
   attn_fwd_kernel<HDP, HALF><<<grid, ATT_THREADS, smem, st>>>(p);
+  prof_end(prof, st, 4.0 * p.B * p.heads * (double)p.Nq * p.Nk * p.hd, 1);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -562,6 +564,7 @@ static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
   const long long n = (long long)p.B * p.Nq * p.heads;
   long long gd = cdiv(n, 256);
   if (gd > (long long)sm_count() * 16) gd = (long long)sm_count() * 16;
+  const int prof = prof_begin(st);
   attn_delta_kernel<HALF><<<(unsigned)gd, 256, 0, st>>>(p);
   B200_LAUNCH_OK();
   dim3 gq((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
@@ -569,6 +572,7 @@ static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
   B200_LAUNCH_OK();
   dim3 gk((unsigned)cdiv(p.Nk, ATT_BK), (unsigned)p.heads, (unsigned)p.B);
   attn_bwd_dkv_kernel<HDP, HALF><<<gk, ATT_THREADS, smem_dkv, st>>>(p);
+  prof_end(prof, st, 8.0 * p.B * p.heads * (double)p.Nq * p.Nk * p.hd, 2);
   B200_LAUNCH_OK();
   return 0;
 }

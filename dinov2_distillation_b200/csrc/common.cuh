@@ -12,6 +12,9 @@ namespace b200 {
 void set_error(const std::string& msg);
 void count_launch(int n = 1);
 int sm_count();
+// per-launch timing hooks (no-ops unless b200_profile_enable(1)); cat: 0 GEMM, 1 attention fwd, 2 attention bwd
+int prof_begin(cudaStream_t st);
+void prof_end(int idx, cudaStream_t st, double flops, int cat);
 
 #define B200_CHECK_ARG(cond, msg)                                                      \
   do {                                                                                 \

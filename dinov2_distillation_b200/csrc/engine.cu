@@ -40,6 +40,7 @@ struct Gemm {
   Gemm& fp16_operands() { d.a_is_fp16 = 1; d.b_is_fp16 = 1; return *this; }
   Gemm& out16_fp16() { d.out16_is_fp16 = 1; return *this; }
   Gemm& aux_fp16() { d.aux_is_fp16 = 1; return *this; }
+  Gemm& algo_scale(float f) { d.algo_flops_scale = f; return *this; }
   // wgrad form: both operands token-major (contraction over rows), fp32 atomic accumulate, split over the contraction
   Gemm& wgrad() {
     d.a_mn_major = 1; d.b_mn_major = 1; d.atomic_add = 1;
@@ -442,7 +443,7 @@ extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_pro
   // the conv feeds BN -> ReLU with no residual around it: run it as a 3-term split fp16 product (K -> 3K)
   B200_TRY(b200_nchw_to_tokens(x, s.xt, w.xt32, B, Cs, HW, 0, stream));
   B200_TRY(b200_split3_16(w.xt32, w.xt3, M, Cs, 0, 1, stream));
-  B200_TRY(Gemm(w.xt3, 3 * Cs, w.wc3, 3 * Cs, Mi, D, 3 * Cs).fp16_operands().bias(p->conv_b).out32(s.y, D).run(stream));
+  B200_TRY(Gemm(w.xt3, 3 * Cs, w.wc3, 3 * Cs, Mi, D, 3 * Cs).fp16_operands().algo_scale(1.f / 3.f).bias(p->conv_b).out32(s.y, D).run(stream));
   if (c->training) {
     B200_TRY(zero_f32(w.sums, 2 * D, st));
     B200_TRY(b200_bn_stats(s.y, w.sums, Mi, D, stream));
@@ -553,7 +554,9 @@ extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_pro
   B200_TRY(b200_axpy(w.sums2 + D, g->bn_w, 1.0f, D, stream));
   B200_TRY(b200_bn_relu_pos_bwd_apply(w.dz32, s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.sums2, w.dy16, c->training ? 1 : 0, Mi, D, stream));
   // conv1x1
-  B200_TRY(b200_colsum(w.dy16, 1, D, g->conv_b, Mi, D, stream));
+  // with batch statistics the column sums of dy vanish identically (sum_r yhat = 0): BN cancels the conv bias
+  // (losses/scalekd.py:199-200), so its gradient is exactly zero; only the running-statistics (eval) path needs the sum.
+  if (!c->training) B200_TRY(b200_colsum(w.dy16, 1, D, g->conv_b, Mi, D, stream));
   B200_TRY(Gemm(w.dy16, D, s.xt, Cs, D, Cs, Mi).out32(g->conv_w, Cs).wgrad().run(stream));
   if (dx) {
     B200_TRY(Gemm(w.dy16, D, w.wcT, D, Mi, Cs, D).out32(w.dxt32, Cs).run(stream));

@@ -44,6 +44,7 @@ struct GemmParams {
   int vec_ok;  // all leading dims / pointers allow 16-byte vector access
   int out16_fp16, aux_fp16;  // 16-bit output / aux element type: 0 = bf16, 1 = fp16
   uint32_t idesc;            // tcgen05 instruction descriptor (operand formats, majors, tile shape)
+  float algo_scale;          // profiling: algorithmic flops / executed flops
 };
 
 template <int BN>
@@ -411,7 +412,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_set = true;
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  const int prof = prof_begin(st);
   kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  prof_end(prof, st, 2.0 * p.M * p.N * p.K * p.algo_scale, 0);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -489,6 +492,7 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   if (p.out_bf16) vec = vec && al16(p.out_bf16) && p.ldo16 % 8 == 0;
   if (p.out_bf16_pre) vec = vec && al16(p.out_bf16_pre) && p.ldo16_pre % 8 == 0;
   p.vec_ok = vec ? 1 : 0;
+  p.algo_scale = d->algo_flops_scale > 0.f ? d->algo_flops_scale : 1.0f;
   p.out16_fp16 = d->out16_is_fp16 ? 1 : 0;
   p.aux_fp16 = d->aux_is_fp16 ? 1 : 0;
   // a_format / b_format: 0 = F16, 1 = BF16 (bits 7-9 / 10-12)

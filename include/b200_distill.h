@@ -33,6 +33,11 @@ int b200_abi_version(void);
 /* number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches). */
 long long b200_launch_count(void);
 void b200_reset_launch_count(void);
+/* Per-launch device timing of the dense kernels (CUDA events on the launch stream), for bench.py's roofline object.
+ * Categories: 0 = tcgen05 GEMM (2MNK flops), 1 = attention forward (4 Nq Nk D), 2 = attention backward (8 Nq Nk D).
+ * b200_profile_read synchronises the recorded events, fills sums per category and clears the records. */
+void b200_profile_enable(int on);
+int b200_profile_read(int n_cat, double* ms, double* flops, long long* launches);
 
 /* ------------------------------------------------------------------------------------------------ GEMM (tcgen05)
  * C[M,N] = epilogue(A * B^T): bf16 operands staged by TMA (128B swizzle), tcgen05.mma with fp32 accumulators in TMEM.
@@ -65,6 +70,8 @@ typedef struct b200_gemm_desc {
   /* 16-bit element types: 0 = bf16 (default), 1 = fp16. The ScaleKD projector FORWARD runs fp16 operands (the
    * reference's own default is fp16 AMP, train.py:263); gradients stay bf16 for range. A and B may differ. */
   int a_is_fp16, b_is_fp16, out16_is_fp16, aux_is_fp16;
+  /* profiling only: algorithmic flops = algo_flops_scale * 2MNK (0 means 1; 1/3 for the 3-term split product) */
+  float algo_flops_scale;
 } b200_gemm_desc;
 
 int b200_gemm_bf16(const b200_gemm_desc* d, void* stream);
