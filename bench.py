@@ -230,6 +230,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -257,17 +259,27 @@ def main():
     layers = [n.split("_")[1] for n, *_ in wl["losses"]]
     feats = {k: dev[k].clone().requires_grad_(True) for k in layers}
 
+    graphed = None
+    if not args.no_graph:
+        from dinov2_distillation_b200.distill import GraphedDistillStep
+        graphed = GraphedDistillStep(step, dev["img"], {k: dev[k] for k in layers}, arena)
+
     def hot_path(img, feats):
-        """One step with inputs resident in HBM."""
-        if arena is not None:
-            arena.zero()
-        for f in feats.values():
-            f.grad = None
-        T = step.teacher(img)["feature_map"]
-        if not layers:
-            return T
-        out = step._compute_losses({"student": feats, "teacher": T})
-        out["loss"].backward()
+        """One step with inputs resident in HBM (img / feats=None: reuse the graph's static input buffers)."""
+        if graphed is not None:
+            out, _ = graphed(img, feats)
+            if not layers:
+                out = out["teacher"]
+        else:
+            if arena is not None:
+                arena.zero()
+            for f in feats.values():
+                f.grad = None
+            T = step.teacher(img)["feature_map"]
+            if not layers:
+                return T
+            out = step._compute_losses({"student": feats, "teacher": T})
+            out["loss"].backward()
         if arena is not None and world > 1:
             w = arena.allreduce_mean()
             if w is not None:
@@ -280,8 +292,9 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    res_img, res_feats = (None, None) if graphed is not None else (dev["img"], feats)
     for _ in range(args.warmup):
-        hot_path(dev["img"], feats)
+        hot_path(res_img, res_feats)
     sync_all()
 
     # ---- timed region: device-resident inputs, CUDA events, max over ranks
@@ -291,10 +304,16 @@ def main():
         sync_all()
         e0.record()
         for _ in range(args.steps):
-            hot_path(dev["img"], feats)
+            hot_path(res_img, res_feats)
         e1.record()
         sync_all()
     launches = int(lib.b200_launch_count())
+    if graphed is not None:
+        # graph replays do not pass through the library's launch counter: count one eager step instead
+        lib.b200_reset_launch_count()
+        graphed._run()
+        torch.cuda.synchronize()
+        launches = int(lib.b200_launch_count()) * args.steps
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -310,9 +329,12 @@ def main():
 
     def e2e_step():
         nonlocal d2h
-        img = host["img"].to(device, non_blocking=True)
-        f = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in layers}
-        out = hot_path(img, f)
+        if graphed is not None:
+            out = hot_path(host["img"], {k: host[k] for k in layers})   # async H2D into the graph's static inputs
+        else:
+            img = host["img"].to(device, non_blocking=True)
+            f = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in layers}
+            out = hot_path(img, f)
         if layers:
             vals = torch.stack([v.detach().float().reshape(()) for _, v in sorted(out.items())])
         else:
@@ -322,18 +344,20 @@ def main():
         torch.cuda.current_stream().synchronize()  # the user reads the loss every step
         return float(metrics_host[0])
 
-    for _ in range(2):
-        e2e_step()
-    sync_all()
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = wl["batch"] * world * args.steps / (float(t.item()) / 1e3)
+    e2e_value = None
+    if not args.no_e2e:
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = wl["batch"] * world * args.steps / (float(t.item()) / 1e3)
 
     # ---- roofline leg: per-launch CUDA-event timing of the dense kernels over the same steps (rank 0 reports)
     roofline, extra = None, {}
@@ -341,8 +365,11 @@ def main():
         import ctypes as C
         lib.b200_profile_enable(1)
         nprof = max(2, min(args.steps, 5))
-        for _ in range(nprof):
-            hot_path(dev["img"], feats)
+        for _ in range(nprof):   # eager launches (events bracket each dense kernel); not part of `value`
+            if graphed is not None:
+                graphed._run()
+            else:
+                hot_path(dev["img"], feats)
         torch.cuda.synchronize()
         ms_c, fl_c, n_c = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
         L.check(lib.b200_profile_read(3, ms_c, fl_c, n_c), "profile_read")
@@ -386,6 +413,7 @@ def main():
                        "student_features": "synthetic (student network out of scope)", "parallelism": f"dp{world}",
                        "precision": "teacher bf16 operands / fp32 accum+residual; projector fwd fp16 operands, bwd bf16",
                        "l2": "per-step working set (activations >> 126 MB L2) ; no explicit flush",
+                       "launch": "eager" if graphed is None else "one CUDA graph replay per step",
                        "algorithmic_gflop_per_image": gf},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

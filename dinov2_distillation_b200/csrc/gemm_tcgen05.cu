@@ -20,6 +20,9 @@ namespace b200 {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;   // warps 0-3: TMA / MMA / TMEM alloc / spare
+constexpr int EPI_STAGE_BYTES = 0;
 
 struct GemmParams {
   int M, N, K;
@@ -54,9 +57,12 @@ struct TileCfg {
   static constexpr int STAGES = (BN == 128) ? 6 : (BN == 192 ? 5 : 4);
   static constexpr int TMEM_STRIDE = (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * TMEM_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue for 32 consecutive columns of one accumulator row (thread = row): 128-bit vector loads / stores along the
+// row. (A shared-memory transposed, lane = column variant was measured 3x slower: the epilogue is instruction bound.)
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok, int row, int n0, float (&v)[32],
                                                bool first_split) {
   if (!row_ok || n0 >= p.N) return;
@@ -97,7 +103,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
   }
   if (p.act == B200_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
   } else if (p.act == B200_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -119,7 +125,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
     }
     if (p.aux_mode == B200_AUX_DGELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(a[j]);
+      for (int j = 0; j < 32; ++j) v[j] *= dgelu_fast(a[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
@@ -188,14 +194,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
 }
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -215,7 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -296,7 +302,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    const int quad = warp & 3;
+    const int quad = warp & 3;            // TMEM lanes 32*quad .. +31 (hardware: warp id % 4)
+    const int half = (warp - 4) >> 2;     // which 32-column blocks of the tile this warp drains
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -304,20 +311,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int r = t - ks * tiles_mn;
       const int m0 = (r / p.n_tiles) * BM;
       const int n0 = (r % p.n_tiles) * BN;
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row0 = m0 + quad * 32;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t raw[32];
         tmem_ld_32x32(taddr + c * 32, raw);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        epilogue_chunk(p, row_ok, row, n0 + c * 32, v, ks == 0);
+        epilogue_chunk(p, row0 + lane < p.M, row0 + lane, n0 + c * 32, v, ks == 0);
       }
       tc_fence_before();
       __syncwarp();
@@ -413,7 +419,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   const int prof = prof_begin(st);
-  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
   prof_end(prof, st, 2.0 * p.M * p.N * p.K * p.algo_scale, 0);
   B200_LAUNCH_OK();
   return 0;

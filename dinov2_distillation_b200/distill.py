@@ -96,3 +96,56 @@ class DistillationStep(nn.Module):
         return losses["loss"]
 
     forward = training_step
+
+
+class GraphedDistillStep:
+    """The hot path of one training step captured ONCE into a CUDA graph and replayed: teacher forward -> ScaleKD
+    forward -> backward to the student features and the ScaleKD parameters (~450 kernel launches at config.yaml
+    shapes), with no Python, ctypes or allocator work on the critical path. Static input buffers are refreshed by
+    (async) copies; outputs are static tensors that the next replay overwrites.
+
+        g = GraphedDistillStep(step, img_example, {'res4': f4, 'res5': f5}, arena)
+        losses, feat_grads = g(img, {'res4': f4, 'res5': f5})     # feat_grads feed the student's own backward
+
+    The student network stays outside the graph (stock PyTorch, as in the reference)."""
+
+    def __init__(self, step: "DistillationStep", img: torch.Tensor, feats: Dict[str, torch.Tensor], arena=None,
+                 warmup: int = 3):
+        if not img.is_cuda:
+            raise RuntimeError("GraphedDistillStep needs CUDA tensors: there is no CPU fallback")
+        self.step, self.arena = step, arena
+        self.img = img.detach().clone()
+        self.feats = {k: v.detach().clone().requires_grad_(True) for k, v in feats.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+        self.feat_grads = {k: v.grad for k, v in self.feats.items()}
+
+    def _run(self):
+        if self.arena is not None:
+            self.arena.zero()
+        for f in self.feats.values():
+            f.grad = None
+        T = self.step.teacher(self.img)[self.step.teacher_key]
+        if not self.feats:
+            return {"teacher": T}
+        out = self.step._compute_losses({"student": self.feats, "teacher": T})
+        out["loss"].backward()
+        return {k: v.detach() for k, v in out.items()}
+
+    def __call__(self, img: Optional[torch.Tensor] = None, feats: Optional[Dict[str, torch.Tensor]] = None):
+        if img is not None and img.data_ptr() != self.img.data_ptr():
+            self.img.copy_(img, non_blocking=True)
+        if feats is not None:
+            for k, v in feats.items():
+                if v.data_ptr() != self.feats[k].data_ptr():
+                    self.feats[k].data.copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out, self.feat_grads
