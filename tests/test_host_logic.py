@@ -1,0 +1,205 @@
+"""CPU: host-side logic of the drop-in shells -- schema handling, error behaviour (no silent CPU fallback), batch
+sharding, the flat gradient arena and the 2-rank gloo data-parallel path."""
+import os
+import socket
+import warnings
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+warnings.simplefilter("ignore")
+
+
+def _kw(**over):
+    kw = dict(name="scalekd_res5", alpha=[0.08, 0.06], student_dims=16, teacher_dims=32, query_hw=[3, 3], pos_hw=[3, 3],
+              pos_dims=32, window_shapes=[1, 1], self_query=True, softmax_scale=[5.0, 5.0], num_heads=4)
+    kw.update(over)
+    return kw
+
+
+def test_scalekd_schema_and_parameter_names():
+    from dinov2_distillation_b200.scalekd import LOSS_REGISTRY, ScaleKD
+    assert LOSS_REGISTRY["scalekd"] is ScaleKD
+    m = ScaleKD(**_kw())
+    keys = set(m.state_dict().keys())
+    for pj in ("projector_0", "projector_1"):
+        for k in ("pos_embed", "proj_student.0.weight", "proj_student.0.bias", "proj_student.1.weight",
+                  "proj_student.1.running_mean", "proj_student.1.running_var", "proj_student.1.num_batches_tracked",
+                  "pos_attention.q.weight", "pos_attention.k.bias", "pos_attention.v.weight", "pos_attention.proj.bias",
+                  "ffn.layers.0.0.weight", "ffn.layers.1.bias", "norm.weight", "norm_2.bias", "query.weight"):
+            assert f"{pj}.{k}" in keys, k
+    assert m.projector_0.pos_embed.shape == (1, 32, 3, 3)
+    m2 = ScaleKD(**_kw(self_query=False))
+    assert not any("query.weight" in k for k in m2.state_dict())
+    # vits14 / Cs=512 / 16x16 / self_query: SURVEY.md section 8 (a9) counts 4 337 664 parameters
+    big = ScaleKD(**_kw(student_dims=512, teacher_dims=384, query_hw=[16, 16], pos_hw=[16, 16], pos_dims=384, num_heads=24))
+    assert sum(p.numel() for p in big.parameters()) == 4337664
+
+
+def test_scalekd_errors_like_the_reference_and_never_falls_back_to_cpu():
+    from dinov2_distillation_b200 import _lib
+    from dinov2_distillation_b200.scalekd import ScaleKD
+    m = ScaleKD(**_kw(self_query=False))
+    with pytest.raises(NotImplementedError, match="There is no query"):
+        m.project_feat_spat(torch.randn(1, 16, 3, 3))
+    m = ScaleKD(**_kw())
+    with pytest.raises(_lib.B200Error, match="no CPU fallback"):
+        m(torch.randn(1, 16, 3, 3), torch.randn(1, 32, 3, 3))
+    with pytest.raises(_lib.B200Error, match="no CPU fallback"):
+        m.get_spat_loss(torch.randn(1, 9, 32), torch.randn(1, 32, 3, 3))
+    with pytest.raises(ValueError):
+        ScaleKD(**_kw(teacher_dims=30, pos_dims=30, num_heads=4))   # reference: RuntimeError inside reshape
+    with pytest.raises(NotImplementedError):
+        ScaleKD(**_kw(window_shapes=[2, 2])).cpu().projector_0(torch.randn(1, 16, 3, 3))
+
+
+def test_teacher_shell_surface():
+    from dinov2_distillation_b200 import _lib
+    from dinov2_distillation_b200.teacher import DINOv2ViT, TEACHER_CONFIGS
+    assert sorted(TEACHER_CONFIGS) == ["dinov2_vitb14", "dinov2_vitg14", "dinov2_vitl14", "dinov2_vits14"]
+    with pytest.raises(KeyError):
+        DINOv2ViT("dinov2_vitx14")
+    t = DINOv2ViT("dinov2_vits14")
+    assert all(not p.requires_grad for p in t.parameters())
+    assert len(t.model.blocks) == 12 and not t.model.training
+    keys = set(t.model.state_dict().keys())
+    for k in ("cls_token", "pos_embed", "mask_token", "patch_embed.proj.weight", "blocks.0.norm1.weight",
+              "blocks.11.attn.qkv.bias", "blocks.3.ls1.gamma", "blocks.5.mlp.fc2.weight", "norm.bias"):
+        assert k in keys, k
+    assert t.model.pos_embed.shape == (1, 1370, 384)
+    with pytest.raises(_lib.B200Error, match="no CPU fallback"):
+        t(torch.randn(1, 3, 224, 224))
+    with pytest.raises(_lib.B200Error, match="no CPU fallback"):
+        t.model.blocks[9](torch.randn(1, 256, 384))
+    g = DINOv2ViT("dinov2_vitg14")
+    assert "blocks.0.mlp.w12.weight" in g.model.state_dict() and g.model.blocks[0].mlp.w12.weight.shape == (8192, 1536)
+    assert abs(sum(p.numel() for p in g.parameters()) - 1136.5e6) / 1136.5e6 < 0.005
+
+
+def test_distillation_step_mirrors_reference_orchestration():
+    from dinov2_distillation_b200.distill import DistillationStep
+    from dinov2_distillation_b200.teacher import DINOv2ViT
+    specs = [{"type": "scalekd", "weight": 1.0, "kwargs": _kw(name="scalekd_res4", teacher_dims=384, pos_dims=384, num_heads=16)},
+             {"type": "scalekd", "weight": 0.5, "kwargs": _kw(name="scalekd_res5", teacher_dims=384, pos_dims=384, num_heads=24, self_query=False)}]
+    step = DistillationStep(None, DINOv2ViT("dinov2_vits14"), specs)
+    assert sorted(step.losses.keys()) == ["scalekd_res4", "scalekd_res5"]
+    assert step.loss_weights == {"scalekd_res4": 1.0, "scalekd_res5": 0.5}
+    step.train()
+    assert not step.teacher.training and step.losses.training
+
+    class Rec(torch.nn.Module):
+        def __init__(self, i, log):
+            super().__init__()
+            self.i, self.log = i, log
+
+        def forward(self, x):
+            self.log.append(self.i)
+            return x
+
+    log = []
+    step.teacher.model.blocks = torch.nn.ModuleList([Rec(i, log) for i in range(12)])
+    step._forward_specific_stage(torch.zeros(1, 4, 8), "res4")
+    assert log == [9, 10]
+    log.clear()
+    step._forward_specific_stage(torch.zeros(1, 4, 8), "res3")
+    assert log == []
+
+
+def test_shard_batch_covers_everything_once():
+    from dinov2_distillation_b200.distributed import shard_batch
+    for gb, w in ((256, 8), (64, 1), (10, 4), (7, 8)):
+        seen = [i for r in range(w) for i in shard_batch(gb, r, w)]
+        assert seen == list(range(gb))
+
+
+def test_flat_grad_arena_accumulates_autograd_in_place():
+    from dinov2_distillation_b200.distributed import FlatGradArena
+    lin = torch.nn.Linear(4, 3)
+    arena = FlatGradArena(lin.parameters(), extra_numel=5)
+    assert arena.numel == 4 * 3 + 3 + 5 and arena.extra.numel() == 5
+    x = torch.randn(2, 4)
+    lin(x).sum().backward()
+    assert lin.weight.grad.data_ptr() == arena.buffer.data_ptr()
+    assert torch.allclose(arena.buffer[:12].view(3, 4), x.sum(0).expand(3, 4))
+    arena.zero()
+    assert arena.buffer.abs().sum() == 0 and lin.weight.grad.data_ptr() == arena.buffer.data_ptr()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from dinov2_distillation_b200 import distributed as D
+    r, w, _ = D.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    arena = D.FlatGradArena(model.parameters())
+    data = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+    idx = list(D.shard_batch(8, r, w))
+    arena.zero()
+    loss = model(data[idx]).pow(2).sum() / len(idx)      # per-rank mean, like the reference's loss / N (scalekd.py:86)
+    loss.backward()
+    arena.allreduce_mean()
+    m = D.reduce_metrics({"loss": loss.detach(), "b": torch.tensor(float(r))})
+    q.put((r, arena.buffer.clone(), float(m["loss"]), float(m["b"])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce_matches_single_process():
+    """world_size=2 on CPU (gloo): sharded batch + one flat mean-allreduce == the full-batch gradient."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    data = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+    full = model(data).pow(2).sum() / 8
+    full.backward()
+    ref = torch.cat([p.grad.flatten() for p in model.parameters()])
+    assert torch.allclose(res[0][1], ref, atol=1e-5) and torch.allclose(res[1][1], ref, atol=1e-5)
+    assert abs(res[0][2] - full.item()) < 1e-5 and abs(res[0][3] - 0.5) < 1e-6
+
+
+def test_plugin_install_rebinds_the_reference_plugin_points():
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip("/root/reference not present")
+    sk, dm = ref_shims.import_reference()
+    ref_scalekd = sk.ScaleKD
+    os.environ["NCCL_P2P_DISABLE"] = "1"
+    import dinov2_distillation_b200.plugin as plugin
+    from dinov2_distillation_b200.scalekd import ScaleKD
+    try:
+        touched = plugin.install()
+        assert dm.LOSS_REGISTRY["scalekd"] is ScaleKD
+        assert "NCCL_P2P_DISABLE" not in os.environ
+        assert any("LOSS_REGISTRY" in k for k in touched)
+        # the reference's own _initialize_loss now builds B200 modules from the config schema
+        mod = dm.DistillationModule.__new__(dm.DistillationModule)
+        torch.nn.Module.__init__(mod)
+        mod.cfg = type("Cfg", (), {"loss": {"losses": [{"type": "scalekd", "weight": 1, "kwargs": _kw(name="scalekd_res5")}]}})()
+        mod._initialize_loss()
+        assert isinstance(mod.losses["scalekd_res5"], ScaleKD)
+    finally:
+        dm.LOSS_REGISTRY["scalekd"] = ref_scalekd
+        sk.ScaleKD = ref_scalekd
+        import losses
+        losses.ScaleKD = ref_scalekd
+        dm.ScaleKD = ref_scalekd
