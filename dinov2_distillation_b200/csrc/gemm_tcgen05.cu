@@ -20,7 +20,8 @@ namespace b200 {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant
+constexpr int EPI_WARPS = 16;                      // four warps per TMEM lane quadrant
+constexpr int EPI_W = 16;                          // accumulator columns per tcgen05.ld (keeps the epilogue < 100 registers)
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;   // warps 0-3: TMA / MMA / TMEM alloc / spare
 constexpr int EPI_STAGE_BYTES = 0;
 
@@ -63,20 +64,21 @@ struct TileCfg {
 
 // Epilogue for 32 consecutive columns of one accumulator row (thread = row): 128-bit vector loads / stores along the
 // row. (A shared-memory transposed, lane = column variant was measured 3x slower: the epilogue is instruction bound.)
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok, int row, int n0, float (&v)[32],
+template <int W>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok, int row, int n0, float (&v)[W],
                                                bool first_split) {
   if (!row_ok || n0 >= p.N) return;
-  const bool full = (n0 + 32 <= p.N) && p.vec_ok;
+  const bool full = (n0 + W <= p.N) && p.vec_ok;
   if (p.bias != nullptr && first_split) {
     if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < W; j += 4) {
         float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < W; ++j)
         if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
     }
   }
@@ -89,7 +91,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
     __nv_bfloat16* dst = p.out_bf16_pre + orow * p.ldo16_pre + n0;
     if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < W; j += 8) {
         uint4 u;
         u.x = pack16(v[j], v[j + 1], p.out16_fp16); u.y = pack16(v[j + 2], v[j + 3], p.out16_fp16);
         u.z = pack16(v[j + 4], v[j + 5], p.out16_fp16); u.w = pack16(v[j + 6], v[j + 7], p.out16_fp16);
@@ -97,23 +99,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < W; ++j)
         if (n0 + j < p.N) store16(dst + j, v[j], p.out16_fp16);
     }
   }
   if (p.act == B200_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+    for (int j = 0; j < W; ++j) v[j] = gelu_fast(v[j]);
   } else if (p.act == B200_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
   if (p.aux_mode != B200_AUX_NONE) {
     const __nv_bfloat16* ax = p.aux + (long long)row * p.ldaux + n0;
-    float a[32];
+    float a[W];
     if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < W; j += 8) {
         uint4 u = __ldg(reinterpret_cast<const uint4*>(ax + j));
         float2 f0 = unpack16(u.x, p.aux_fp16), f1 = unpack16(u.y, p.aux_fp16), f2 = unpack16(u.z, p.aux_fp16), f3 = unpack16(u.w, p.aux_fp16);
         a[j] = f0.x; a[j + 1] = f0.y; a[j + 2] = f1.x; a[j + 3] = f1.y;
@@ -121,26 +123,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? load16(ax + j, p.aux_fp16) : 0.0f;
+      for (int j = 0; j < W; ++j) a[j] = (n0 + j < p.N) ? load16(ax + j, p.aux_fp16) : 0.0f;
     }
     if (p.aux_mode == B200_AUX_DGELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= dgelu_fast(a[j]);
+      for (int j = 0; j < W; ++j) v[j] *= dgelu_fast(a[j]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
+      for (int j = 0; j < W; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
     }
   }
   if (p.col_scale != nullptr) {
     if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < W; j += 4) {
         float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0 + j));
         v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < W; ++j)
         if (n0 + j < p.N) v[j] *= __ldg(p.col_scale + n0 + j);
     }
   }
@@ -149,13 +151,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
     const float* rs = p.residual + rr * p.ldres + n0;
     if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < W; j += 4) {
         float4 r = *reinterpret_cast<const float4*>(rs + j);
         v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < W; ++j)
         if (n0 + j < p.N) v[j] += rs[j];
     }
   }
@@ -163,15 +165,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
     float* dst = p.out_f32 + orow * p.ldo32 + n0;
     if (p.atomic_add) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < W; ++j)
         if (n0 + j < p.N) atomicAdd(dst + j, v[j]);
     } else if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
+      for (int j = 0; j < W; j += 4)
         *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < W; ++j)
         if (n0 + j < p.N) dst[j] = v[j];
     }
   }
@@ -179,7 +181,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
     __nv_bfloat16* dst = p.out_bf16 + orow * p.ldo16 + n0;
     if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < W; j += 8) {
         uint4 u;
         u.x = pack16(v[j], v[j + 1], p.out16_fp16); u.y = pack16(v[j + 2], v[j + 3], p.out16_fp16);
         u.z = pack16(v[j + 4], v[j + 5], p.out16_fp16); u.w = pack16(v[j + 6], v[j + 7], p.out16_fp16);
@@ -187,7 +189,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < W; ++j)
         if (n0 + j < p.N) store16(dst + j, v[j], p.out16_fp16);
     }
   }
@@ -303,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;            // TMEM lanes 32*quad .. +31 (hardware: warp id % 4)
-    const int half = (warp - 4) >> 2;     // which 32-column blocks of the tile this warp drains
+    const int part = (warp - 4) >> 2;     // which EPI_W-column blocks of the tile this warp drains
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -316,14 +318,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        uint32_t raw[32];
-        tmem_ld_32x32(taddr + c * 32, raw);
+      for (int c = part; c < BN / EPI_W; c += EPI_WARPS / 4) {
+        uint32_t raw[EPI_W];
+        tmem_ld_32x16(taddr + c * EPI_W, raw);
         tmem_ld_wait();
-        float v[32];
+        float v[EPI_W];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        epilogue_chunk(p, row0 + lane < p.M, row0 + lane, n0 + c * 32, v, ks == 0);
+        for (int j = 0; j < EPI_W; ++j) v[j] = __uint_as_float(raw[j]);
+        epilogue_chunk<EPI_W>(p, row0 + lane < p.M, row0 + lane, n0 + c * EPI_W, v, ks == 0);
       }
       tc_fence_before();
       __syncwarp();
