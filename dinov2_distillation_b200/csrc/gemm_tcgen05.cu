@@ -8,48 +8,13 @@
 //
 // C[M,N] = A * B^T.  Operands may be K-major (contraction contiguous; the nn.Linear layout) or MN-major (output dim
 // contiguous; used by wgrad dW = dY^T X where both operands are token-major).
-#include "common.cuh"
-#include "ptx.cuh"
-#include "../../include/b200_distill.h"
+#include "gemm_common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 #include <unordered_map>
 
 namespace b200 {
-
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 16;                      // four warps per TMEM lane quadrant
-constexpr int EPI_W = 16;                          // accumulator columns per tcgen05.ld (keeps the epilogue < 100 registers)
-constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;   // warps 0-3: TMA / MMA / TMEM alloc / spare
-constexpr int EPI_STAGE_BYTES = 0;
-
-struct GemmParams {
-  int M, N, K;
-  int m_tiles, n_tiles, num_kb, kb_per_split, split_k, total_tiles;
-  const float* bias;
-  int act;
-  const __nv_bfloat16* aux;
-  long long ldaux;
-  int aux_mode;
-  const float* col_scale;
-  const float* residual;
-  long long ldres;
-  int res_row_period;
-  float* out_f32;
-  long long ldo32;
-  int atomic_add;
-  __nv_bfloat16* out_bf16;
-  long long ldo16;
-  __nv_bfloat16* out_bf16_pre;
-  long long ldo16_pre;
-  int out_row_period, out_row_pad;
-  int vec_ok;  // all leading dims / pointers allow 16-byte vector access
-  int out16_fp16, aux_fp16;  // 16-bit output / aux element type: 0 = bf16, 1 = fp16
-  uint32_t idesc;            // tcgen05 instruction descriptor (operand formats, majors, tile shape)
-  float algo_scale;          // profiling: algorithmic flops / executed flops
-};
 
 template <int BN>
 struct TileCfg {
@@ -61,139 +26,6 @@ struct TileCfg {
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-// Epilogue for 32 consecutive columns of one accumulator row (thread = row): 128-bit vector loads / stores along the
-// row. (A shared-memory transposed, lane = column variant was measured 3x slower: the epilogue is instruction bound.)
-template <int W>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok, int row, int n0, float (&v)[W],
-                                               bool first_split) {
-  if (!row_ok || n0 >= p.N) return;
-  const bool full = (n0 + W <= p.N) && p.vec_ok;
-  if (p.bias != nullptr && first_split) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < W; j += 4) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
-    }
-  }
-  long long orow = row;
-  if (p.out_row_period > 0) {
-    orow = (long long)(row / p.out_row_period) * (p.out_row_period + p.out_row_pad) + p.out_row_pad +
-           row % p.out_row_period;
-  }
-  if (p.out_bf16_pre != nullptr) {
-    __nv_bfloat16* dst = p.out_bf16_pre + orow * p.ldo16_pre + n0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < W; j += 8) {
-        uint4 u;
-        u.x = pack16(v[j], v[j + 1], p.out16_fp16); u.y = pack16(v[j + 2], v[j + 3], p.out16_fp16);
-        u.z = pack16(v[j + 4], v[j + 5], p.out16_fp16); u.w = pack16(v[j + 6], v[j + 7], p.out16_fp16);
-        *reinterpret_cast<uint4*>(dst + j) = u;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (n0 + j < p.N) store16(dst + j, v[j], p.out16_fp16);
-    }
-  }
-  if (p.act == B200_ACT_GELU) {
-#pragma unroll
-    for (int j = 0; j < W; ++j) v[j] = gelu_fast(v[j]);
-  } else if (p.act == B200_ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j], 0.0f);
-  }
-  if (p.aux_mode != B200_AUX_NONE) {
-    const __nv_bfloat16* ax = p.aux + (long long)row * p.ldaux + n0;
-    float a[W];
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < W; j += 8) {
-        uint4 u = __ldg(reinterpret_cast<const uint4*>(ax + j));
-        float2 f0 = unpack16(u.x, p.aux_fp16), f1 = unpack16(u.y, p.aux_fp16), f2 = unpack16(u.z, p.aux_fp16), f3 = unpack16(u.w, p.aux_fp16);
-        a[j] = f0.x; a[j + 1] = f0.y; a[j + 2] = f1.x; a[j + 3] = f1.y;
-        a[j + 4] = f2.x; a[j + 5] = f2.y; a[j + 6] = f3.x; a[j + 7] = f3.y;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j) a[j] = (n0 + j < p.N) ? load16(ax + j, p.aux_fp16) : 0.0f;
-    }
-    if (p.aux_mode == B200_AUX_DGELU) {
-#pragma unroll
-      for (int j = 0; j < W; ++j) v[j] *= dgelu_fast(a[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
-    }
-  }
-  if (p.col_scale != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < W; j += 4) {
-        float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0 + j));
-        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (n0 + j < p.N) v[j] *= __ldg(p.col_scale + n0 + j);
-    }
-  }
-  if (p.residual != nullptr && first_split) {
-    const long long rr = p.res_row_period > 0 ? (row % p.res_row_period) : orow;
-    const float* rs = p.residual + rr * p.ldres + n0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < W; j += 4) {
-        float4 r = *reinterpret_cast<const float4*>(rs + j);
-        v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (n0 + j < p.N) v[j] += rs[j];
-    }
-  }
-  if (p.out_f32 != nullptr) {
-    float* dst = p.out_f32 + orow * p.ldo32 + n0;
-    if (p.atomic_add) {
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (n0 + j < p.N) atomicAdd(dst + j, v[j]);
-    } else if (full) {
-#pragma unroll
-      for (int j = 0; j < W; j += 4)
-        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (n0 + j < p.N) dst[j] = v[j];
-    }
-  }
-  if (p.out_bf16 != nullptr) {
-    __nv_bfloat16* dst = p.out_bf16 + orow * p.ldo16 + n0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < W; j += 8) {
-        uint4 u;
-        u.x = pack16(v[j], v[j + 1], p.out16_fp16); u.y = pack16(v[j + 2], v[j + 3], p.out16_fp16);
-        u.z = pack16(v[j + 4], v[j + 5], p.out16_fp16); u.w = pack16(v[j + 6], v[j + 7], p.out16_fp16);
-        *reinterpret_cast<uint4*>(dst + j) = u;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (n0 + j < p.N) store16(dst + j, v[j], p.out16_fp16);
-    }
-  }
-}
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -325,6 +157,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[EPI_W];
 #pragma unroll
         for (int j = 0; j < EPI_W; ++j) v[j] = __uint_as_float(raw[j]);
+        if (p.dbg & 1) {
+          if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1];
+          continue;
+        }
         epilogue_chunk<EPI_W>(p, row0 + lane < p.M, row0 + lane, n0 + c * EPI_W, v, ks == 0);
       }
       tc_fence_before();
@@ -361,9 +197,10 @@ static EncodeTiledFn get_encode_fn() {
 struct MapKey {
   const void* ptr;
   uint64_t d0, d1, ld;
-  uint32_t b0, b1;
+  uint32_t b0, b1, esize, swizzle;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1 && esize == o.esize &&
+           swizzle == o.swizzle;
   }
 };
 struct MapKeyHash {
@@ -373,16 +210,18 @@ struct MapKeyHash {
     h ^= k.d1 * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
     h ^= k.ld * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
     h ^= (uint64_t(k.b0) << 32 | k.b1) + (h << 6) + (h >> 2);
+    h ^= (uint64_t(k.esize) << 32 | k.swizzle) + (h << 6) + (h >> 2);
     return h;
   }
 };
 
-// 2-D bf16 tensor map: dim0 (contiguous) x dim1 rows with row pitch ld elements; box b0 x b1; 128B swizzle.
-int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
-                       uint32_t b1) {
+// 2-D tensor map: dim0 (contiguous) x dim1 rows with row pitch ld elements of esize bytes (2: 16-bit, 4: fp32);
+// box b0 x b1; swizzle 128 / 64 / 32 bytes. Encoded maps are cached by (pointer, shape, box).
+int make_tensor_map_ex(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
+                       uint32_t b1, int swizzle) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, d0, d1, ld, b0, b1};
+  MapKey key{ptr, d0, d1, ld, b0, b1, (uint32_t)esize, (uint32_t)swizzle};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -391,16 +230,19 @@ int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t 
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -4; }
   cuuint64_t gdim[2] = {d0, d1};
-  cuuint64_t gstride[1] = {ld * 2};
+  cuuint64_t gstride[1] = {ld * (uint64_t)esize};
   cuuint32_t box[2] = {b0, b1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) ptr=%p dims=(%llu,%llu) ld=%llu box=(%u,%u)", (int)r,
-             ptr, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) ptr=%p esize=%d dims=(%llu,%llu) ld=%llu box=(%u,%u)",
+             (int)r, ptr, esize, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
     set_error(buf);
     return -4;
   }
@@ -408,6 +250,12 @@ int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t 
   if (cache.size() > 8192) cache.clear();
   cache.emplace(key, *out);
   return 0;
+}
+
+// operand maps: 16-bit elements, 128-byte swizzle
+int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
+                       uint32_t b1) {
+  return make_tensor_map_ex(out, ptr, 2, d0, d1, ld, b0, b1, 128);
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -436,7 +284,14 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
   return launch_gemm<BN, false, true>(ta, tb, p, st);
 }
 
+int gemm_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
 static int pick_bn(int N, int m_tiles) {
+  static const int forced = gemm_env_int("B200_GEMM_BN", 0);
+  if (forced == 128 || forced == 192 || forced == 256) return forced;
   // fewest wasted columns first; among equals prefer the widest tile (less smem traffic per MMA).
   const int cands[3] = {256, 192, 128};
   int best = 128;
@@ -501,6 +356,8 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   if (p.out_bf16_pre) vec = vec && al16(p.out_bf16_pre) && p.ldo16_pre % 8 == 0;
   p.vec_ok = vec ? 1 : 0;
   p.algo_scale = d->algo_flops_scale > 0.f ? d->algo_flops_scale : 1.0f;
+  static const int dbg = gemm_env_int("B200_GEMM_DBG", 0);
+  p.dbg = dbg;
   p.out16_fp16 = d->out16_is_fp16 ? 1 : 0;
   p.aux_fp16 = d->aux_is_fp16 ? 1 : 0;
   // a_format / b_format: 0 = F16, 1 = BF16 (bits 7-9 / 10-12)
@@ -508,6 +365,16 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   if (d->a_is_fp16) p.idesc &= ~(7u << 7);
   if (d->b_is_fp16) p.idesc &= ~(7u << 10);
 
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    GemmParams p2 = p;
+    const int rv = launch_gemm_v2(d, p2, st);
+    if (rv <= 0) return rv;
+  }
+  if (!d->a_mn_major && !d->b_mn_major && split == 1) {
+    const int r2 = launch_gemm_2cta(d, p, st);
+    if (r2 <= 0) return r2;
+  }
   CUtensorMap ta, tb;
   if (!d->a_mn_major) {
     B200_TRY(make_tensor_map_2d(&ta, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM));
@@ -519,7 +386,6 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   } else {
     B200_TRY(make_tensor_map_2d(&tb, d->B, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, BK));
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool amn = d->a_mn_major != 0, bmn = d->b_mn_major != 0;
   if (bn == 256) return dispatch_major<256>(amn, bmn, ta, tb, p, st);
   if (bn == 192) return dispatch_major<192>(amn, bmn, ta, tb, p, st);

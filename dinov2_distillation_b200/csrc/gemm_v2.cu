@@ -1,0 +1,672 @@
+// tcgen05 GEMM, second generation: the mainloop of gemm_tcgen05.cu / gemm_tcgen05_2cta.cu with an epilogue built for the
+// small-K shapes of the ViT-S/B teacher, where the epilogue -- not the tensor pipe -- sets the pace.
+//
+//   warp 0        : TMA producer (one elected lane)
+//   warp 1        : MMA issuer   (one elected lane; the leader CTA only in CTA-pair mode)
+//   warp 2        : TMEM allocate / free
+//   warps 4..11   : epilogue. Warp w drains TMEM lanes 32*(w%4)..+31 (hardware rule: warp id % 4) and every second
+//                   32-column unit of the tile. Per unit: tcgen05.ld 32x32b.x32 (thread = row, 32 fp32 columns) ->
+//                   bias / activation / aux / LayerScale / residual in registers -> 16-byte st.shared into a swizzled
+//                   32-row staging tile -> ONE bulk tensor store (cp.async.bulk.tensor, or cp.reduce.async.bulk.tensor
+//                   .add for in-place residual streams and split-K) issued by lane 0. Row-strided 16-byte global stores
+//                   of the first generation (32 sectors per warp store) are gone, tails are clipped by the tensor map,
+//                   and operands the epilogue reads (fp32 residual, 16-bit aux) arrive by TMA one unit ahead.
+//
+// Output modes (template EPI): 0 = 16-bit output (+ optional pre-activation copy, ReLU, dGELU/dReLU aux),
+//                              1 = 16-bit output with GELU, 2 = fp32 output (LayerScale, residual, accumulate).
+#include "gemm_common.cuh"
+
+#include <stdlib.h>
+
+namespace b200 {
+
+constexpr int V2_EPI_WARPS = 8;
+constexpr int V2_THREADS = 128 + V2_EPI_WARPS * 32;
+constexpr int V2_EPI_WARP_BYTES = 8192;   // two 4 KB staging tiles per epilogue warp
+constexpr int V2_EPI_BYTES = V2_EPI_WARPS * V2_EPI_WARP_BYTES;
+
+template <int BN, bool PAIR>
+struct V2Cfg {
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;   // rows of B this CTA stages per k-block
+  static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int RING_BUDGET = 232448 - 1024 - 512 - V2_EPI_BYTES;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_STRIDE = (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * TMEM_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + V2_EPI_BYTES + 1024 + 512;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t v2_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void v2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by both CTAs of a pair; clearing the peer bit makes the transaction bytes land on CTA 0's barrier
+__device__ __forceinline__ void v2_tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c0,
+                                                    int c1) {
+  const uint32_t bar = smem_u32(leader_bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void v2_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void v2_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void v2_mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void v2_tmem_alloc_pair(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void v2_tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// shared -> global bulk tensor store / reduce-add (bulk async-group completion)
+__device__ __forceinline__ void v2_tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void v2_tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void v2_tma_load_2d_s(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void v2_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void v2_bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void v2_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void v2_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 v2_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// GELU(x) = max(x, 0) - |x| * Phi(-|x|), Phi(-a) = 2^q(a) with q a degree-5 fit of log2(Phi(-a)) on [0, 8] (max abs error
+// of the product 1.7e-5, relative 3.5e-4 where |gelu| > 1e-4; the leading coefficient is negative, so larger |x| decay
+// to the exact limit). One MUFU (ex2) + 7 FMA-pipe instructions per element: the fc1 epilogue was MUFU bound with the
+// two-transcendental erf form.
+__device__ __forceinline__ float v2_phi_neg(float a) {
+  float q = fmaf(-3.046068783e-04f, a, 5.602596781e-03f);
+  q = fmaf(q, a, -4.712946504e-02f);
+  q = fmaf(q, a, -4.664196592e-01f);
+  q = fmaf(q, a, -1.147315491e+00f);
+  q = fmaf(q, a, -1.000508484e+00f);
+  return ex2_approx(q);
+}
+__device__ __forceinline__ float v2_gelu(float x) {
+  const float a = fabsf(x);
+  return fmaf(-a, v2_phi_neg(a), fmaxf(x, 0.0f));
+}
+__device__ __forceinline__ float v2_dgelu(float x) {
+  const float e = v2_phi_neg(fabsf(x));
+  const float cdf = x > 0.0f ? 1.0f - e : e;
+  const float pdf = 0.39894228040143268f * ex2_approx(-0.72134752044448170f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue of one tile
+// One warp: 32 rows (TMEM lanes of its quadrant) x the units u = half, half + 2, ... of the tile's BN / 32 column units.
+template <int BN, int EPI>
+__device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmX,
+                                                 uint32_t taddr, int row0, int n0, uint32_t stage_smem, uint64_t* xbar,
+                                                 uint32_t& xphase, int half, int lane, bool first_split, bool use_x,
+                                                 bool reduce_out, uint64_t* tempty, bool pair, uint32_t* out_toggle) {
+  constexpr int UNITS = BN / 64;                         // units per warp
+  constexpr bool F32 = EPI == 2;
+  constexpr int ROWB = F32 ? 128 : 64;                   // staging row bytes (32 columns)
+  constexpr int CHUNKS = ROWB / 16;
+  constexpr uint32_t UNIT_BYTES = 32 * ROWB;
+  const uint32_t sw = F32 ? (lane & 7) : ((lane >> 1) & 3);
+  const uint32_t row_off = lane * ROWB;
+  // staging tiles of this warp: F32: [0] = output, [1] = residual load. 16-bit: [0],[1] = outputs (alternating; [1] is
+  // the pre-activation copy when one is requested), [2] = aux load.
+  const uint32_t buf_x = stage_smem + (F32 ? 4096u : 4096u);
+  const bool has_pre = !F32 && p.out_bf16_pre != nullptr;
+
+  // valid units of this warp (columns beyond N are clipped; nu is warp-uniform)
+  int nu = 0;
+#pragma unroll
+  for (int i = 0; i < UNITS; ++i)
+    if (n0 + (half + 2 * i) * 32 < p.N) nu = i + 1;
+  if (nu == 0) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (pair) v2_mbar_arrive_cta(tempty, 0);
+      else mbar_arrive(tempty);
+    }
+    return;
+  }
+
+  uint32_t raw[2][32];
+  if (use_x && lane == 0) {
+    mbar_expect_tx(xbar, UNIT_BYTES);
+    v2_tma_load_2d_s(buf_x, tmX, xbar, n0 + half * 32, row0);
+  }
+  tmem_ld_32x32(taddr + half * 32, raw[0]);
+#pragma unroll
+  for (int i = 0; i < UNITS; ++i) {
+    if (i >= nu) break;
+    const int u = half + 2 * i;
+    const int c0 = n0 + u * 32;
+    const bool next_ok = i + 1 < nu;
+    tmem_ld_wait();
+    if (next_ok) {
+      tmem_ld_32x32(taddr + (u + 2) * 32, raw[(i + 1) & 1]);
+    } else {
+      // all tcgen05.ld of this tile have completed: hand the accumulator buffer back to the MMA warp right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (pair) v2_mbar_arrive_cta(tempty, 0);
+        else mbar_arrive(tempty);
+      }
+    }
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[i & 1][j]);
+    if (p.dbg & 1) {   // B200_GEMM_DBG=1: mainloop-only floor (drain TMEM, no epilogue math, no stores)
+      if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1];
+      if (use_x) { mbar_wait(xbar, xphase); xphase ^= 1; __syncwarp();
+        if (next_ok && lane == 0) { mbar_expect_tx(xbar, UNIT_BYTES); v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + 64, row0); } }
+      continue;
+    }
+    const bool full = c0 + 32 <= p.N;
+    if (p.bias != nullptr && first_split) {
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < p.N) v[j] += __ldg(p.bias + c0 + j);
+      }
+    }
+    if constexpr (!F32) {
+      // ---- 16-bit output
+      uint32_t buf_o = stage_smem + ((*out_toggle & 1u) ? 2048u : 0u);
+      if (has_pre) buf_o = stage_smem;
+      // the staging tile about to be overwritten must have been read by its previous bulk store
+      if (lane == 0) {
+        if (has_pre) v2_bulk_wait_read<0>();
+        else v2_bulk_wait_read<1>();
+      }
+      __syncwarp();
+      if (has_pre) {
+        const uint32_t bp = stage_smem + 2048u + row_off;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int j = c * 8;
+          v2_sts128(bp + ((c ^ sw) << 4), pack16(v[j], v[j + 1], p.out16_fp16), pack16(v[j + 2], v[j + 3], p.out16_fp16),
+                    pack16(v[j + 4], v[j + 5], p.out16_fp16), pack16(v[j + 6], v[j + 7], p.out16_fp16));
+        }
+      }
+      if constexpr (EPI == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v2_gelu(v[j]);
+      } else {
+        if (p.act == B200_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (use_x) {
+          mbar_wait(xbar, xphase);
+          xphase ^= 1;
+          const uint32_t bx = buf_x + row_off;
+          float a[32];
+#pragma unroll
+          for (int c = 0; c < CHUNKS; ++c) {
+            const uint4 q = v2_lds128(bx + ((c ^ sw) << 4));
+            const float2 f0 = unpack16(q.x, p.aux_fp16), f1 = unpack16(q.y, p.aux_fp16), f2 = unpack16(q.z, p.aux_fp16),
+                         f3 = unpack16(q.w, p.aux_fp16);
+            const int j = c * 8;
+            a[j] = f0.x; a[j + 1] = f0.y; a[j + 2] = f1.x; a[j + 3] = f1.y;
+            a[j + 4] = f2.x; a[j + 5] = f2.y; a[j + 6] = f3.x; a[j + 7] = f3.y;
+          }
+          __syncwarp();   // every lane has read the aux tile: it may be refilled
+          if (next_ok && lane == 0) {
+            mbar_expect_tx(xbar, UNIT_BYTES);
+            v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + 64, row0);
+          }
+          if (p.aux_mode == B200_AUX_DGELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= v2_dgelu(a[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
+          }
+        }
+      }
+      const uint32_t bo = buf_o + row_off;
+      if (p.out16_fp16) {
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int j = c * 8;
+          v2_sts128(bo + ((c ^ sw) << 4), pack16(v[j], v[j + 1], 1), pack16(v[j + 2], v[j + 3], 1),
+                    pack16(v[j + 4], v[j + 5], 1), pack16(v[j + 6], v[j + 7], 1));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int j = c * 8;
+          v2_sts128(bo + ((c ^ sw) << 4), pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                    pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        v2_tma_store_2d(tmO, buf_o, c0, row0);
+        if (has_pre)
+          v2_tma_store_2d(tmX, stage_smem + 2048u, c0, row0);
+        v2_bulk_commit();
+      }
+      *out_toggle ^= 1u;
+    } else {
+      // ---- fp32 output
+      if (p.col_scale != nullptr) {
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + c0 + j));
+            v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < p.N) v[j] *= __ldg(p.col_scale + c0 + j);
+        }
+      }
+      if (use_x) {
+        mbar_wait(xbar, xphase);
+        xphase ^= 1;
+        const uint32_t bx = buf_x + row_off;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const uint4 q = v2_lds128(bx + ((c ^ sw) << 4));
+          const int j = c * 4;
+          v[j] += __uint_as_float(q.x); v[j + 1] += __uint_as_float(q.y);
+          v[j + 2] += __uint_as_float(q.z); v[j + 3] += __uint_as_float(q.w);
+        }
+        __syncwarp();
+        if (next_ok && lane == 0) {
+          mbar_expect_tx(xbar, UNIT_BYTES);
+          v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + 64, row0);
+        }
+      }
+      if (lane == 0) v2_bulk_wait_read<0>();
+      __syncwarp();
+      const uint32_t bo = stage_smem + row_off;
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int j = c * 4;
+        v2_sts128(bo + ((c ^ sw) << 4), __float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]),
+                  __float_as_uint(v[j + 3]));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (reduce_out) v2_tma_reduce_add_2d(tmO, stage_smem, c0, row0);
+        else v2_tma_store_2d(tmO, stage_smem, c0, row0);
+        v2_bulk_commit();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int BN, bool PAIR, bool MN, int EPI>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX, const GemmParams p,
+               const int use_x, const int reduce_out) {
+  using Cfg = V2Cfg<BN, PAIR>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int TILE_M = PAIR ? 256 : 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + V2_EPI_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* x_bar = tempty_bar + 2;                      // one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + V2_EPI_WARPS);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? v2_cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (use_x || (EPI != 2 && p.out_bf16_pre != nullptr)) tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], (PAIR ? 2 : 1) * V2_EPI_WARPS);
+    }
+    for (int s = 0; s < V2_EPI_WARPS; ++s) mbar_init(&x_bar[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    if constexpr (PAIR) v2_tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  if constexpr (PAIR) v2_cluster_sync();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = worker; t < p.total_tiles; t += workers) {
+        const int ks = t / tiles_mn;
+        const int r = t - ks * tiles_mn;
+        const int m0 = (r / p.n_tiles) * TILE_M + (int)rank * 128;
+        const int n0 = (r % p.n_tiles) * BN + (int)rank * Cfg::B_ROWS * (PAIR ? 1 : 0);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + A_TILE_BYTES;
+          if constexpr (PAIR) {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            v2_tma_load_2d_pair(sA, &tmA, &full_bar[stage], kb * BK, m0);
+            v2_tma_load_2d_pair(sB, &tmB, &full_bar[stage], kb * BK, n0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if constexpr (!MN) {
+              tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m0);
+              tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      const uint32_t idesc = p.idesc;
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = worker; t < p.total_tiles; t += workers) {
+        const int ks = t / tiles_mn;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::TMEM_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                   : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                   : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if constexpr (PAIR) v2_mma_pair(d_tmem, da, db, idesc, acc);
+            else tc_mma_bf16(d_tmem, da, db, idesc, acc);
+          }
+          if constexpr (PAIR) v2_commit_pair(&empty_bar[stage]);
+          else tc_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (PAIR) v2_commit_pair(&tfull_bar[as]);
+        else tc_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int quad = warp & 3;            // TMEM lanes 32*quad .. +31 (hardware: warp id % 4)
+    const int half = ew >> 2;             // which of the two interleaved unit sets
+    const uint32_t stage_smem = smem_u32(epi_smem + ew * V2_EPI_WARP_BYTES);
+    uint64_t* xbar = &x_bar[ew];
+    uint32_t xphase = 0;
+    uint32_t out_toggle = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = worker; t < p.total_tiles; t += workers) {
+      const int ks = t / tiles_mn;
+      const int r = t - ks * tiles_mn;
+      const int m0 = (r / p.n_tiles) * TILE_M + (int)rank * 128;
+      const int n0 = (r % p.n_tiles) * BN;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
+      v2_epilogue_tile<BN, EPI>(p, &tmO, &tmX, taddr, m0 + quad * 32, n0, stage_smem, xbar, xphase, half, lane, ks == 0,
+                                use_x != 0, reduce_out != 0, &tempty_bar[as], PAIR, &out_toggle);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    // bulk stores read shared memory asynchronously: the CTA must not exit before they are done
+    if (lane == 0) v2_bulk_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  if constexpr (PAIR) v2_cluster_sync();
+  else __syncthreads();
+  if (warp == 2) {
+    if constexpr (PAIR) v2_tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <int BN, bool PAIR, bool MN, int EPI>
+static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                     const GemmParams& p, int use_x, int reduce_out, cudaStream_t st) {
+  using Cfg = V2Cfg<BN, PAIR>;
+  auto kern = gemm_v2_kernel<BN, PAIR, MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int workers = PAIR ? sm_count() / 2 : sm_count();
+  if (workers > p.total_tiles) workers = p.total_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(PAIR ? workers * 2 : workers);
+  cfg.blockDim = dim3(V2_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  const int prof = prof_begin(st);
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tx, p, use_x, reduce_out));
+  prof_end(prof, st, 2.0 * p.M * p.N * p.K * p.algo_scale, 0);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <int BN, bool PAIR, bool MN>
+static int v2_dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                           const CUtensorMap& tx, const GemmParams& p, int use_x, int reduce_out, cudaStream_t st) {
+  if constexpr (MN) {
+    return v2_launch<BN, PAIR, MN, 2>(ta, tb, to, tx, p, use_x, reduce_out, st);
+  } else {
+    if (epi == 0) return v2_launch<BN, PAIR, MN, 0>(ta, tb, to, tx, p, use_x, reduce_out, st);
+    if (epi == 1) return v2_launch<BN, PAIR, MN, 1>(ta, tb, to, tx, p, use_x, reduce_out, st);
+    return v2_launch<BN, PAIR, MN, 2>(ta, tb, to, tx, p, use_x, reduce_out, st);
+  }
+}
+
+template <bool PAIR, bool MN>
+static int v2_dispatch_bn(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                          const CUtensorMap& tx, const GemmParams& p, int use_x, int reduce_out, cudaStream_t st) {
+  if (bn == 256) return v2_dispatch_epi<256, PAIR, MN>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  if (bn == 192) return v2_dispatch_epi<192, PAIR, MN>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  return v2_dispatch_epi<128, PAIR, MN>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+}
+
+// tile width: fewest (waves x tile cost); wide tiles amortise the A traffic, narrow ones the wave quantisation
+static int v2_pick_bn(int N, long long row_tiles, int workers) {
+  static const int forced = gemm_env_int("B200_GEMM_BN", 0);
+  if (forced == 128 || forced == 192 || forced == 256) return forced;
+  const int cands[3] = {256, 192, 128};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long long tiles = cdiv(N, bn) * row_tiles;
+    const double cost = double(cdiv(tiles, workers)) * (bn + 24);   // +24: per-tile fixed cost (pipeline fill / drain)
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+// Returns 1 when the problem is outside what this kernel handles (the caller falls back to the first-generation
+// kernels), 0 on success, negative on error.
+int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
+  static const int enabled = gemm_env_int("B200_GEMM_V2", 1);
+  if (!enabled) return 1;
+  const bool mn = d->a_mn_major && d->b_mn_major;
+  if (d->a_mn_major != d->b_mn_major) return 1;
+  if (d->out_row_period > 0 || d->res_row_period > 0) return 1;
+  const bool f32 = d->out_f32 != nullptr;
+  if (f32 && d->out_bf16) return 1;
+  if (f32 && (d->out_bf16_pre || d->aux_mode != 0 || d->act != 0)) return 1;
+  if (!f32 && (d->col_scale || d->residual || d->atomic_add)) return 1;
+  if (!f32 && d->out_bf16_pre && d->aux) return 1;
+  if (!f32 && d->act == B200_ACT_GELU && d->aux) return 1;
+  if (mn && !f32) return 1;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (f32 && (!al16(d->out_f32) || d->ldo32 % 4 != 0)) return 1;
+  if (!f32 && (!al16(d->out_bf16) || d->ldo16 % 8 != 0)) return 1;
+  if (d->residual && (!al16(d->residual) || d->ldres % 4 != 0)) return 1;
+  if (d->aux && d->aux_mode && (!al16(d->aux) || d->ldaux % 8 != 0)) return 1;
+  if (d->out_bf16_pre && (!al16(d->out_bf16_pre) || d->ldo16_pre % 8 != 0)) return 1;
+  if (d->bias && !al16(d->bias)) return 1;
+  if (d->col_scale && !al16(d->col_scale)) return 1;
+  if (d->N % 4 != 0) return 1;
+
+  static const int pair_mode = gemm_env_int("B200_GEMM_2CTA", -1);   // -1 auto, 0 never, 1 whenever possible
+  bool pair = false;
+  if (!mn && p.split_k == 1 && d->M >= 1024 && d->N >= 128) {
+    // the CTA pair halves the B traffic per SM; it pays once the mainloop is long enough to be operand bound
+    pair = pair_mode == 1 || (pair_mode < 0 && d->K >= 1024);
+  }
+  const int tile_m = pair ? 256 : 128;
+  const int workers = pair ? sm_count() / 2 : sm_count();
+  p.m_tiles = (int)cdiv(d->M, tile_m);
+  const int bn = v2_pick_bn(d->N, (long long)p.m_tiles * p.split_k, workers);
+  p.n_tiles = (int)cdiv(d->N, bn);
+  p.total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+  p.idesc = make_idesc_bf16(tile_m, bn, mn, mn);
+  if (d->a_is_fp16) p.idesc &= ~(7u << 7);
+  if (d->b_is_fp16) p.idesc &= ~(7u << 10);
+
+  const bool inplace = f32 && d->residual && (const void*)d->residual == (const void*)d->out_f32 && d->ldres == d->ldo32;
+  static const int inplace_red = gemm_env_int("B200_GEMM_INPLACE_RED", 1);
+  int reduce_out = (f32 && d->atomic_add) ? 1 : 0;
+  int use_x = 0;
+  if (f32 && d->residual) {
+    if (inplace && inplace_red && !d->atomic_add) reduce_out = 1;
+    else use_x = 1;
+  }
+  if (!f32 && d->aux && d->aux_mode) use_x = 1;
+  if (use_x && p.split_k > 1) return 1;
+
+  CUtensorMap ta, tb, to, tx;
+  const int bsw = pair ? bn / 2 : bn;
+  if (!mn) {
+    B200_TRY(make_tensor_map_2d(&ta, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM));
+    B200_TRY(make_tensor_map_2d(&tb, d->B, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, (uint32_t)bsw));
+  } else {
+    B200_TRY(make_tensor_map_2d(&ta, d->A, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, 64, BK));
+    B200_TRY(make_tensor_map_2d(&tb, d->B, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, BK));
+  }
+  if (f32) {
+    B200_TRY(make_tensor_map_ex(&to, d->out_f32, 4, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo32, 32, 32, 128));
+    if (use_x) B200_TRY(make_tensor_map_ex(&tx, d->residual, 4, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldres, 32, 32, 128));
+    else tx = to;
+  } else {
+    B200_TRY(make_tensor_map_ex(&to, d->out_bf16, 2, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo16, 32, 32, 64));
+    if (use_x) B200_TRY(make_tensor_map_ex(&tx, d->aux, 2, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldaux, 32, 32, 64));
+    else if (d->out_bf16_pre) B200_TRY(make_tensor_map_ex(&tx, d->out_bf16_pre, 2, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo16_pre, 32, 32, 64));
+    else tx = to;
+  }
+  const int epi = f32 ? 2 : (d->act == B200_ACT_GELU ? 1 : 0);
+  if (mn) return v2_dispatch_bn<false, true>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  if (pair) return v2_dispatch_bn<true, false>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  return v2_dispatch_bn<false, false>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+}
+
+}  // namespace b200

@@ -105,6 +105,65 @@ def test_gemm_epilogues():
     assert out.view(M // period, period + pad, N)[:, 0, :].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("M,N,K", [(1030, 768, 384), (2048, 512, 2048), (520, 200, 320), (16448, 1152, 384)])
+def test_gemm_tma_epilogue_paths(M, N, K):
+    """Every epilogue of the bulk-store GEMM (gemm_v2.cu): 16-bit and fp32 outputs, separate and in-place residual,
+    16-bit aux by TMA, pre-activation copy, row / column tails, and the CTA-pair mainloop (M >= 1024 and K >= 1024)."""
+    ops = _ops()
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    bias = torch.randn(N, device="cuda")
+    gamma = torch.rand(N, device="cuda") + 0.1
+    res = torch.randn(M, N, device="cuda")
+    plain = a.float() @ b.float().t()
+    acc = plain + bias
+    # fp32: plain, bias, separate residual, in-place residual with LayerScale
+    assert rel_err(ops.gemm(a, b), plain) < 2e-3
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, bias=bias, residual=res, out=out)
+    assert rel_err(out, res + acc) < 2e-3
+    ops.gemm(a, b, bias=bias, col_scale=gamma, residual=res, out=out)
+    assert rel_err(out, res + gamma * acc) < 2e-3
+    x = res.clone()
+    ops.gemm(a, b, bias=bias, col_scale=gamma, residual=x, out=x)
+    assert rel_err(x, res + gamma * acc) < 2e-3
+    # accumulate into an existing fp32 buffer (split-K form with one split)
+    y = res.clone()
+    ops.gemm(a, b, out=y, atomic_add=True)
+    assert rel_err(y - res, plain) < 2e-3
+    # 16-bit: bias, relu, gelu (+ pre-activation copy), fp16 output
+    assert rel_err(ops.gemm(a, b, bias=bias, out_dtype=torch.bfloat16), acc) < 6e-3
+    assert rel_err(ops.gemm(a, b, bias=bias, act="relu", out_dtype=torch.bfloat16), torch.relu(acc)) < 6e-3
+    o, pre = ops.gemm(a, b, bias=bias, act="gelu", out_dtype=torch.bfloat16, out_pre=True)
+    assert rel_err(o, torch.nn.functional.gelu(acc)) < 6e-3
+    assert rel_err(pre, acc) < 6e-3
+    o, pre = ops.gemm(a, b, bias=bias, act="relu", out_dtype=torch.bfloat16, out_pre=True)
+    assert rel_err(o, torch.relu(acc)) < 6e-3 and rel_err(pre, acc) < 6e-3
+    ah, bh = a.to(torch.float16), b.to(torch.float16)
+    o16 = ops.gemm(ah, bh, bias=bias, out_dtype=torch.float16)
+    assert o16.dtype == torch.float16 and rel_err(o16, ah.float() @ bh.float().t() + bias) < 2e-3
+    # 16-bit output x f(aux): dGELU (bf16 aux) and dReLU (fp16 aux)
+    aux = bf(torch.randn(M, N, device="cuda"))
+    xa = aux.float()
+    dg = 0.5 * (1 + torch.erf(xa / math.sqrt(2))) + xa * torch.exp(-0.5 * xa * xa) / math.sqrt(2 * math.pi)
+    assert rel_err(ops.gemm(a, b, aux=aux, aux_mode="dgelu", out_dtype=torch.bfloat16), plain * dg) < 6e-3
+    auxh = torch.randn(M, N, device="cuda").to(torch.float16)
+    assert rel_err(ops.gemm(a, b, aux=auxh, aux_mode="drelu", out_dtype=torch.bfloat16), plain * (auxh.float() > 0)) < 6e-3
+
+
+def test_gelu_epilogue_matches_erf_gelu():
+    """The one-MUFU GELU of the 16-bit epilogue against erf-GELU over the whole useful range (identity GEMM)."""
+    ops = _ops()
+    K = 64
+    x = torch.linspace(-12.0, 12.0, 4096 * K, device="cuda").reshape(4096, K)
+    a = bf(x)
+    eye = bf(torch.eye(K, device="cuda"))
+    out = ops.gemm(a, eye, act="gelu", out_dtype=torch.bfloat16).float()
+    ref = torch.nn.functional.gelu(a.float())
+    # bf16 output rounding (2^-9 relative) dominates; the approximation itself is 1.7e-5 absolute
+    assert ((out - ref).abs() <= 4e-3 * ref.abs() + 4e-5).all(), (out - ref).abs().max().item()
+
+
 def test_gemm_odd_n_tail():
     ops = _ops()
     M, N, K = 200, 72, 64

@@ -8,13 +8,24 @@ import torch
 from dinov2_distillation_b200 import ops
 
 def bench(fn, iters=20):
+    """Device time per call: the `iters` launches are replayed from ONE CUDA graph, so host launch cost is excluded."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        fn()
+        s.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3  # us
@@ -38,7 +49,10 @@ def main():
         ("wgrad conv (MN)", 384, 1024, 16384, dict(wgrad=True)),
         ("wgrad DxD (MN)", 384, 384, 16384, dict(wgrad=True)),
     ]
+    filt = sys.argv[1] if len(sys.argv) > 1 else None
     for name, M, N, K, o in shapes:
+        if filt and filt not in name:
+            continue
         if o.get("wgrad"):
             a = torch.randn(K, M, device=dev).bfloat16()
             b = torch.randn(K, N, device=dev).bfloat16()
@@ -57,7 +71,7 @@ def main():
             fn = lambda: ops.gemm(a, b, bias=bias, act=o.get("act", "none"), residual=res, out=out)
         us = bench(fn)
         tf = 2.0 * M * N * K / us / 1e6
-        ref = bench(lambda: torch.matmul(a.t() if o.get("wgrad") else a, b if o.get("wgrad") else b.t()))
+        ref = float('nan') if filt else bench(lambda: torch.matmul(a.t() if o.get("wgrad") else a, b if o.get("wgrad") else b.t()))
         print(f"{name:22s} M={M:6d} N={N:5d} K={K:5d}  {us:8.1f} us  {tf:7.1f} TFLOP/s   (torch.matmul {ref:8.1f} us {2.0*M*N*K/ref/1e6:7.1f} TF/s)")
 
 if __name__ == "__main__":
