@@ -93,9 +93,11 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def __enter__(self):
+        if self.proc is not None and self.proc.poll() is None:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -327,10 +329,20 @@ def main():
     metrics_host = torch.empty(16, dtype=torch.float32).pin_memory()
     d2h = 0
 
-    def e2e_step():
+    def e2e_step(last=False):
         nonlocal d2h
         if graphed is not None:
-            out = hot_path(host["img"], {k: host[k] for k in layers})   # async H2D into the graph's static inputs
+            # this step's inputs were staged H2D (side stream) while the previous step computed; stage the next
+            # step's inputs now so that its copy overlaps this step -- every step still copies its own batch
+            out, _ = graphed.run_staged()
+            if not layers:
+                out = out["teacher"]
+            if arena is not None and world > 1:
+                w = arena.allreduce_mean()
+                if w is not None:
+                    w.wait()
+            if not last:
+                graphed.stage_inputs(host["img"], {k: host[k] for k in layers})
         else:
             img = host["img"].to(device, non_blocking=True)
             f = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in layers}
@@ -346,14 +358,20 @@ def main():
 
     e2e_value = None
     if not args.no_e2e:
+        if graphed is not None:
+            graphed.stage_inputs(host["img"], {k: host[k] for k in layers})
         for _ in range(2):
             e2e_step()
+        e2e_step(last=True)
         sync_all()
-        e0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        e1.record()
-        sync_all()
+        with clocks:
+            e0.record()
+            if graphed is not None:
+                graphed.stage_inputs(host["img"], {k: host[k] for k in layers})   # step 0's copy is inside the region
+            for i in range(args.steps):
+                e2e_step(last=(i == args.steps - 1))
+            e1.record()
+            sync_all()
         t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -381,10 +399,17 @@ def main():
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        traffic = None
+        try:
+            # measured once per change under `ncu --set full` (never inside a timed run); see profiles/
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["gemm_v2_kernel"]["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         if n_c[0] > 0 and ms_c[0] > 0:
             ach = fl_c[0] / (ms_c[0] * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+            roofline = {"bound": "tensor", "kernel": "gemm_v2_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_gemm_v2_ncu_full.md)",
+                        "peak_source": peak_src,
                         "launches_per_step": n_c[0] / nprof, "avg_launch_us": ms_c[0] * 1e3 / n_c[0],
                         "algorithmic_gflop_per_launch": fl_c[0] / n_c[0] / 1e9,
                         "share_of_step": (ms_c[0] / nprof) / ms_per_step}

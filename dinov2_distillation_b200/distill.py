@@ -149,3 +149,34 @@ class GraphedDistillStep:
                     self.feats[k].data.copy_(v, non_blocking=True)
         self.graph.replay()
         return self.out, self.feat_grads
+
+    # ---- input pipeline: the NEXT step's host batch travels H2D on a side stream while the current step computes
+    def stage_inputs(self, img_host: torch.Tensor, feats_host: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """Start the asynchronous host->device copy of the next step's (pinned) inputs into device staging buffers.
+        `run_staged()` then moves them into the graph's static inputs (device->device, a few tens of microseconds)
+        and replays. One staging set is enough: the copy waits until the previous set has been consumed."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_img = torch.empty_like(self.img)
+            self._stage_feats = {k: torch.empty_like(v.data) for k, v in self.feats.items()}
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream())
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)
+        with torch.cuda.stream(cs):
+            self._stage_img.copy_(img_host, non_blocking=True)
+            for k, v in (feats_host or {}).items():
+                self._stage_feats[k].copy_(v, non_blocking=True)
+            self._stage_ready.record(cs)
+
+    def run_staged(self):
+        """Consume the staged inputs (see `stage_inputs`) and replay the captured step."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_ready)
+        self.img.copy_(self._stage_img, non_blocking=True)
+        for k, v in self._stage_feats.items():
+            self.feats[k].data.copy_(v, non_blocking=True)
+        self._stage_free.record(cur)
+        self.graph.replay()
+        return self.out, self.feat_grads
