@@ -585,10 +585,18 @@ static int launch_bwd(const AttnParams& p, cudaStream_t st) {
 
 using namespace b200;
 
+namespace b200 {
+int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st);   // attention_tc.cu (tcgen05, head_dim 64)
+}
+
 extern "C" int b200_attention_fwd(const b200_attn_desc* d, void* stream) {
   AttnParams p{};
   B200_TRY(fill_params(d, p, false));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const int r = launch_attention_tc_fwd(d, st);
+    if (r <= 0) return r;
+  }
   if (p.hd <= 16) return launch_fwd<16>(p, st);
   if (p.hd <= 32) return launch_fwd<32>(p, st);
   if (p.hd <= 48) return launch_fwd<48>(p, st);

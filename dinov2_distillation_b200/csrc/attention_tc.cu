@@ -1,0 +1,441 @@
+// tcgen05 attention forward for head_dim 64 and short sequences (Nk <= 272: the 224-pixel teacher, N = 257, and the
+// re-used teacher blocks, N = 256).  (hub Attention.forward, reached through models/backbones/dinov2.py:32 and
+// train/distillation_module.py:177.)
+//
+// With the whole key range resident, a 128-query tile needs ONE QK^T and ONE PV: no online-softmax rescaling.
+//   S[128, Nk] = Q K^T        tcgen05.mma  SS  (Q: smem K-major, K: smem K-major)   -> TMEM columns [0, 272)
+//   P = exp2(scale*S - max)   4 softmax warps, thread = row: tcgen05.ld, two passes (max, then exp), bf16 pairs written
+//                             back with tcgen05.st                                  -> TMEM columns [288, 424)
+//   O[128, 64] = P V          tcgen05.mma  TS  (P: TMEM, V: smem MN-major)          -> TMEM columns [448, 512)
+//   O / rowsum -> bf16 -> swizzled smem -> one bulk tensor store per warp.
+// Persistent CTAs walk (batch, head) units; K/V are loaded once per unit by TMA (3-D maps over the fused qkv tensor,
+// rows past the sequence end zero-filled) and every 128-row query tile of the unit re-uses them. S, P and O live in
+// disjoint TMEM columns, so QK^T of the next tile runs under the epilogue of the current one.
+// A query count that leaves a short tail (Nq mod 128 <= 8 -- the teacher's 257 = 2*128 + 1) would waste a whole MMA
+// tile on it; those rows are computed by an otherwise idle warp on the CUDA cores from the same shared-memory K/V.
+//
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warp 3: tail rows   warps 4-7: softmax + epilogue
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/b200_distill.h"
+
+#include <stdlib.h>
+
+namespace b200 {
+
+int make_tensor_map_3d(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                       uint64_t ld2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle);
+
+constexpr int ATC_THREADS = 256;
+constexpr int ATC_NKP_MAX = 272;                 // keys, padded to a multiple of 16
+constexpr int ATC_KV_ROWS = 272;
+constexpr int ATC_KV_BOX = 136;                  // two TMA boxes of 136 rows
+constexpr int ATC_Q_BYTES = 128 * 128;           // 128 rows x 64 bf16
+constexpr int ATC_KV_BYTES = ATC_KV_ROWS * 128;  // 34816
+constexpr int ATC_TAIL_MAX = 8;                  // query rows left to the CUDA-core warp
+constexpr uint32_t ATC_TMEM_S = 0, ATC_TMEM_P = 288, ATC_TMEM_O = 448;
+// shared memory map (bytes from the 1024-aligned base)
+constexpr int ATC_OFF_Q = 0;                                   // [2][16384]
+constexpr int ATC_OFF_K = ATC_OFF_Q + 2 * ATC_Q_BYTES;         // [2][34816]
+constexpr int ATC_OFF_V = ATC_OFF_K + 2 * ATC_KV_BYTES;        // [2][34816]
+constexpr int ATC_OFF_O = ATC_OFF_V + 2 * ATC_KV_BYTES;        // [4][4096] output staging, one tile per epilogue warp
+constexpr int ATC_OFF_PB = ATC_OFF_O + 4 * 4096;               // [272] fp32 probabilities of a tail row
+constexpr int ATC_OFF_BAR = ATC_OFF_PB + 2048;
+constexpr int ATC_SMEM_BYTES = ATC_OFF_BAR + 256 + 1024;
+
+struct AttnTcParams {
+  int B, heads, Nq, Nk, nkp;
+  int n_qt;                  // 128-row query tiles per (b, h) on the tensor path
+  int tail0, tail_n;         // first tail row / number of tail rows (CUDA-core path)
+  float scale_log2;
+  float* lse;
+  const __nv_bfloat16* q; long long q_bs, q_ts;
+  __nv_bfloat16* o; long long o_bs, o_ts;
+  uint32_t idesc_qk1, idesc_qk2, idesc_pv;
+  int n1, n2;                // QK^T column split (n1 <= 256, n2 = nkp - n1)
+};
+
+__device__ __forceinline__ void atc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void atc_tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void atc_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void atc_tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ float atc_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                   const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_OFF_BAR);
+  uint64_t* q_full = bars;          // [2]
+  uint64_t* q_empty = bars + 2;     // [2]
+  uint64_t* kv_full = bars + 4;     // [2]
+  uint64_t* kv_empty = bars + 6;    // [2]
+  uint64_t* s_full = bars + 8;      // [1]
+  uint64_t* p_full = bars + 9;      // [1]
+  uint64_t* o_full = bars + 10;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], p.tail_n > 0 ? 2 : 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_units = p.B * p.heads;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int item = 0, uc = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+        const int b = u / p.heads, h = u - b * p.heads;
+        const int kb = uc & 1;
+        for (int qt = 0; qt < p.n_qt; ++qt, ++item) {
+          const int qb = item & 1;
+          mbar_wait(&q_empty[qb], ((item >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[qb], ATC_Q_BYTES);
+          tma_load_3d(smem + ATC_OFF_Q + qb * ATC_Q_BYTES, &tmQ, &q_full[qb], h * 64, qt * 128, b);
+          if (qt == 0) {
+            mbar_wait(&kv_empty[kb], ((uc >> 1) & 1) ^ 1);
+            mbar_expect_tx(&kv_full[kb], 2 * ATC_KV_BYTES);
+            uint8_t* sK = smem + ATC_OFF_K + kb * ATC_KV_BYTES;
+            uint8_t* sV = smem + ATC_OFF_V + kb * ATC_KV_BYTES;
+            tma_load_3d(sK, &tmK, &kv_full[kb], h * 64, 0, b);
+            tma_load_3d(sK + ATC_KV_BOX * 128, &tmK, &kv_full[kb], h * 64, ATC_KV_BOX, b);
+            tma_load_3d(sV, &tmV, &kv_full[kb], h * 64, 0, b);
+            tma_load_3d(sV + ATC_KV_BOX * 128, &tmV, &kv_full[kb], h * 64, ATC_KV_BOX, b);
+          }
+        }
+        if (p.n_qt == 0) {   // only tail rows: still stage K/V for the tail warp
+          mbar_wait(&kv_empty[kb], ((uc >> 1) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[kb], 2 * ATC_KV_BYTES);
+          uint8_t* sK = smem + ATC_OFF_K + kb * ATC_KV_BYTES;
+          uint8_t* sV = smem + ATC_OFF_V + kb * ATC_KV_BYTES;
+          tma_load_3d(sK, &tmK, &kv_full[kb], h * 64, 0, b);
+          tma_load_3d(sK + ATC_KV_BOX * 128, &tmK, &kv_full[kb], h * 64, ATC_KV_BOX, b);
+          tma_load_3d(sV, &tmV, &kv_full[kb], h * 64, 0, b);
+          tma_load_3d(sV + ATC_KV_BOX * 128, &tmV, &kv_full[kb], h * 64, ATC_KV_BOX, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      int item = 0, uc = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+        const int kb = uc & 1;
+        const uint32_t k_addr = smem_u32(smem + ATC_OFF_K + kb * ATC_KV_BYTES);
+        const uint32_t v_addr = smem_u32(smem + ATC_OFF_V + kb * ATC_KV_BYTES);
+        mbar_wait(&kv_full[kb], (uc >> 1) & 1);
+        for (int qt = 0; qt < p.n_qt; ++qt, ++item) {
+          const int qb = item & 1;
+          const uint32_t q_addr = smem_u32(smem + ATC_OFF_Q + qb * ATC_Q_BYTES);
+          mbar_wait(&q_full[qb], (item >> 1) & 1);
+          tc_fence_after();
+          // S = Q K^T  (S columns are free: the softmax warps finished reading them before p_full of the last item)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = make_smem_desc_sw128(q_addr + ks * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(k_addr + ks * 32, 16, 1024);
+            tc_mma_bf16(tmem_base + ATC_TMEM_S, da, db, p.idesc_qk1, ks > 0 ? 1u : 0u);
+            if (p.n2 > 0) {
+              const uint64_t db2 = make_smem_desc_sw128(k_addr + 256 * 128 + ks * 32, 16, 1024);
+              tc_mma_bf16(tmem_base + ATC_TMEM_S + 256, da, db2, p.idesc_qk2, ks > 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&q_empty[qb]);
+          tc_commit(s_full);
+          // O = P V
+          mbar_wait(p_full, item & 1);
+          tc_fence_after();
+          const int ksteps = p.nkp >> 4;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
+            atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, ks > 0 ? 1u : 0u);
+          }
+          tc_commit(o_full);
+          if (qt == p.n_qt - 1) tc_commit(&kv_empty[kb]);
+        }
+        if (p.n_qt == 0) mbar_arrive(&kv_empty[kb]);
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ tail rows on the CUDA cores
+    if (p.tail_n > 0) {
+      float* pb = reinterpret_cast<float*>(smem + ATC_OFF_PB);
+      int uc = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+        const int b = u / p.heads, h = u - b * p.heads;
+        const int kb = uc & 1;
+        const uint8_t* sK = smem + ATC_OFF_K + kb * ATC_KV_BYTES;
+        const uint8_t* sV = smem + ATC_OFF_V + kb * ATC_KV_BYTES;
+        mbar_wait(&kv_full[kb], (uc >> 1) & 1);
+        for (int tr = 0; tr < p.tail_n; ++tr) {
+          const int row = p.tail0 + tr;
+          const __nv_bfloat16* qrow = p.q + (long long)b * p.q_bs + (long long)row * p.q_ts + h * 64;
+          float qf[64];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
+            const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+            qf[c * 8 + 0] = f0.x; qf[c * 8 + 1] = f0.y; qf[c * 8 + 2] = f1.x; qf[c * 8 + 3] = f1.y;
+            qf[c * 8 + 4] = f2.x; qf[c * 8 + 5] = f2.y; qf[c * 8 + 6] = f3.x; qf[c * 8 + 7] = f3.y;
+          }
+          // scores: lane handles keys lane, lane + 32, ...
+          float sc[(ATC_KV_ROWS + 31) / 32];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int t = 0; t < (ATC_KV_ROWS + 31) / 32; ++t) {
+            const int j = lane + 32 * t;
+            float acc = 0.f;
+            if (j < p.Nk) {
+              const uint8_t* kr = sK + j * 128;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 w = *reinterpret_cast<const uint4*>(kr + ((c ^ (j & 7)) << 4));
+                const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+                acc = fmaf(qf[c * 8 + 0], f0.x, acc); acc = fmaf(qf[c * 8 + 1], f0.y, acc);
+                acc = fmaf(qf[c * 8 + 2], f1.x, acc); acc = fmaf(qf[c * 8 + 3], f1.y, acc);
+                acc = fmaf(qf[c * 8 + 4], f2.x, acc); acc = fmaf(qf[c * 8 + 5], f2.y, acc);
+                acc = fmaf(qf[c * 8 + 6], f3.x, acc); acc = fmaf(qf[c * 8 + 7], f3.y, acc);
+              }
+              acc *= p.scale_log2;
+              mx = fmaxf(mx, acc);
+            } else {
+              acc = -INFINITY;
+            }
+            sc[t] = acc;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          float sum = 0.f;
+#pragma unroll
+          for (int t = 0; t < (ATC_KV_ROWS + 31) / 32; ++t) {
+            const int j = lane + 32 * t;
+            const float e = atc_ex2(sc[t] - mx);
+            sum += e;
+            if (j < ATC_KV_ROWS) pb[j] = e;
+          }
+          sum = warp_sum(sum);
+          __syncwarp();
+          // output: lane owns dims 2*lane, 2*lane + 1
+          float a0 = 0.f, a1 = 0.f;
+          const int chunk = lane >> 2, within = (lane & 3) << 2;
+          for (int j = 0; j < p.Nk; ++j) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sV + j * 128 + ((chunk ^ (j & 7)) << 4) + within);
+            const float2 f = unpack_bf16(w);
+            const float pj = pb[j];
+            a0 = fmaf(pj, f.x, a0);
+            a1 = fmaf(pj, f.y, a1);
+          }
+          const float inv = 1.f / sum;
+          __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)row * p.o_ts + h * 64;
+          *reinterpret_cast<uint32_t*>(orow + 2 * lane) = pack_bf16(a0 * inv, a1 * inv);
+          if (p.lse != nullptr && lane == 0)
+            p.lse[((long long)b * p.heads + h) * p.Nq + row] = (mx + log2f(sum)) * 0.6931471805599453f;
+          __syncwarp();
+        }
+        if (lane == 0) mbar_arrive(&kv_empty[kb]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
+    const int quad = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + ATC_TMEM_S;
+    const uint32_t t_p = tmem_base + lane_base + ATC_TMEM_P;
+    const uint32_t t_o = tmem_base + lane_base + ATC_TMEM_O;
+    const uint32_t stage = smem_u32(smem + ATC_OFF_O + quad * 4096);
+    const uint32_t row_off = lane * 128, sw = lane & 7;
+    const int n_chunks = (p.nkp + 31) >> 5;
+    int item = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int b = u / p.heads, h = u - b * p.heads;
+      for (int qt = 0; qt < p.n_qt; ++qt, ++item) {
+        mbar_wait(s_full, item & 1);
+        tc_fence_after();
+        // pass 1: row maximum of the raw scores
+        float mx = -INFINITY;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(t_s + c * 32, raw);
+          tmem_ld_wait();
+          if (c * 32 + 32 <= p.Nk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < p.Nk) mx = fmaxf(mx, __uint_as_float(raw[j]));
+          }
+        }
+        const float ms = mx * p.scale_log2;
+        // pass 2: P = exp2(scale * S - max) as bf16 pairs, row sum in fp32
+        float sum = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(t_s + c * 32, raw);
+          tmem_ld_wait();
+          float e[32];
+          if (c * 32 + 32 <= p.Nk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) e[j] = atc_ex2(fmaf(__uint_as_float(raw[j]), p.scale_log2, -ms));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              e[j] = (c * 32 + j < p.Nk) ? atc_ex2(fmaf(__uint_as_float(raw[j]), p.scale_log2, -ms)) : 0.f;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            sum += e[2 * j] + e[2 * j + 1];
+            pk[j] = pack_bf16(e[2 * j], e[2 * j + 1]);
+          }
+          atc_tmem_st_32x16(t_p + c * 16, pk);
+        }
+        atc_tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // epilogue: O / sum -> bf16 -> swizzled staging tile -> bulk tensor store
+        mbar_wait(o_full, item & 1);
+        tc_fence_after();
+        const float inv = 1.f / sum;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t raw[32];
+          tmem_ld_32x32(t_o + half * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = c * 8;
+            const uint32_t w0 = pack_bf16(__uint_as_float(raw[j]) * inv, __uint_as_float(raw[j + 1]) * inv);
+            const uint32_t w1 = pack_bf16(__uint_as_float(raw[j + 2]) * inv, __uint_as_float(raw[j + 3]) * inv);
+            const uint32_t w2 = pack_bf16(__uint_as_float(raw[j + 4]) * inv, __uint_as_float(raw[j + 5]) * inv);
+            const uint32_t w3 = pack_bf16(__uint_as_float(raw[j + 6]) * inv, __uint_as_float(raw[j + 7]) * inv);
+            const uint32_t addr = stage + row_off + (((half * 4 + c) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        const int row0 = qt * 128 + quad * 32;
+        if (lane == 0) {
+          atc_tma_store_3d(&tmO, stage, h * 64, row0, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.lse != nullptr && row0 + lane < p.Nq)
+          p.lse[((long long)b * p.heads + h) * p.Nq + row0 + lane] = (ms + log2f(sum)) * 0.6931471805599453f;
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// Returns 1 when the problem is outside this kernel's envelope (the caller falls back to the mma.sync kernel).
+int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("B200_ATTN_TC");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return 1;
+  if (d->hd != 64 || d->qkvo_is_fp16 || d->Nk > ATC_NKP_MAX || d->Nk < 16 || d->q_bs == 0) return 1;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(d->q) || !al16(d->k) || !al16(d->v) || !al16(d->o)) return 1;
+  if (d->q_ts % 8 || d->k_ts % 8 || d->v_ts % 8 || d->o_ts % 8 || d->q_bs % 8 || d->k_bs % 8 || d->v_bs % 8 || d->o_bs % 8)
+    return 1;
+  AttnTcParams p{};
+  p.B = d->B; p.heads = d->heads; p.Nq = d->Nq; p.Nk = d->Nk;
+  p.nkp = (d->Nk + 15) & ~15;
+  const int rem = d->Nq % 128;
+  if (rem > 0 && rem <= ATC_TAIL_MAX) {
+    p.n_qt = d->Nq / 128; p.tail0 = p.n_qt * 128; p.tail_n = rem;
+  } else {
+    p.n_qt = (d->Nq + 127) / 128; p.tail0 = 0; p.tail_n = 0;
+  }
+  if (p.n_qt == 0 || d->scale <= 0.f) return 1;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.lse = d->lse;
+  p.q = static_cast<const __nv_bfloat16*>(d->q); p.q_bs = d->q_bs; p.q_ts = d->q_ts;
+  p.o = static_cast<__nv_bfloat16*>(d->o); p.o_bs = d->o_bs; p.o_ts = d->o_ts;
+  p.n1 = p.nkp > 256 ? 256 : p.nkp;
+  p.n2 = p.nkp - p.n1;
+  p.idesc_qk1 = make_idesc_bf16(128, p.n1, false, false);
+  p.idesc_qk2 = p.n2 > 0 ? make_idesc_bf16(128, p.n2, false, false) : 0u;
+  p.idesc_pv = make_idesc_bf16(128, 64, false, true);
+
+  const uint64_t cols = (uint64_t)d->heads * 64;
+  CUtensorMap tq, tk, tv, to;
+  B200_TRY(make_tensor_map_3d(&tq, d->q, 2, cols, (uint64_t)d->Nq, (uint64_t)d->B, (uint64_t)d->q_ts, (uint64_t)d->q_bs, 64, 128, 1, 128));
+  B200_TRY(make_tensor_map_3d(&tk, d->k, 2, cols, (uint64_t)d->Nk, (uint64_t)d->B, (uint64_t)d->k_ts, (uint64_t)d->k_bs, 64, ATC_KV_BOX, 1, 128));
+  B200_TRY(make_tensor_map_3d(&tv, d->v, 2, cols, (uint64_t)d->Nk, (uint64_t)d->B, (uint64_t)d->v_ts, (uint64_t)d->v_bs, 64, ATC_KV_BOX, 1, 128));
+  B200_TRY(make_tensor_map_3d(&to, d->o, 2, cols, (uint64_t)d->Nq, (uint64_t)d->B, (uint64_t)d->o_ts, (uint64_t)d->o_bs, 64, 32, 1, 128));
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int units = d->B * d->heads;
+  const int grid = units < sm_count() ? units : sm_count();
+  const int prof = prof_begin(st);
+  attn_tc_fwd_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tk, tv, to, p);
+  prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace b200

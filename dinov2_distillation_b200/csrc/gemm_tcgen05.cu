@@ -252,6 +252,59 @@ int make_tensor_map_ex(CUtensorMap* out, const void* ptr, int esize, uint64_t d0
   return 0;
 }
 
+// 3-D tensor map (attention operands: head columns x tokens x batch). ld1 / ld2: element pitch of dim 1 / dim 2.
+int make_tensor_map_3d(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                       uint64_t ld2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle) {
+  struct Key3 {
+    const void* ptr; uint64_t d0, d1, d2, ld1, ld2; uint32_t b0, b1, b2, es_sw;
+    bool operator==(const Key3& o) const {
+      return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld1 == o.ld1 && ld2 == o.ld2 && b0 == o.b0 &&
+             b1 == o.b1 && b2 == o.b2 && es_sw == o.es_sw;
+    }
+  };
+  struct Key3Hash {
+    size_t operator()(const Key3& k) const {
+      size_t h = reinterpret_cast<size_t>(k.ptr);
+      const uint64_t v[8] = {k.d0, k.d1, k.d2, k.ld1, k.ld2, (uint64_t(k.b0) << 32) | k.b1, k.b2, k.es_sw};
+      for (uint64_t x : v) h ^= x * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+      return h;
+    }
+  };
+  static std::mutex mu;
+  static std::unordered_map<Key3, CUtensorMap, Key3Hash> cache;
+  Key3 key{ptr, d0, d1, d2, ld1, ld2, b0, b1, b2, (uint32_t)(esize * 1000 + swizzle)};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -4; }
+  if (d2 == 1 && ld2 == 0) ld2 = ld1 * d1;
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {ld1 * (uint64_t)esize, ld2 * (uint64_t)esize};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[320];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p dims=(%llu,%llu,%llu) ld=(%llu,%llu) box=(%u,%u,%u)",
+             (int)r, ptr, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)ld1, (unsigned long long)ld2, b0, b1, b2);
+    set_error(buf);
+    return -4;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
 // operand maps: 16-bit elements, 128-byte swizzle
 int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
                        uint32_t b1) {

@@ -244,6 +244,31 @@ def test_attention_fwd_bwd(hd, heads, Nq, Nk):
     assert rel_err(dq, qr.grad) < 2e-2, rel_err(dq, qr.grad)
 
 
+@pytest.mark.parametrize("B,heads,Nq,Nk", [(3, 6, 256, 256), (5, 6, 257, 257), (2, 12, 200, 200), (2, 3, 264, 264),
+                                           (2, 4, 130, 130), (1, 2, 300, 257), (2, 6, 64, 272), (70, 6, 257, 257)])
+def test_attention_tc_head64(B, heads, Nq, Nk):
+    """tcgen05 one-shot attention (attention_tc.cu): full / partial query tiles, CUDA-core tail rows (Nq mod 128 <= 8),
+    key padding to 16, more units than SMs, strided q/k/v out of a fused qkv tensor, and the log-sum-exp output."""
+    ops = _ops()
+    hd = 64
+    D = hd * heads
+    scale = hd ** -0.5
+    if Nq == Nk:
+        qkv = bf(torch.randn(B, Nq, 3 * D, device="cuda") * 0.7)
+        q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    else:
+        q = bf(torch.randn(B, Nq, D, device="cuda") * 0.7)
+        k = bf(torch.randn(B, Nk, D, device="cuda") * 0.7)
+        v = bf(torch.randn(B, Nk, D, device="cuda"))
+    o, lse = ops.attention_fwd(q, k, v, heads, scale)
+    ref = _attn_ref(q.float(), k.float(), v.float(), heads, scale)
+    assert rel_err(o, ref) < 6e-3, rel_err(o, ref)
+    qh = q.float().reshape(B, Nq, heads, hd).transpose(1, 2)
+    kh = k.float().reshape(B, Nk, heads, hd).transpose(1, 2)
+    lse_ref = torch.logsumexp(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    assert (lse - lse_ref).abs().max().item() < 2e-3, (lse - lse_ref).abs().max().item()
+
+
 @pytest.mark.parametrize("hd,heads,N", [(16, 24, 256), (24, 16, 256), (64, 4, 150), (96, 2, 70)])
 def test_attention_fp16_forward_bf16_grads(hd, heads, N):
     """ScaleKD projector precision policy: q/k/v/o fp16, gradients bf16."""
