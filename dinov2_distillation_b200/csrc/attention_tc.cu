@@ -4,17 +4,21 @@
 //
 // With the whole key range resident, a 128-query tile needs ONE QK^T and ONE PV: no online-softmax rescaling.
 //   S[128, Nk] = Q K^T        tcgen05.mma  SS  (Q: smem K-major, K: smem K-major)   -> TMEM columns [0, 272)
-//   P = exp2(scale*S - max)   4 softmax warps, thread = row: tcgen05.ld, two passes (max, then exp), bf16 pairs written
-//                             back with tcgen05.st                                  -> TMEM columns [288, 424)
+//   P = exp2(scale*S - max)   8 softmax warps (two per TMEM lane quadrant, interleaved 32-column chunks), thread = row:
+//                             the warp's whole share of the S row (<= 160 values) is pulled into registers with ONE
+//                             round of tcgen05.ld -- S is then free, so QK^T of the next tile runs under this tile's
+//                             exponentials -- partial row maxima meet in shared memory, bf16 pairs are written back
+//                             with tcgen05.st                                       -> TMEM columns [288, 424)
 //   O[128, 64] = P V          tcgen05.mma  TS  (P: TMEM, V: smem MN-major)          -> TMEM columns [448, 512)
 //   O / rowsum -> bf16 -> swizzled smem -> one bulk tensor store per warp.
 // Persistent CTAs walk (batch, head) units; K/V are loaded once per unit by TMA (3-D maps over the fused qkv tensor,
 // rows past the sequence end zero-filled) and every 128-row query tile of the unit re-uses them. S, P and O live in
 // disjoint TMEM columns, so QK^T of the next tile runs under the epilogue of the current one.
 // A query count that leaves a short tail (Nq mod 128 <= 8 -- the teacher's 257 = 2*128 + 1) would waste a whole MMA
-// tile on it; those rows are computed by an otherwise idle warp on the CUDA cores from the same shared-memory K/V.
+// tile on it; those rows are computed by an otherwise idle warp with mma.sync from the same shared-memory K/V.
 //
-//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warp 3: tail rows   warps 4-7: softmax + epilogue
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warp 3: tail rows   warps 4-11: softmax + epilogue
+// Registers are re-balanced with setmaxnreg: 104 for warps 0-3, 200 for the softmax warps (the S row lives there).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/b200_distill.h"
@@ -26,7 +30,8 @@ namespace b200 {
 int make_tensor_map_3d(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
                        uint64_t ld2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle);
 
-constexpr int ATC_THREADS = 256;
+constexpr int ATC_THREADS = 384;
+constexpr int ATC_SM_WARPS = 8;
 constexpr int ATC_NKP_MAX = 272;                 // keys, padded to a multiple of 16
 constexpr int ATC_KV_ROWS = 272;
 constexpr int ATC_KV_BOX = 136;                  // two TMA boxes of 136 rows
@@ -38,9 +43,10 @@ constexpr uint32_t ATC_TMEM_S = 0, ATC_TMEM_P = 288, ATC_TMEM_O = 448;
 constexpr int ATC_OFF_Q = 0;                                   // [2][16384]
 constexpr int ATC_OFF_K = ATC_OFF_Q + 2 * ATC_Q_BYTES;         // [2][34816]
 constexpr int ATC_OFF_V = ATC_OFF_K + 2 * ATC_KV_BYTES;        // [2][34816]
-constexpr int ATC_OFF_O = ATC_OFF_V + 2 * ATC_KV_BYTES;        // [4][4096] output staging, one tile per epilogue warp
-constexpr int ATC_OFF_PB = ATC_OFF_O + 4 * 4096;               // [272] fp32 probabilities of a tail row
-constexpr int ATC_OFF_BAR = ATC_OFF_PB + 2048;
+constexpr int ATC_OFF_O = ATC_OFF_V + 2 * ATC_KV_BYTES;        // [8][2048] output staging, one 32x32 tile per softmax warp
+constexpr int ATC_OFF_PB = ATC_OFF_O + 8 * 2048;               // tail-row scratch
+constexpr int ATC_OFF_X = ATC_OFF_PB + 13312;                  // (tail: [8][272] fp32 scores, [8][272] bf16 P, [8] 1/sum)                   // [2][2][128] fp32: partial row max / row sum per column half
+constexpr int ATC_OFF_BAR = ATC_OFF_X + 2048;
 constexpr int ATC_SMEM_BYTES = ATC_OFF_BAR + 256 + 1024;
 
 struct AttnTcParams {
@@ -53,6 +59,7 @@ struct AttnTcParams {
   __nv_bfloat16* o; long long o_bs, o_ts;
   uint32_t idesc_qk1, idesc_qk2, idesc_pv;
   int n1, n2;                // QK^T column split (n1 <= 256, n2 = nkp - n1)
+  long long* dbg;            // B200_ATTN_DBG=1: per-phase clock64 stamps of CTA 0 ([item][16])
 };
 
 __device__ __forceinline__ void atc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -77,6 +84,25 @@ __device__ __forceinline__ void atc_tma_store_3d(const CUtensorMap* m, uint32_t 
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+#define ATC_STAMP(slot)                                                                        \
+  do {                                                                                          \
+    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item < 8) p.dbg[item * 16 + (slot)] = clock64(); \
+  } while (0)
+
+__device__ __forceinline__ void atc_ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void atc_ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void atc_mma_sync(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ float atc_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -95,9 +121,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* kv_full = bars + 4;     // [2]
   uint64_t* kv_empty = bars + 6;    // [2]
   uint64_t* s_full = bars + 8;      // [1]
-  uint64_t* p_full = bars + 9;      // [1]
-  uint64_t* o_full = bars + 10;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* o_full = bars + 9;      // [1]
+  uint64_t* s_free = bars + 10;     // [1] S columns drained into registers
+  uint64_t* p_full = bars + 11;     // [2] P published in two groups: chunks 0..3 (each warp's first two), then the rest
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -116,8 +143,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&kv_empty[i], p.tail_n > 0 ? 2 : 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    for (int i = 0; i < 2; ++i) mbar_init(&p_full[i], ATC_SM_WARPS);
     mbar_init(o_full, 1);
+    mbar_init(s_free, ATC_SM_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -127,6 +155,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const int n_units = p.B * p.heads;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
@@ -175,8 +205,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const int qb = item & 1;
           const uint32_t q_addr = smem_u32(smem + ATC_OFF_Q + qb * ATC_Q_BYTES);
           mbar_wait(&q_full[qb], (item >> 1) & 1);
+          if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 8] = clock64();
+          if (item > 0) mbar_wait(s_free, (item - 1) & 1);   // the previous tile's S row is in registers
           tc_fence_after();
-          // S = Q K^T  (S columns are free: the softmax warps finished reading them before p_full of the last item)
+          if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 9] = clock64();
+          // S = Q K^T
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t da = make_smem_desc_sw128(q_addr + ks * 32, 16, 1024);
@@ -189,13 +222,26 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           tc_commit(&q_empty[qb]);
           tc_commit(s_full);
-          // O = P V
-          mbar_wait(p_full, item & 1);
-          tc_fence_after();
-          const int ksteps = p.nkp >> 4;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
-            atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, ks > 0 ? 1u : 0u);
+          // O = P V in two groups (k-steps 0..7 = keys 0..127, then the rest) as the softmax warps publish P: the first
+          // group runs under the remaining exponentials. (Finer groups starve: this warp shares its scheduler with two
+          // softmax warps that are always eligible.)
+          {
+            const int ksteps = p.nkp >> 4;
+            const int split = ksteps < 8 ? ksteps : 8;
+            mbar_wait(&p_full[0], item & 1);
+            tc_fence_after();
+            for (int ks = 0; ks < split; ++ks) {
+              const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
+              atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, ks > 0 ? 1u : 0u);
+            }
+            if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 10] = clock64();
+            mbar_wait(&p_full[1], item & 1);
+            tc_fence_after();
+            for (int ks = split; ks < ksteps; ++ks) {
+              const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
+              atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, 1u);
+            }
+            if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 11] = clock64();
           }
           tc_commit(o_full);
           if (qt == p.n_qt - 1) tc_commit(&kv_empty[kb]);
@@ -204,9 +250,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 3) {
-    // ------------------------------------------------------------------ tail rows on the CUDA cores
+    // ------------------------------------------------------------------ tail rows (Nq mod 128 <= 8) on the legacy MMA path
+    // One warp, mma.sync m16n8k16 straight from the TMA-swizzled K/V tiles (ldmatrix with the 128B-swizzle address
+    // math): ~700 instructions per unit where a scalar version needed ~4500 and became the critical path.
     if (p.tail_n > 0) {
-      float* pb = reinterpret_cast<float*>(smem + ATC_OFF_PB);
+      float* ssc = reinterpret_cast<float*>(smem + ATC_OFF_PB);                                 // [8][272] scaled scores
+      __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(smem + ATC_OFF_PB + 8 * 272 * 4);     // [8][272] probabilities
+      float* stat = reinterpret_cast<float*>(smem + ATC_OFF_PB + 8 * 272 * 6);                   // [8] 1/sum
+      const int g = lane >> 2, t = lane & 3, mi = lane >> 3, rr = lane & 7;
       int uc = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
         const int b = u / p.heads, h = u - b * p.heads;
@@ -214,144 +265,199 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint8_t* sK = smem + ATC_OFF_K + kb * ATC_KV_BYTES;
         const uint8_t* sV = smem + ATC_OFF_V + kb * ATC_KV_BYTES;
         mbar_wait(&kv_full[kb], (uc >> 1) & 1);
-        for (int tr = 0; tr < p.tail_n; ++tr) {
-          const int row = p.tail0 + tr;
-          const __nv_bfloat16* qrow = p.q + (long long)b * p.q_bs + (long long)row * p.q_ts + h * 64;
-          float qf[64];
+        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && uc < 4) p.dbg[uc * 16 + 12] = clock64();
+        // A fragments of the tail queries: fragment rows 0..7 = tail rows (zero beyond tail_n), rows 8..15 unused
+        uint32_t qa[4][2];
+        {
+          const __nv_bfloat16* qrow = p.q + (long long)b * p.q_bs + (long long)(p.tail0 + g) * p.q_ts + h * 64;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
-            const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
-            qf[c * 8 + 0] = f0.x; qf[c * 8 + 1] = f0.y; qf[c * 8 + 2] = f1.x; qf[c * 8 + 3] = f1.y;
-            qf[c * 8 + 4] = f2.x; qf[c * 8 + 5] = f2.y; qf[c * 8 + 6] = f3.x; qf[c * 8 + 7] = f3.y;
+          for (int ks = 0; ks < 4; ++ks) {
+            qa[ks][0] = g < p.tail_n ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 2 * t)) : 0u;
+            qa[ks][1] = g < p.tail_n ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + 2 * t)) : 0u;
           }
-          // scores: lane handles keys lane, lane + 32, ...
-          float sc[(ATC_KV_ROWS + 31) / 32];
+        }
+        // scores: two 8-key blocks per step
+        for (int nb = 0; nb < (p.nkp >> 3); nb += 2) {
+          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const int row = (nb + (mi >> 1)) * 8 + rr, chunk = ks * 2 + (mi & 1);
+            uint32_t bf[4];
+            atc_ldsm_x4(bf, sK + row * 128 + ((chunk ^ (row & 7)) << 4));
+            const uint32_t a[4] = {qa[ks][0], 0u, qa[ks][1], 0u};
+            atc_mma_sync(c0, a, bf[0], bf[1]);
+            atc_mma_sync(c1, a, bf[2], bf[3]);
+          }
+          *reinterpret_cast<float2*>(ssc + g * 272 + nb * 8 + 2 * t) = make_float2(c0[0] * p.scale_log2, c0[1] * p.scale_log2);
+          *reinterpret_cast<float2*>(ssc + g * 272 + (nb + 1) * 8 + 2 * t) = make_float2(c1[0] * p.scale_log2, c1[1] * p.scale_log2);
+        }
+        __syncwarp();
+        // softmax, one tail row at a time across the warp
+        for (int r = 0; r < p.tail_n; ++r) {
           float mx = -INFINITY;
-#pragma unroll
-          for (int t = 0; t < (ATC_KV_ROWS + 31) / 32; ++t) {
-            const int j = lane + 32 * t;
-            float acc = 0.f;
-            if (j < p.Nk) {
-              const uint8_t* kr = sK + j * 128;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const uint4 w = *reinterpret_cast<const uint4*>(kr + ((c ^ (j & 7)) << 4));
-                const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
-                acc = fmaf(qf[c * 8 + 0], f0.x, acc); acc = fmaf(qf[c * 8 + 1], f0.y, acc);
-                acc = fmaf(qf[c * 8 + 2], f1.x, acc); acc = fmaf(qf[c * 8 + 3], f1.y, acc);
-                acc = fmaf(qf[c * 8 + 4], f2.x, acc); acc = fmaf(qf[c * 8 + 5], f2.y, acc);
-                acc = fmaf(qf[c * 8 + 6], f3.x, acc); acc = fmaf(qf[c * 8 + 7], f3.y, acc);
-              }
-              acc *= p.scale_log2;
-              mx = fmaxf(mx, acc);
-            } else {
-              acc = -INFINITY;
-            }
-            sc[t] = acc;
-          }
+          for (int j = lane; j < p.Nk; j += 32) mx = fmaxf(mx, ssc[r * 272 + j]);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
           float sum = 0.f;
-#pragma unroll
-          for (int t = 0; t < (ATC_KV_ROWS + 31) / 32; ++t) {
-            const int j = lane + 32 * t;
-            const float e = atc_ex2(sc[t] - mx);
+          for (int j = lane; j < p.nkp; j += 32) {
+            const float e = j < p.Nk ? atc_ex2(ssc[r * 272 + j] - mx) : 0.f;
             sum += e;
-            if (j < ATC_KV_ROWS) pb[j] = e;
+            sp[r * 272 + j] = __float2bfloat16(e);
           }
           sum = warp_sum(sum);
-          __syncwarp();
-          // output: lane owns dims 2*lane, 2*lane + 1
-          float a0 = 0.f, a1 = 0.f;
-          const int chunk = lane >> 2, within = (lane & 3) << 2;
-          for (int j = 0; j < p.Nk; ++j) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(sV + j * 128 + ((chunk ^ (j & 7)) << 4) + within);
-            const float2 f = unpack_bf16(w);
-            const float pj = pb[j];
-            a0 = fmaf(pj, f.x, a0);
-            a1 = fmaf(pj, f.y, a1);
+          if (lane == 0) {
+            stat[r] = 1.f / sum;
+            if (p.lse != nullptr)
+              p.lse[((long long)b * p.heads + h) * p.Nq + p.tail0 + r] = (mx + log2f(sum)) * 0.6931471805599453f;
           }
-          const float inv = 1.f / sum;
-          __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)row * p.o_ts + h * 64;
-          *reinterpret_cast<uint32_t*>(orow + 2 * lane) = pack_bf16(a0 * inv, a1 * inv);
-          if (p.lse != nullptr && lane == 0)
-            p.lse[((long long)b * p.heads + h) * p.Nq + row] = (mx + log2f(sum)) * 0.6931471805599453f;
-          __syncwarp();
         }
+        __syncwarp();
+        // O = P V
+        float oc[8][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) { oc[nb][0] = oc[nb][1] = oc[nb][2] = oc[nb][3] = 0.f; }
+        for (int ks = 0; ks < (p.nkp >> 4); ++ks) {
+          uint32_t a[4] = {0u, 0u, 0u, 0u};
+          if (g < p.tail_n) {
+            a[0] = *reinterpret_cast<const uint32_t*>(sp + g * 272 + ks * 16 + 2 * t);
+            a[2] = *reinterpret_cast<const uint32_t*>(sp + g * 272 + ks * 16 + 8 + 2 * t);
+          }
+#pragma unroll
+          for (int nb = 0; nb < 8; nb += 2) {
+            const int key = ks * 16 + (mi & 1) * 8 + rr, chunk = nb + (mi >> 1);
+            uint32_t bf[4];
+            atc_ldsm_x4_t(bf, sV + key * 128 + ((chunk ^ (key & 7)) << 4));
+            atc_mma_sync(oc[nb], a, bf[0], bf[1]);
+            atc_mma_sync(oc[nb + 1], a, bf[2], bf[3]);
+          }
+        }
+        if (g < p.tail_n) {
+          const float inv = stat[g];
+          __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)(p.tail0 + g) * p.o_ts + h * 64;
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb)
+            *reinterpret_cast<uint32_t*>(orow + nb * 8 + 2 * t) = pack_bf16(oc[nb][0] * inv, oc[nb][1] * inv);
+        }
+        __syncwarp();
+        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && uc < 4) p.dbg[uc * 16 + 13] = clock64();
         if (lane == 0) mbar_arrive(&kv_empty[kb]);
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
-    const int quad = warp & 3;
+    const int ew = warp - 4;
+    const int quad = warp & 3;            // TMEM lanes 32*quad .. +31 (hardware: warp id % 4)
+    const int hf = ew >> 2;               // column half: chunks hf, hf + 2, ... of 32 S columns; O columns 32*hf .. +31
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t t_s = tmem_base + lane_base + ATC_TMEM_S;
     const uint32_t t_p = tmem_base + lane_base + ATC_TMEM_P;
     const uint32_t t_o = tmem_base + lane_base + ATC_TMEM_O;
-    const uint32_t stage = smem_u32(smem + ATC_OFF_O + quad * 4096);
-    const uint32_t row_off = lane * 128, sw = lane & 7;
+    const uint32_t stage = smem_u32(smem + ATC_OFF_O + ew * 2048);
+    const uint32_t row_off = lane * 64, sw = (lane >> 1) & 3;   // 64-byte rows, SWIZZLE_64B
+    float* xmax = reinterpret_cast<float*>(smem + ATC_OFF_X);    // [2 halves][128 rows]
+    float* xsum = xmax + 256;                                    // [2 halves][128 rows]
+    const int row_in_tile = quad * 32 + lane;
     const int n_chunks = (p.nkp + 31) >> 5;
+    constexpr int MAXC = 5;               // chunks per warp: ceil(9 / 2)
     int item = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int b = u / p.heads, h = u - b * p.heads;
       for (int qt = 0; qt < p.n_qt; ++qt, ++item) {
+        if (ew == 0) ATC_STAMP(0);
         mbar_wait(s_full, item & 1);
         tc_fence_after();
-        // pass 1: row maximum of the raw scores
-        float mx = -INFINITY;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(t_s + c * 32, raw);
-          tmem_ld_wait();
-          if (c * 32 + 32 <= p.Nk) {
+        if (ew == 0) ATC_STAMP(1);
+        // the warp's share of the S row -> registers, then S is free for the next tile's QK^T
+        uint32_t sv[MAXC][32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < p.Nk) mx = fmaxf(mx, __uint_as_float(raw[j]));
-          }
+        for (int i = 0; i < MAXC; ++i) {
+          const int c = hf + 2 * i;
+          if (c < n_chunks) tmem_ld_32x32(t_s + c * 32, sv[i]);
         }
-        const float ms = mx * p.scale_log2;
-        // pass 2: P = exp2(scale * S - max) as bf16 pairs, row sum in fp32
-        float sum = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(t_s + c * 32, raw);
-          tmem_ld_wait();
-          float e[32];
-          if (c * 32 + 32 <= p.Nk) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) e[j] = atc_ex2(fmaf(__uint_as_float(raw[j]), p.scale_log2, -ms));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              e[j] = (c * 32 + j < p.Nk) ? atc_ex2(fmaf(__uint_as_float(raw[j]), p.scale_log2, -ms)) : 0.f;
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            sum += e[2 * j] + e[2 * j + 1];
-            pk[j] = pack_bf16(e[2 * j], e[2 * j + 1]);
-          }
-          atc_tmem_st_32x16(t_p + c * 16, pk);
-        }
-        atc_tmem_st_wait();
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        // epilogue: O / sum -> bf16 -> swizzled staging tile -> bulk tensor store
+        if (lane == 0) mbar_arrive(s_free);
+        if (ew == 0) ATC_STAMP(2);
+        // columns past Nk (zero-filled keys) must not take part: only the last chunk can hold any
+        if ((p.Nk & 31) != 0) {
+#pragma unroll
+          for (int i = 0; i < MAXC; ++i) {
+            const int c = hf + 2 * i;
+            if (c == n_chunks - 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j >= p.Nk) sv[i][j] = 0xff800000u;   // -inf
+            }
+          }
+        }
+        // row maximum: own columns, then the partner warp's through shared memory
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+          if (hf + 2 * i < n_chunks) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sv[i][j]));
+          }
+        }
+        xmax[hf * 128 + row_in_tile] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        mx = fmaxf(mx, xmax[(hf ^ 1) * 128 + row_in_tile]);
+        const float ms = mx * p.scale_log2;
+        if (ew == 0) ATC_STAMP(3);
+        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2] = clock64();
+        // P = exp2(scale * S - max) as bf16 pairs (tcgen05.st), published chunk by chunk; partial row sum in fp32
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+          const int c = hf + 2 * i;
+          if (c < n_chunks) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float e0 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j]), p.scale_log2, -ms));
+              const float e1 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j + 1]), p.scale_log2, -ms));
+              sum += e0 + e1;
+              pk[j] = pack_bf16(e0, e1);
+            }
+            atc_tmem_st_32x16(t_p + c * 16, pk);
+            const bool last = (i == MAXC - 1) || (c + 2 >= n_chunks);
+            if (i == 1 && !last) {
+              // first group (chunks 0..3) complete for this warp
+              atc_tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&p_full[0]);
+            }
+            if (last) {
+              xsum[hf * 128 + row_in_tile] = sum;
+              atc_tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (i <= 1) mbar_arrive(&p_full[0]);   // short rows: everything is in the first group
+                mbar_arrive(&p_full[1]);
+              }
+            }
+          }
+        }
+        if (ew == 0) ATC_STAMP(4);
+        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2 + 1] = clock64();
+        // epilogue: this warp's 32 output columns: O / sum -> bf16 -> swizzled staging tile -> bulk tensor store
         mbar_wait(o_full, item & 1);
+        if (ew == 0) ATC_STAMP(5);   // (every softmax warp published its last chunk before this completes: xsum is visible)
         tc_fence_after();
+        sum += xsum[(hf ^ 1) * 128 + row_in_tile];
         const float inv = 1.f / sum;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
           uint32_t raw[32];
-          tmem_ld_32x32(t_o + half * 32, raw);
+          tmem_ld_32x32(t_o + hf * 32, raw);
           tmem_ld_wait();
+          if (ew == 0) ATC_STAMP(7);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int j = c * 8;
@@ -359,7 +465,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t w1 = pack_bf16(__uint_as_float(raw[j + 2]) * inv, __uint_as_float(raw[j + 3]) * inv);
             const uint32_t w2 = pack_bf16(__uint_as_float(raw[j + 4]) * inv, __uint_as_float(raw[j + 5]) * inv);
             const uint32_t w3 = pack_bf16(__uint_as_float(raw[j + 6]) * inv, __uint_as_float(raw[j + 7]) * inv);
-            const uint32_t addr = stage + row_off + (((half * 4 + c) ^ sw) << 4);
+            const uint32_t addr = stage + row_off + ((c ^ sw) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
           }
         }
@@ -368,11 +474,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         const int row0 = qt * 128 + quad * 32;
         if (lane == 0) {
-          atc_tma_store_3d(&tmO, stage, h * 64, row0, b);
+          atc_tma_store_3d(&tmO, stage, h * 64 + hf * 32, row0, b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (p.lse != nullptr && row0 + lane < p.Nq)
+        if (hf == 0 && p.lse != nullptr && row0 + lane < p.Nq)
           p.lse[((long long)b * p.heads + h) * p.Nq + row0 + lane] = (ms + log2f(sum)) * 0.6931471805599453f;
+        if (ew == 0) ATC_STAMP(6);
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -392,7 +499,7 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
   if (!enabled) return 1;
-  if (d->hd != 64 || d->qkvo_is_fp16 || d->Nk > ATC_NKP_MAX || d->Nk < 16 || d->q_bs == 0) return 1;
+  if (d->hd != 64 || d->qkvo_is_fp16 || d->Nk > ATC_NKP_MAX || d->Nk < 33 || d->q_bs == 0) return 1;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(d->q) || !al16(d->k) || !al16(d->v) || !al16(d->o)) return 1;
   if (d->q_ts % 8 || d->k_ts % 8 || d->v_ts % 8 || d->o_ts % 8 || d->q_bs % 8 || d->k_bs % 8 || d->v_bs % 8 || d->o_bs % 8)
@@ -422,7 +529,7 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   B200_TRY(make_tensor_map_3d(&tq, d->q, 2, cols, (uint64_t)d->Nq, (uint64_t)d->B, (uint64_t)d->q_ts, (uint64_t)d->q_bs, 64, 128, 1, 128));
   B200_TRY(make_tensor_map_3d(&tk, d->k, 2, cols, (uint64_t)d->Nk, (uint64_t)d->B, (uint64_t)d->k_ts, (uint64_t)d->k_bs, 64, ATC_KV_BOX, 1, 128));
   B200_TRY(make_tensor_map_3d(&tv, d->v, 2, cols, (uint64_t)d->Nk, (uint64_t)d->B, (uint64_t)d->v_ts, (uint64_t)d->v_bs, 64, ATC_KV_BOX, 1, 128));
-  B200_TRY(make_tensor_map_3d(&to, d->o, 2, cols, (uint64_t)d->Nq, (uint64_t)d->B, (uint64_t)d->o_ts, (uint64_t)d->o_bs, 64, 32, 1, 128));
+  B200_TRY(make_tensor_map_3d(&to, d->o, 2, cols, (uint64_t)d->Nq, (uint64_t)d->B, (uint64_t)d->o_ts, (uint64_t)d->o_bs, 32, 32, 1, 64));
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -432,9 +539,30 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   const int units = d->B * d->heads;
   const int grid = units < sm_count() ? units : sm_count();
   const int prof = prof_begin(st);
+  static long long* dbg_buf = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) { const char* e = getenv("B200_ATTN_DBG"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
+  if (dbg_on && dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 9 * 16 * sizeof(long long)); }
+  if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 9 * 16 * sizeof(long long), st);
+  p.dbg = dbg_on ? dbg_buf : nullptr;
   attn_tc_fwd_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tk, tv, to, p);
   prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
   B200_LAUNCH_OK();
+  if (dbg_on) {
+    long long h[9 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_buf, sizeof h, cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    for (int it = 0; it < 8; ++it) {
+      if (h[it * 16] == 0) break;
+      fprintf(stderr, "[attn_tc dbg] item %d:", it);
+      for (int s2 = 0; s2 < 16; ++s2) fprintf(stderr, " %s%lld", s2 == 8 ? "| mma " : (s2 == 12 ? "| tail " : (s2 == 14 ? "| w8 " : "")), h[it * 16 + s2] ? h[it * 16 + s2] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "[attn_tc dbg] item 4 exp start/end per softmax warp:");
+    for (int w = 0; w < 8; ++w) fprintf(stderr, " w%d %lld-%lld", w + 4, h[128 + 2 * w] - t0, h[129 + 2 * w] - t0);
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 

@@ -3,7 +3,7 @@
 # The raw-metric and source pages are exported to CSV on the GPU box; the .ncu-rep itself is only kept when small
 # (gpurun brings back at most 64 MiB).
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-roofline --no-e2e --no-graph ${BENCH_ARGS:-}"
+CMD="${NCU_CMD:-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-roofline --no-e2e --no-graph ${BENCH_ARGS:-}}"
 $CMD > gpurun_out/plain_full_$2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:$1 -s ${3:-60} -c ${NCU_COUNT:-6} -o gpurun_out/prof_$2 -f $CMD > gpurun_out/ncu_full_$2.log 2>&1
 echo "ncu exit $?"
