@@ -218,6 +218,8 @@ def build_gpu_step(wl, device):
         host[name.split("_")[1]] = torch.randn(B, cs, g, g, generator=gen).pin_memory()
     params = [p for p in step.losses.parameters()]
     arena = D.FlatGradArena(params) if params else None
+    if arena is not None:
+        arena.enable_direct_accumulation(step.losses)   # backward kernels add straight into the arena views
     return step, host, arena
 
 

@@ -148,6 +148,12 @@ SIGNATURES = {
                                 c_vp, _sz, c_vp]),
     "b200_projector_bwd": (_i, [C.POINTER(ProjectorConfig), C.POINTER(ProjectorParams), C.POINTER(ProjectorGrads),
                                 c_fp, c_fp, c_fp, _i, c_fp, _i, c_fp, c_vp, c_vp, _sz, c_vp]),
+    "b200_projector_tokens_bytes": (_sz, [C.POINTER(ProjectorConfig), _i]),
+    "b200_projector_tokenize": (_i, [C.POINTER(ProjectorConfig), c_fp, _i, c_vp, c_vp, _sz, c_vp]),
+    "b200_projector_fwd_tok": (_i, [C.POINTER(ProjectorConfig), C.POINTER(ProjectorParams), c_fp, c_fp, _i, c_fp, c_vp,
+                                    c_vp, _sz, c_vp, c_vp]),
+    "b200_projector_bwd_tok": (_i, [C.POINTER(ProjectorConfig), C.POINTER(ProjectorParams), C.POINTER(ProjectorGrads),
+                                    c_fp, c_fp, c_fp, _i, c_fp, _i, c_fp, c_vp, c_vp, _sz, c_vp, c_vp]),
 }
 
 _lib = None
@@ -172,7 +178,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the ABI and the header drifted apart
         fn.restype = res
         fn.argtypes = args
-    if lib.b200_abi_version() != 1:
+    if lib.b200_abi_version() != 2:
         raise B200Error("libb200distill.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -125,6 +125,25 @@ __device__ __forceinline__ float dgelu_fast(float x) {
   return cdf + x * pdf;
 }
 
+// Multi-job parameter preparation (elementwise.cu: param_prep_kernel)
+enum { PREP_CAST16 = 0, PREP_SPLIT3_RIGHT = 1, PREP_COPY32 = 2, PREP_TRANSPOSE16 = 3, PREP_TRANSPOSE32 = 4 };
+constexpr int PREP_MAX_JOBS = 12;
+struct PrepJob {
+  const float* src;
+  void* dst;
+  int type, rows, cols, fp16;   // flat jobs cover rows*cols elements; transposes read [rows, cols]
+  long long out_ld;             // transposes: output row pitch (elements)
+};
+struct PrepJobs {
+  PrepJob j[PREP_MAX_JOBS];
+  int n;
+  void add(int type, const float* src, void* dst, int rows, int cols, int fp16 = 0, long long out_ld = 0) {
+    if (n < PREP_MAX_JOBS) j[n] = PrepJob{src, dst, type, rows, cols, fp16, out_ld};
+    ++n;
+  }
+};
+int launch_param_prep(const PrepJobs& jobs, cudaStream_t st);
+
 // Bump allocator over a caller-provided workspace (256-byte aligned carve-outs).
 struct Arena {
   uint8_t* base;

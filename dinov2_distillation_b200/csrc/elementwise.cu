@@ -624,6 +624,98 @@ static int launch_colreduce(const T* x, long long ldx, float* out, int rows, int
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ parameter prep
+// One launch for all the per-step working copies of a projector's fp32 master parameters (casts, the 3-term split of
+// the conv weight, transposed bf16 copies for the dgrad GEMMs, bias concatenation, pos_embed to token-major): these were
+// 10 (forward) and 7 (backward) launches of a few microseconds each. blockIdx.y selects the job.
+__global__ void __launch_bounds__(256) param_prep_kernel(const PrepJobs jobs) {
+  const PrepJob& jb = jobs.j[blockIdx.y];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (jb.type == PREP_CAST16 || jb.type == PREP_COPY32) {
+    const long long n = (long long)jb.rows * jb.cols;
+    const long long n4 = n >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(jb.src);
+    for (long long i = (long long)blockIdx.x * 256 + tid; i < n4; i += (long long)gridDim.x * 256) {
+      const float4 v = __ldg(src4 + i);
+      if (jb.type == PREP_COPY32) {
+        reinterpret_cast<float4*>(jb.dst)[i] = v;
+      } else {
+        uint2 u;
+        u.x = pack16(v.x, v.y, jb.fp16);
+        u.y = pack16(v.z, v.w, jb.fp16);
+        reinterpret_cast<uint2*>(jb.dst)[i] = u;
+      }
+    }
+    if (blockIdx.x == 0 && tid < (int)(n & 3)) {   // tail (n not a multiple of 4)
+      const long long i = (n4 << 2) + tid;
+      if (jb.type == PREP_COPY32) static_cast<float*>(jb.dst)[i] = jb.src[i];
+      else store16(static_cast<__nv_bfloat16*>(jb.dst) + i, jb.src[i], jb.fp16);
+    }
+  } else if (jb.type == PREP_SPLIT3_RIGHT) {
+    const int K = jb.cols, K4 = K >> 2;
+    const long long n4 = (long long)jb.rows * K4;
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(jb.dst);
+    for (long long i = (long long)blockIdx.x * 256 + tid; i < n4; i += (long long)gridDim.x * 256) {
+      const long long r = i / K4;
+      const int c4 = (int)(i - r * K4);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(jb.src) + i);
+      const float f[4] = {v.x, v.y, v.z, v.w};
+      float hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        hi[e] = jb.fp16 ? __half2float(__float2half_rn(f[e])) : __bfloat162float(__float2bfloat16(f[e]));
+        lo[e] = f[e] - hi[e];
+      }
+      uint2 uh, ul;
+      uh.x = pack16(hi[0], hi[1], jb.fp16); uh.y = pack16(hi[2], hi[3], jb.fp16);
+      ul.x = pack16(lo[0], lo[1], jb.fp16); ul.y = pack16(lo[2], lo[3], jb.fp16);
+      __nv_bfloat16* o = out + r * 3 * K + c4 * 4;
+      *reinterpret_cast<uint2*>(o) = uh;          // [hi | lo | hi]: right operand of the split product
+      *reinterpret_cast<uint2*>(o + K) = ul;
+      *reinterpret_cast<uint2*>(o + 2 * K) = uh;
+    }
+  } else {
+    // PREP_TRANSPOSE16 / PREP_TRANSPOSE32: out[c * out_ld + r] = in[r * cols + c], 32 x 32 tiles through shared memory
+    __shared__ float tile[32][33];
+    const int tiles_c = (jb.cols + 31) >> 5, tiles_r = (jb.rows + 31) >> 5;
+    for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+      const int r0 = (t / tiles_c) << 5, c0 = (t % tiles_c) << 5;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + threadIdx.y + 8 * k, c = c0 + threadIdx.x;
+        tile[threadIdx.y + 8 * k][threadIdx.x] = (r < jb.rows && c < jb.cols) ? __ldg(jb.src + (long long)r * jb.cols + c) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + threadIdx.y + 8 * k, r = r0 + threadIdx.x;
+        if (c < jb.cols && r < jb.rows) {
+          const float v = tile[threadIdx.x][threadIdx.y + 8 * k];
+          if (jb.type == PREP_TRANSPOSE32) static_cast<float*>(jb.dst)[(long long)c * jb.out_ld + r] = v;
+          else store16(static_cast<__nv_bfloat16*>(jb.dst) + (long long)c * jb.out_ld + r, v, jb.fp16);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int launch_param_prep(const PrepJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0) return 0;
+  B200_CHECK_ARG(jobs.n <= PREP_MAX_JOBS, "too many prep jobs");
+  for (int i = 0; i < jobs.n; ++i) {
+    const PrepJob& j = jobs.j[i];
+    B200_CHECK_ARG(j.src && j.dst && j.rows > 0 && j.cols > 0, "bad prep job");
+    if (j.type == PREP_CAST16 || j.type == PREP_COPY32 || j.type == PREP_SPLIT3_RIGHT)
+      B200_CHECK_ARG((reinterpret_cast<uintptr_t>(j.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(j.dst) & 15) == 0,
+                     "prep job alignment");
+    if (j.type == PREP_SPLIT3_RIGHT) B200_CHECK_ARG(j.cols % 4 == 0, "split3 needs K % 4 == 0");
+  }
+  param_prep_kernel<<<dim3(48, (unsigned)jobs.n), dim3(32, 8), 0, st>>>(jobs);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace b200
 
 using namespace b200;

@@ -409,9 +409,34 @@ extern "C" size_t b200_projector_save_bytes(const b200_projector_config* c, int 
   return a.used() + 256;
 }
 
-extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_projector_params* p, const float* x,
-                                  const float* query, int B, float* out, void* save, void* ws, size_t ws_bytes,
-                                  void* stream) {
+// shared student tokens of one ScaleKD (both projectors read the same preds_S): [xt bf16 [M,Cs] | xt3 fp16 [M,3Cs]]
+static size_t proj_tokens_xt3_offset(const b200_projector_config* c, int B) {
+  const size_t xt = (size_t)B * c->HW * c->Cs * 2;
+  return (xt + 255) & ~size_t(255);
+}
+
+extern "C" size_t b200_projector_tokens_bytes(const b200_projector_config* c, int B) {
+  if (!c || B <= 0) return 0;
+  return proj_tokens_xt3_offset(c, B) + (size_t)B * c->HW * c->Cs * 3 * 2 + 256;
+}
+
+extern "C" int b200_projector_tokenize(const b200_projector_config* c, const float* x, int B, void* tokens, void* ws,
+                                       size_t ws_bytes, void* stream) {
+  B200_TRY(check_proj_cfg(c, B));
+  B200_CHECK_ARG(x && tokens && ws, "null argument");
+  const long long M = (long long)B * c->HW;
+  B200_CHECK_ARG(ws_bytes >= (size_t)M * c->Cs * 4, "workspace too small");
+  bf16* xt = static_cast<bf16*>(tokens);
+  h16* xt3 = reinterpret_cast<h16*>(static_cast<uint8_t*>(tokens) + proj_tokens_xt3_offset(c, B));
+  float* xt32 = static_cast<float*>(ws);
+  B200_TRY(b200_nchw_to_tokens(x, xt, xt32, B, c->Cs, c->HW, 0, stream));
+  B200_TRY(b200_split3_16(xt32, xt3, M, c->Cs, 0, 1, stream));
+  return 0;
+}
+
+static int projector_fwd_impl(const b200_projector_config* c, const b200_projector_params* p, const float* x,
+                              const float* query, int B, float* out, void* save, void* ws, size_t ws_bytes,
+                              const void* tokens, void* stream) {
   B200_TRY(check_proj_cfg(c, B));
   B200_CHECK_ARG(p && x && out && save && ws, "null argument");
   B200_CHECK_ARG(query != nullptr || p->query_w != nullptr, "There is no query!");
@@ -428,22 +453,33 @@ extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_pro
   carve_proj_fwd_ws(wa, c, B, w);
   B200_CHECK_ARG(wa.ok(), "workspace too small");
 
-  // fp16 working copies of the fp32 master weights
-  B200_TRY(b200_split3_16(p->conv_w, w.wc3, D, Cs, 1, 1, stream));
-  B200_TRY(b200_cast_f32_f16(p->q_w, w.wq, (long long)D * D, stream));
-  B200_TRY(b200_cast_f32_f16(p->k_w, w.wkv, (long long)D * D, stream));
-  B200_TRY(b200_cast_f32_f16(p->v_w, w.wkv + (long long)D * D, (long long)D * D, stream));
-  B200_TRY(b200_cast_f32_f16(p->p_w, w.wp, (long long)D * D, stream));
-  B200_TRY(b200_cast_f32_f16(p->ffn1_w, w.w1, 4LL * D * D, stream));
-  B200_TRY(b200_cast_f32_f16(p->ffn2_w, w.w2, 4LL * D * D, stream));
-  B200_CUDA_OK(cudaMemcpyAsync(w.bkv, p->k_b, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  B200_CUDA_OK(cudaMemcpyAsync(w.bkv + D, p->v_b, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // per-step working copies of the fp32 master parameters, one launch: fp16 casts, 3-term split of the conv weight,
+  // [k_b | v_b], pos_embed -> token-major
+  {
+    PrepJobs jobs{};
+    jobs.add(PREP_SPLIT3_RIGHT, p->conv_w, w.wc3, D, Cs, 1);
+    jobs.add(PREP_CAST16, p->q_w, w.wq, D, D, 1);
+    jobs.add(PREP_CAST16, p->k_w, w.wkv, D, D, 1);
+    jobs.add(PREP_CAST16, p->v_w, w.wkv + (long long)D * D, D, D, 1);
+    jobs.add(PREP_CAST16, p->p_w, w.wp, D, D, 1);
+    jobs.add(PREP_CAST16, p->ffn1_w, w.w1, 4 * D, D, 1);
+    jobs.add(PREP_CAST16, p->ffn2_w, w.w2, D, 4 * D, 1);
+    jobs.add(PREP_COPY32, p->k_b, w.bkv, 1, D);
+    jobs.add(PREP_COPY32, p->v_b, w.bkv + D, 1, D);
+    jobs.add(PREP_TRANSPOSE32, p->pos_embed, w.pos_t, D, HW, 0, D);   // [D, HW] -> [HW, D]
+    B200_TRY(launch_param_prep(jobs, st));
+  }
 
   // proj_student: conv1x1 -> BN -> ReLU, + pos_embed            (losses/scalekd.py:199-201, :238)
   // the conv feeds BN -> ReLU with no residual around it: run it as a 3-term split fp16 product (K -> 3K)
-  B200_TRY(b200_nchw_to_tokens(x, s.xt, w.xt32, B, Cs, HW, 0, stream));
-  B200_TRY(b200_split3_16(w.xt32, w.xt3, M, Cs, 0, 1, stream));
-  B200_TRY(Gemm(w.xt3, 3 * Cs, w.wc3, 3 * Cs, Mi, D, 3 * Cs).fp16_operands().algo_scale(1.f / 3.f).bias(p->conv_b).out32(s.y, D).run(stream));
+  const h16* xt3 = w.xt3;
+  if (tokens != nullptr) {
+    xt3 = reinterpret_cast<const h16*>(static_cast<const uint8_t*>(tokens) + proj_tokens_xt3_offset(c, B));
+  } else {
+    B200_TRY(b200_nchw_to_tokens(x, s.xt, w.xt32, B, Cs, HW, 0, stream));
+    B200_TRY(b200_split3_16(w.xt32, w.xt3, M, Cs, 0, 1, stream));
+  }
+  B200_TRY(Gemm(xt3, 3 * Cs, w.wc3, 3 * Cs, Mi, D, 3 * Cs).fp16_operands().algo_scale(1.f / 3.f).bias(p->conv_b).out32(s.y, D).run(stream));
   if (c->training) {
     B200_TRY(zero_f32(w.sums, 2 * D, st));
     B200_TRY(b200_bn_stats(s.y, w.sums, Mi, D, stream));
@@ -453,7 +489,6 @@ extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_pro
     B200_TRY(b200_bn_finalize(nullptr, s.bn_mean, s.bn_rstd, p->bn_running_mean, p->bn_running_var, c->bn_momentum,
                               c->bn_eps, Mi, D, stream));
   }
-  B200_TRY(b200_nchw_to_tokens(p->pos_embed, nullptr, w.pos_t, 1, D, HW, 0, stream));
   B200_TRY(b200_bn_relu_pos_fwd(s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.pos_t, w.z32, s.z, Mi, D, HW, 1, stream));
 
   // cross attention: q from the query tokens, k/v from the student tokens      (losses/scalekd.py:299-316)
@@ -474,10 +509,22 @@ extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_pro
   return 0;
 }
 
-extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_projector_params* p,
-                                  const b200_projector_grads* g, const float* x, const float* query, const float* dout,
-                                  int B, float* dx, int dx_accumulate, float* dquery, const void* save, void* ws,
-                                  size_t ws_bytes, void* stream) {
+extern "C" int b200_projector_fwd(const b200_projector_config* c, const b200_projector_params* p, const float* x,
+                                  const float* query, int B, float* out, void* save, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  return projector_fwd_impl(c, p, x, query, B, out, save, ws, ws_bytes, nullptr, stream);
+}
+
+extern "C" int b200_projector_fwd_tok(const b200_projector_config* c, const b200_projector_params* p, const float* x,
+                                      const float* query, int B, float* out, void* save, void* ws, size_t ws_bytes,
+                                      const void* tokens, void* stream) {
+  return projector_fwd_impl(c, p, x, query, B, out, save, ws, ws_bytes, tokens, stream);
+}
+
+static int projector_bwd_impl(const b200_projector_config* c, const b200_projector_params* p,
+                              const b200_projector_grads* g, const float* x, const float* query, const float* dout,
+                              int B, float* dx, int dx_accumulate, float* dquery, const void* save, void* ws,
+                              size_t ws_bytes, const void* tokens, void* stream) {
   B200_TRY(check_proj_cfg(c, B));
   B200_CHECK_ARG(p && g && dout && save && ws, "null argument");
   (void)x;
@@ -494,14 +541,18 @@ extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_pro
   carve_proj_bwd_ws(wa, c, B, w);
   B200_CHECK_ARG(wa.ok(), "workspace too small");
 
-  // transposed bf16 weights for the dgrad GEMMs
-  B200_TRY(b200_transpose_f32_bf16(p->ffn2_w, w.w2T, D, 4 * D, nullptr, stream));   // [D,4D] -> [4D, D]
-  B200_TRY(b200_transpose_f32_bf16(p->ffn1_w, w.w1T, 4 * D, D, nullptr, stream));   // [4D,D] -> [D, 4D]
-  B200_TRY(b200_transpose_f32_bf16(p->p_w, w.wpT, D, D, nullptr, stream));
-  B200_TRY(b200_transpose_f32_bf16_ld(p->k_w, w.wkvT, D, D, 2 * D, nullptr, stream));      // [D, 2D]: [Wk^T | Wv^T]
-  B200_TRY(b200_transpose_f32_bf16_ld(p->v_w, w.wkvT + D, D, D, 2 * D, nullptr, stream));
-  B200_TRY(b200_transpose_f32_bf16(p->q_w, w.wqT, D, D, nullptr, stream));
-  B200_TRY(b200_transpose_f32_bf16(p->conv_w, w.wcT, D, Cs, nullptr, stream));       // [D,Cs] -> [Cs, D]
+  // transposed bf16 weights for the dgrad GEMMs, one launch
+  {
+    PrepJobs jobs{};
+    jobs.add(PREP_TRANSPOSE16, p->ffn2_w, w.w2T, D, 4 * D, 0, D);        // [D,4D] -> [4D, D]
+    jobs.add(PREP_TRANSPOSE16, p->ffn1_w, w.w1T, 4 * D, D, 0, 4 * D);    // [4D,D] -> [D, 4D]
+    jobs.add(PREP_TRANSPOSE16, p->p_w, w.wpT, D, D, 0, D);
+    jobs.add(PREP_TRANSPOSE16, p->k_w, w.wkvT, D, D, 0, 2 * D);          // [D, 2D]: [Wk^T | Wv^T]
+    jobs.add(PREP_TRANSPOSE16, p->v_w, w.wkvT + D, D, D, 0, 2 * D);
+    jobs.add(PREP_TRANSPOSE16, p->q_w, w.wqT, D, D, 0, D);
+    jobs.add(PREP_TRANSPOSE16, p->conv_w, w.wcT, D, Cs, 0, D);           // [D,Cs] -> [Cs, D]
+    B200_TRY(launch_param_prep(jobs, st));
+  }
 
   // norm_2
   B200_TRY(b200_layernorm_bwd(dout, s.u32, p->ln2_w, s.mean2, s.rstd2, nullptr, w.du32, w.du16, g->ln2_w, g->ln2_b, Mi, D, stream));
@@ -557,10 +608,24 @@ extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_pro
   // with batch statistics the column sums of dy vanish identically (sum_r yhat = 0): BN cancels the conv bias
   // (losses/scalekd.py:199-200), so its gradient is exactly zero; only the running-statistics (eval) path needs the sum.
   if (!c->training) B200_TRY(b200_colsum(w.dy16, 1, D, g->conv_b, Mi, D, stream));
-  B200_TRY(Gemm(w.dy16, D, s.xt, Cs, D, Cs, Mi).out32(g->conv_w, Cs).wgrad().run(stream));
+  B200_TRY(Gemm(w.dy16, D, tokens ? static_cast<const bf16*>(tokens) : s.xt, Cs, D, Cs, Mi).out32(g->conv_w, Cs).wgrad().run(stream));
   if (dx) {
     B200_TRY(Gemm(w.dy16, D, w.wcT, D, Mi, Cs, D).out32(w.dxt32, Cs).run(stream));
     B200_TRY(b200_tokens_to_nchw(w.dxt32, dx, B, Cs, HW, dx_accumulate, stream));
   }
   return 0;
+}
+
+extern "C" int b200_projector_bwd(const b200_projector_config* c, const b200_projector_params* p,
+                                  const b200_projector_grads* g, const float* x, const float* query, const float* dout,
+                                  int B, float* dx, int dx_accumulate, float* dquery, const void* save, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  return projector_bwd_impl(c, p, g, x, query, dout, B, dx, dx_accumulate, dquery, save, ws, ws_bytes, nullptr, stream);
+}
+
+extern "C" int b200_projector_bwd_tok(const b200_projector_config* c, const b200_projector_params* p,
+                                      const b200_projector_grads* g, const float* x, const float* query,
+                                      const float* dout, int B, float* dx, int dx_accumulate, float* dquery,
+                                      const void* save, void* ws, size_t ws_bytes, const void* tokens, void* stream) {
+  return projector_bwd_impl(c, p, g, x, query, dout, B, dx, dx_accumulate, dquery, save, ws, ws_bytes, tokens, stream);
 }

@@ -114,6 +114,8 @@ class GraphedDistillStep:
         if not img.is_cuda:
             raise RuntimeError("GraphedDistillStep needs CUDA tensors: there is no CPU fallback")
         self.step, self.arena = step, arena
+        if arena is not None:
+            arena.enable_direct_accumulation(step.losses)
         self.img = img.detach().clone()
         self.feats = {k: v.detach().clone().requires_grad_(True) for k, v in feats.items()}
         side = torch.cuda.Stream()

@@ -62,6 +62,17 @@ class FlatGradArena:
             self.views.append(v)
         self.extra = self.buffer[off:]
 
+    @staticmethod
+    def enable_direct_accumulation(module: torch.nn.Module, on: bool = True) -> int:
+        """Let every sub-module that supports it (ScaleKD's AttentionProjector) add its parameter gradients straight
+        into the arena views from inside its backward kernels. Returns the number of modules switched."""
+        n = 0
+        for m in module.modules():
+            if hasattr(m, "accumulate_into_grad"):
+                m.accumulate_into_grad = bool(on)
+                n += 1
+        return n
+
     def zero(self) -> None:
         self.buffer.zero_()
         for p, v in zip(self.params, self.views):  # re-attach if an optimizer set grads to None

@@ -8,6 +8,7 @@ backward run in libb200distill.so; the nn.Modules below only own the fp32 master
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -71,7 +72,7 @@ class _ProjectorFn(torch.autograd.Function):
     _PARAM_ORDER (query_w last, possibly None)."""
 
     @staticmethod
-    def forward(ctx, proj, x, query, *params):
+    def forward(ctx, proj, tokens, x, query, *params):
         lib = L.load()
         cfg = proj._cfg(training=proj.training)
         B = x.shape[0]
@@ -88,9 +89,11 @@ class _ProjectorFn(torch.autograd.Function):
         save = torch.empty(lib.b200_projector_save_bytes(C.byref(cfg), B), dtype=torch.uint8, device=x.device)
         ws_bytes = lib.b200_projector_ws_bytes(C.byref(cfg), B)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        L.check(lib.b200_projector_fwd(C.byref(cfg), C.byref(pstruct), x.data_ptr(),
-                                       None if query is None else query.data_ptr(), B, out.data_ptr(), save.data_ptr(),
-                                       ws.data_ptr(), ws_bytes, _stream()), "projector_fwd")
+        L.check(lib.b200_projector_fwd_tok(C.byref(cfg), C.byref(pstruct), x.data_ptr(),
+                                           None if query is None else query.data_ptr(), B, out.data_ptr(),
+                                           save.data_ptr(), ws.data_ptr(), ws_bytes,
+                                           None if tokens is None else tokens.data_ptr(), _stream()), "projector_fwd")
+        ctx.tokens = tokens   # shared student tokens (ScaleKD tokenises preds_S once for both projectors)
         if proj.training:
             bn.num_batches_tracked += 1
         ctx.proj, ctx.cfg, ctx.pstruct = proj, cfg, pstruct
@@ -111,32 +114,43 @@ class _ProjectorFn(torch.autograd.Function):
         params = []
         for present in ctx.param_present:
             params.append(live.pop(0) if present else None)
-        # one flat zeroed buffer for every parameter gradient (the C side accumulates into it)
-        sizes = [0 if p is None else p.numel() for p in params]
-        flat = torch.zeros(sum(sizes), device=x.device, dtype=torch.float32)
+        # The C side ACCUMULATES every parameter gradient into the buffer it is given. Default: one flat zeroed buffer,
+        # returned to autograd. With `accumulate_into_grad` (set by the flat gradient arena / graphed step) the kernels
+        # add straight into the existing fp32 `.grad` (a view of the arena) and autograd gets None: that removes one
+        # AccumulateGrad add kernel per parameter (21 per projector) from the step.
+        direct = [bool(ctx.proj.accumulate_into_grad) and p is not None and p.grad is not None
+                  and p.grad.dtype == torch.float32 and p.grad.is_contiguous() and p.grad.is_cuda for p in params]
+        sizes = [0 if (p is None or d) else p.numel() for p, d in zip(params, direct)]
+        flat = torch.zeros(sum(sizes), device=x.device, dtype=torch.float32) if sum(sizes) else None
         grads, off = [], 0
         gstruct = L.ProjectorGrads()
-        for (field, _), p, n in zip(_PARAM_ORDER, params, sizes):
+        for (field, _), p, n, d in zip(_PARAM_ORDER, params, sizes, direct):
             if p is None:
                 grads.append(None)
                 setattr(gstruct, field, None)
+                continue
+            if d:
+                grads.append(None)
+                setattr(gstruct, field, p.grad.data_ptr())
                 continue
             gview = flat[off:off + n].view_as(p)
             off += n
             grads.append(gview)
             setattr(gstruct, field, gview.data_ptr())
-        need_dx = ctx.needs_input_grad[1]
-        need_dq = ctx.has_query and ctx.needs_input_grad[2]
+        need_dx = ctx.needs_input_grad[2]
+        need_dq = ctx.has_query and ctx.needs_input_grad[3]
         dx = torch.empty_like(x) if need_dx else None
         dquery = torch.empty_like(query) if need_dq else None
         ws_bytes = lib.b200_projector_ws_bytes(C.byref(cfg), B)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        L.check(lib.b200_projector_bwd(C.byref(cfg), C.byref(pstruct), C.byref(gstruct), x.data_ptr(),
-                                       None if query is None else query.data_ptr(), dout.data_ptr(), B,
-                                       None if dx is None else dx.data_ptr(), 0,
-                                       None if dquery is None else dquery.data_ptr(), save.data_ptr(), ws.data_ptr(),
-                                       ws_bytes, _stream()), "projector_bwd")
-        return (None, dx, dquery, *grads)
+        tokens = ctx.tokens
+        L.check(lib.b200_projector_bwd_tok(C.byref(cfg), C.byref(pstruct), C.byref(gstruct), x.data_ptr(),
+                                           None if query is None else query.data_ptr(), dout.data_ptr(), B,
+                                           None if dx is None else dx.data_ptr(), 0,
+                                           None if dquery is None else dquery.data_ptr(), save.data_ptr(),
+                                           ws.data_ptr(), ws_bytes, None if tokens is None else tokens.data_ptr(),
+                                           _stream()), "projector_bwd")
+        return (None, None, dx, dquery, *grads)
 
 
 class AttentionProjector(nn.Module):
@@ -145,6 +159,8 @@ class AttentionProjector(nn.Module):
     def __init__(self, student_dims, teacher_dims, hw_dims, pos_dims, window_shapes=(1, 1), self_query=True,
                  softmax_scale=1., num_heads=8):
         super().__init__()
+        # backward kernels add into existing .grad buffers instead of returning gradients (see _ProjectorFn.backward)
+        self.accumulate_into_grad = False
         self.hw_dims = tuple(int(v) for v in hw_dims)
         self.student_dims = int(student_dims)
         self.teacher_dims = int(teacher_dims)
@@ -186,7 +202,21 @@ class AttentionProjector(nn.Module):
             out.append(obj if ok else None)
         return out
 
-    def forward(self, x, query=None):
+    def tokenize(self, x: torch.Tensor) -> torch.Tensor:
+        """Token-major working copies of the student features (bf16 tokens + 3-term fp16 split), to be shared by the
+        two projectors of a ScaleKD via `forward(x, tokens=...)`."""
+        lib = L.load()
+        cfg = self._cfg(training=self.training)
+        B = x.shape[0]
+        x = x.contiguous().float()
+        tok = torch.empty(lib.b200_projector_tokens_bytes(C.byref(cfg), B), dtype=torch.uint8, device=x.device)
+        ws_bytes = lib.b200_projector_ws_bytes(C.byref(cfg), B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        L.check(lib.b200_projector_tokenize(C.byref(cfg), x.data_ptr(), B, tok.data_ptr(), ws.data_ptr(), ws_bytes,
+                                            _stream()), "projector_tokenize")
+        return tok
+
+    def forward(self, x, query=None, tokens=None):
         if query is None and self.query is None:
             raise NotImplementedError("There is no query!")
         if self.pos_attention.window_shapes != (1, 1):
@@ -196,7 +226,7 @@ class AttentionProjector(nn.Module):
         H, W = self.hw_dims
         if tuple(x.shape[1:]) != (self.student_dims, H, W):
             raise ValueError(f"expected student features [B,{self.student_dims},{H},{W}], got {tuple(x.shape)}")
-        return _ProjectorFn.apply(self, x.float(), None if query is None else query.float(), *self._params())
+        return _ProjectorFn.apply(self, tokens, x.float(), None if query is None else query.float(), *self._params())
 
 
 # ------------------------------------------------------------------------------------------------ loss terms
@@ -280,11 +310,27 @@ class ScaleKD(nn.Module):
         return {"spatial_loss": spat_loss, "frequency_loss": freq_loss, "spatial_similarity": spatial_similarity,
                 "frequency_similarity": frequency_similarity, "loss": spat_loss + freq_loss}
 
+    def _shared_tokens(self, preds_S: torch.Tensor):
+        """Both projectors read the same preds_S (scalekd.py:27-46, distillation_module.py:230-231): tokenise it once.
+        The cache holds the latest tensor only."""
+        H, W = self.projector_0.hw_dims
+        if not (preds_S.is_cuda and preds_S.dtype == torch.float32 and preds_S.is_contiguous()
+                and tuple(preds_S.shape[1:]) == (self.projector_0.student_dims, H, W)):
+            return None   # the projector's own checks / conversions apply
+        cached = getattr(self, "_tok_cache", None)
+        # identity of the tensor OBJECT (weak reference), not of its storage address: the caching allocator hands the
+        # same address to the next step's features
+        if cached is not None and cached[0]() is preds_S and cached[1] == (preds_S._version, self.training):
+            return cached[2]
+        tok = self.projector_0.tokenize(preds_S.detach())
+        self._tok_cache = (weakref.ref(preds_S), (preds_S._version, self.training), tok)
+        return tok
+
     def project_feat_spat(self, preds_S, query=None):
-        return self.projector_0(preds_S, query=query)
+        return self.projector_0(preds_S, query=query, tokens=self._shared_tokens(preds_S))
 
     def project_feat_freq(self, preds_S, query=None):
-        return self.projector_1(preds_S, query=query)
+        return self.projector_1(preds_S, query=query, tokens=self._shared_tokens(preds_S))
 
     def get_spat_loss(self, preds_S: torch.Tensor, preds_T: torch.Tensor):
         """alpha[0]/B * sum (S^ - T^)^2 over channel-normalised features, and the mean cosine (scalekd.py:67-92)."""

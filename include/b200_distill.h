@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 const char* b200_last_error(void);
 int b200_abi_version(void);
@@ -261,6 +261,21 @@ int b200_projector_fwd(const b200_projector_config* c, const b200_projector_para
 int b200_projector_bwd(const b200_projector_config* c, const b200_projector_params* p, const b200_projector_grads* g,
                        const float* x, const float* query, const float* dout, int B, float* dx, int dx_accumulate,
                        float* dquery, const void* save, void* ws, size_t ws_bytes, void* stream);
+
+/* Both projectors of one ScaleKD (projector_0 / projector_1, losses/scalekd.py:27-46) read the same preds_S. Tokenise it
+ * once -- NCHW fp32 -> token-major bf16 + the 3-term fp16 split the conv1x1 consumes -- and hand the result to the
+ * *_tok variants (tokens == NULL: identical to the plain entry points, which tokenise privately). The buffer must stay
+ * alive until both backward calls have run. ws: b200_projector_ws_bytes() is enough. */
+size_t b200_projector_tokens_bytes(const b200_projector_config* c, int B);
+int b200_projector_tokenize(const b200_projector_config* c, const float* x, int B, void* tokens, void* ws,
+                            size_t ws_bytes, void* stream);
+int b200_projector_fwd_tok(const b200_projector_config* c, const b200_projector_params* p, const float* x,
+                           const float* query, int B, float* out, void* save, void* ws, size_t ws_bytes,
+                           const void* tokens, void* stream);
+int b200_projector_bwd_tok(const b200_projector_config* c, const b200_projector_params* p,
+                           const b200_projector_grads* g, const float* x, const float* query, const float* dout, int B,
+                           float* dx, int dx_accumulate, float* dquery, const void* save, void* ws, size_t ws_bytes,
+                           const void* tokens, void* stream);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,34 @@ def test_scalekd_golden_tiny():
     assert int(sd["projector_0.proj_student.1.num_batches_tracked"]) == 1
 
 
+def test_direct_accumulation_into_grad_arena_matches_autograd_path():
+    """FlatGradArena.enable_direct_accumulation: the backward kernels add into the arena views of `.grad` instead of
+    returning gradients to autograd. Same numbers as the default path, twice accumulated = twice the gradient."""
+    scalekd, _, _ = _mods()
+    from dinov2_distillation_b200.distributed import FlatGradArena
+    g = torch.load(os.path.join(GOLDEN, "scalekd_tiny.pt"))
+    m = scalekd.ScaleKD(**g["kwargs"])
+    m.load_state_dict(g["state_dict"])
+    m = m.cuda().train()
+    S = g["preds_S"].cuda()
+    T = g["preds_T"].cuda()
+    m(S.clone().requires_grad_(True), T)["loss"].backward()
+    ref = {k: p.grad.clone() for k, p in m.named_parameters()}
+    arena = FlatGradArena(m.parameters())
+    assert FlatGradArena.enable_direct_accumulation(m) == 2
+    arena.zero()
+    for _ in range(2):
+        S2 = S.clone().requires_grad_(True)
+        m(S2, T)["loss"].backward()
+    for k, p in m.named_parameters():
+        assert p.grad.data_ptr() >= arena.buffer.data_ptr()
+        scale = ref[k].norm().item()
+        if scale < 1e-6:
+            continue
+        assert rel(p.grad, 2 * ref[k]) < 2e-3, (k, rel(p.grad, 2 * ref[k]))
+    assert rel(S2.grad, g["grad_S"]) <= GRAD_RTOL
+
+
 def test_scalekd_golden_cfg1():
     """BASELINE.json configs[0] loss shapes (vits14 + resnet_18 res5, B=2)."""
     scalekd, _, _ = _mods()
