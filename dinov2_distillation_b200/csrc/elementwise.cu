@@ -711,7 +711,7 @@ int launch_param_prep(const PrepJobs& jobs, cudaStream_t st) {
                      "prep job alignment");
     if (j.type == PREP_SPLIT3_RIGHT) B200_CHECK_ARG(j.cols % 4 == 0, "split3 needs K % 4 == 0");
   }
-  param_prep_kernel<<<dim3(48, (unsigned)jobs.n), dim3(32, 8), 0, st>>>(jobs);
+  param_prep_kernel<<<dim3(192, (unsigned)jobs.n), dim3(32, 8), 0, st>>>(jobs);
   B200_LAUNCH_OK();
   return 0;
 }

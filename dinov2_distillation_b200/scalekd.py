@@ -310,27 +310,25 @@ class ScaleKD(nn.Module):
         return {"spatial_loss": spat_loss, "frequency_loss": freq_loss, "spatial_similarity": spatial_similarity,
                 "frequency_similarity": frequency_similarity, "loss": spat_loss + freq_loss}
 
-    def _shared_tokens(self, preds_S: torch.Tensor):
-        """Both projectors read the same preds_S (scalekd.py:27-46, distillation_module.py:230-231): tokenise it once.
-        The cache holds the latest tensor only."""
+    def _tokenize(self, preds_S: torch.Tensor):
         H, W = self.projector_0.hw_dims
         if not (preds_S.is_cuda and preds_S.dtype == torch.float32 and preds_S.is_contiguous()
                 and tuple(preds_S.shape[1:]) == (self.projector_0.student_dims, H, W)):
             return None   # the projector's own checks / conversions apply
-        cached = getattr(self, "_tok_cache", None)
-        # identity of the tensor OBJECT (weak reference), not of its storage address: the caching allocator hands the
-        # same address to the next step's features
-        if cached is not None and cached[0]() is preds_S and cached[1] == (preds_S._version, self.training):
-            return cached[2]
-        tok = self.projector_0.tokenize(preds_S.detach())
-        self._tok_cache = (weakref.ref(preds_S), (preds_S._version, self.training), tok)
-        return tok
+        return self.projector_0.tokenize(preds_S.detach())
 
     def project_feat_spat(self, preds_S, query=None):
-        return self.projector_0(preds_S, query=query, tokens=self._shared_tokens(preds_S))
+        """Both projectors read the same preds_S (scalekd.py:27-46, distillation_module.py:230-231): it is tokenised
+        HERE, every call, and handed over ONCE to the project_feat_freq call that follows with the same tensor object
+        (never across steps: a step's input may be refreshed in place, e.g. the static buffers of a CUDA graph)."""
+        tok = self._tokenize(preds_S)
+        self._tok_handover = None if tok is None else (weakref.ref(preds_S), preds_S._version, tok)
+        return self.projector_0(preds_S, query=query, tokens=tok)
 
     def project_feat_freq(self, preds_S, query=None):
-        return self.projector_1(preds_S, query=query, tokens=self._shared_tokens(preds_S))
+        h, self._tok_handover = getattr(self, "_tok_handover", None), None
+        tok = h[2] if (h is not None and h[0]() is preds_S and h[1] == preds_S._version) else self._tokenize(preds_S)
+        return self.projector_1(preds_S, query=query, tokens=tok)
 
     def get_spat_loss(self, preds_S: torch.Tensor, preds_T: torch.Tensor):
         """alpha[0]/B * sum (S^ - T^)^2 over channel-normalised features, and the mean cosine (scalekd.py:67-92)."""

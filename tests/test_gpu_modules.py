@@ -281,6 +281,58 @@ def test_pipeline_golden_tiny():
     check_param_grads({k: (p.grad, g["grads"][k]) for k, p in step.losses.named_parameters() if k in g["grads"]})
 
 
+def test_graphed_step_follows_new_inputs_and_matches_eager():
+    """GraphedDistillStep (one CUDA graph per step, direct accumulation into the gradient arena, staged H2D inputs):
+    every replay must see the CURRENT images / student features -- nothing derived from the inputs may be cached
+    across steps -- and reproduce the eager step's losses and gradients."""
+    _, teacher, distill = _mods()
+    from dinov2_distillation_b200.distributed import FlatGradArena
+    from oracle import dinov2_ref
+    g = torch.load(os.path.join(GOLDEN, "pipeline_tiny.pt"))
+    cfg = dinov2_ref.VitCfg(*g["teacher_cfg"])
+    t, _, _ = _teacher_pair(cfg, seed=21, pos_grid=4)
+    t.model.load_state_dict(g["teacher_sd"])
+    step = distill.DistillationStep(None, t, g["specs"])
+    step.losses.load_state_dict(g["losses_sd"])
+    step = step.cuda().train()
+    img_a = g["img"].cuda()
+    feats_a = {k: v.cuda() for k, v in g["feats"].items()}
+    gen = torch.Generator().manual_seed(123)
+    img_b = torch.randn(img_a.shape, generator=gen).cuda()
+    feats_b = {k: torch.randn(v.shape, generator=gen).cuda() for k, v in feats_a.items()}
+
+    def eager(img, feats):
+        for p in step.losses.parameters():
+            p.grad = None
+        f = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+        out = step._compute_losses({"student": f, "teacher": step.teacher(img)["feature_map"]})
+        out["loss"].backward()
+        return ({k: v.detach().clone() for k, v in out.items()}, {k: v.grad.clone() for k, v in f.items()},
+                {k: p.grad.clone() for k, p in step.losses.named_parameters() if p.grad is not None})
+
+    ref_a, ref_b = eager(img_a, feats_a), eager(img_b, feats_b)
+    assert abs(ref_a[0]["loss"].item() - ref_b[0]["loss"].item()) > 1e-4   # the two batches are distinguishable
+    for p in step.losses.parameters():
+        p.grad = None
+    arena = FlatGradArena(step.losses.parameters())
+    graphed = distill.GraphedDistillStep(step, img_a, feats_a, arena)
+    for (img, feats), ref in (((img_b, feats_b), ref_b), ((img_a, feats_a), ref_a), ((img_b, feats_b), ref_b)):
+        out, fgrads = graphed(img, feats)
+        torch.cuda.synchronize()
+        for k, v in ref[0].items():
+            assert abs(out[k].item() - v.item()) <= 2e-3 * max(abs(v.item()), 1e-3), (k, out[k].item(), v.item())
+        for k, v in ref[1].items():
+            assert rel(fgrads[k], v) <= 2e-3, (k, rel(fgrads[k], v))
+        for k, p in step.losses.named_parameters():
+            if k in ref[2] and ref[2][k].norm().item() > 1e-6:
+                assert rel(p.grad, ref[2][k]) <= 5e-3, (k, rel(p.grad, ref[2][k]))
+    # staged inputs: host -> device on a side stream, consumed by the next replay
+    graphed.stage_inputs(img_a.cpu().pin_memory(), {k: v.cpu().pin_memory() for k, v in feats_a.items()})
+    out, _ = graphed.run_staged()
+    torch.cuda.synchronize()
+    assert abs(out["loss"].item() - ref_a[0]["loss"].item()) <= 2e-3 * abs(ref_a[0]["loss"].item())
+
+
 def test_cfg2_shapes_vs_oracle_port():
     """config.yaml losses (res4 heads 16 self-query + res5 heads 24) on vits14 dims, B=4, against the oracle port."""
     _, teacher, distill = _mods()
