@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "../../include/b200_distill.h"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 constexpr int ATT_BQ = 64;   // rows per CTA (4 warps x 16)
@@ -24,6 +26,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -225,15 +232,15 @@ attn_fwd_kernel(const AttnParams p) {
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float a0 = exp2f(m0 - mx0), a1 = exp2f(m1 - mx1);
+    const float a0 = ex2_fast(m0 - mx0), a1 = ex2_fast(m1 - mx1);
     m0 = mx0; m1 = mx1;
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-      s[nb][0] = exp2f(s[nb][0] - mx0);
-      s[nb][1] = exp2f(s[nb][1] - mx0);
-      s[nb][2] = exp2f(s[nb][2] - mx1);
-      s[nb][3] = exp2f(s[nb][3] - mx1);
+      s[nb][0] = ex2_fast(s[nb][0] - mx0);
+      s[nb][1] = ex2_fast(s[nb][1] - mx0);
+      s[nb][2] = ex2_fast(s[nb][2] - mx1);
+      s[nb][3] = ex2_fast(s[nb][3] - mx1);
       rs0 += s[nb][0] + s[nb][1];
       rs1 += s[nb][2] + s[nb][3];
     }
@@ -495,6 +502,242 @@ attn_bwd_dkv_kernel(const AttnParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward: fused
+// One CTA per (batch, head) when every key fits one pass (Nk <= 256: the 224-pixel configurations). S and dP are
+// computed ONCE per (query block, key) instead of once in each of the dQ and dK/dV kernels, and nothing is reduced
+// through atomics:
+//   warp w owns keys [32w, 32w+32): S^T and dP^T for its keys against the current 64-query block (mma.sync), P^T and
+//   dS^T in registers, dV += P^T dO and dK += dS^T Q accumulate in registers over the query blocks;
+//   dS^T of all keys is staged (bf16) in shared memory, and after one barrier the 8 warps split the 64 x hd block of
+//   dQ = dS K between them (contraction over ALL keys, so every dQ block is complete and written once).
+constexpr int ATTF_KEYS = 256;
+constexpr int ATTF_THREADS = 256;
+constexpr int ATTF_DS_PITCH = 64 + 8;
+
+template <int HDP>
+__device__ __forceinline__ void load_rows(__nv_bfloat16* s, const __nv_bfloat16* g, int rows, int row0, int nrows,
+                                          long long ts, int hd, int nthreads) {
+  constexpr int CH = HDP / 8;
+  constexpr int PITCH = HDP + ATT_PAD;
+  for (int i = threadIdx.x; i < rows * CH; i += nthreads) {
+    const int r = i / CH, c = i - r * CH;
+    const int gr = row0 + r;
+    const bool ok = (gr < nrows) && (c * 8 < hd);
+    const __nv_bfloat16* src = ok ? g + (long long)gr * ts + c * 8 : g;
+    cp_async16(s + r * PITCH + c * 8, src, ok ? 16 : 0);
+  }
+}
+
+// A fragments of 16 rows starting at `row0` of a row-major smem tile
+template <int HDP>
+__device__ __forceinline__ void load_a_frags_at(uint32_t (&a)[HDP / 16][4], const __nv_bfloat16* s, int row0, int lane) {
+  constexpr int PITCH = HDP + ATT_PAD;
+#pragma unroll
+  for (int kb = 0; kb < HDP / 16; ++kb)
+    ldsm_x4(a[kb], s + (row0 + (lane & 15)) * PITCH + kb * 16 + (lane >> 4) * 8);
+}
+
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+
+// fp16 -> bf16 copy of a [rows][HDP] tile (same padded layout); every thread converts 8 elements at a time
+template <int HDP>
+__device__ __forceinline__ void tile_h2b(__nv_bfloat16* dst, const __nv_bfloat16* src, int rows, int nthreads) {
+  constexpr int CH = HDP / 8;
+  constexpr int PITCH = HDP + ATT_PAD;
+  for (int i = threadIdx.x; i < rows * CH; i += nthreads) {
+    const int r = i / CH, c = i - r * CH;
+    uint4 u = *reinterpret_cast<const uint4*>(src + r * PITCH + c * 8);
+    u.x = h2_to_bf2(u.x); u.y = h2_to_bf2(u.y); u.z = h2_to_bf2(u.z); u.w = h2_to_bf2(u.w);
+    *reinterpret_cast<uint4*>(dst + r * PITCH + c * 8) = u;
+  }
+}
+
+template <int HDP, bool HALF>
+__global__ void __launch_bounds__(ATTF_THREADS, HDP == 16 ? 2 : 1)
+attn_bwd_fused_kernel(const AttnParams p) {
+  constexpr int PITCH = HDP + ATT_PAD;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [256][PITCH]
+  __nv_bfloat16* sV = sK + ATTF_KEYS * PITCH;                               // [256][PITCH]
+  __nv_bfloat16* sQ = sV + ATTF_KEYS * PITCH;                               // [2][64][PITCH]
+  __nv_bfloat16* sdO = sQ + 2 * 64 * PITCH;                                 // [2][64][PITCH]
+  __nv_bfloat16* sdS = sdO + 2 * 64 * PITCH;                                // [256][72]  dS^T (key-major)
+  float* sLse = reinterpret_cast<float*>(sdS + ATTF_KEYS * ATTF_DS_PITCH);  // [2][64]
+  float* sDl = sLse + 2 * 64;                                               // [2][64]
+  // fp16 forward operands (ScaleKD projector): bf16 copies of K and of the current Q block for the gradient products
+  __nv_bfloat16* sKb = HALF ? reinterpret_cast<__nv_bfloat16*>(sDl + 2 * 64) : sK;   // [256][PITCH]
+  __nv_bfloat16* sQb = HALF ? sKb + ATTF_KEYS * PITCH : sQ;                           // [64][PITCH]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3, mi = lane >> 3, rr = lane & 7;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const __nv_bfloat16* gq = p.q + (long long)b * p.q_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gdo = p.d_o + (long long)b * p.do_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gk = p.k + (long long)b * p.k_bs + (long long)h * p.hd;
+  const __nv_bfloat16* gv = p.v + (long long)b * p.v_bs + (long long)h * p.hd;
+  const float* lse = p.lse + ((long long)b * p.heads + h) * p.Nq;
+  const float* dl = p.delta + ((long long)b * p.heads + h) * p.Nq;
+  const float log2e = 1.4426950408889634f;
+
+  auto load_q_side = [&](int buf, int qt) {
+    load_rows<HDP>(sQ + buf * 64 * PITCH, gq, 64, qt * 64, p.Nq, p.q_ts, p.hd, ATTF_THREADS);
+    load_rows<HDP>(sdO + buf * 64 * PITCH, gdo, 64, qt * 64, p.Nq, p.do_ts, p.hd, ATTF_THREADS);
+    if (threadIdx.x < 64) {
+      const int r = qt * 64 + threadIdx.x;
+      sLse[buf * 64 + threadIdx.x] = r < p.Nq ? lse[r] * log2e : INFINITY;   // +inf: P = 0 for rows past Nq
+      sDl[buf * 64 + threadIdx.x] = r < p.Nq ? dl[r] : 0.f;
+    }
+  };
+
+  load_rows<HDP>(sK, gk, ATTF_KEYS, 0, p.Nk, p.k_ts, p.hd, ATTF_THREADS);
+  load_rows<HDP>(sV, gv, ATTF_KEYS, 0, p.Nk, p.v_ts, p.hd, ATTF_THREADS);
+  load_q_side(0, 0);
+  cp_async_commit();
+
+  const int key0 = warp * 32;
+  float dk[2][HDP / 8][4], dv[2][HDP / 8][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      dk[m][i][0] = dk[m][i][1] = dk[m][i][2] = dk[m][i][3] = 0.f;
+      dv[m][i][0] = dv[m][i][1] = dv[m][i][2] = dv[m][i][3] = 0.f;
+    }
+
+  const int n_qt = (p.Nq + 63) / 64;
+  const int ksteps = (p.Nk + 15) / 16;       // contraction length of the dQ product (keys)
+  for (int it = 0; it < n_qt; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < n_qt) {
+      load_q_side(buf ^ 1, it + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();   // (A) Q/dO block `it` (and K/V on the first pass) have landed; every warp is past dQ of block it-1
+    const __nv_bfloat16* tQ = sQ + buf * 64 * PITCH;
+    const __nv_bfloat16* tdO = sdO + buf * 64 * PITCH;
+    if constexpr (HALF) {
+      if (it == 0) tile_h2b<HDP>(sKb, sK, ATTF_KEYS, ATTF_THREADS);
+      tile_h2b<HDP>(sQb, tQ, 64, ATTF_THREADS);
+      __syncthreads();
+    }
+    const __nv_bfloat16* tQb = HALF ? sQb : tQ;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int krow = key0 + m * 16;
+      float st[8][4], dpt[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+        dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+      }
+      {
+        uint32_t ka[HDP / 16][4];
+        load_a_frags_at<HDP>(ka, sK, krow, lane);
+        mma_a_tT<HDP, HALF, false>(st, ka, tQ, lane);        // S^T[key, q] (fp16 operands when the forward ran fp16)
+      }
+      {
+        uint32_t va[HDP / 16][4];
+        load_a_frags_at<HDP>(va, sV, krow, lane);
+        if constexpr (HALF) cvt_frags_h2b<HDP>(va);          // V meets the bf16 gradient dO
+        mma_a_tT<HDP, false, false>(dpt, va, tdO, lane);     // dP^T[key, q]
+      }
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const float2 l2 = *reinterpret_cast<const float2*>(sLse + buf * 64 + nb * 8 + 2 * t4);
+        const float2 d2 = *reinterpret_cast<const float2*>(sDl + buf * 64 + nb * 8 + 2 * t4);
+        const float p0 = ex2_fast(fmaf(st[nb][0], p.scale_log2, -l2.x));
+        const float p1 = ex2_fast(fmaf(st[nb][1], p.scale_log2, -l2.y));
+        const float p2 = ex2_fast(fmaf(st[nb][2], p.scale_log2, -l2.x));
+        const float p3 = ex2_fast(fmaf(st[nb][3], p.scale_log2, -l2.y));
+        st[nb][0] = p0; st[nb][1] = p1; st[nb][2] = p2; st[nb][3] = p3;            // P^T
+        dpt[nb][0] = p0 * (dpt[nb][0] - d2.x); dpt[nb][1] = p1 * (dpt[nb][1] - d2.y);   // dS^T
+        dpt[nb][2] = p2 * (dpt[nb][2] - d2.x); dpt[nb][3] = p3 * (dpt[nb][3] - d2.y);
+      }
+      if (krow + 16 > p.Nk) {   // warp-uniform: keys past Nk (zero-filled rows) take no part
+        const bool kok0 = krow + g < p.Nk, kok1 = krow + g + 8 < p.Nk;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          if (!kok0) { st[nb][0] = st[nb][1] = 0.f; dpt[nb][0] = dpt[nb][1] = 0.f; }
+          if (!kok1) { st[nb][2] = st[nb][3] = 0.f; dpt[nb][2] = dpt[nb][3] = 0.f; }
+        }
+      }
+      mma_p_t<HDP, false, false>(dv[m], st, tdO, lane);      // dV += P^T dO
+      mma_p_t<HDP, false, false>(dk[m], dpt, tQb, lane);     // dK += dS^T Q
+      // stage dS^T (bf16) for the dQ product: rows = keys, columns = the 64 queries of this block
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const int col = nb * 8 + 2 * t4;
+        *reinterpret_cast<uint32_t*>(sdS + (krow + g) * ATTF_DS_PITCH + col) = pack_bf16(dpt[nb][0], dpt[nb][1]);
+        *reinterpret_cast<uint32_t*>(sdS + (krow + g + 8) * ATTF_DS_PITCH + col) = pack_bf16(dpt[nb][2], dpt[nb][3]);
+      }
+    }
+    __syncthreads();   // (B) dS^T of every key is staged
+    // dQ[64 q, hd] = dS[64 q, keys] K[keys, hd]: warp -> (16-row query tile, slice of the hd columns)
+    {
+      constexpr int NBW = HDP / 16;            // 8-column blocks per warp (the two warps of a query tile split hd)
+      const int mt = warp & 3, nb0 = (warp >> 2) * NBW;
+      float dq[NBW][4];
+#pragma unroll
+      for (int i = 0; i < NBW; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+      for (int ks = 0; ks < ksteps; ++ks) {
+        uint32_t a[4];
+        // A = dS (row = query, k = key), read transposed from the key-major staging tile
+        ldsm_x4_t(a, sdS + (ks * 16 + (mi >> 1) * 8 + rr) * ATTF_DS_PITCH + mt * 16 + (mi & 1) * 8);
+        if constexpr (NBW == 1) {
+          uint32_t bfr[2];
+          ldsm_x2_t(bfr, sKb + (ks * 16 + (lane & 15)) * PITCH + nb0 * 8);
+          mma_bf16(dq[0], a, bfr[0], bfr[1]);
+        } else {
+#pragma unroll
+          for (int nb = 0; nb < NBW; nb += 2) {
+            uint32_t bfr[4];
+            ldsm_x4_t(bfr, sKb + (ks * 16 + (mi & 1) * 8 + rr) * PITCH + (nb0 + nb + (mi >> 1)) * 8);
+            mma_bf16(dq[nb], a, bfr[0], bfr[1]);
+            mma_bf16(dq[nb + 1], a, bfr[2], bfr[3]);
+          }
+        }
+      }
+      const int r0 = it * 64 + mt * 16 + g, r1 = r0 + 8;
+      __nv_bfloat16* gdq = p.dq + (long long)b * p.dq_bs + (long long)h * p.hd;
+#pragma unroll
+      for (int nb = 0; nb < NBW; ++nb) {
+        const int col = (nb0 + nb) * 8 + 2 * t4;
+        if (col < p.hd) {
+          if (r0 < p.Nq) *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * p.dq_ts + col) = pack_bf16(dq[nb][0] * p.scale, dq[nb][1] * p.scale);
+          if (r1 < p.Nq) *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * p.dq_ts + col) = pack_bf16(dq[nb][2] * p.scale, dq[nb][3] * p.scale);
+        }
+      }
+    }
+  }
+  __nv_bfloat16* gdk = p.dk + (long long)b * p.dk_bs + (long long)h * p.hd;
+  __nv_bfloat16* gdv = p.dv + (long long)b * p.dv_bs + (long long)h * p.hd;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int kr0 = key0 + m * 16 + g, kr1 = kr0 + 8;
+#pragma unroll
+    for (int nb = 0; nb < HDP / 8; ++nb) {
+      const int col = nb * 8 + 2 * t4;
+      if (col < p.hd) {
+        if (kr0 < p.Nk) {
+          *reinterpret_cast<uint32_t*>(gdk + (long long)kr0 * p.dk_ts + col) = pack_bf16(dk[m][nb][0] * p.scale, dk[m][nb][1] * p.scale);
+          *reinterpret_cast<uint32_t*>(gdv + (long long)kr0 * p.dv_ts + col) = pack_bf16(dv[m][nb][0], dv[m][nb][1]);
+        }
+        if (kr1 < p.Nk) {
+          *reinterpret_cast<uint32_t*>(gdk + (long long)kr1 * p.dk_ts + col) = pack_bf16(dk[m][nb][2] * p.scale, dk[m][nb][3] * p.scale);
+          *reinterpret_cast<uint32_t*>(gdv + (long long)kr1 * p.dv_ts + col) = pack_bf16(dv[m][nb][2], dv[m][nb][3]);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static int fill_params(const b200_attn_desc* d, AttnParams& p, bool bwd) {
   B200_CHECK_ARG(d != nullptr, "null descriptor");
@@ -567,6 +810,21 @@ static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
   const int prof = prof_begin(st);
   attn_delta_kernel<HALF><<<(unsigned)gd, 256, 0, st>>>(p);
   B200_LAUNCH_OK();
+  if constexpr (HDP == 16 || HDP == 32 || HDP == 64) {
+    static int fused_on = -1;
+    if (fused_on < 0) { const char* e = getenv("B200_ATTN_BWD_FUSED"); fused_on = (e && e[0] == '0') ? 0 : 1; }
+    if (fused_on && p.Nk <= ATTF_KEYS) {
+      constexpr size_t smem_f = size_t(2 * ATTF_KEYS + 4 * 64) * (HDP + ATT_PAD) * 2 + size_t(ATTF_KEYS) * ATTF_DS_PITCH * 2 +
+                                4 * 64 * sizeof(float) + (HALF ? size_t(ATTF_KEYS + 64) * (HDP + ATT_PAD) * 2 : 0);
+      static bool once_f = false;
+      if (!once_f) { B200_TRY(set_smem(attn_bwd_fused_kernel<HDP, HALF>, smem_f)); once_f = true; }
+      dim3 gf((unsigned)p.heads, (unsigned)p.B);
+      attn_bwd_fused_kernel<HDP, HALF><<<gf, ATTF_THREADS, smem_f, st>>>(p);
+      prof_end(prof, st, 8.0 * p.B * p.heads * (double)p.Nq * p.Nk * p.hd, 2);
+      B200_LAUNCH_OK();
+      return 0;
+    }
+  }
   dim3 gq((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
   attn_bwd_dq_kernel<HDP, HALF><<<gq, ATT_THREADS, smem_dq, st>>>(p);
   B200_LAUNCH_OK();
