@@ -213,18 +213,13 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
         if (next_ok && lane == 0) { mbar_expect_tx(xbar, UNIT_BYTES); v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + 64, row0); } }
       continue;
     }
-    const bool full = c0 + 32 <= p.N;
+    // (N is a multiple of 32 on this path -- launch_gemm_v2 sends ragged N to the first-generation kernel -- so there
+    // is no per-column tail code: the if-converted tail branches were ~170 predicated-off issue slots per unit)
     if (p.bias != nullptr && first_split) {
-      if (full) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < p.N) v[j] += __ldg(p.bias + c0 + j);
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     }
     if constexpr (!F32) {
@@ -310,16 +305,10 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
     } else {
       // ---- fp32 output
       if (p.col_scale != nullptr) {
-        if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + c0 + j));
-            v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < p.N) v[j] *= __ldg(p.col_scale + c0 + j);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + c0 + j));
+          v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
         }
       }
       if (use_x) {
@@ -615,7 +604,7 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   if (d->out_bf16_pre && (!al16(d->out_bf16_pre) || d->ldo16_pre % 8 != 0)) return 1;
   if (d->bias && !al16(d->bias)) return 1;
   if (d->col_scale && !al16(d->col_scale)) return 1;
-  if (d->N % 4 != 0) return 1;
+  if (d->N % 32 != 0) return 1;   // ragged N: first-generation kernel (per-column tail handling)
 
   static const int pair_mode = gemm_env_int("B200_GEMM_2CTA", -1);   // -1 auto, 0 never, 1 whenever possible
   bool pair = false;
