@@ -51,6 +51,7 @@ class AttnDesc(C.Structure):
         ("dk", c_vp), ("dk_bs", c_ll), ("dk_ts", c_ll),
         ("dv", c_vp), ("dv_bs", c_ll), ("dv_ts", c_ll),
         ("qkvo_is_fp16", C.c_int),
+        ("dq_colsum", c_fp), ("dk_colsum", c_fp), ("dv_colsum", c_fp),
     ]
 
 
@@ -117,6 +118,7 @@ SIGNATURES = {
     "b200_write_cls_rows": (_i, [c_fp, c_fp, c_fp, _i, _i, _i, c_vp]),
     "b200_layernorm_fwd": (_i, [c_fp, c_fp, c_fp, _f, c_fp, c_vp, c_fp, c_fp, _i, _i, _i, _i, _i, c_vp]),
     "b200_layernorm_bwd": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, c_fp, c_fp, _i, _i, c_vp]),
+    "b200_layernorm_bwd_colsum": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, c_fp, c_fp, c_fp, _i, _i, c_vp]),
     "b200_bn_stats": (_i, [c_fp, c_fp, _i, _i, c_vp]),
     "b200_bn_finalize": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, _f, _f, _i, _i, c_vp]),
     "b200_bn_relu_pos_fwd": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_vp, _i, _i, _i, _i, c_vp]),

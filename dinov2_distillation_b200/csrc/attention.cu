@@ -160,6 +160,7 @@ struct AttnParams {
   const __nv_bfloat16* o_in;
   __nv_bfloat16 *o, *dq, *dk, *dv;
   float *lse, *delta;
+  float *dq_colsum, *dk_colsum, *dv_colsum;   // optional fp32 [heads*hd] accumulators (bias gradients of the q/k/v projections)
   long long q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, do_bs, do_ts, dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts;
   int B, heads, Nq, Nk, hd;
   float scale, scale_log2;
@@ -569,7 +570,8 @@ attn_bwd_fused_kernel(const AttnParams p) {
   float* sLse = reinterpret_cast<float*>(sdS + ATTF_KEYS * ATTF_DS_PITCH);  // [2][64]
   float* sDl = sLse + 2 * 64;                                               // [2][64]
   // fp16 forward operands (ScaleKD projector): bf16 copies of K and of the current Q block for the gradient products
-  __nv_bfloat16* sKb = HALF ? reinterpret_cast<__nv_bfloat16*>(sDl + 2 * 64) : sK;   // [256][PITCH]
+  float* sSum = sDl + 2 * 64;                                               // [3][64] column sums of dQ / dK / dV
+  __nv_bfloat16* sKb = HALF ? reinterpret_cast<__nv_bfloat16*>(sSum + 3 * 64) : sK;  // [256][PITCH]
   __nv_bfloat16* sQb = HALF ? sKb + ATTF_KEYS * PITCH : sQ;                           // [64][PITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -597,6 +599,8 @@ attn_bwd_fused_kernel(const AttnParams p) {
   load_rows<HDP>(sV, gv, ATTF_KEYS, 0, p.Nk, p.v_ts, p.hd, ATTF_THREADS);
   load_q_side(0, 0);
   cp_async_commit();
+  const bool want_sums = p.dk_colsum != nullptr;   // the three go together
+  if (want_sums && threadIdx.x < 3 * 64) sSum[threadIdx.x] = 0.f;   // (ordered before use by the barriers below)
 
   const int key0 = warp * 32;
   float dk[2][HDP / 8][4], dv[2][HDP / 8][4];
@@ -610,6 +614,9 @@ attn_bwd_fused_kernel(const AttnParams p) {
 
   const int n_qt = (p.Nq + 63) / 64;
   const int ksteps = (p.Nk + 15) / 16;       // contraction length of the dQ product (keys)
+  float dq_cs[HDP / 16][2];                  // this lane's column partials of dQ over all query blocks
+#pragma unroll
+  for (int i = 0; i < HDP / 16; ++i) { dq_cs[i][0] = 0.f; dq_cs[i][1] = 0.f; }
   for (int it = 0; it < n_qt; ++it) {
     const int buf = it & 1;
     if (it + 1 < n_qt) {
@@ -707,12 +714,54 @@ attn_bwd_fused_kernel(const AttnParams p) {
       const int r0 = it * 64 + mt * 16 + g, r1 = r0 + 8;
       __nv_bfloat16* gdq = p.dq + (long long)b * p.dq_bs + (long long)h * p.hd;
 #pragma unroll
+      for (int nb = 0; nb < NBW; ++nb) {   // (rows past Nq carry dS = 0)
+        dq_cs[nb][0] += dq[nb][0] + dq[nb][2];
+        dq_cs[nb][1] += dq[nb][1] + dq[nb][3];
+      }
+#pragma unroll
       for (int nb = 0; nb < NBW; ++nb) {
         const int col = (nb0 + nb) * 8 + 2 * t4;
         if (col < p.hd) {
           if (r0 < p.Nq) *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * p.dq_ts + col) = pack_bf16(dq[nb][0] * p.scale, dq[nb][1] * p.scale);
           if (r1 < p.Nq) *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * p.dq_ts + col) = pack_bf16(dq[nb][2] * p.scale, dq[nb][3] * p.scale);
         }
+      }
+    }
+  }
+  if (want_sums) {
+    // bias gradients of the q / k / v projections: column sums over this head's rows, reduced over the 8 lanes that
+    // share a column pair, then over the warps in shared memory, then ONE global atomic per column per CTA
+    constexpr int NBW = HDP / 16;
+    const int nb0 = (warp >> 2) * NBW;
+#pragma unroll
+    for (int nb = 0; nb < NBW; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float v = dq_cs[nb][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0) atomicAdd(&sSum[(nb0 + nb) * 8 + 2 * t4 + e], v * p.scale);
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < HDP / 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float vk = (dk[0][nb][e] + dk[0][nb][e + 2]) + (dk[1][nb][e] + dk[1][nb][e + 2]);
+        float vv = (dv[0][nb][e] + dv[0][nb][e + 2]) + (dv[1][nb][e] + dv[1][nb][e + 2]);
+        vk += __shfl_xor_sync(0xffffffffu, vk, 4); vk += __shfl_xor_sync(0xffffffffu, vk, 8); vk += __shfl_xor_sync(0xffffffffu, vk, 16);
+        vv += __shfl_xor_sync(0xffffffffu, vv, 4); vv += __shfl_xor_sync(0xffffffffu, vv, 8); vv += __shfl_xor_sync(0xffffffffu, vv, 16);
+        if (g == 0) {
+          atomicAdd(&sSum[64 + nb * 8 + 2 * t4 + e], vk * p.scale);
+          atomicAdd(&sSum[128 + nb * 8 + 2 * t4 + e], vv);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * 64) {
+      const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+      if (col < p.hd) {
+        float* dst = which == 0 ? p.dq_colsum : (which == 1 ? p.dk_colsum : p.dv_colsum);
+        atomicAdd(dst + h * p.hd + col, sSum[threadIdx.x]);
       }
     }
   }
@@ -767,6 +816,9 @@ static int fill_params(const b200_attn_desc* d, AttnParams& p, bool bwd) {
     p.dq = static_cast<__nv_bfloat16*>(d->dq); p.dq_bs = d->dq_bs; p.dq_ts = d->dq_ts;
     p.dk = static_cast<__nv_bfloat16*>(d->dk); p.dk_bs = d->dk_bs; p.dk_ts = d->dk_ts;
     p.dv = static_cast<__nv_bfloat16*>(d->dv); p.dv_bs = d->dv_bs; p.dv_ts = d->dv_ts;
+    B200_CHECK_ARG((d->dq_colsum != nullptr) == (d->dk_colsum != nullptr) && (d->dk_colsum != nullptr) == (d->dv_colsum != nullptr),
+                   "dq_colsum / dk_colsum / dv_colsum go together");
+    p.dq_colsum = d->dq_colsum; p.dk_colsum = d->dk_colsum; p.dv_colsum = d->dv_colsum;
   }
   return 0;
 }
@@ -815,7 +867,7 @@ static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
     if (fused_on < 0) { const char* e = getenv("B200_ATTN_BWD_FUSED"); fused_on = (e && e[0] == '0') ? 0 : 1; }
     if (fused_on && p.Nk <= ATTF_KEYS) {
       constexpr size_t smem_f = size_t(2 * ATTF_KEYS + 4 * 64) * (HDP + ATT_PAD) * 2 + size_t(ATTF_KEYS) * ATTF_DS_PITCH * 2 +
-                                4 * 64 * sizeof(float) + (HALF ? size_t(ATTF_KEYS + 64) * (HDP + ATT_PAD) * 2 : 0);
+                                7 * 64 * sizeof(float) + (HALF ? size_t(ATTF_KEYS + 64) * (HDP + ATT_PAD) * 2 : 0);
       static bool once_f = false;
       if (!once_f) { B200_TRY(set_smem(attn_bwd_fused_kernel<HDP, HALF>, smem_f)); once_f = true; }
       dim3 gf((unsigned)p.heads, (unsigned)p.B);
@@ -832,6 +884,14 @@ static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
   attn_bwd_dkv_kernel<HDP, HALF><<<gk, ATT_THREADS, smem_dkv, st>>>(p);
   prof_end(prof, st, 8.0 * p.B * p.heads * (double)p.Nq * p.Nk * p.hd, 2);
   B200_LAUNCH_OK();
+  if (p.dk_colsum != nullptr) {   // two-kernel path: the column sums come from a pass over the bf16 outputs
+    const int cols = p.heads * p.hd;
+    for (int bb = 0; bb < p.B; ++bb) {
+      B200_TRY(b200_colsum(p.dq + (long long)bb * p.dq_bs, 1, p.dq_ts, p.dq_colsum, p.Nq, cols, st));
+      B200_TRY(b200_colsum(p.dk + (long long)bb * p.dk_bs, 1, p.dk_ts, p.dk_colsum, p.Nk, cols, st));
+      B200_TRY(b200_colsum(p.dv + (long long)bb * p.dv_bs, 1, p.dv_ts, p.dv_colsum, p.Nk, cols, st));
+    }
+  }
   return 0;
 }
 template <int HDP>

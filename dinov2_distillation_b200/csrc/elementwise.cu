@@ -228,13 +228,13 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dw,
-                     float* __restrict__ db, int rows, int D) {
+                     float* __restrict__ db, float* __restrict__ dx_colsum, int rows, int D) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_d = 1.0f / (float)D;
-  float4 aw[NV], ab[NV];
+  float4 aw[NV], ab[NV], ao[NV];   // column partials: dw, db and (dx_colsum) the output itself
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { aw[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < NV; ++i) { aw[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ao[i] = make_float4(0, 0, 0, 0); }
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
     const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)r * D);
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)r * D);
@@ -273,6 +273,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
           const float4 rr = reinterpret_cast<const float4*>(dres + (long long)r * D)[c4];
           o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
         }
+        if (dx_colsum) { ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w; }
         if (dx) reinterpret_cast<float4*>(dx + (long long)r * D)[c4] = o;
         if (dx16) {
           uint2 u;
@@ -304,6 +305,23 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       }
       atomicAdd(dw + c, sw);
       atomicAdd(db + c, sb);
+    }
+    if (dx_colsum) __syncthreads();
+  }
+  if (dx_colsum) {
+    // column sums of the OUTPUT (the bias gradient of the linear layer that produced this LayerNorm's input)
+    extern __shared__ float red[];
+    const int wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) reinterpret_cast<float4*>(red + (long long)wid * D)[c4] = ao[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float so = 0.f;
+      for (int k = 0; k < warps_per_block; ++k) so += red[(long long)k * D + c];
+      atomicAdd(dx_colsum + c, so);
     }
   }
 }
@@ -598,16 +616,16 @@ static int launch_ln_fwd(const float* x, const float* w, const float* b, float e
 
 template <int NV>
 static int launch_ln_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
-                         const float* dres, float* dx, void* dx16, float* dw, float* db, int rows, int D,
-                         cudaStream_t st) {
+                         const float* dres, float* dx, void* dx16, float* dw, float* db, float* dx_colsum, int rows,
+                         int D, cudaStream_t st) {
   auto kern = layernorm_bwd_kernel<NV>;
-  size_t smem = dw ? size_t(8) * 2 * D * sizeof(float) : 0;
+  size_t smem = dw ? size_t(8) * 2 * D * sizeof(float) : (dx_colsum ? size_t(8) * D * sizeof(float) : 0);
   if (smem > 48 * 1024) {
     static bool set = false;
     if (!set) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
   }
-  const int grid = grid_for(rows, 8 * 4, dw ? 2 : 8);
-  kern<<<grid, 256, smem, st>>>(dy, x, w, mean, rstd, dres, dx, static_cast<__nv_bfloat16*>(dx16), dw, db, rows, D);
+  const int grid = grid_for(rows, 8 * 4, (dw || dx_colsum) ? 2 : 8);
+  kern<<<grid, 256, smem, st>>>(dy, x, w, mean, rstd, dres, dx, static_cast<__nv_bfloat16*>(dx16), dw, db, dx_colsum, rows, D);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -853,15 +871,21 @@ extern "C" int b200_layernorm_fwd(const float* x, const float* w, const float* b
 extern "C" int b200_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean,
                                   const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dw, float* db,
                                   int rows, int D, void* stream) {
+  return b200_layernorm_bwd_colsum(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, nullptr, rows, D, stream);
+}
+
+extern "C" int b200_layernorm_bwd_colsum(const float* dy, const float* x, const float* w, const float* mean,
+                                         const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dw,
+                                         float* db, float* dx_colsum, int rows, int D, void* stream) {
   B200_CHECK_ARG(dy && x && w && mean && rstd && rows > 0, "bad args");
   B200_CHECK_ARG((dw == nullptr) == (db == nullptr), "dw and db go together");
   B200_CHECK_ARG(D % 4 == 0 && D > 0 && D <= LN_MAX_V4 * 128, "D must be a multiple of 4 and <= 1536");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nv = (int)cdiv(D, 128);
-  if (nv <= 3) return launch_ln_bwd<3>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, rows, D, st);
-  if (nv <= 6) return launch_ln_bwd<6>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, rows, D, st);
-  if (nv <= 8) return launch_ln_bwd<8>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, rows, D, st);
-  return launch_ln_bwd<12>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, rows, D, st);
+  if (nv <= 3) return launch_ln_bwd<3>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, dx_colsum, rows, D, st);
+  if (nv <= 6) return launch_ln_bwd<6>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, dx_colsum, rows, D, st);
+  if (nv <= 8) return launch_ln_bwd<8>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, dx_colsum, rows, D, st);
+  return launch_ln_bwd<12>(dy, x, w, mean, rstd, dres, dx, dx_bf16, dw, db, dx_colsum, rows, D, st);
 }
 
 extern "C" int b200_bn_stats(const float* y, float* sums, int M, int D, void* stream) {

@@ -555,18 +555,19 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   }
 
   // norm_2
-  B200_TRY(b200_layernorm_bwd(dout, s.u32, p->ln2_w, s.mean2, s.rstd2, nullptr, w.du32, w.du16, g->ln2_w, g->ln2_b, Mi, D, stream));
+  // (the column sums of du are the ffn2 bias gradient: produced by the same pass)
+  B200_TRY(b200_layernorm_bwd_colsum(dout, s.u32, p->ln2_w, s.mean2, s.rstd2, nullptr, w.du32, w.du16, g->ln2_w, g->ln2_b,
+                                     g->ffn2_b, Mi, D, stream));
   // FFN: u = g + W2 relu(W1 g + b1) + b2
-  B200_TRY(b200_colsum(w.du32, 0, D, g->ffn2_b, Mi, D, stream));
   B200_TRY(wgrad_from_fp16(w.du16, D, s.h, M, 4 * D, w.act16, g->ffn2_w, D, stream));
   B200_TRY(Gemm(w.du16, D, w.w2T, D, Mi, 4 * D, D).aux(s.h, 4 * D, B200_AUX_DRELU).aux_fp16().out16(w.dh16, 4 * D).run(stream));
   B200_TRY(b200_colsum(w.dh16, 1, 4 * D, g->ffn1_b, Mi, 4 * D, stream));
   B200_TRY(wgrad_from_fp16(w.dh16, 4 * D, s.g, M, D, w.act16, g->ffn1_w, 4 * D, stream));
   B200_TRY(Gemm(w.dh16, 4 * D, w.w1T, 4 * D, Mi, D, 4 * D).residual(w.du32, D).out32(w.dg32, D).run(stream));
   // norm
-  B200_TRY(b200_layernorm_bwd(w.dg32, s.f32, p->ln1_w, s.mean1, s.rstd1, nullptr, w.df32, w.df16, g->ln1_w, g->ln1_b, Mi, D, stream));
-  // attention output projection: f = Wp o + bp + z
-  B200_TRY(b200_colsum(w.df32, 0, D, g->p_b, Mi, D, stream));
+  B200_TRY(b200_layernorm_bwd_colsum(w.dg32, s.f32, p->ln1_w, s.mean1, s.rstd1, nullptr, w.df32, w.df16, g->ln1_w, g->ln1_b,
+                                     g->p_b, Mi, D, stream));
+  // attention output projection: f = Wp o + bp + z   (p_b gradient = column sums of df, fused above)
   B200_TRY(wgrad_from_fp16(w.df16, D, s.o, M, D, w.act16, g->p_w, D, stream));
   B200_TRY(Gemm(w.df16, D, w.wpT, D, Mi, D, D).out16(w.do16, D).run(stream));
   // attention core (q/k/v/o fp16 from the forward; gradients bf16)
@@ -577,22 +578,21 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   ad.dq = w.dq16; ad.dq_bs = (long long)HW * D; ad.dq_ts = D;
   ad.dk = w.dkv16; ad.dv = w.dkv16 + D;
   ad.dk_bs = ad.dv_bs = (long long)HW * 2 * D; ad.dk_ts = ad.dv_ts = 2 * D;
+  // q / k / v bias gradients = column sums of dq / dk / dv over every (image, token): produced inside the attention
+  // backward (for a batch-invariant self query the sum over images of dq is the same quantity)
+  ad.dq_colsum = g->q_b; ad.dk_colsum = g->k_b; ad.dv_colsum = g->v_b;
   B200_TRY(b200_attention_bwd(&ad, stream));
   // q path
   if (ext) {
-    B200_TRY(b200_colsum(w.dq16, 1, D, g->q_b, Mi, D, stream));
     B200_TRY(wgrad_from_fp16(w.dq16, D, s.qsrc, M, D, w.act16, g->q_w, D, stream));
     if (dquery) B200_TRY(Gemm(w.dq16, D, w.wqT, D, Mi, D, D).out32(dquery, D).run(stream));
   } else {
     B200_TRY(b200_batch_sum_bf16(w.dq16, w.dqs32, w.dqs16, B, (long long)HW * D, stream));
-    B200_TRY(b200_colsum(w.dqs32, 0, D, g->q_b, HW, D, stream));
     B200_TRY(wgrad_from_fp16(w.dqs16, D, s.qsrc, HW, D, w.act16, g->q_w, D, stream));
     if (g->query_w)
       B200_TRY(Gemm(w.dqs16, D, w.wqT, D, HW, D, D).residual(g->query_w, D).out32(g->query_w, D).run(stream));
   }
   // k / v path
-  B200_TRY(b200_colsum(w.dkv16, 1, 2 * D, g->k_b, Mi, D, stream));
-  B200_TRY(b200_colsum(w.dkv16 + D, 1, 2 * D, g->v_b, Mi, D, stream));
   B200_TRY(wgrad_from_fp16(w.dkv16, 2 * D, s.z, M, D, w.act16, g->k_w, D, stream));
   B200_TRY(Gemm(w.dkv16 + D, 2 * D, w.act16, D, D, D, Mi).out32(g->v_w, D).wgrad().run(stream));  // act16 still holds z
   B200_TRY(Gemm(w.dkv16, 2 * D, w.wkvT, 2 * D, Mi, D, 2 * D).residual(w.df32, D).out32(w.dz32, D).run(stream));

@@ -112,6 +112,12 @@ int b200_layernorm_fwd(const float* x, const float* w, const float* b, float eps
 int b200_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                        const float* dres, float* dx, void* dx_bf16, float* dw, float* db, int rows, int D,
                        void* stream);
+/* same; dx_colsum (fp32 [D], accumulated, may be NULL) additionally receives the column sums of the output dx: the bias
+ * gradient of the linear layer feeding this LayerNorm (losses/scalekd.py:243-245: ffn2 / proj biases), which saves a
+ * separate pass over dx. */
+int b200_layernorm_bwd_colsum(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                              const float* dres, float* dx, void* dx_bf16, float* dw, float* db, float* dx_colsum,
+                              int rows, int D, void* stream);
 
 /* BatchNorm2d on token-major y [M, D] (training statistics over M = B*H*W rows). losses/scalekd.py:200
  * stats: sums[0:D] = sum_r y, sums[D:2D] = sum_r y^2 (buffer must be zeroed).  */
@@ -166,6 +172,9 @@ typedef struct b200_attn_desc {
   void* dv; long long dv_bs, dv_ts;       /* bf16 */
   /* 1: q, k, v, o are fp16 (ScaleKD projector forward precision); gradients d_o/dq/dk/dv are always bf16 */
   int qkvo_is_fp16;
+  /* backward only, optional (all three or none): fp32 [heads*hd], ACCUMULATED column sums of dq / dk / dv over
+   * (batch, tokens) -- the bias gradients of the q / k / v projections (losses/scalekd.py:277-279) */
+  float* dq_colsum; float* dk_colsum; float* dv_colsum;
 } b200_attn_desc;
 int b200_attention_fwd(const b200_attn_desc* d, void* stream);
 int b200_attention_bwd(const b200_attn_desc* d, void* stream);
