@@ -171,6 +171,7 @@ struct AttnParams {
 template <int HDP, bool HALF>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const AttnParams p) {
+  pdl_wait();   // PDL (common.cuh): launched through launch_pdl(); multi-wave grid, so no early pdl_trigger()
   constexpr int PITCH = HDP + ATT_PAD;
   constexpr int TILE = 64 * PITCH;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -279,6 +280,7 @@ attn_fwd_kernel(const AttnParams p) {
 // delta[b, h, q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
 template <bool HALF>
 __global__ void attn_delta_kernel(const AttnParams p) {
+  pdl_wait();   // PDL (common.cuh): launched through launch_pdl(); multi-wave grid, so no early pdl_trigger()
   const long long n = (long long)p.B * p.Nq * p.heads;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int h = (int)(i % p.heads);
@@ -307,6 +309,7 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 template <int HDP, bool HALF>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const AttnParams p) {
+  pdl_wait();   // PDL (common.cuh): launched through launch_pdl(); multi-wave grid, so no early pdl_trigger()
   constexpr int PITCH = HDP + ATT_PAD;
   constexpr int TILE = 64 * PITCH;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -397,6 +400,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
 template <int HDP, bool HALF>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const AttnParams p) {
+  pdl_wait();   // PDL (common.cuh): launched through launch_pdl(); multi-wave grid, so no early pdl_trigger()
   constexpr int PITCH = HDP + ATT_PAD;
   constexpr int TILE = 64 * PITCH;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -560,6 +564,7 @@ __device__ __forceinline__ void tile_h2b(__nv_bfloat16* dst, const __nv_bfloat16
 template <int HDP, bool HALF>
 __global__ void __launch_bounds__(ATTF_THREADS, HDP == 16 ? 2 : 1)
 attn_bwd_fused_kernel(const AttnParams p) {
+  pdl_wait();   // PDL (common.cuh): launched through launch_pdl(); multi-wave grid, so no early pdl_trigger()
   constexpr int PITCH = HDP + ATT_PAD;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [256][PITCH]
@@ -836,7 +841,7 @@ static int launch_fwd_t(const AttnParams& p, cudaStream_t st) {
   if (!once) { B200_TRY(set_smem(attn_fwd_kernel<HDP, HALF>, smem)); once = true; }
   dim3 grid((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
   const int prof = prof_begin(st);
-  attn_fwd_kernel<HDP, HALF><<<grid, ATT_THREADS, smem, st>>>(p);
+  B200_CUDA_OK(launch_pdl(attn_fwd_kernel<HDP, HALF>, dim3(grid), dim3(ATT_THREADS), smem, st, p));
   prof_end(prof, st, 4.0 * p.B * p.heads * (double)p.Nq * p.Nk * p.hd, 1);
   B200_LAUNCH_OK();
   return 0;
@@ -860,7 +865,7 @@ static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
   long long gd = cdiv(n, 256);
   if (gd > (long long)sm_count() * 16) gd = (long long)sm_count() * 16;
   const int prof = prof_begin(st);
-  attn_delta_kernel<HALF><<<(unsigned)gd, 256, 0, st>>>(p);
+  B200_CUDA_OK(launch_pdl(attn_delta_kernel<HALF>, dim3((unsigned)gd), dim3(256), 0, st, p));
   B200_LAUNCH_OK();
   if constexpr (HDP == 16 || HDP == 32 || HDP == 64) {
     static int fused_on = -1;
@@ -871,17 +876,17 @@ static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
       static bool once_f = false;
       if (!once_f) { B200_TRY(set_smem(attn_bwd_fused_kernel<HDP, HALF>, smem_f)); once_f = true; }
       dim3 gf((unsigned)p.heads, (unsigned)p.B);
-      attn_bwd_fused_kernel<HDP, HALF><<<gf, ATTF_THREADS, smem_f, st>>>(p);
+      B200_CUDA_OK(launch_pdl(attn_bwd_fused_kernel<HDP, HALF>, dim3(gf), dim3(ATTF_THREADS), smem_f, st, p));
       prof_end(prof, st, 8.0 * p.B * p.heads * (double)p.Nq * p.Nk * p.hd, 2);
       B200_LAUNCH_OK();
       return 0;
     }
   }
   dim3 gq((unsigned)cdiv(p.Nq, ATT_BQ), (unsigned)p.heads, (unsigned)p.B);
-  attn_bwd_dq_kernel<HDP, HALF><<<gq, ATT_THREADS, smem_dq, st>>>(p);
+  B200_CUDA_OK(launch_pdl(attn_bwd_dq_kernel<HDP, HALF>, dim3(gq), dim3(ATT_THREADS), smem_dq, st, p));
   B200_LAUNCH_OK();
   dim3 gk((unsigned)cdiv(p.Nk, ATT_BK), (unsigned)p.heads, (unsigned)p.B);
-  attn_bwd_dkv_kernel<HDP, HALF><<<gk, ATT_THREADS, smem_dkv, st>>>(p);
+  B200_CUDA_OK(launch_pdl(attn_bwd_dkv_kernel<HDP, HALF>, dim3(gk), dim3(ATT_THREADS), smem_dkv, st, p));
   prof_end(prof, st, 8.0 * p.B * p.heads * (double)p.Nq * p.Nk * p.hd, 2);
   B200_LAUNCH_OK();
   if (p.dk_colsum != nullptr) {   // two-kernel path: the column sums come from a pass over the bf16 outputs

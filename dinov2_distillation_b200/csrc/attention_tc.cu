@@ -154,6 +154,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_units = p.B * p.heads;
+  pdl_trigger();   // PDL: the prologue above overlapped the previous kernel's tail
+  pdl_wait();
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
@@ -545,7 +547,7 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   if (dbg_on && dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 9 * 16 * sizeof(long long)); }
   if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 9 * 16 * sizeof(long long), st);
   p.dbg = dbg_on ? dbg_buf : nullptr;
-  attn_tc_fwd_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tk, tv, to, p);
+  B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, p));
   prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
   B200_LAUNCH_OK();
   if (dbg_on) {

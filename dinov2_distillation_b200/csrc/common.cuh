@@ -125,6 +125,30 @@ __device__ __forceinline__ float dgelu_fast(float x) {
   return cdf + x * pdf;
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl() may be scheduled while its predecessor
+// in the stream is still draining; it MUST call pdl_wait() before its first access to global memory the predecessor may
+// have written (or may still read). pdl_trigger() lets the NEXT kernel start being scheduled; single-wave / persistent
+// kernels call it early, multi-wave kernels leave it to the implicit trigger at exit (early dependents would only sit
+// on SM resources their own later waves need). B200_PDL=0 turns the launch attribute off (plain stream order).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // Multi-job parameter preparation (elementwise.cu: param_prep_kernel)
 enum { PREP_CAST16 = 0, PREP_SPLIT3_RIGHT = 1, PREP_COPY32 = 2, PREP_TRANSPOSE16 = 3, PREP_TRANSPOSE32 = 4 };
 constexpr int PREP_MAX_JOBS = 12;

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/b200_distill.h"
 
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -24,6 +25,15 @@ int sm_count() {
     }
   }
   return sms;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 // ---- optional per-launch timing of the dense kernels (bench.py's roofline leg): CUDA events on the launch stream

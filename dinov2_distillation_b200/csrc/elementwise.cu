@@ -17,6 +17,8 @@ static inline int grid_for(long long work_items, int per_block, int max_blocks_p
 // ------------------------------------------------------------------------------------------------ cast
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n,
                                      int fp16) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -31,6 +33,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 }
 
 __global__ void cast_f16_bf16_kernel(const __half* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const long long n8 = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
@@ -54,6 +58,8 @@ __global__ void cast_f16_bf16_kernel(const __half* __restrict__ x, __nv_bfloat16
 // BatchNorm -> ReLU with no residual around it (conv1x1 of proj_student), where mask flips dominate the gradient error.
 __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K,
                               int right, int fp16) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int K4 = K >> 2;
   const long long n4 = rows * K4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -83,6 +89,7 @@ template <typename TOut, bool ACC>
 __global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict__ out, int rows, int cols,
                                  const float* __restrict__ row_scale, long long in_bstride, long long out_bstride,
                                  float* __restrict__ out2_f32, long long out_ld, int fp16) {
+  pdl_wait();   // PDL: launched through launch_pdl(); multi-wave grid, no early trigger
   __shared__ float tile[32][33];
   in += (long long)blockIdx.z * in_bstride;
   out += (long long)blockIdx.z * out_bstride;
@@ -116,6 +123,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict_
 // ------------------------------------------------------------------------------------------------ patch im2col
 __global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W,
                                     int Kp) {
+  pdl_wait();   // PDL: launched through launch_pdl(); multi-wave grid, no early trigger
   extern __shared__ float srow[];  // [3*14][W]
   const int Wp = W / 14, Hp = H / 14;
   const int b = blockIdx.x / Hp, ph = blockIdx.x % Hp;
@@ -152,6 +160,8 @@ __global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16
 
 __global__ void write_cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls,
                                       const float* __restrict__ pos, int B, int N, int D) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i - b * D;
@@ -166,6 +176,8 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float eps,
                      float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int rows, int D, int in_period, int in_pad, int fp16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_d = 1.0f / (float)D;
@@ -229,6 +241,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dw,
                      float* __restrict__ db, float* __restrict__ dx_colsum, int rows, int D) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_d = 1.0f / (float)D;
@@ -333,6 +347,8 @@ template <typename T, bool SQ>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out, int rows, int cols,
                  int rows_per_block) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   __shared__ float4 sh[8][32];
   __shared__ float4 sh2[8][32];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
@@ -375,6 +391,8 @@ colreduce_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out
 }
 
 __global__ void zero_kernel(float* __restrict__ p, long long n) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] = 0.f;
 }
@@ -382,6 +400,8 @@ __global__ void zero_kernel(float* __restrict__ p, long long n) {
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
                                    int M, int D) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   if (sums != nullptr) {
@@ -406,6 +426,8 @@ bn_relu_pos_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
                        const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ pos,
                        float* __restrict__ z32, __nv_bfloat16* __restrict__ z16, long long M, int D, int HW,
                        int fp16) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int D4 = D >> 2;
   const long long n4 = M * D4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -437,6 +459,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
                      float* __restrict__ sums2, int M, int D, int rows_per_block) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   __shared__ float4 sh[8][32];
   __shared__ float4 sh2[8][32];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
@@ -482,6 +506,8 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, c
                     const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
                     const float* __restrict__ sums2, __nv_bfloat16* __restrict__ dy16, int batch_stats, long long M,
                     int D) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int D4 = D >> 2;
   const long long n4 = M * D4;
   const float invM = 1.0f / (float)M;
@@ -518,6 +544,8 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, c
 
 __global__ void batch_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int B, long long n,
                                  int accumulate) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 a = make_float4(0, 0, 0, 0);
@@ -533,6 +561,8 @@ __global__ void batch_sum_kernel(const float* __restrict__ x, float* __restrict_
 
 __global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ x12, __nv_bfloat16* __restrict__ out, long long rows,
                               int H) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int H8 = H >> 3;
   const long long n = rows * H8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -555,6 +585,8 @@ __global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ x12, __nv_bfloat
 
 __global__ void batch_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ o32,
                                       __nv_bfloat16* __restrict__ o16, int B, long long n) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 a = make_float4(0, 0, 0, 0);
@@ -574,12 +606,16 @@ __global__ void batch_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float
 }
 
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float a, long long n) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] += a * x[i];
 }
 
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, const __nv_bfloat16* __restrict__ dout,
                                   __nv_bfloat16* __restrict__ dx12, long long rows, int H) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int H8 = H >> 3;
   const long long n = rows * H8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -608,8 +644,8 @@ template <int NV>
 static int launch_ln_fwd(const float* x, const float* w, const float* b, float eps, float* y32, void* y16, float* mean,
                          float* rstd, int rows, int D, int in_period, int in_pad, int fp16, cudaStream_t st) {
   const int grid = grid_for(rows, 8, 8);
-  layernorm_fwd_kernel<NV><<<grid, 256, 0, st>>>(x, w, b, eps, y32, static_cast<__nv_bfloat16*>(y16), mean, rstd, rows,
-                                                 D, in_period, in_pad, fp16);
+  B200_CUDA_OK(launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(256), 0, st, x, w, b, eps, y32,
+                          static_cast<__nv_bfloat16*>(y16), mean, rstd, rows, D, in_period, in_pad, fp16));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -625,7 +661,8 @@ static int launch_ln_bwd(const float* dy, const float* x, const float* w, const 
     if (!set) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
   }
   const int grid = grid_for(rows, 8 * 4, (dw || dx_colsum) ? 2 : 8);
-  kern<<<grid, 256, smem, st>>>(dy, x, w, mean, rstd, dres, dx, static_cast<__nv_bfloat16*>(dx16), dw, db, dx_colsum, rows, D);
+  B200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(256), smem, st, dy, x, w, mean, rstd, dres, dx,
+                          static_cast<__nv_bfloat16*>(dx16), dw, db, dx_colsum, rows, D));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -637,7 +674,7 @@ static int launch_colreduce(const T* x, long long ldx, float* out, int rows, int
   int rpb = (int)cdiv(rows, gy);
   if (rpb < 64) rpb = 64;
   gy = (int)cdiv(rows, rpb);
-  colreduce_kernel<T, SQ><<<dim3(gx, gy), dim3(32, 8), 0, st>>>(x, ldx, out, rows, cols, rpb);
+  B200_CUDA_OK(launch_pdl(colreduce_kernel<T, SQ>, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, st, x, ldx, out, rows, cols, rpb));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -647,6 +684,8 @@ static int launch_colreduce(const T* x, long long ldx, float* out, int rows, int
 // the conv weight, transposed bf16 copies for the dgrad GEMMs, bias concatenation, pos_embed to token-major): these were
 // 10 (forward) and 7 (backward) launches of a few microseconds each. blockIdx.y selects the job.
 __global__ void __launch_bounds__(256) param_prep_kernel(const PrepJobs jobs) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const PrepJob& jb = jobs.j[blockIdx.y];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if (jb.type == PREP_CAST16 || jb.type == PREP_COPY32) {
@@ -729,7 +768,7 @@ int launch_param_prep(const PrepJobs& jobs, cudaStream_t st) {
                      "prep job alignment");
     if (j.type == PREP_SPLIT3_RIGHT) B200_CHECK_ARG(j.cols % 4 == 0, "split3 needs K % 4 == 0");
   }
-  param_prep_kernel<<<dim3(192, (unsigned)jobs.n), dim3(32, 8), 0, st>>>(jobs);
+  B200_CUDA_OK(launch_pdl(param_prep_kernel, dim3(dim3(192, (unsigned)jobs.n)), dim3(dim3(32, 8)), 0, st, jobs));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -742,8 +781,8 @@ extern "C" int b200_cast_f32_bf16(const float* x, void* y, long long n, void* st
   B200_CHECK_ARG(x && y && n >= 0, "bad args");
   if (n == 0) return 0;
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "alignment");
-  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<__nv_bfloat16*>(y), n, 0);
+  B200_CUDA_OK(launch_pdl(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      x, static_cast<__nv_bfloat16*>(y), n, 0));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -752,8 +791,8 @@ extern "C" int b200_cast_f32_f16(const float* x, void* y, long long n, void* str
   B200_CHECK_ARG(x && y && n >= 0, "bad args");
   if (n == 0) return 0;
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "alignment");
-  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<__nv_bfloat16*>(y), n, 1);
+  B200_CUDA_OK(launch_pdl(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      x, static_cast<__nv_bfloat16*>(y), n, 1));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -762,8 +801,8 @@ extern "C" int b200_cast_f16_bf16(const void* x, void* y, long long n, void* str
   B200_CHECK_ARG(x && y && n >= 0, "bad args");
   if (n == 0) return 0;
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "alignment");
-  cast_f16_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<__nv_bfloat16*>(y), n);
+  B200_CUDA_OK(launch_pdl(cast_f16_bf16_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __half*>(x), static_cast<__nv_bfloat16*>(y), n));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -771,8 +810,8 @@ extern "C" int b200_cast_f16_bf16(const void* x, void* y, long long n, void* str
 extern "C" int b200_split3_16(const float* x, void* out, long long rows, int K, int right_operand, int out_is_fp16,
                               void* stream) {
   B200_CHECK_ARG(x && out && rows > 0 && K > 0 && K % 4 == 0, "bad args");
-  split3_kernel<<<grid_for(rows * K / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<__nv_bfloat16*>(out), rows, K, right_operand ? 1 : 0, out_is_fp16 ? 1 : 0);
+  B200_CUDA_OK(launch_pdl(split3_kernel, dim3(grid_for(rows * K / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      x, static_cast<__nv_bfloat16*>(out), rows, K, right_operand ? 1 : 0, out_is_fp16 ? 1 : 0));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -781,8 +820,8 @@ extern "C" int b200_transpose_f32_bf16(const float* in, void* out, int rows, int
                                        void* stream) {
   B200_CHECK_ARG(in && out && rows > 0 && cols > 0, "bad args");
   dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), 1);
-  transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, rows, 0);
+  B200_CUDA_OK(launch_pdl(transpose_kernel<__nv_bfloat16, false>, dim3(grid), dim3(dim3(32, 8)), 0, static_cast<cudaStream_t>(stream), 
+      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, rows, 0));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -791,8 +830,8 @@ extern "C" int b200_transpose_f32_bf16_ld(const float* in, void* out, int rows, 
                                           const float* row_scale, void* stream) {
   B200_CHECK_ARG(in && out && rows > 0 && cols > 0 && out_ld >= rows, "bad args");
   dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), 1);
-  transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, out_ld, 0);
+  B200_CUDA_OK(launch_pdl(transpose_kernel<__nv_bfloat16, false>, dim3(grid), dim3(dim3(32, 8)), 0, static_cast<cudaStream_t>(stream), 
+      in, static_cast<__nv_bfloat16*>(out), rows, cols, row_scale, 0, 0, nullptr, out_ld, 0));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -803,11 +842,11 @@ extern "C" int b200_nchw_to_tokens(const float* x, void* tok_bf16, float* tok_f3
   dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(C, 32), (unsigned)B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tok_bf16) {
-    transpose_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, st>>>(
-        x, static_cast<__nv_bfloat16*>(tok_bf16), C, HW, nullptr, (long long)C * HW, (long long)C * HW, tok_f32, C, tok16_is_fp16);
+    B200_CUDA_OK(launch_pdl(transpose_kernel<__nv_bfloat16, false>, dim3(grid), dim3(dim3(32, 8)), 0, st, 
+        x, static_cast<__nv_bfloat16*>(tok_bf16), C, HW, nullptr, (long long)C * HW, (long long)C * HW, tok_f32, C, tok16_is_fp16));
   } else {
-    transpose_kernel<float, false><<<grid, dim3(32, 8), 0, st>>>(x, tok_f32, C, HW, nullptr, (long long)C * HW,
-                                                                  (long long)C * HW, nullptr, C, 0);
+    B200_CUDA_OK(launch_pdl(transpose_kernel<float, false>, dim3(grid), dim3(dim3(32, 8)), 0, st, x, tok_f32, C, HW, nullptr, (long long)C * HW,
+                                                                  (long long)C * HW, nullptr, C, 0));
   }
   B200_LAUNCH_OK();
   return 0;
@@ -818,11 +857,11 @@ extern "C" int b200_tokens_to_nchw(const float* tok, float* x, int B, int C, int
   dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(HW, 32), (unsigned)B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (accumulate) {
-    transpose_kernel<float, true><<<grid, dim3(32, 8), 0, st>>>(tok, x, HW, C, nullptr, (long long)C * HW,
-                                                                 (long long)C * HW, nullptr, HW, 0);
+    B200_CUDA_OK(launch_pdl(transpose_kernel<float, true>, dim3(grid), dim3(dim3(32, 8)), 0, st, tok, x, HW, C, nullptr, (long long)C * HW,
+                                                                 (long long)C * HW, nullptr, HW, 0));
   } else {
-    transpose_kernel<float, false><<<grid, dim3(32, 8), 0, st>>>(tok, x, HW, C, nullptr, (long long)C * HW,
-                                                                  (long long)C * HW, nullptr, HW, 0);
+    B200_CUDA_OK(launch_pdl(transpose_kernel<float, false>, dim3(grid), dim3(dim3(32, 8)), 0, st, tok, x, HW, C, nullptr, (long long)C * HW,
+                                                                  (long long)C * HW, nullptr, HW, 0));
   }
   B200_LAUNCH_OK();
   return 0;
@@ -841,16 +880,16 @@ extern "C" int b200_patch_im2col(const float* img, void* out, int B, int H, int 
       set_to = smem;
     }
   }
-  patch_im2col_kernel<<<B * (H / 14), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      img, static_cast<__nv_bfloat16*>(out), H, W, Kp);
+  B200_CUDA_OK(launch_pdl(patch_im2col_kernel, dim3(B * (H / 14)), dim3(256), smem, static_cast<cudaStream_t>(stream), 
+      img, static_cast<__nv_bfloat16*>(out), H, W, Kp));
   B200_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200_write_cls_rows(float* x, const float* cls, const float* pos, int B, int N, int D, void* stream) {
   B200_CHECK_ARG(x && cls && pos && B > 0 && N > 0 && D > 0, "bad args");
-  write_cls_rows_kernel<<<(unsigned)cdiv((long long)B * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, cls, pos, B, N, D);
+  B200_CUDA_OK(launch_pdl(write_cls_rows_kernel, dim3((unsigned)cdiv((long long)B * D, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      x, cls, pos, B, N, D));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -897,8 +936,8 @@ extern "C" int b200_bn_finalize(const float* sums, float* mean, float* rstd, flo
                                 float momentum, float eps, int M, int D, void* stream) {
   B200_CHECK_ARG(mean && rstd && D > 0, "bad args");
   B200_CHECK_ARG(sums || (running_mean && running_var), "need batch sums or running statistics");
-  bn_finalize_kernel<<<(unsigned)cdiv(D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      sums, mean, rstd, running_mean, running_var, momentum, eps, M, D);
+  B200_CUDA_OK(launch_pdl(bn_finalize_kernel, dim3((unsigned)cdiv(D, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      sums, mean, rstd, running_mean, running_var, momentum, eps, M, D));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -907,8 +946,8 @@ extern "C" int b200_bn_relu_pos_fwd(const float* y, const float* mean, const flo
                                     const float* b, const float* pos, float* z_f32, void* z_bf16, int M, int D, int HW,
                                     int z16_is_fp16, void* stream) {
   B200_CHECK_ARG(y && mean && rstd && w && b && pos && (z_f32 || z_bf16) && M > 0 && D % 4 == 0 && HW > 0, "bad args");
-  bn_relu_pos_fwd_kernel<<<grid_for((long long)M * D / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      y, mean, rstd, w, b, pos, z_f32, static_cast<__nv_bfloat16*>(z_bf16), M, D, HW, z16_is_fp16);
+  B200_CUDA_OK(launch_pdl(bn_relu_pos_fwd_kernel, dim3(grid_for((long long)M * D / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      y, mean, rstd, w, b, pos, z_f32, static_cast<__nv_bfloat16*>(z_bf16), M, D, HW, z16_is_fp16));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -923,7 +962,7 @@ extern "C" int b200_bn_relu_pos_bwd_reduce(const float* dz, const float* y, cons
   int rpb = (int)cdiv(M, gy);
   if (rpb < 64) rpb = 64;
   gy = (int)cdiv(M, rpb);
-  bn_bwd_reduce_kernel<<<dim3(gx, gy), dim3(32, 8), 0, st>>>(dz, y, mean, rstd, w, b, sums2, M, D, rpb);
+  B200_CUDA_OK(launch_pdl(bn_bwd_reduce_kernel, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, st, dz, y, mean, rstd, w, b, sums2, M, D, rpb));
   B200_LAUNCH_OK();
   if (dpos) {
     B200_CHECK_ARG(M % HW == 0 && ((long long)HW * D) % 4 == 0, "M must be a multiple of HW");
@@ -937,8 +976,8 @@ extern "C" int b200_bn_relu_pos_bwd_apply(const float* dz, const float* y, const
                                           int use_batch_stats, int M, int D, void* stream) {
   B200_CHECK_ARG(dz && y && mean && rstd && w && b && dy_bf16 && M > 0 && D % 4 == 0, "bad args");
   B200_CHECK_ARG(!use_batch_stats || sums2, "batch statistics need sums2");
-  bn_bwd_apply_kernel<<<grid_for((long long)M * D / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dz, y, mean, rstd, w, b, sums2, static_cast<__nv_bfloat16*>(dy_bf16), use_batch_stats, M, D);
+  B200_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for((long long)M * D / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      dz, y, mean, rstd, w, b, sums2, static_cast<__nv_bfloat16*>(dy_bf16), use_batch_stats, M, D));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -952,39 +991,39 @@ extern "C" int b200_colsum(const void* x, int x_is_bf16, long long ldx, float* o
 
 extern "C" int b200_batch_sum(const float* x, float* out, int B, long long n, void* stream) {
   B200_CHECK_ARG(x && out && B > 0 && n > 0 && n % 4 == 0, "bad args");
-  batch_sum_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, B, n, 1);
+  B200_CUDA_OK(launch_pdl(batch_sum_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, out, B, n, 1));
   B200_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200_swiglu(const void* x12, void* out, int rows, int H, void* stream) {
   B200_CHECK_ARG(x12 && out && rows > 0 && H > 0 && H % 8 == 0, "bad args");
-  swiglu_kernel<<<grid_for((long long)rows * H / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x12), static_cast<__nv_bfloat16*>(out), rows, H);
+  B200_CUDA_OK(launch_pdl(swiglu_kernel, dim3(grid_for((long long)rows * H / 8, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(x12), static_cast<__nv_bfloat16*>(out), rows, H));
   B200_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200_batch_sum_bf16(const void* x, float* out_f32, void* out_bf16, int B, long long n, void* stream) {
   B200_CHECK_ARG(x && (out_f32 || out_bf16) && B > 0 && n > 0 && n % 4 == 0, "bad args");
-  batch_sum_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), out_f32, static_cast<__nv_bfloat16*>(out_bf16), B, n);
+  B200_CUDA_OK(launch_pdl(batch_sum_bf16_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(x), out_f32, static_cast<__nv_bfloat16*>(out_bf16), B, n));
   B200_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200_axpy(const float* x, float* y, float a, long long n, void* stream) {
   B200_CHECK_ARG(x && y && n > 0, "bad args");
-  axpy_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, a, n);
+  B200_CUDA_OK(launch_pdl(axpy_kernel, dim3(grid_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, y, a, n));
   B200_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200_swiglu_bwd(const void* x12, const void* d_out, void* d_x12, int rows, int H, void* stream) {
   B200_CHECK_ARG(x12 && d_out && d_x12 && rows > 0 && H > 0 && H % 8 == 0, "bad args");
-  swiglu_bwd_kernel<<<grid_for((long long)rows * H / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  B200_CUDA_OK(launch_pdl(swiglu_bwd_kernel, dim3(grid_for((long long)rows * H / 8, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x12), static_cast<const __nv_bfloat16*>(d_out),
-      static_cast<__nv_bfloat16*>(d_x12), rows, H);
+      static_cast<__nv_bfloat16*>(d_x12), rows, H));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -992,7 +1031,7 @@ extern "C" int b200_swiglu_bwd(const void* x12, const void* d_out, void* d_x12, 
 namespace b200 {
 int zero_f32(float* p, long long n, cudaStream_t st) {
   if (n <= 0) return 0;
-  zero_kernel<<<grid_for(n, 1024, 4), 256, 0, st>>>(p, n);
+  B200_CUDA_OK(launch_pdl(zero_kernel, dim3(grid_for(n, 1024, 4)), dim3(256), 0, st, p, n));
   B200_LAUNCH_OK();
   return 0;
 }

@@ -399,6 +399,9 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_trigger();
+  pdl_wait();
 
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
@@ -531,13 +534,15 @@ static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cfg.blockDim = dim3(V2_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = PAIR ? 2 : 1;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   const int prof = prof_begin(st);
   B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tx, p, use_x, reduce_out));
   prof_end(prof, st, 2.0 * p.M * p.N * p.K * p.algo_scale, 0);

@@ -17,6 +17,8 @@ static inline long long ws_acc_floats() { return 4; }
 // mean over the HW tokens of each image: out[b, c] = 1/HW sum_p x[b, skip + p, c]
 __global__ void __launch_bounds__(256)
 token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int HW, int D, long long bstride, int skip) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   __shared__ float4 sh[8][32];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int b = blockIdx.y;
@@ -70,6 +72,8 @@ __device__ __forceinline__ RowStats row_stats(const float* __restrict__ s, const
 __global__ void __launch_bounds__(256)
 kd_loss_fwd_kernel(const float* __restrict__ S, const float* __restrict__ T, int rows, int HW, int D, int Nt,
                    int t_skip, const float* __restrict__ ms, const float* __restrict__ mt, float* __restrict__ acc) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float loss = 0.f, sim = 0.f;
   for (int r = blockIdx.x * wpb + wid; r < rows; r += gridDim.x * wpb) {
@@ -96,6 +100,8 @@ kd_loss_fwd_kernel(const float* __restrict__ S, const float* __restrict__ T, int
 
 __global__ void kd_loss_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, float loss_scale,
                                         float sim_scale) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   out[0] = acc[0] * loss_scale;
   out[1] = acc[1] * sim_scale;
 }
@@ -104,6 +110,8 @@ __global__ void __launch_bounds__(256)
 kd_loss_bwd_kernel(const float* __restrict__ S, const float* __restrict__ T, int rows, int HW, int D, int Nt,
                    int t_skip, const float* __restrict__ ms, const float* __restrict__ mt,
                    const float* __restrict__ g_out, float loss_scale, float sim_scale, float* __restrict__ dS) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const float gl = g_out[0] * loss_scale, gs = g_out[1] * sim_scale;
   for (int r = blockIdx.x * wpb + wid; r < rows; r += gridDim.x * wpb) {
@@ -143,6 +151,8 @@ kd_loss_bwd_kernel(const float* __restrict__ S, const float* __restrict__ T, int
 // dS[b, p, c] -= md[b, c]
 __global__ void __launch_bounds__(256)
 sub_token_mean_kernel(float* __restrict__ dS, const float* __restrict__ md, long long rows, int HW, int D) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   const int D4 = D >> 2;
   const long long n4 = rows * D4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -160,6 +170,8 @@ sub_token_mean_kernel(float* __restrict__ dS, const float* __restrict__ md, long
 __global__ void __launch_bounds__(256)
 dct_zero_dc_idct_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int D, long long x_bs,
                         long long x_ts) {
+  pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
+  pdl_wait();
   extern __shared__ float smem[];
   const int RR = R * R;
   float* A = smem;             // [RR][8]
@@ -232,18 +244,18 @@ extern "C" int b200_kd_loss_fwd(const float* S, const float* T, int B, int HW, i
   float* mt = ms + (long long)B * D;
   if (freq) {
     dim3 grid((unsigned)cdiv(D, 128), (unsigned)B);
-    token_mean_kernel<<<grid, dim3(32, 8), 0, st>>>(S, ms, HW, D, (long long)HW * D, 0);
+    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 8)), 0, st, S, ms, HW, D, (long long)HW * D, 0));
     B200_LAUNCH_OK();
-    token_mean_kernel<<<grid, dim3(32, 8), 0, st>>>(T, mt, HW, D, (long long)Nt * D, t_skip);
+    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 8)), 0, st, T, mt, HW, D, (long long)Nt * D, t_skip));
     B200_LAUNCH_OK();
   }
   const int rows = B * HW;
   long long g = cdiv(rows, 8);
   if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-  kd_loss_fwd_kernel<<<(unsigned)g, 256, 0, st>>>(S, T, rows, HW, D, Nt, t_skip, freq ? ms : nullptr,
-                                                  freq ? mt : nullptr, ws);
+  B200_CUDA_OK(launch_pdl(kd_loss_fwd_kernel, dim3((unsigned)g), dim3(256), 0, st, S, T, rows, HW, D, Nt, t_skip, freq ? ms : nullptr,
+                                                  freq ? mt : nullptr, ws));
   B200_LAUNCH_OK();
-  kd_loss_finalize_kernel<<<1, 1, 0, st>>>(ws, out, alpha / (float)B, 1.0f / (float)rows);
+  B200_CUDA_OK(launch_pdl(kd_loss_finalize_kernel, dim3(1), dim3(1), 0, st, ws, out, alpha / (float)B, 1.0f / (float)rows));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -259,17 +271,17 @@ extern "C" int b200_kd_loss_bwd(const float* S, const float* T, int B, int HW, i
   const int rows = B * HW;
   long long g = cdiv(rows, 8);
   if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-  kd_loss_bwd_kernel<<<(unsigned)g, 256, 0, st>>>(S, T, rows, HW, D, Nt, t_skip, freq ? ms : nullptr,
-                                                  freq ? mt : nullptr, g_out, alpha / (float)B, 1.0f / (float)rows, dS);
+  B200_CUDA_OK(launch_pdl(kd_loss_bwd_kernel, dim3((unsigned)g), dim3(256), 0, st, S, T, rows, HW, D, Nt, t_skip, freq ? ms : nullptr,
+                                                  freq ? mt : nullptr, g_out, alpha / (float)B, 1.0f / (float)rows, dS));
   B200_LAUNCH_OK();
   if (freq) {
     dim3 grid((unsigned)cdiv(D, 128), (unsigned)B);
-    token_mean_kernel<<<grid, dim3(32, 8), 0, st>>>(dS, md, HW, D, (long long)HW * D, 0);
+    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 8)), 0, st, dS, md, HW, D, (long long)HW * D, 0));
     B200_LAUNCH_OK();
     long long n4 = (long long)rows * D / 4;
     long long gg = cdiv(n4, 256);
     if (gg > (long long)sm_count() * 8) gg = (long long)sm_count() * 8;
-    sub_token_mean_kernel<<<(unsigned)gg, 256, 0, st>>>(dS, md, rows, HW, D);
+    B200_CUDA_OK(launch_pdl(sub_token_mean_kernel, dim3((unsigned)gg), dim3(256), 0, st, dS, md, rows, HW, D));
     B200_LAUNCH_OK();
   }
   return 0;
@@ -288,7 +300,7 @@ extern "C" int b200_dct_zero_dc_idct(const float* x, float* y, int B, int R, int
     }
   }
   dim3 grid((unsigned)cdiv(D, 8), (unsigned)B);
-  dct_zero_dc_idct_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, y, R, D, x_bs, x_ts);
+  B200_CUDA_OK(launch_pdl(dct_zero_dc_idct_kernel, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), x, y, R, D, x_bs, x_ts));
   B200_LAUNCH_OK();
   return 0;
 }
