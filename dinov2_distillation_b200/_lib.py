@@ -158,6 +158,8 @@ SIGNATURES = {
                                     c_fp, c_fp, c_fp, _i, c_fp, _i, c_fp, c_vp, c_vp, _sz, c_vp, c_vp]),
 }
 
+ABI_VERSION = 2   # include/b200_distill.h: B200_ABI_VERSION
+
 _lib = None
 
 
@@ -180,7 +182,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the ABI and the header drifted apart
         fn.restype = res
         fn.argtypes = args
-    if lib.b200_abi_version() != 2:
+    if lib.b200_abi_version() != ABI_VERSION:
         raise B200Error("libb200distill.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -21,7 +21,7 @@ def _declared_symbols():
 def test_library_loads_and_exports_every_declared_symbol():
     from dinov2_distillation_b200 import _lib
     lib = _lib.load()
-    assert lib.b200_abi_version() == 2
+    assert lib.b200_abi_version() == _lib.ABI_VERSION == 2
     declared = _declared_symbols()
     assert len(declared) >= 40
     missing = [s for s in declared if not hasattr(lib, s)]
