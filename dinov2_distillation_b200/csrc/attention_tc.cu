@@ -58,7 +58,10 @@ struct AttnTcParams {
   const __nv_bfloat16* q; long long q_bs, q_ts;
   __nv_bfloat16* o; long long o_bs, o_ts;
   uint32_t idesc_qk1, idesc_qk2, idesc_pv;
-  int n1, n2;                // QK^T column split (n1 <= 256, n2 = nkp - n1)
+  int n1, n2;                // QK^T column split of the LAST key block (n1 <= 256, n2 = nkp - n1)
+  int nblk;                  // key blocks per query tile: 1 (whole key range resident, Nk <= 272) or ceil(Nk / 256)
+  int nk_last, nkp_last;     // keys / padded keys of the last block (all other blocks hold 256)
+  uint32_t idesc_qk_full;    // QK^T of a full 256-key block
   long long* dbg;            // B200_ATTN_DBG=1: per-phase clock64 stamps of CTA 0 ([item][16])
 };
 
@@ -109,6 +112,10 @@ __device__ __forceinline__ float atc_ex2(float x) {
   return y;
 }
 
+// MULTI = false: the whole key range is resident (one block of up to 272 keys per query tile, 5 S chunks per softmax warp,
+// the output is read once from TMEM). MULTI = true: key blocks of 256 with online softmax (4 chunks per warp plus the
+// running 32-column output accumulator in registers).
+template <bool MULTI>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -161,94 +168,95 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    // K/V tiles: one load per (batch, head) unit when the whole key range fits (nblk == 1: every query tile of the unit
+    // re-uses it), else one per (query tile, key block) through the same two-deep ring.
     if (elect_one()) {
-      int item = 0, uc = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+      int qc = 0, kvc = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int b = u / p.heads, h = u - b * p.heads;
-        const int kb = uc & 1;
-        for (int qt = 0; qt < p.n_qt; ++qt, ++item) {
-          const int qb = item & 1;
-          mbar_wait(&q_empty[qb], ((item >> 1) & 1) ^ 1);
+        for (int qt = 0; qt < p.n_qt; ++qt, ++qc) {
+          const int qb = qc & 1;
+          mbar_wait(&q_empty[qb], ((qc >> 1) & 1) ^ 1);
           mbar_expect_tx(&q_full[qb], ATC_Q_BYTES);
           tma_load_3d(smem + ATC_OFF_Q + qb * ATC_Q_BYTES, &tmQ, &q_full[qb], h * 64, qt * 128, b);
-          if (qt == 0) {
-            mbar_wait(&kv_empty[kb], ((uc >> 1) & 1) ^ 1);
+          for (int j = 0; j < p.nblk; ++j) {
+            if (p.nblk == 1 && qt > 0) break;
+            const int kb = kvc & 1;
+            mbar_wait(&kv_empty[kb], ((kvc >> 1) & 1) ^ 1);
             mbar_expect_tx(&kv_full[kb], 2 * ATC_KV_BYTES);
             uint8_t* sK = smem + ATC_OFF_K + kb * ATC_KV_BYTES;
             uint8_t* sV = smem + ATC_OFF_V + kb * ATC_KV_BYTES;
-            tma_load_3d(sK, &tmK, &kv_full[kb], h * 64, 0, b);
-            tma_load_3d(sK + ATC_KV_BOX * 128, &tmK, &kv_full[kb], h * 64, ATC_KV_BOX, b);
-            tma_load_3d(sV, &tmV, &kv_full[kb], h * 64, 0, b);
-            tma_load_3d(sV + ATC_KV_BOX * 128, &tmV, &kv_full[kb], h * 64, ATC_KV_BOX, b);
+            const int r0 = j * 256;
+            tma_load_3d(sK, &tmK, &kv_full[kb], h * 64, r0, b);
+            tma_load_3d(sK + ATC_KV_BOX * 128, &tmK, &kv_full[kb], h * 64, r0 + ATC_KV_BOX, b);
+            tma_load_3d(sV, &tmV, &kv_full[kb], h * 64, r0, b);
+            tma_load_3d(sV + ATC_KV_BOX * 128, &tmV, &kv_full[kb], h * 64, r0 + ATC_KV_BOX, b);
+            ++kvc;
           }
-        }
-        if (p.n_qt == 0) {   // only tail rows: still stage K/V for the tail warp
-          mbar_wait(&kv_empty[kb], ((uc >> 1) & 1) ^ 1);
-          mbar_expect_tx(&kv_full[kb], 2 * ATC_KV_BYTES);
-          uint8_t* sK = smem + ATC_OFF_K + kb * ATC_KV_BYTES;
-          uint8_t* sV = smem + ATC_OFF_V + kb * ATC_KV_BYTES;
-          tma_load_3d(sK, &tmK, &kv_full[kb], h * 64, 0, b);
-          tma_load_3d(sK + ATC_KV_BOX * 128, &tmK, &kv_full[kb], h * 64, ATC_KV_BOX, b);
-          tma_load_3d(sV, &tmV, &kv_full[kb], h * 64, 0, b);
-          tma_load_3d(sV + ATC_KV_BOX * 128, &tmV, &kv_full[kb], h * 64, ATC_KV_BOX, b);
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      int item = 0, uc = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
-        const int kb = uc & 1;
-        const uint32_t k_addr = smem_u32(smem + ATC_OFF_K + kb * ATC_KV_BYTES);
-        const uint32_t v_addr = smem_u32(smem + ATC_OFF_V + kb * ATC_KV_BYTES);
-        mbar_wait(&kv_full[kb], (uc >> 1) & 1);
-        for (int qt = 0; qt < p.n_qt; ++qt, ++item) {
-          const int qb = item & 1;
+      int item = 0, qc = 0, kvc = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (int qt = 0; qt < p.n_qt; ++qt, ++qc) {
+          const int qb = qc & 1;
           const uint32_t q_addr = smem_u32(smem + ATC_OFF_Q + qb * ATC_Q_BYTES);
-          mbar_wait(&q_full[qb], (item >> 1) & 1);
-          if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 8] = clock64();
-          if (item > 0) mbar_wait(s_free, (item - 1) & 1);   // the previous tile's S row is in registers
-          tc_fence_after();
-          if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 9] = clock64();
-          // S = Q K^T
+          mbar_wait(&q_full[qb], (qc >> 1) & 1);
+          for (int j = 0; j < p.nblk; ++j, ++item) {
+            const bool kv_new = p.nblk > 1 || qt == 0;
+            if (kv_new) mbar_wait(&kv_full[kvc & 1], (kvc >> 1) & 1);
+            const int kb = (kv_new ? kvc : kvc - 1) & 1;
+            const uint32_t k_addr = smem_u32(smem + ATC_OFF_K + kb * ATC_KV_BYTES);
+            const uint32_t v_addr = smem_u32(smem + ATC_OFF_V + kb * ATC_KV_BYTES);
+            const bool last_blk = j == p.nblk - 1;
+            const int nkp = last_blk ? p.nkp_last : 256;
+            if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 8] = clock64();
+            if (item > 0) mbar_wait(s_free, (item - 1) & 1);   // the previous block's S row is in registers
+            tc_fence_after();
+            if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 9] = clock64();
+            // S = Q K_j^T
+            const uint32_t id1 = last_blk ? p.idesc_qk1 : p.idesc_qk_full;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = make_smem_desc_sw128(q_addr + ks * 32, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(k_addr + ks * 32, 16, 1024);
-            tc_mma_bf16(tmem_base + ATC_TMEM_S, da, db, p.idesc_qk1, ks > 0 ? 1u : 0u);
-            if (p.n2 > 0) {
-              const uint64_t db2 = make_smem_desc_sw128(k_addr + 256 * 128 + ks * 32, 16, 1024);
-              tc_mma_bf16(tmem_base + ATC_TMEM_S + 256, da, db2, p.idesc_qk2, ks > 0 ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da = make_smem_desc_sw128(q_addr + ks * 32, 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(k_addr + ks * 32, 16, 1024);
+              tc_mma_bf16(tmem_base + ATC_TMEM_S, da, db, id1, ks > 0 ? 1u : 0u);
+              if (last_blk && p.n2 > 0) {
+                const uint64_t db2 = make_smem_desc_sw128(k_addr + 256 * 128 + ks * 32, 16, 1024);
+                tc_mma_bf16(tmem_base + ATC_TMEM_S + 256, da, db2, p.idesc_qk2, ks > 0 ? 1u : 0u);
+              }
             }
+            if (last_blk) tc_commit(&q_empty[qb]);
+            tc_commit(s_full);
+            // O_j = P V_j in two groups (k-steps 0..7 = keys 0..127, then the rest) as the softmax warps publish P: the
+            // first group runs under the remaining exponentials. (Finer groups starve: this warp shares its scheduler
+            // with two softmax warps that are always eligible.)
+            {
+              const int ksteps = nkp >> 4;
+              const int split = ksteps < 8 ? ksteps : 8;
+              mbar_wait(&p_full[0], item & 1);
+              tc_fence_after();
+              for (int ks = 0; ks < split; ++ks) {
+                const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
+                atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, ks > 0 ? 1u : 0u);
+              }
+              if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 10] = clock64();
+              mbar_wait(&p_full[1], item & 1);
+              tc_fence_after();
+              for (int ks = split; ks < ksteps; ++ks) {
+                const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
+                atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, 1u);
+              }
+              if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 11] = clock64();
+            }
+            tc_commit(o_full);
+            if (p.nblk > 1 || qt == p.n_qt - 1) tc_commit(&kv_empty[kb]);
+            if (kv_new) ++kvc;
           }
-          tc_commit(&q_empty[qb]);
-          tc_commit(s_full);
-          // O = P V in two groups (k-steps 0..7 = keys 0..127, then the rest) as the softmax warps publish P: the first
-          // group runs under the remaining exponentials. (Finer groups starve: this warp shares its scheduler with two
-          // softmax warps that are always eligible.)
-          {
-            const int ksteps = p.nkp >> 4;
-            const int split = ksteps < 8 ? ksteps : 8;
-            mbar_wait(&p_full[0], item & 1);
-            tc_fence_after();
-            for (int ks = 0; ks < split; ++ks) {
-              const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
-              atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, ks > 0 ? 1u : 0u);
-            }
-            if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 10] = clock64();
-            mbar_wait(&p_full[1], item & 1);
-            tc_fence_after();
-            for (int ks = split; ks < ksteps; ++ks) {
-              const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
-              atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, 1u);
-            }
-            if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 11] = clock64();
-          }
-          tc_commit(o_full);
-          if (qt == p.n_qt - 1) tc_commit(&kv_empty[kb]);
         }
-        if (p.n_qt == 0) mbar_arrive(&kv_empty[kb]);
       }
     }
   } else if (warp == 3) {
@@ -361,117 +369,149 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float* xmax = reinterpret_cast<float*>(smem + ATC_OFF_X);    // [2 halves][128 rows]
     float* xsum = xmax + 256;                                    // [2 halves][128 rows]
     const int row_in_tile = quad * 32 + lane;
-    const int n_chunks = (p.nkp + 31) >> 5;
-    constexpr int MAXC = 5;               // chunks per warp: ceil(9 / 2)
+    constexpr int MAXC = MULTI ? 4 : 5;   // chunks per warp: 8 / 2 for 256-key blocks, ceil(9 / 2) for a resident range of 272
     int item = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int b = u / p.heads, h = u - b * p.heads;
-      for (int qt = 0; qt < p.n_qt; ++qt, ++item) {
-        if (ew == 0) ATC_STAMP(0);
-        mbar_wait(s_full, item & 1);
-        tc_fence_after();
-        if (ew == 0) ATC_STAMP(1);
-        // the warp's share of the S row -> registers, then S is free for the next tile's QK^T
-        uint32_t sv[MAXC][32];
+      for (int qt = 0; qt < p.n_qt; ++qt) {
+        // online-softmax state of this thread's row over the key blocks (one block when the key range is resident):
+        // running maximum of the raw scores, this warp's partial row sum, and its 32 output columns
+        float m_run = -INFINITY, sum = 0.f;
+        float o_acc[32];
+        if constexpr (MULTI) {
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-          const int c = hf + 2 * i;
-          if (c < n_chunks) tmem_ld_32x32(t_s + c * 32, sv[i]);
+          for (int j2 = 0; j2 < 32; ++j2) o_acc[j2] = 0.f;
         }
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);
-        if (ew == 0) ATC_STAMP(2);
-        // columns past Nk (zero-filled keys) must not take part: only the last chunk can hold any
-        if ((p.Nk & 31) != 0) {
+        for (int j = 0; j < p.nblk; ++j, ++item) {
+          const bool last_blk = j == p.nblk - 1;
+          const int nk = last_blk ? p.nk_last : 256;
+          const int nkp = last_blk ? p.nkp_last : 256;
+          const int n_chunks = (nkp + 31) >> 5;
+          if (ew == 0) ATC_STAMP(0);
+          mbar_wait(s_full, item & 1);
+          tc_fence_after();
+          if (ew == 0) ATC_STAMP(1);
+          // the warp's share of the S row -> registers, then S is free for the next block's QK^T
+          uint32_t sv[MAXC][32];
 #pragma unroll
           for (int i = 0; i < MAXC; ++i) {
             const int c = hf + 2 * i;
-            if (c == n_chunks - 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c * 32 + j >= p.Nk) sv[i][j] = 0xff800000u;   // -inf
-            }
+            if (c < n_chunks) tmem_ld_32x32(t_s + c * 32, sv[i]);
           }
-        }
-        // row maximum: own columns, then the partner warp's through shared memory
-        float mx = -INFINITY;
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
+          if (ew == 0) ATC_STAMP(2);
+          // columns past the block's keys (zero-filled rows) must not take part: only the last chunk can hold any
+          if ((nk & 31) != 0) {
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-          if (hf + 2 * i < n_chunks) {
+            for (int i = 0; i < MAXC; ++i) {
+              const int c = hf + 2 * i;
+              if (c == n_chunks - 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sv[i][j]));
-          }
-        }
-        xmax[hf * 128 + row_in_tile] = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-        mx = fmaxf(mx, xmax[(hf ^ 1) * 128 + row_in_tile]);
-        const float ms = mx * p.scale_log2;
-        if (ew == 0) ATC_STAMP(3);
-        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2] = clock64();
-        // P = exp2(scale * S - max) as bf16 pairs (tcgen05.st), published chunk by chunk; partial row sum in fp32
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-          const int c = hf + 2 * i;
-          if (c < n_chunks) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float e0 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j]), p.scale_log2, -ms));
-              const float e1 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j + 1]), p.scale_log2, -ms));
-              sum += e0 + e1;
-              pk[j] = pack_bf16(e0, e1);
-            }
-            atc_tmem_st_32x16(t_p + c * 16, pk);
-            const bool last = (i == MAXC - 1) || (c + 2 >= n_chunks);
-            if (i == 1 && !last) {
-              // first group (chunks 0..3) complete for this warp
-              atc_tmem_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&p_full[0]);
-            }
-            if (last) {
-              xsum[hf * 128 + row_in_tile] = sum;
-              atc_tmem_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if (i <= 1) mbar_arrive(&p_full[0]);   // short rows: everything is in the first group
-                mbar_arrive(&p_full[1]);
+                for (int j2 = 0; j2 < 32; ++j2)
+                  if (c * 32 + j2 >= nk) sv[i][j2] = 0xff800000u;   // -inf
               }
             }
           }
+          // block maximum: own columns, then the partner warp's through shared memory; fold into the running maximum
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < MAXC; ++i) {
+            if (hf + 2 * i < n_chunks) {
+#pragma unroll
+              for (int j2 = 0; j2 < 32; ++j2) mx = fmaxf(mx, __uint_as_float(sv[i][j2]));
+            }
+          }
+          xmax[hf * 128 + row_in_tile] = mx;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+          mx = fmaxf(mx, xmax[(hf ^ 1) * 128 + row_in_tile]);
+          // (no second barrier: the partner cannot reach its next xmax write before this warp has published P for this
+          // block -- the o_full wait below needs every warp's P)
+          const float m_new = fmaxf(m_run, mx);
+          const float alpha = atc_ex2((m_run - m_new) * p.scale_log2);   // 0 on the first block (m_run = -inf)
+          m_run = m_new;
+          const float ms = m_new * p.scale_log2;
+          if (ew == 0) ATC_STAMP(3);
+          if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2] = clock64();
+          // P = exp2(scale * S - max) as bf16 pairs (tcgen05.st), published in two groups; partial row sum in fp32
+          sum *= alpha;
+#pragma unroll
+          for (int i = 0; i < MAXC; ++i) {
+            const int c = hf + 2 * i;
+            if (c < n_chunks) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int j2 = 0; j2 < 16; ++j2) {
+                const float e0 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j2]), p.scale_log2, -ms));
+                const float e1 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j2 + 1]), p.scale_log2, -ms));
+                sum += e0 + e1;
+                pk[j2] = pack_bf16(e0, e1);
+              }
+              atc_tmem_st_32x16(t_p + c * 16, pk);
+              const bool last = (i == MAXC - 1) || (c + 2 >= n_chunks);
+              if (i == 1 && !last) {
+                // first group (chunks 0..3) complete for this warp
+                atc_tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[0]);
+              }
+              if (last) {
+                if (last_blk) xsum[hf * 128 + row_in_tile] = sum;   // read by the partner after the o_full wait
+                atc_tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (i <= 1) mbar_arrive(&p_full[0]);   // short rows: everything is in the first group
+                  mbar_arrive(&p_full[1]);
+                }
+              }
+            }
+          }
+          if (hf >= n_chunks) {   // a short last block leaves this warp without columns: publish nothing, twice
+            if (last_blk) xsum[hf * 128 + row_in_tile] = sum;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&p_full[0]); mbar_arrive(&p_full[1]); }
+          }
+          if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2 + 1] = clock64();
+          if (ew == 0) ATC_STAMP(4);
+          // this block's contribution to the warp's 32 output columns: o = alpha * o + P V_j
+          mbar_wait(o_full, item & 1);
+          tc_fence_after();
+          if (ew == 0) ATC_STAMP(5);
+          {
+            uint32_t raw[32];
+            tmem_ld_32x32(t_o + hf * 32, raw);
+            tmem_ld_wait();
+            if constexpr (MULTI) {
+#pragma unroll
+              for (int j2 = 0; j2 < 32; ++j2) o_acc[j2] = fmaf(o_acc[j2], alpha, __uint_as_float(raw[j2]));
+            } else {
+#pragma unroll
+              for (int j2 = 0; j2 < 32; ++j2) o_acc[j2] = __uint_as_float(raw[j2]);
+            }
+          }
+          tc_fence_before();   // (orders the O read before the next block's P publish, i.e. before PV overwrites O)
         }
-        if (ew == 0) ATC_STAMP(4);
-        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2 + 1] = clock64();
-        // epilogue: this warp's 32 output columns: O / sum -> bf16 -> swizzled staging tile -> bulk tensor store
-        mbar_wait(o_full, item & 1);
-        if (ew == 0) ATC_STAMP(5);   // (every softmax warp published its last chunk before this completes: xsum is visible)
-        tc_fence_after();
+        // epilogue: O / sum -> bf16 -> swizzled staging tile -> bulk tensor store
         sum += xsum[(hf ^ 1) * 128 + row_in_tile];
         const float inv = 1.f / sum;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-        {
-          uint32_t raw[32];
-          tmem_ld_32x32(t_o + hf * 32, raw);
-          tmem_ld_wait();
-          if (ew == 0) ATC_STAMP(7);
+        if (ew == 0) ATC_STAMP(7);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int j = c * 8;
-            const uint32_t w0 = pack_bf16(__uint_as_float(raw[j]) * inv, __uint_as_float(raw[j + 1]) * inv);
-            const uint32_t w1 = pack_bf16(__uint_as_float(raw[j + 2]) * inv, __uint_as_float(raw[j + 3]) * inv);
-            const uint32_t w2 = pack_bf16(__uint_as_float(raw[j + 4]) * inv, __uint_as_float(raw[j + 5]) * inv);
-            const uint32_t w3 = pack_bf16(__uint_as_float(raw[j + 6]) * inv, __uint_as_float(raw[j + 7]) * inv);
-            const uint32_t addr = stage + row_off + ((c ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-          }
+        for (int c = 0; c < 4; ++c) {
+          const int j2 = c * 8;
+          const uint32_t w0 = pack_bf16(o_acc[j2] * inv, o_acc[j2 + 1] * inv);
+          const uint32_t w1 = pack_bf16(o_acc[j2 + 2] * inv, o_acc[j2 + 3] * inv);
+          const uint32_t w2 = pack_bf16(o_acc[j2 + 4] * inv, o_acc[j2 + 5] * inv);
+          const uint32_t w3 = pack_bf16(o_acc[j2 + 6] * inv, o_acc[j2 + 7] * inv);
+          const uint32_t addr = stage + row_off + ((c ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
         }
-        tc_fence_before();
         fence_proxy_async();
         __syncwarp();
         const int row0 = qt * 128 + quad * 32;
@@ -480,7 +520,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (hf == 0 && p.lse != nullptr && row0 + lane < p.Nq)
-          p.lse[((long long)b * p.heads + h) * p.Nq + row0 + lane] = (ms + log2f(sum)) * 0.6931471805599453f;
+          p.lse[((long long)b * p.heads + h) * p.Nq + row0 + lane] = (m_run * p.scale_log2 + log2f(sum)) * 0.6931471805599453f;
         if (ew == 0) ATC_STAMP(6);
       }
     }
@@ -501,16 +541,23 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
   if (!enabled) return 1;
-  if (d->hd != 64 || d->qkvo_is_fp16 || d->Nk > ATC_NKP_MAX || d->Nk < 33 || d->q_bs == 0) return 1;
+  if (d->hd != 64 || d->qkvo_is_fp16 || d->Nk < 33 || d->q_bs == 0) return 1;
+  static int long_on = -1;
+  if (long_on < 0) { const char* e = getenv("B200_ATTN_TC_LONG"); long_on = (e && e[0] == '0') ? 0 : 1; }
+  if (d->Nk > ATC_NKP_MAX && !long_on) return 1;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(d->q) || !al16(d->k) || !al16(d->v) || !al16(d->o)) return 1;
   if (d->q_ts % 8 || d->k_ts % 8 || d->v_ts % 8 || d->o_ts % 8 || d->q_bs % 8 || d->k_bs % 8 || d->v_bs % 8 || d->o_bs % 8)
     return 1;
   AttnTcParams p{};
   p.B = d->B; p.heads = d->heads; p.Nq = d->Nq; p.Nk = d->Nk;
-  p.nkp = (d->Nk + 15) & ~15;
+  // key blocks: the whole range when it fits the S columns (<= 272), else blocks of 256 with online softmax
+  p.nblk = d->Nk <= ATC_NKP_MAX ? 1 : (d->Nk + 255) / 256;
+  p.nk_last = d->Nk - (p.nblk - 1) * 256;
+  p.nkp_last = (p.nk_last + 15) & ~15;
+  p.nkp = p.nkp_last;
   const int rem = d->Nq % 128;
-  if (rem > 0 && rem <= ATC_TAIL_MAX) {
+  if (p.nblk == 1 && rem > 0 && rem <= ATC_TAIL_MAX) {
     p.n_qt = d->Nq / 128; p.tail0 = p.n_qt * 128; p.tail_n = rem;
   } else {
     p.n_qt = (d->Nq + 127) / 128; p.tail0 = 0; p.tail_n = 0;
@@ -520,10 +567,11 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   p.lse = d->lse;
   p.q = static_cast<const __nv_bfloat16*>(d->q); p.q_bs = d->q_bs; p.q_ts = d->q_ts;
   p.o = static_cast<__nv_bfloat16*>(d->o); p.o_bs = d->o_bs; p.o_ts = d->o_ts;
-  p.n1 = p.nkp > 256 ? 256 : p.nkp;
-  p.n2 = p.nkp - p.n1;
+  p.n1 = p.nkp_last > 256 ? 256 : p.nkp_last;
+  p.n2 = p.nkp_last - p.n1;
   p.idesc_qk1 = make_idesc_bf16(128, p.n1, false, false);
   p.idesc_qk2 = p.n2 > 0 ? make_idesc_bf16(128, p.n2, false, false) : 0u;
+  p.idesc_qk_full = make_idesc_bf16(128, 256, false, false);
   p.idesc_pv = make_idesc_bf16(128, 64, false, true);
 
   const uint64_t cols = (uint64_t)d->heads * 64;
@@ -535,7 +583,8 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
     attr_set = true;
   }
   const int units = d->B * d->heads;
@@ -547,7 +596,8 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   if (dbg_on && dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 9 * 16 * sizeof(long long)); }
   if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 9 * 16 * sizeof(long long), st);
   p.dbg = dbg_on ? dbg_buf : nullptr;
-  B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, p));
+  if (p.nblk > 1) B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, p));
+  else B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, p));
   prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
   B200_LAUNCH_OK();
   if (dbg_on) {

@@ -245,10 +245,13 @@ def test_attention_fwd_bwd(hd, heads, Nq, Nk):
 
 
 @pytest.mark.parametrize("B,heads,Nq,Nk", [(3, 6, 256, 256), (5, 6, 257, 257), (2, 12, 200, 200), (2, 3, 264, 264),
-                                           (2, 4, 130, 130), (1, 2, 300, 257), (2, 6, 64, 272), (70, 6, 257, 257)])
+                                           (2, 4, 130, 130), (1, 2, 300, 257), (2, 6, 64, 272), (70, 6, 257, 257),
+                                           (2, 16, 1370, 1370), (1, 3, 200, 600), (2, 2, 520, 273), (1, 2, 1025, 1024)])
 def test_attention_tc_head64(B, heads, Nq, Nk):
-    """tcgen05 one-shot attention (attention_tc.cu): full / partial query tiles, CUDA-core tail rows (Nq mod 128 <= 8),
-    key padding to 16, more units than SMs, strided q/k/v out of a fused qkv tensor, and the log-sum-exp output."""
+    """tcgen05 attention (attention_tc.cu): resident key range (Nk <= 272, one QK^T / PV per query tile) and key blocks
+    of 256 with online softmax (518-pixel sequence lengths); full / partial query tiles, tail rows on mma.sync
+    (Nq mod 128 <= 8), key padding to 16, ragged last key block, more units than SMs, strided q/k/v out of a fused qkv
+    tensor, and the log-sum-exp output."""
     ops = _ops()
     hd = 64
     D = hd * heads

@@ -11,6 +11,7 @@ from tools.gemm_bench import bench
 def main():
     shapes = [("teacher vits14 @224", 64, 6, 64, 257, torch.bfloat16, 1.0), ("stage blocks", 64, 6, 64, 256, torch.bfloat16, 1.0),
               ("teacher vitb14 @224 B=32", 32, 12, 64, 257, torch.bfloat16, 1.0),
+              ("teacher vitl14 @518 B=32", 32, 16, 64, 1370, torch.bfloat16, 1.0),
               ("projector res4 hd24", 64, 16, 24, 256, torch.float16, 5.0), ("projector res5 hd16", 64, 24, 16, 256, torch.float16, 5.0)]
     for name, B, heads, hd, N, dt, ss in shapes:
         D = heads * hd

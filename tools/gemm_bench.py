@@ -39,6 +39,7 @@ def main():
         ("vits proj +res", 16448, 384, 384, dict(bias=True, res=True)),
         ("vits fc1 gelu", 16448, 1536, 384, dict(bias=True, act="gelu", out="bf16")),
         ("vits fc1 noact", 16448, 1536, 384, dict(bias=True, out="bf16")),
+        ("vits fc1 nobias", 16448, 1536, 384, dict(out="bf16")),
         ("vits fc2 +res", 16448, 384, 1536, dict(bias=True, res=True)),
         ("vitb qkv", 8224, 2304, 768, dict(bias=True, out="bf16")),
         ("vitb fc1 gelu", 8224, 3072, 768, dict(bias=True, act="gelu", out="bf16")),
