@@ -33,6 +33,7 @@ class GemmDesc(C.Structure):
         ("out_row_period", C.c_int), ("out_row_pad", C.c_int),
         ("a_is_fp16", C.c_int), ("b_is_fp16", C.c_int), ("out16_is_fp16", C.c_int), ("aux_is_fp16", C.c_int),
         ("algo_flops_scale", C.c_float),
+        ("out_batch_period", C.c_int), ("out_batch_stride", c_ll),
     ]
 
 

@@ -41,6 +41,8 @@ struct Gemm {
   Gemm& out16_fp16() { d.out16_is_fp16 = 1; return *this; }
   Gemm& aux_fp16() { d.aux_is_fp16 = 1; return *this; }
   Gemm& algo_scale(float f) { d.algo_flops_scale = f; return *this; }
+  Gemm& out_batched(int period, long long stride) { d.out_batch_period = period; d.out_batch_stride = stride; return *this; }
+  Gemm& accumulate(int on) { d.atomic_add = on; return *this; }
   // wgrad form: both operands token-major (contraction over rows), fp32 atomic accumulate, split over the contraction
   Gemm& wgrad() {
     d.a_mn_major = 1; d.b_mn_major = 1; d.atomic_add = 1;
@@ -610,8 +612,14 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   if (!c->training) B200_TRY(b200_colsum(w.dy16, 1, D, g->conv_b, Mi, D, stream));
   B200_TRY(Gemm(w.dy16, D, tokens ? static_cast<const bf16*>(tokens) : s.xt, Cs, D, Cs, Mi).out32(g->conv_w, Cs).wgrad().run(stream));
   if (dx) {
-    B200_TRY(Gemm(w.dy16, D, w.wcT, D, Mi, Cs, D).out32(w.dxt32, Cs).run(stream));
-    B200_TRY(b200_tokens_to_nchw(w.dxt32, dx, B, Cs, HW, dx_accumulate, stream));
+    if (HW % 32 == 0 && Cs % 8 == 0) {
+      // dX in NCHW straight out of the GEMM: dx[b] [Cs, HW] = Wc^T [Cs, D] . dy_b^T -- operand roles swapped, columns
+      // (b, hw) batched with period HW through a 3-D output tensor map; no token-major intermediate, no transpose
+      B200_TRY(Gemm(w.wcT, D, w.dy16, D, Cs, Mi, D).out32(dx, HW).out_batched(HW, (long long)Cs * HW).accumulate(dx_accumulate ? 1 : 0).run(stream));
+    } else {
+      B200_TRY(Gemm(w.dy16, D, w.wcT, D, Mi, Cs, D).out32(w.dxt32, Cs).run(stream));
+      B200_TRY(b200_tokens_to_nchw(w.dxt32, dx, B, Cs, HW, dx_accumulate, stream));
+    }
   }
   return 0;
 }

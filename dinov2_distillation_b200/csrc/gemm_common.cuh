@@ -34,6 +34,7 @@ struct GemmParams {
   __nv_bfloat16* out_bf16_pre;
   long long ldo16_pre;
   int out_row_period, out_row_pad;
+  int out_bp;                // fp32 output batched along columns with this period (3-D output tensor map); 0 = plain 2-D
   int vec_ok;  // all leading dims / pointers allow 16-byte vector access
   int out16_fp16, aux_fp16;  // 16-bit output / aux element type: 0 = bf16, 1 = fp16
   uint32_t idesc;            // tcgen05 instruction descriptor (operand formats, majors, tile shape)
@@ -183,6 +184,8 @@ int launch_gemm_2cta(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st);
 int gemm_env_int(const char* name, int dflt);
 int make_tensor_map_ex(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
                        uint32_t b1, int swizzle);
+int make_tensor_map_3d(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                       uint64_t ld2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle);
 // second-generation kernel (gemm_v2.cu); same return convention as launch_gemm_2cta
 int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st);
 

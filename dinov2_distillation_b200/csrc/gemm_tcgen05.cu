@@ -424,6 +424,7 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
     const int rv = launch_gemm_v2(d, p2, st);
     if (rv <= 0) return rv;
   }
+  B200_CHECK_ARG(d->out_batch_period <= 0, "out_batch_period is only implemented by the bulk-store kernel (see launch_gemm_v2)");
   if (!d->a_mn_major && !d->b_mn_major && split == 1) {
     const int r2 = launch_gemm_2cta(d, p, st);
     if (r2 <= 0) return r2;

@@ -101,6 +101,16 @@ __device__ __forceinline__ void v2_tma_reduce_add_2d(const CUtensorMap* m, uint3
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void v2_tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void v2_tma_reduce_add_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void v2_tma_load_2d_s(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -340,8 +350,15 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        if (reduce_out) v2_tma_reduce_add_2d(tmO, stage_smem, c0, row0);
-        else v2_tma_store_2d(tmO, stage_smem, c0, row0);
+        if (p.out_bp > 0) {   // columns batched with period out_bp: (column in batch, row, batch)
+          const int bi = c0 / p.out_bp, cb = c0 - bi * p.out_bp;
+          if (reduce_out) v2_tma_reduce_add_3d(tmO, stage_smem, cb, row0, bi);
+          else v2_tma_store_3d(tmO, stage_smem, cb, row0, bi);
+        } else if (reduce_out) {
+          v2_tma_reduce_add_2d(tmO, stage_smem, c0, row0);
+        } else {
+          v2_tma_store_2d(tmO, stage_smem, c0, row0);
+        }
         v2_bulk_commit();
       }
     }
@@ -595,6 +612,11 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   if (d->a_mn_major != d->b_mn_major) return 1;
   if (d->out_row_period > 0 || d->res_row_period > 0) return 1;
   const bool f32 = d->out_f32 != nullptr;
+  if (d->out_batch_period > 0) {
+    B200_CHECK_ARG(f32 && !d->residual && d->out_batch_period % 32 == 0 && d->N % d->out_batch_period == 0 &&
+                       d->N % 32 == 0 && d->out_batch_stride % 4 == 0 && d->ldo32 % 4 == 0 && !d->a_mn_major && !d->b_mn_major,
+                   "out_batch_period needs a plain fp32 output with 32-aligned batches");
+  }
   if (f32 && d->out_bf16) return 1;
   if (f32 && (d->out_bf16_pre || d->aux_mode != 0 || d->act != 0)) return 1;
   if (!f32 && (d->col_scale || d->residual || d->atomic_add)) return 1;
@@ -647,7 +669,12 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
     B200_TRY(make_tensor_map_2d(&ta, d->A, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, 64, BK));
     B200_TRY(make_tensor_map_2d(&tb, d->B, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, BK));
   }
-  if (f32) {
+  p.out_bp = d->out_batch_period > 0 ? d->out_batch_period : 0;
+  if (f32 && p.out_bp > 0) {
+    B200_TRY(make_tensor_map_3d(&to, d->out_f32, 4, (uint64_t)p.out_bp, (uint64_t)d->M, (uint64_t)(d->N / p.out_bp),
+                                (uint64_t)d->ldo32, (uint64_t)d->out_batch_stride, 32, 32, 1, 128));
+    tx = to;
+  } else if (f32) {
     B200_TRY(make_tensor_map_ex(&to, d->out_f32, 4, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo32, 32, 32, 128));
     if (use_x) B200_TRY(make_tensor_map_ex(&tx, d->residual, 4, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldres, 32, 32, 128));
     else tx = to;

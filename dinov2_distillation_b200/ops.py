@@ -42,7 +42,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
          aux_mode: str = "none", col_scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          res_row_period: int = 0, out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None,
          atomic_add: bool = False, split_k: int = 1, out_pre: bool = False, out_row_period: int = 0,
-         out_row_pad: int = 0):
+         out_row_pad: int = 0, out_batch_period: int = 0):
     """C = epilogue(A @ B^T). K-major: a [M,K], b [N,K]. MN-major: a [K,M], b [K,N] (contraction over rows)."""
     _need_cuda(a, b, bias, aux, col_scale, residual, out)
     assert a.dtype in (torch.bfloat16, torch.float16) and b.dtype in (torch.bfloat16, torch.float16)
@@ -72,6 +72,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
         assert residual.dtype == torch.float32
         d.residual, d.ldres, d.res_row_period = residual.data_ptr(), residual.stride(0), res_row_period
     out_rows = M if out_row_period <= 0 else (M // out_row_period) * (out_row_period + out_row_pad)
+    if out_batch_period > 0:
+        # columns batched with period P: out is [N / P, M, P] fp32 (element (r, n) -> out[n // P, r, n % P])
+        assert out is not None and out.dtype == torch.float32 and out.dim() == 3 and out.is_contiguous()
+        assert tuple(out.shape) == (N // out_batch_period, M, out_batch_period)
+        d.out_batch_period, d.out_batch_stride = out_batch_period, out.stride(0)
+        d.out_f32, d.ldo32, d.atomic_add = out.data_ptr(), out.stride(1), int(atomic_add)
+        L.check(L.load().b200_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
+        return out
     if out is None:
         out = torch.empty(out_rows, N, device=a.device, dtype=out_dtype)
     pre = None

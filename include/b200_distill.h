@@ -72,6 +72,10 @@ typedef struct b200_gemm_desc {
   int a_is_fp16, b_is_fp16, out16_is_fp16, aux_is_fp16;
   /* profiling only: algorithmic flops = algo_flops_scale * 2MNK (0 means 1; 1/3 for the 3-term split product) */
   float algo_flops_scale;
+  /* batched-column fp32 output: period P > 0 sends element (r, n) to out_f32[(n / P) * out_batch_stride + r * ldo32 +
+   * n % P] -- with the operand roles swapped (A = W^T, B = token-major dY) the input gradient of the 1x1 conv lands
+   * directly in NCHW (P = H*W, ldo32 = H*W, stride = C*H*W) with no transpose pass. P % 32 == 0, N % P == 0. */
+  int out_batch_period; long long out_batch_stride;
 } b200_gemm_desc;
 
 int b200_gemm_bf16(const b200_gemm_desc* d, void* stream);

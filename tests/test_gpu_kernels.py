@@ -151,6 +151,23 @@ def test_gemm_tma_epilogue_paths(M, N, K):
     assert rel_err(ops.gemm(a, b, aux=auxh, aux_mode="drelu", out_dtype=torch.bfloat16), plain * (auxh.float() > 0)) < 6e-3
 
 
+def test_gemm_batched_column_output_writes_nchw():
+    """dX of the 1x1 conv straight into NCHW: A = W^T [C, D], B = token-major dY [B*HW, D], columns batched with
+    period HW through the 3-D output tensor map (plain store and accumulate)."""
+    ops = _ops()
+    Bt, HW, Cc, D = 5, 256, 512, 384
+    wT = bf(torch.randn(Cc, D, device="cuda") / math.sqrt(D))
+    dy = bf(torch.randn(Bt * HW, D, device="cuda"))
+    ref = torch.einsum("cd,bhd->bch", wT.float(), dy.float().view(Bt, HW, D))
+    out = torch.empty(Bt, Cc, HW, device="cuda")
+    ops.gemm(wT, dy, out=out, out_batch_period=HW)
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+    base = torch.randn(Bt, Cc, HW, device="cuda")
+    out2 = base.clone()
+    ops.gemm(wT, dy, out=out2, out_batch_period=HW, atomic_add=True)
+    assert rel_err(out2 - base, ref) < 2e-3
+
+
 def test_gelu_epilogue_matches_erf_gelu():
     """The one-MUFU GELU of the 16-bit epilogue against erf-GELU over the whole useful range (identity GEMM)."""
     ops = _ops()
