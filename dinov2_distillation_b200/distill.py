@@ -51,6 +51,20 @@ class DistillationStep(nn.Module):
             feat = self.teacher.model.blocks[i](feat)
         return feat
 
+    # The spatial and the frequency branch of a stage are independent until their losses are added (each: projector ->
+    # re-used teacher blocks -> loss term). With `two_streams` they are issued on two CUDA streams: the kernels of one
+    # branch fill the SMs the partial last wave of the other leaves idle (a 16 384 x 384 GEMM is 1.7 waves of tiles), and
+    # autograd replays each branch's backward on its forward stream, so the backward overlaps the same way. Stream
+    # fork / join is captured by GraphedDistillStep like any other dependency.
+    two_streams = True
+
+    def _branch_streams(self, ref: torch.Tensor):
+        if not (self.two_streams and ref.is_cuda):
+            return None, None
+        if getattr(self, "_side_stream", None) is None or self._side_stream.device != ref.device:
+            self._side_stream = torch.cuda.Stream(device=ref.device)
+        return torch.cuda.current_stream(ref.device), self._side_stream
+
     def _compute_losses(self, features):
         total_loss = 0
         loss_dict = {}
@@ -59,8 +73,12 @@ class DistillationStep(nn.Module):
             layer = name.split("_")[1]
             loss_fn, weight = self.losses[name], self.loss_weights[name]
             s_feat = features["student"][layer]
+            main, side = self._branch_streams(s_feat)
             if "res5" in name:
-                loss = loss_fn(s_feat, features["teacher"], query_s=spatial_query, query_f=frequency_query)
+                if side is not None and hasattr(loss_fn, "forward_two_streams"):
+                    loss = loss_fn.forward_two_streams(s_feat, features["teacher"], spatial_query, frequency_query, main, side)
+                else:
+                    loss = loss_fn(s_feat, features["teacher"], query_s=spatial_query, query_f=frequency_query)
                 loss_dict[f"{name}_total_loss"] = loss["loss"] * weight
                 loss_dict[f"{name}_frequency_loss"] = loss["frequency_loss"] * weight
                 loss_dict[f"{name}_spatial_loss"] = loss["spatial_loss"] * weight
@@ -68,14 +86,28 @@ class DistillationStep(nn.Module):
                 loss_dict[f"{name}_frequency_similarity"] = loss["frequency_similarity"]
                 total_loss = total_loss + loss["loss"] * weight
                 break
-            feat_spat = loss_fn.project_feat_spat(s_feat, query=spatial_query)
-            feat_freq = loss_fn.project_feat_freq(s_feat, query=frequency_query)
-            feat_spat = self._forward_specific_stage(feat_spat, layer)
-            feat_freq = self._forward_specific_stage(feat_freq, layer)
+            if side is None or not hasattr(loss_fn, "tokenize_for_both"):
+                feat_spat = loss_fn.project_feat_spat(s_feat, query=spatial_query)
+                feat_freq = loss_fn.project_feat_freq(s_feat, query=frequency_query)
+                feat_spat = self._forward_specific_stage(feat_spat, layer)
+                feat_freq = self._forward_specific_stage(feat_freq, layer)
+                spatial_loss, spatial_similarity = loss_fn.get_spat_loss(feat_spat, features["teacher"])
+                # sic: the reference scores the "frequency" branch of non-res5 stages with the SPATIAL loss (:236-237)
+                frequency_loss, frequency_similarity = loss_fn.get_spat_loss(feat_freq, features["teacher"])
+            else:
+                tok = loss_fn.tokenize_for_both(s_feat)          # shared by both projectors; before the fork
+                side.wait_stream(main)
+                feat_spat = loss_fn.projector_0(s_feat, query=spatial_query, tokens=tok)
+                feat_spat = self._forward_specific_stage(feat_spat, layer)
+                spatial_loss, spatial_similarity = loss_fn.get_spat_loss(feat_spat, features["teacher"])
+                with torch.cuda.stream(side):
+                    feat_freq = loss_fn.projector_1(s_feat, query=frequency_query, tokens=tok)
+                    feat_freq = self._forward_specific_stage(feat_freq, layer)
+                    frequency_loss, frequency_similarity = loss_fn.get_spat_loss(feat_freq, features["teacher"])
+                main.wait_stream(side)
+                for t in (feat_freq, frequency_loss, frequency_similarity):   # allocated on `side`, read on `main`
+                    t.record_stream(main)
             spatial_query, frequency_query = feat_spat, feat_freq
-            spatial_loss, spatial_similarity = loss_fn.get_spat_loss(feat_spat, features["teacher"])
-            # sic: the reference scores the "frequency" branch of non-res5 stages with the SPATIAL loss (:236-237)
-            frequency_loss, frequency_similarity = loss_fn.get_spat_loss(feat_freq, features["teacher"])
             loss_dict[f"{name}_total_loss"] = (spatial_loss + frequency_loss) * weight
             loss_dict[f"{name}_frequency_loss"] = frequency_loss * weight
             loss_dict[f"{name}_spatial_loss"] = spatial_loss * weight

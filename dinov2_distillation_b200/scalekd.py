@@ -310,6 +310,27 @@ class ScaleKD(nn.Module):
         return {"spatial_loss": spat_loss, "frequency_loss": freq_loss, "spatial_similarity": spatial_similarity,
                 "frequency_similarity": frequency_similarity, "loss": spat_loss + freq_loss}
 
+    def tokenize_for_both(self, preds_S: torch.Tensor):
+        """Shared token-major working copy of preds_S for `projector_0(x, tokens=...)` / `projector_1(x, tokens=...)`
+        (None when preds_S needs the projector's own conversions)."""
+        return self._tokenize(preds_S)
+
+    def forward_two_streams(self, preds_S, preds_T, query_s, query_f, main, side):
+        """`forward` with the spatial branch on `main` and the frequency branch on `side` (see
+        distill.DistillationStep.two_streams). Same result; the caller has made `main` current."""
+        tok = self._tokenize(preds_S)
+        side.wait_stream(main)
+        preds_S_spat = self.projector_0(preds_S, query=query_s, tokens=tok)
+        spat_loss, spatial_similarity = self.get_spat_loss(preds_S_spat, preds_T)
+        with torch.cuda.stream(side):
+            preds_S_freq = self.projector_1(preds_S, query=query_f, tokens=tok)
+            freq_loss, frequency_similarity = self.get_freq_loss(preds_S_freq, preds_T)
+        main.wait_stream(side)
+        for t in (freq_loss, frequency_similarity):   # allocated on `side`, read on `main`
+            t.record_stream(main)
+        return {"spatial_loss": spat_loss, "frequency_loss": freq_loss, "spatial_similarity": spatial_similarity,
+                "frequency_similarity": frequency_similarity, "loss": spat_loss + freq_loss}
+
     def _tokenize(self, preds_S: torch.Tensor):
         H, W = self.projector_0.hw_dims
         if not (preds_S.is_cuda and preds_S.dtype == torch.float32 and preds_S.is_contiguous()

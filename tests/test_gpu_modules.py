@@ -312,6 +312,15 @@ def test_graphed_step_follows_new_inputs_and_matches_eager():
 
     ref_a, ref_b = eager(img_a, feats_a), eager(img_b, feats_b)
     assert abs(ref_a[0]["loss"].item() - ref_b[0]["loss"].item()) > 1e-4   # the two batches are distinguishable
+    # spatial / frequency branches on two CUDA streams (default) == everything on one stream
+    step.two_streams = False
+    one = eager(img_a, feats_a)
+    step.two_streams = True
+    for k, v in ref_a[0].items():
+        assert abs(one[0][k].item() - v.item()) <= 1e-5 * max(abs(v.item()), 1e-3), (k, one[0][k].item(), v.item())
+    for k, v in ref_a[2].items():
+        if v.norm().item() > 1e-6:
+            assert rel(one[2][k], v) <= 2e-3, (k, rel(one[2][k], v))
     for p in step.losses.parameters():
         p.grad = None
     arena = FlatGradArena(step.losses.parameters())
