@@ -65,19 +65,47 @@ class DistillationStep(nn.Module):
             self._side_stream = torch.cuda.Stream(device=ref.device)
         return torch.cuda.current_stream(ref.device), self._side_stream
 
+    def teacher_async(self, batch):
+        """Frozen-teacher forward on its own CUDA stream: the projectors and the re-used teacher blocks of the loss path
+        do not read the teacher features until the loss terms, so the ~90-kernel teacher chain overlaps them. Returns
+        (feature_map, event); pass the event as features['teacher_ready'] and `_compute_losses` waits for it right
+        before the first use."""
+        dev = batch.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_teacher_stream", None) is None or self._teacher_stream.device != dev:
+            self._teacher_stream = torch.cuda.Stream(device=dev)
+        ts = self._teacher_stream
+        ts.wait_stream(main)
+        with torch.cuda.stream(ts), torch.no_grad():
+            T = self.teacher(batch)[self.teacher_key]
+            ev = torch.cuda.Event()
+            ev.record(ts)
+        T.record_stream(main)
+        return T, ev
+
+    @staticmethod
+    def _await(ready):
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
+
     def _compute_losses(self, features):
         total_loss = 0
         loss_dict = {}
         spatial_query = frequency_query = None
+        ready = features.get("teacher_ready")
         for name in sorted(self.losses.keys()):
             layer = name.split("_")[1]
             loss_fn, weight = self.losses[name], self.loss_weights[name]
             s_feat = features["student"][layer]
             main, side = self._branch_streams(s_feat)
+            if side is not None and ready is not None:
+                features["teacher"].record_stream(side)   # produced on the teacher stream, read on both branches
             if "res5" in name:
                 if side is not None and hasattr(loss_fn, "forward_two_streams"):
-                    loss = loss_fn.forward_two_streams(s_feat, features["teacher"], spatial_query, frequency_query, main, side)
+                    loss = loss_fn.forward_two_streams(s_feat, features["teacher"], spatial_query, frequency_query, main, side,
+                                                       teacher_ready=ready)
                 else:
+                    self._await(ready)
                     loss = loss_fn(s_feat, features["teacher"], query_s=spatial_query, query_f=frequency_query)
                 loss_dict[f"{name}_total_loss"] = loss["loss"] * weight
                 loss_dict[f"{name}_frequency_loss"] = loss["frequency_loss"] * weight
@@ -91,6 +119,7 @@ class DistillationStep(nn.Module):
                 feat_freq = loss_fn.project_feat_freq(s_feat, query=frequency_query)
                 feat_spat = self._forward_specific_stage(feat_spat, layer)
                 feat_freq = self._forward_specific_stage(feat_freq, layer)
+                self._await(ready)
                 spatial_loss, spatial_similarity = loss_fn.get_spat_loss(feat_spat, features["teacher"])
                 # sic: the reference scores the "frequency" branch of non-res5 stages with the SPATIAL loss (:236-237)
                 frequency_loss, frequency_similarity = loss_fn.get_spat_loss(feat_freq, features["teacher"])
@@ -99,11 +128,13 @@ class DistillationStep(nn.Module):
                 side.wait_stream(main)
                 feat_spat = loss_fn.projector_0(s_feat, query=spatial_query, tokens=tok)
                 feat_spat = self._forward_specific_stage(feat_spat, layer)
-                spatial_loss, spatial_similarity = loss_fn.get_spat_loss(feat_spat, features["teacher"])
                 with torch.cuda.stream(side):
                     feat_freq = loss_fn.projector_1(s_feat, query=frequency_query, tokens=tok)
                     feat_freq = self._forward_specific_stage(feat_freq, layer)
+                    self._await(ready)
                     frequency_loss, frequency_similarity = loss_fn.get_spat_loss(feat_freq, features["teacher"])
+                self._await(ready)
+                spatial_loss, spatial_similarity = loss_fn.get_spat_loss(feat_spat, features["teacher"])
                 main.wait_stream(side)
                 for t in (feat_freq, frequency_loss, frequency_similarity):   # allocated on `side`, read on `main`
                     t.record_stream(main)
@@ -118,6 +149,9 @@ class DistillationStep(nn.Module):
         return loss_dict
 
     def _extract_features(self, batch):
+        if batch.is_cuda and self.two_streams:
+            teacher_features, ready = self.teacher_async(batch)     # overlaps the student and the projectors
+            return {"student": self.student(batch), "teacher": teacher_features, "teacher_ready": ready}
         with torch.no_grad():
             teacher_features = self.teacher(batch)[self.teacher_key]
         return {"student": self.student(batch), "teacher": teacher_features}
@@ -167,10 +201,14 @@ class GraphedDistillStep:
             self.arena.zero()
         for f in self.feats.values():
             f.grad = None
-        T = self.step.teacher(self.img)[self.step.teacher_key]
-        if not self.feats:
-            return {"teacher": T}
-        out = self.step._compute_losses({"student": self.feats, "teacher": T})
+        if not self.feats or not self.step.two_streams:
+            T = self.step.teacher(self.img)[self.step.teacher_key]
+            if not self.feats:
+                return {"teacher": T}
+            out = self.step._compute_losses({"student": self.feats, "teacher": T})
+        else:
+            T, ready = self.step.teacher_async(self.img)
+            out = self.step._compute_losses({"student": self.feats, "teacher": T, "teacher_ready": ready})
         out["loss"].backward()
         return {k: v.detach() for k, v in out.items()}
 

@@ -315,16 +315,20 @@ class ScaleKD(nn.Module):
         (None when preds_S needs the projector's own conversions)."""
         return self._tokenize(preds_S)
 
-    def forward_two_streams(self, preds_S, preds_T, query_s, query_f, main, side):
+    def forward_two_streams(self, preds_S, preds_T, query_s, query_f, main, side, teacher_ready=None):
         """`forward` with the spatial branch on `main` and the frequency branch on `side` (see
         distill.DistillationStep.two_streams). Same result; the caller has made `main` current."""
         tok = self._tokenize(preds_S)
         side.wait_stream(main)
         preds_S_spat = self.projector_0(preds_S, query=query_s, tokens=tok)
-        spat_loss, spatial_similarity = self.get_spat_loss(preds_S_spat, preds_T)
         with torch.cuda.stream(side):
             preds_S_freq = self.projector_1(preds_S, query=query_f, tokens=tok)
+            if teacher_ready is not None:      # preds_T may still be in flight on the teacher's own stream
+                side.wait_event(teacher_ready)
             freq_loss, frequency_similarity = self.get_freq_loss(preds_S_freq, preds_T)
+        if teacher_ready is not None:
+            main.wait_event(teacher_ready)
+        spat_loss, spatial_similarity = self.get_spat_loss(preds_S_spat, preds_T)
         main.wait_stream(side)
         for t in (freq_loss, frequency_similarity):   # allocated on `side`, read on `main`
             t.record_stream(main)
