@@ -162,7 +162,7 @@ template <int BN, int EPI>
 __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmX,
                                                  uint32_t taddr, int row0, int n0, uint32_t stage_smem, uint64_t* xbar,
                                                  uint32_t& xphase, int half, int lane, bool first_split, bool use_x,
-                                                 bool reduce_out, uint64_t* tempty, bool pair, uint32_t* out_toggle) {
+                                                 bool reduce_out, uint64_t* tempty, bool pair, uint32_t* out_toggle, uint32_t vec_smem) {
   constexpr int UNITS = BN / 64;                         // units per warp
   constexpr bool F32 = EPI == 2;
   constexpr int ROWB = F32 ? 128 : 64;                   // staging row bytes (32 columns)
@@ -226,10 +226,19 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
     // (N is a multiple of 32 on this path -- launch_gemm_v2 sends ragged N to the first-generation kernel -- so there
     // is no per-column tail code: the if-converted tail branches were ~170 predicated-off issue slots per unit)
     if (p.bias != nullptr && first_split) {
+      if (vec_smem != 0) {   // staged in this warp's spare shared memory before the accumulator wait (broadcast reads)
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        for (int j = 0; j < 32; j += 4) {
+          const uint4 q = v2_lds128(vec_smem + i * 128 + j * 4);
+          v[j] += __uint_as_float(q.x); v[j + 1] += __uint_as_float(q.y);
+          v[j + 2] += __uint_as_float(q.z); v[j + 3] += __uint_as_float(q.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
       }
     }
     if constexpr (!F32) {
@@ -315,10 +324,19 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
     } else {
       // ---- fp32 output
       if (p.col_scale != nullptr) {
+        if (vec_smem != 0) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + c0 + j));
-          v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+          for (int j = 0; j < 32; j += 4) {
+            const uint4 q = v2_lds128(vec_smem + 512 + i * 128 + j * 4);
+            v[j] *= __uint_as_float(q.x); v[j + 1] *= __uint_as_float(q.y);
+            v[j + 2] *= __uint_as_float(q.z); v[j + 3] *= __uint_as_float(q.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + c0 + j));
+            v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+          }
         }
       }
       if (use_x) {
@@ -512,11 +530,30 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int r = t - ks * tiles_mn;
       const int m0 = (r / p.n_tiles) * TILE_M + (int)rank * 128;
       const int n0 = (r % p.n_tiles) * BN;
+      // per-column epilogue vectors (bias, LayerScale) of this warp's units -> its spare staging bytes, while the
+      // accumulator is still being produced: first touch of a new column range is an L2 round trip per unit otherwise
+      // (16-bit: bytes 6144.. are free; fp32: the residual tile's 4 KB when no residual is loaded)
+      uint32_t vec_smem = 0;
+      if (EPI != 2 || !use_x) {
+        vec_smem = stage_smem + (EPI != 2 ? 6144u : 4096u);
+        const int ui = lane >> 3, c = n0 + (half + 2 * ui) * 32 + (lane & 7) * 4;
+        if (ui < BN / 64 && c < p.N) {
+          if (p.bias != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+            v2_sts128(vec_smem + ui * 128 + (lane & 7) * 16, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+          }
+          if (EPI == 2 && p.col_scale != nullptr) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.col_scale + c));
+            v2_sts128(vec_smem + 512 + ui * 128 + (lane & 7) * 16, __float_as_uint(g.x), __float_as_uint(g.y), __float_as_uint(g.z), __float_as_uint(g.w));
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
       v2_epilogue_tile<BN, EPI>(p, &tmO, &tmX, taddr, m0 + quad * 32, n0, stage_smem, xbar, xphase, half, lane, ks == 0,
-                                use_x != 0, reduce_out != 0, &tempty_bar[as], PAIR, &out_toggle);
+                                use_x != 0, reduce_out != 0, &tempty_bar[as], PAIR, &out_toggle, vec_smem);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     // bulk stores read shared memory asynchronously: the CTA must not exit before they are done
