@@ -151,6 +151,9 @@ SIGNATURES = {
                                 c_vp, _sz, c_vp]),
     "b200_projector_bwd": (_i, [C.POINTER(ProjectorConfig), C.POINTER(ProjectorParams), C.POINTER(ProjectorGrads),
                                 c_fp, c_fp, c_fp, _i, c_fp, _i, c_fp, c_vp, c_vp, _sz, c_vp]),
+    "b200_sqnorm_f32": (_i, [c_fp, c_ll, c_fp, c_vp]),
+    "b200_adamw_step": (_i, [c_fp, c_fp, c_fp, c_fp, c_ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i, c_fp,
+                            c_fp, C.c_float, c_vp]),
     "b200_projector_tokens_bytes": (_sz, [C.POINTER(ProjectorConfig), _i]),
     "b200_projector_tokenize": (_i, [C.POINTER(ProjectorConfig), c_fp, _i, c_vp, c_vp, _sz, c_vp]),
     "b200_projector_fwd_tok": (_i, [C.POINTER(ProjectorConfig), C.POINTER(ProjectorParams), c_fp, c_fp, _i, c_fp, c_vp,

@@ -290,6 +290,18 @@ int b200_projector_bwd_tok(const b200_projector_config* c, const b200_projector_
                            float* dx, int dx_accumulate, float* dquery, const void* save, void* ws, size_t ws_bytes,
                            const void* tokens, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ optimizer step (next row f2)
+ * Global-norm clip + AdamW over flat fp32 arenas (parameters, gradients, first / second moments): the arithmetic of
+ * torch.optim.AdamW (train/distillation_module.py:440-502; config/config.yaml:25-30) after Lightning's
+ * gradient_clip_val (train.py:267-268), for the loss-module parameters.
+ * b200_sqnorm_f32: out_accum[0] += sum x^2.  b200_adamw_step: g is scaled by min(1, max_grad_norm / (sqrt(grad_sqnorm[0] +
+ * extra_sqnorm[0]) + 1e-6)) (extra: e.g. the student's share of the global norm; NULL = 0; max_grad_norm <= 0: no clip);
+ * step is the 1-based step count (bias correction). */
+int b200_sqnorm_f32(const float* x, long long n, float* out_accum, void* stream);
+int b200_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, const float* grad_sqnorm, const float* extra_sqnorm,
+                    float max_grad_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -410,3 +410,39 @@ def test_gemm_fp16_operands(adt, bdt, mn):
     out16 = ops.gemm(aa, bb, a_mn_major=mn, b_mn_major=mn, out_dtype=torch.float16, act="relu")
     assert out16.dtype == torch.float16
     assert rel_err(out16, torch.relu(ref)) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ optimizer (next row f2)
+@pytest.mark.parametrize("clip", [None, 1.0])
+def test_arena_adamw_matches_torch_adamw_with_global_norm_clip(clip):
+    """ArenaAdamW (two launches over flat arenas) == torch.optim.AdamW after torch.nn.utils.clip_grad_norm_, including
+    the student's share of the global norm passed in as a device scalar."""
+    from dinov2_distillation_b200.distributed import FlatGradArena
+    from dinov2_distillation_b200.optim import ArenaAdamW
+    torch.manual_seed(5)
+    shapes = [(384, 512, 1, 1), (384,), (1, 384, 16, 16), (1536, 384), (7,)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda") * 0.1) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    student = torch.nn.Parameter(torch.randn(1000, device="cuda"))      # not in the arena: only its norm takes part
+    arena = FlatGradArena(ours)
+    opt = ArenaAdamW(arena, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01, max_grad_norm=clip)
+    topt = torch.optim.AdamW(ref, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01)
+    for it in range(4):
+        arena.zero()
+        scale = 10.0 if it % 2 == 0 else 0.01       # clipped and unclipped steps
+        for p, r in zip(ours, ref):
+            gr = torch.randn_like(p) * scale
+            p.grad.copy_(gr)
+            r.grad = gr.clone()
+        student.grad = torch.randn_like(student) * scale
+        extra = (student.grad ** 2).sum().reshape(1)
+        if clip is not None:
+            torch.nn.utils.clip_grad_norm_(ref + [student], clip)
+        topt.step()
+        opt.step(extra_sq_norm=extra if clip is not None else None)
+        if clip is not None and it % 2 == 0:   # the arena's share of the (pre-clip) global norm, reduced on the device
+            want = math.sqrt(sum((p_.grad.float() ** 2).sum().item() for p_ in ours))
+            assert abs(opt.grad_norm().item() - want) <= 1e-4 * want
+    for p, r in zip(ours, ref):
+        assert rel_err(p.data, r.data) < 1e-6, rel_err(p.data, r.data)
+        assert p.data.data_ptr() >= opt.flat_params.data_ptr()
