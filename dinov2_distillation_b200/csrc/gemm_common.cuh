@@ -40,6 +40,7 @@ struct GemmParams {
   uint32_t idesc;            // tcgen05 instruction descriptor (operand formats, majors, tile shape)
   float algo_scale;          // profiling: algorithmic flops / executed flops
   int dbg;                   // B200_GEMM_DBG experiments: bit 0 = drain TMEM but skip the epilogue math and stores
+  long long* dbg_buf;        // B200_GEMM_DBG bit 5: per-role wait-cycle counters of CTA 0 (gemm_v2.cu)
 };
 
 // Epilogue for 32 consecutive columns of one accumulator row (thread = row): 128-bit vector loads / stores along the

@@ -411,6 +411,7 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   p.algo_scale = d->algo_flops_scale > 0.f ? d->algo_flops_scale : 1.0f;
   static const int dbg = gemm_env_int("B200_GEMM_DBG", 0);
   p.dbg = dbg;
+  p.dbg_buf = nullptr;
   p.out16_fp16 = d->out16_is_fp16 ? 1 : 0;
   p.aux_fp16 = d->aux_is_fp16 ? 1 : 0;
   // a_format / b_format: 0 = F16, 1 = BF16 (bits 7-9 / 10-12)

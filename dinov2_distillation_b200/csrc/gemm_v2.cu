@@ -4,8 +4,8 @@
 //   warp 0        : TMA producer (one elected lane)
 //   warp 1        : MMA issuer   (one elected lane; the leader CTA only in CTA-pair mode)
 //   warp 2        : TMEM allocate / free
-//   warps 4..11   : epilogue. Warp w drains TMEM lanes 32*(w%4)..+31 (hardware rule: warp id % 4) and every second
-//                   32-column unit of the tile. Per unit: tcgen05.ld 32x32b.x32 (thread = row, 32 fp32 columns) ->
+//   warps 4..     : epilogue, 8 or 16 warps (template EW; 16 when no operand tile has to be staged). Warp w drains TMEM
+//                   lanes 32*(w%4)..+31 (hardware rule: warp id % 4) and every (EW/4)-th 32-column unit of the tile. Per unit: tcgen05.ld 32x32b.x32 (thread = row, 32 fp32 columns) ->
 //                   bias / activation / aux / LayerScale / residual in registers -> 16-byte st.shared into a swizzled
 //                   32-row staging tile -> ONE bulk tensor store (cp.async.bulk.tensor, or cp.reduce.async.bulk.tensor
 //                   .add for in-place residual streams and split-K) issued by lane 0. Row-strided 16-byte global stores
@@ -20,10 +20,11 @@
 
 namespace b200 {
 
-constexpr int V2_EPI_WARPS = 8;
-constexpr int V2_THREADS = 128 + V2_EPI_WARPS * 32;
-constexpr int V2_EPI_WARP_BYTES = 8192;   // two 4 KB staging tiles per epilogue warp
-constexpr int V2_EPI_BYTES = V2_EPI_WARPS * V2_EPI_WARP_BYTES;
+// Epilogue warps per CTA (template EW): 8 warps with 8 KB of staging each (every path), or 16 warps with 4 KB each for
+// the epilogues that need no operand tile (no separate residual / aux / pre-activation copy): four warps per scheduler
+// instead of two hide the tcgen05.ld -> st.shared -> fence -> bulk-store latency chain that paces the K = 384 shapes.
+constexpr int V2_MAX_EPI_WARPS = 16;
+constexpr int V2_EPI_BYTES = 65536;
 
 template <int BN, bool PAIR>
 struct V2Cfg {
@@ -157,14 +158,18 @@ __device__ __forceinline__ float v2_dgelu(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue of one tile
-// One warp: 32 rows (TMEM lanes of its quadrant) x the units u = half, half + 2, ... of the tile's BN / 32 column units.
-template <int BN, int EPI>
+// One warp: 32 rows (TMEM lanes of its quadrant) x the units u = half, half + NG, ... of the tile's BN / 32 column units
+// (NG = EW / 4 warps share a quadrant).
+template <int BN, int EPI, int EW>
 __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmX,
                                                  uint32_t taddr, int row0, int n0, uint32_t stage_smem, uint64_t* xbar,
-                                                 uint32_t& xphase, int half, int lane, bool first_split, bool use_x,
+                                                 uint32_t& xphase, int half, int lane, bool first_split, bool use_x_arg,
                                                  bool reduce_out, uint64_t* tempty, bool pair, uint32_t* out_toggle, uint32_t vec_smem) {
-  constexpr int UNITS = BN / 64;                         // units per warp
+  constexpr int NG = EW / 4;                             // warps per TMEM quadrant
+  constexpr int UNITS = (BN / 32 + NG - 1) / NG;         // units per warp (the last may be absent: BN = 192, NG = 4)
+  constexpr bool PREFETCH = EW == 8;                     // 8 warps: next unit's tcgen05.ld in flight during this one
   constexpr bool F32 = EPI == 2;
+  const bool use_x = EW == 8 && use_x_arg;               // 16 warps: 4 KB of staging per warp, no operand tile
   constexpr int ROWB = F32 ? 128 : 64;                   // staging row bytes (32 columns)
   constexpr int CHUNKS = ROWB / 16;
   constexpr uint32_t UNIT_BYTES = 32 * ROWB;
@@ -179,7 +184,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
   int nu = 0;
 #pragma unroll
   for (int i = 0; i < UNITS; ++i)
-    if (n0 + (half + 2 * i) * 32 < p.N) nu = i + 1;
+    if ((half + NG * i) * 32 < BN && n0 + (half + NG * i) * 32 < p.N) nu = i + 1;
   if (nu == 0) {
     tc_fence_before();
     __syncwarp();
@@ -190,7 +195,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
     return;
   }
 
-  uint32_t raw[2][32];
+  uint32_t raw[PREFETCH ? 2 : 1][32];
   if (use_x && lane == 0) {
     mbar_expect_tx(xbar, UNIT_BYTES);
     v2_tma_load_2d_s(buf_x, tmX, xbar, n0 + half * 32, row0);
@@ -199,13 +204,13 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
 #pragma unroll
   for (int i = 0; i < UNITS; ++i) {
     if (i >= nu) break;
-    const int u = half + 2 * i;
+    const int u = half + NG * i;
     const int c0 = n0 + u * 32;
     const bool next_ok = i + 1 < nu;
     tmem_ld_wait();
-    if (next_ok) {
-      tmem_ld_32x32(taddr + (u + 2) * 32, raw[(i + 1) & 1]);
-    } else {
+    if (PREFETCH && next_ok) {
+      tmem_ld_32x32(taddr + (u + NG) * 32, raw[(i + 1) & 1]);
+    } else if (!next_ok) {
       // all tcgen05.ld of this tile have completed: hand the accumulator buffer back to the MMA warp right away
       tc_fence_before();
       __syncwarp();
@@ -216,11 +221,12 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
     }
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[i & 1][j]);
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[PREFETCH ? (i & 1) : 0][j]);
+    if (!PREFETCH && next_ok) tmem_ld_32x32(taddr + (u + NG) * 32, raw[0]);   // values copied out: refill
     if (p.dbg & 1) {   // B200_GEMM_DBG=1: mainloop-only floor (drain TMEM, no epilogue math, no stores)
       if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1];
       if (use_x) { mbar_wait(xbar, xphase); xphase ^= 1; __syncwarp();
-        if (next_ok && lane == 0) { mbar_expect_tx(xbar, UNIT_BYTES); v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + 64, row0); } }
+        if (next_ok && lane == 0) { mbar_expect_tx(xbar, UNIT_BYTES); v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, row0); } }
       continue;
     }
     // (N is a multiple of 32 on this path -- launch_gemm_v2 sends ragged N to the first-generation kernel -- so there
@@ -285,7 +291,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
           __syncwarp();   // every lane has read the aux tile: it may be refilled
           if (next_ok && lane == 0) {
             mbar_expect_tx(xbar, UNIT_BYTES);
-            v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + 64, row0);
+            v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, row0);
           }
           if (p.aux_mode == B200_AUX_DGELU) {
 #pragma unroll
@@ -297,7 +303,8 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
         }
       }
       const uint32_t bo = buf_o + row_off;
-      if (p.out16_fp16) {
+      if (p.dbg & 16) {
+      } else if (p.out16_fp16) {
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
           const int j = c * 8;
@@ -312,9 +319,9 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
                     pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
         }
       }
-      fence_proxy_async();
+      if (!(p.dbg & 8)) fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(p.dbg & 2)) {
         v2_tma_store_2d(tmO, buf_o, c0, row0);
         if (has_pre)
           v2_tma_store_2d(tmX, stage_smem + 2048u, c0, row0);
@@ -353,21 +360,23 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
         __syncwarp();
         if (next_ok && lane == 0) {
           mbar_expect_tx(xbar, UNIT_BYTES);
-          v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + 64, row0);
+          v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, row0);
         }
       }
       if (lane == 0) v2_bulk_wait_read<0>();
       __syncwarp();
       const uint32_t bo = stage_smem + row_off;
+      if (!(p.dbg & 16)) {
 #pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int j = c * 4;
-        v2_sts128(bo + ((c ^ sw) << 4), __float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]),
-                  __float_as_uint(v[j + 3]));
-      }
-      fence_proxy_async();
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int j = c * 4;
+          v2_sts128(bo + ((c ^ sw) << 4), __float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]),
+                    __float_as_uint(v[j + 3]));
+        }
+      } else if (v[3] == 123.456f) p.out_f32[1] = v[5];
+      if (!(p.dbg & 8)) fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(p.dbg & 2)) {
         if (p.out_bp > 0) {   // columns batched with period out_bp: (column in batch, row, batch)
           const int bi = c0 / p.out_bp, cb = c0 - bi * p.out_bp;
           if (reduce_out) v2_tma_reduce_add_3d(tmO, stage_smem, cb, row0, bi);
@@ -384,8 +393,8 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN, bool PAIR, bool MN, int EPI>
-__global__ void __launch_bounds__(V2_THREADS, 1)
+template <int BN, bool PAIR, bool MN, int EPI, int EW>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX, const GemmParams p,
                const int use_x, const int reduce_out) {
@@ -400,7 +409,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* x_bar = tempty_bar + 2;                      // one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + V2_EPI_WARPS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + V2_MAX_EPI_WARPS);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -420,9 +429,9 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], (PAIR ? 2 : 1) * V2_EPI_WARPS);
+      mbar_init(&tempty_bar[s], (PAIR ? 2 : 1) * EW);
     }
-    for (int s = 0; s < V2_EPI_WARPS; ++s) mbar_init(&x_bar[s], 1);
+    for (int s = 0; s < EW; ++s) mbar_init(&x_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -446,15 +455,18 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
       for (int t = worker; t < p.total_tiles; t += workers) {
         const int ks = t / tiles_mn;
         const int r = t - ks * tiles_mn;
         const int m0 = (r / p.n_tiles) * TILE_M + (int)rank * 128;
         const int n0 = (r % p.n_tiles) * BN + (int)rank * Cfg::B_ROWS * (PAIR ? 1 : 0);
         const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int kb1 = (p.dbg & 4) ? kb0 : min(p.num_kb, kb0 + p.kb_per_split);   // B200_GEMM_DBG=4: epilogue-only floor
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg_buf) { const long long c = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - c; }
+          else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + A_TILE_BYTES;
           if constexpr (PAIR) {
@@ -476,6 +488,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg_buf && blockIdx.x == 0) { p.dbg_buf[0] = clock64() - t_begin; p.dbg_buf[1] = w_empty; }
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
@@ -484,15 +497,20 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      long long w_full = 0, w_tempty = 0, n_t = 0;
+      const long long t_begin = clock64();
       for (int t = worker; t < p.total_tiles; t += workers) {
         const int ks = t / tiles_mn;
         const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        const int kb1 = (p.dbg & 4) ? kb0 : min(p.num_kb, kb0 + p.kb_per_split);
+        ++n_t;
+        if (p.dbg_buf) { const long long c = clock64(); mbar_wait(&tempty_bar[as], aphase ^ 1); w_tempty += clock64() - c; }
+        else mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::TMEM_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if (p.dbg_buf) { const long long c = clock64(); mbar_wait(&full_bar[stage], phase); w_full += clock64() - c; }
+          else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_TILE_BYTES;
@@ -514,17 +532,22 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else tc_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
+      if (p.dbg_buf && blockIdx.x == 0) {
+        p.dbg_buf[2] = clock64() - t_begin; p.dbg_buf[3] = w_full; p.dbg_buf[4] = w_tempty; p.dbg_buf[5] = n_t;
+      }
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int quad = warp & 3;            // TMEM lanes 32*quad .. +31 (hardware: warp id % 4)
-    const int half = ew >> 2;             // which of the two interleaved unit sets
-    const uint32_t stage_smem = smem_u32(epi_smem + ew * V2_EPI_WARP_BYTES);
+    const int half = ew >> 2;             // which of the EW / 4 interleaved unit sets
+    const uint32_t stage_smem = smem_u32(epi_smem + ew * (V2_EPI_BYTES / EW));
     uint64_t* xbar = &x_bar[ew];
     uint32_t xphase = 0;
     uint32_t out_toggle = 0;
     int as = 0;
     uint32_t aphase = 0;
+    long long w_tfull = 0;
+    const long long t_begin = clock64();
     for (int t = worker; t < p.total_tiles; t += workers) {
       const int ks = t / tiles_mn;
       const int r = t - ks * tiles_mn;
@@ -534,7 +557,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // accumulator is still being produced: first touch of a new column range is an L2 round trip per unit otherwise
       // (16-bit: bytes 6144.. are free; fp32: the residual tile's 4 KB when no residual is loaded)
       uint32_t vec_smem = 0;
-      if (EPI != 2 || !use_x) {
+      if (EW == 8 && (EPI != 2 || !use_x)) {
         vec_smem = stage_smem + (EPI != 2 ? 6144u : 4096u);
         const int ui = lane >> 3, c = n0 + (half + 2 * ui) * 32 + (lane & 7) * 4;
         if (ui < BN / 64 && c < p.N) {
@@ -549,16 +572,22 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
-      mbar_wait(&tfull_bar[as], aphase);
+      if (p.dbg_buf) { const long long c = clock64(); mbar_wait(&tfull_bar[as], aphase); w_tfull += clock64() - c; }
+      else mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
-      v2_epilogue_tile<BN, EPI>(p, &tmO, &tmX, taddr, m0 + quad * 32, n0, stage_smem, xbar, xphase, half, lane, ks == 0,
+      v2_epilogue_tile<BN, EPI, EW>(p, &tmO, &tmX, taddr, m0 + quad * 32, n0, stage_smem, xbar, xphase, half, lane, ks == 0,
                                 use_x != 0, reduce_out != 0, &tempty_bar[as], PAIR, &out_toggle, vec_smem);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    const long long t_loop = clock64() - t_begin;
     // bulk stores read shared memory asynchronously: the CTA must not exit before they are done
     if (lane == 0) v2_bulk_wait_all();
     __syncwarp();
+    if (p.dbg_buf && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == EW - 1)) {
+      const int o = ew == 0 ? 6 : 9;
+      p.dbg_buf[o] = t_loop; p.dbg_buf[o + 1] = w_tfull; p.dbg_buf[o + 2] = clock64() - t_begin;
+    }
   }
 
   tc_fence_before();
@@ -571,11 +600,11 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <int BN, bool PAIR, bool MN, int EPI>
+template <int BN, bool PAIR, bool MN, int EPI, int EW>
 static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                      const GemmParams& p, int use_x, int reduce_out, cudaStream_t st) {
   using Cfg = V2Cfg<BN, PAIR>;
-  auto kern = gemm_v2_kernel<BN, PAIR, MN, EPI>;
+  auto kern = gemm_v2_kernel<BN, PAIR, MN, EPI, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -585,7 +614,7 @@ static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   if (workers > p.total_tiles) workers = p.total_tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(PAIR ? workers * 2 : workers);
-  cfg.blockDim = dim3(V2_THREADS);
+  cfg.blockDim = dim3(128 + EW * 32);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
@@ -598,30 +627,46 @@ static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
   const int prof = prof_begin(st);
+  if (p.dbg & 32) {   // wait-cycle counters of CTA 0 (eager launches only: synchronises and prints)
+    static long long* buf = nullptr;
+    if (!buf) cudaMalloc(&buf, 16 * sizeof(long long));
+    cudaMemsetAsync(buf, 0, 16 * sizeof(long long), st);
+    GemmParams q = p;
+    q.dbg_buf = buf;
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tx, q, use_x, reduce_out));
+    cudaStreamSynchronize(st);
+    long long h[16];
+    cudaMemcpy(h, buf, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[gemm_v2 dbg] BN=%d pair=%d epi=%d EW=%d tiles/cta=%lld | producer: total %lld wait_empty %lld | mma: total %lld "
+            "wait_full %lld wait_tempty %lld | epi w0: loop %lld wait_tfull %lld total %lld | epi wlast: loop %lld wait_tfull %lld total %lld\n",
+            BN, (int)PAIR, EPI, EW, h[5], h[0], h[1], h[2], h[3], h[4], h[6], h[7], h[8], h[9], h[10], h[11]);
+    B200_LAUNCH_OK();
+    return 0;
+  }
   B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tx, p, use_x, reduce_out));
   prof_end(prof, st, 2.0 * p.M * p.N * p.K * p.algo_scale, 0);
   B200_LAUNCH_OK();
   return 0;
 }
 
-template <int BN, bool PAIR, bool MN>
+template <int BN, bool PAIR, bool MN, int EW>
 static int v2_dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                            const CUtensorMap& tx, const GemmParams& p, int use_x, int reduce_out, cudaStream_t st) {
   if constexpr (MN) {
-    return v2_launch<BN, PAIR, MN, 2>(ta, tb, to, tx, p, use_x, reduce_out, st);
+    return v2_launch<BN, PAIR, MN, 2, EW>(ta, tb, to, tx, p, use_x, reduce_out, st);
   } else {
-    if (epi == 0) return v2_launch<BN, PAIR, MN, 0>(ta, tb, to, tx, p, use_x, reduce_out, st);
-    if (epi == 1) return v2_launch<BN, PAIR, MN, 1>(ta, tb, to, tx, p, use_x, reduce_out, st);
-    return v2_launch<BN, PAIR, MN, 2>(ta, tb, to, tx, p, use_x, reduce_out, st);
+    if (epi == 0) return v2_launch<BN, PAIR, MN, 0, EW>(ta, tb, to, tx, p, use_x, reduce_out, st);
+    if (epi == 1) return v2_launch<BN, PAIR, MN, 1, EW>(ta, tb, to, tx, p, use_x, reduce_out, st);
+    return v2_launch<BN, PAIR, MN, 2, EW>(ta, tb, to, tx, p, use_x, reduce_out, st);
   }
 }
 
-template <bool PAIR, bool MN>
+template <bool PAIR, bool MN, int EW>
 static int v2_dispatch_bn(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                           const CUtensorMap& tx, const GemmParams& p, int use_x, int reduce_out, cudaStream_t st) {
-  if (bn == 256) return v2_dispatch_epi<256, PAIR, MN>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
-  if (bn == 192) return v2_dispatch_epi<192, PAIR, MN>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
-  return v2_dispatch_epi<128, PAIR, MN>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  if (bn == 256) return v2_dispatch_epi<256, PAIR, MN, EW>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  if (bn == 192) return v2_dispatch_epi<192, PAIR, MN, EW>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  return v2_dispatch_epi<128, PAIR, MN, EW>(epi, ta, tb, to, tx, p, use_x, reduce_out, st);
 }
 
 // tile width: fewest (waves x tile cost); wide tiles amortise the A traffic, narrow ones the wave quantisation
@@ -722,9 +767,16 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
     else tx = to;
   }
   const int epi = f32 ? 2 : (d->act == B200_ACT_GELU ? 1 : 0);
-  if (mn) return v2_dispatch_bn<false, true>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
-  if (pair) return v2_dispatch_bn<true, false>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
-  return v2_dispatch_bn<false, false>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  // 16 epilogue warps when the epilogue stages no operand tile (4 KB of staging per warp is then enough)
+  static const int ew_mode = gemm_env_int("B200_GEMM_EW", 16);
+  const bool ew16 = ew_mode == 16 && !use_x && !pair;
+  if (mn) {
+    if (ew16) return v2_dispatch_bn<false, true, 16>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+    return v2_dispatch_bn<false, true, 8>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  }
+  if (pair) return v2_dispatch_bn<true, false, 8>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  if (ew16) return v2_dispatch_bn<false, false, 16>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+  return v2_dispatch_bn<false, false, 8>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
 }
 
 }  // namespace b200
