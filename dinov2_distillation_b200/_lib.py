@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ("a_is_fp16", C.c_int), ("b_is_fp16", C.c_int), ("out16_is_fp16", C.c_int), ("aux_is_fp16", C.c_int),
         ("algo_flops_scale", C.c_float),
         ("out_batch_period", C.c_int), ("out_batch_stride", c_ll),
+        ("out16_pre_alt", C.c_int),
     ]
 
 
@@ -53,6 +54,7 @@ class AttnDesc(C.Structure):
         ("dv", c_vp), ("dv_bs", c_ll), ("dv_ts", c_ll),
         ("qkvo_is_fp16", C.c_int),
         ("dq_colsum", c_fp), ("dk_colsum", c_fp), ("dv_colsum", c_fp),
+        ("o_alt", c_vp),
     ]
 
 

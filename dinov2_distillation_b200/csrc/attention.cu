@@ -158,7 +158,7 @@ __device__ __forceinline__ void mma_p_t(float (&out)[HDP / 8][4], const float (&
 struct AttnParams {
   const __nv_bfloat16 *q, *k, *v, *d_o;
   const __nv_bfloat16* o_in;
-  __nv_bfloat16 *o, *dq, *dk, *dv;
+  __nv_bfloat16 *o, *o_alt, *dq, *dk, *dv;   // o_alt: optional copy of o in the other 16-bit format (forward)
   float *lse, *delta;
   float *dq_colsum, *dk_colsum, *dv_colsum;   // optional fp32 [heads*hd] accumulators (bias gradients of the q/k/v projections)
   long long q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, do_bs, do_ts, dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts;
@@ -266,6 +266,17 @@ attn_fwd_kernel(const AttnParams p) {
     if (col < p.hd) {
       if (r0 < p.Nq) *reinterpret_cast<uint32_t*>(go + (long long)r0 * p.o_ts + col) = pack_16<HALF>(o[nb][0] * inv0, o[nb][1] * inv0);
       if (r1 < p.Nq) *reinterpret_cast<uint32_t*>(go + (long long)r1 * p.o_ts + col) = pack_16<HALF>(o[nb][2] * inv1, o[nb][3] * inv1);
+    }
+  }
+  if (p.o_alt != nullptr) {
+    __nv_bfloat16* ga = p.o_alt + (long long)b * p.o_bs + (long long)h * p.hd;
+#pragma unroll
+    for (int nb = 0; nb < HDP / 8; ++nb) {
+      const int col = nb * 8 + 2 * t4;
+      if (col < p.hd) {
+        if (r0 < p.Nq) *reinterpret_cast<uint32_t*>(ga + (long long)r0 * p.o_ts + col) = pack_16<!HALF>(o[nb][0] * inv0, o[nb][1] * inv0);
+        if (r1 < p.Nq) *reinterpret_cast<uint32_t*>(ga + (long long)r1 * p.o_ts + col) = pack_16<!HALF>(o[nb][2] * inv1, o[nb][3] * inv1);
+      }
     }
   }
   if (p.lse != nullptr && t4 == 0) {
@@ -806,6 +817,7 @@ static int fill_params(const b200_attn_desc* d, AttnParams& p, bool bwd) {
   p.q = static_cast<const __nv_bfloat16*>(d->q); p.k = static_cast<const __nv_bfloat16*>(d->k);
   p.v = static_cast<const __nv_bfloat16*>(d->v);
   p.o = static_cast<__nv_bfloat16*>(d->o); p.o_in = static_cast<const __nv_bfloat16*>(d->o);
+  p.o_alt = bwd ? nullptr : static_cast<__nv_bfloat16*>(d->o_alt);
   p.lse = d->lse; p.delta = d->delta;
   p.q_bs = d->q_bs; p.q_ts = d->q_ts; p.k_bs = d->k_bs; p.k_ts = d->k_ts; p.v_bs = d->v_bs; p.v_ts = d->v_ts;
   p.o_bs = d->o_bs; p.o_ts = d->o_ts;
@@ -916,7 +928,7 @@ extern "C" int b200_attention_fwd(const b200_attn_desc* d, void* stream) {
   AttnParams p{};
   B200_TRY(fill_params(d, p, false));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  {
+  if (d->o_alt == nullptr) {   // (the tcgen05 kernel writes one output format)
     const int r = launch_attention_tc_fwd(d, st);
     if (r <= 0) return r;
   }

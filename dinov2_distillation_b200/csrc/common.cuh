@@ -168,6 +168,17 @@ struct PrepJobs {
 };
 int launch_param_prep(const PrepJobs& jobs, cudaStream_t st);
 
+// Dual-format variants of three elementwise entries (elementwise.cu): the ScaleKD projector forward saves each activation
+// a wgrad GEMM will need in fp16 (forward operand) AND bf16 (backward operand) from the pass that produces it --
+// tcgen05 kind::f16 cannot mix the two formats in one product, and a separate conversion pass costs a launch each.
+int cast_f32_f16_dual(const float* x, void* y_f16, void* y_bf16, long long n, void* stream);
+int layernorm_fwd_dual(const float* x, const float* w, const float* b, float eps, float* y_f32, void* y16, void* y16_alt,
+                       float* mean, float* rstd, int rows, int D, int in_period, int in_pad, int y16_is_fp16,
+                       void* stream);
+int bn_relu_pos_fwd_dual(const float* y, const float* mean, const float* rstd, const float* w, const float* b,
+                         const float* pos, float* z_f32, void* z16, void* z16_alt, int M, int D, int HW,
+                         int z16_is_fp16, void* stream);
+
 // Bump allocator over a caller-provided workspace (256-byte aligned carve-outs).
 struct Arena {
   uint8_t* base;

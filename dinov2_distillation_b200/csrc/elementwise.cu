@@ -15,8 +15,9 @@ static inline int grid_for(long long work_items, int per_block, int max_blocks_p
 }
 
 // ------------------------------------------------------------------------------------------------ cast
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n,
-                                     int fp16) {
+// y: 16-bit copy in the format `fp16` selects; y_alt (optional): a second copy in the OTHER 16-bit format
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                     __nv_bfloat16* __restrict__ y_alt, long long n, int fp16) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
   const long long n4 = n >> 2;
@@ -27,9 +28,16 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
     u.x = pack16(v.x, v.y, fp16);
     u.y = pack16(v.z, v.w, fp16);
     reinterpret_cast<uint2*>(y)[i] = u;
+    if (y_alt) {
+      u.x = pack16(v.x, v.y, !fp16);
+      u.y = pack16(v.z, v.w, !fp16);
+      reinterpret_cast<uint2*>(y_alt)[i] = u;
+    }
   }
-  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     store16(y + i, x[i], fp16);
+    if (y_alt) store16(y_alt + i, x[i], !fp16);
+  }
 }
 
 __global__ void cast_f16_bf16_kernel(const __half* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
@@ -174,8 +182,9 @@ constexpr int LN_MAX_V4 = 12;  // up to D = 1536 held in registers (one warp per
 template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float eps,
-                     float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int rows, int D, int in_period, int in_pad, int fp16) {
+                     float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y16_alt,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int D, int in_period,
+                     int in_pad, int fp16) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -229,6 +238,12 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
           u.x = pack16(o.x, o.y, fp16);
           u.y = pack16(o.z, o.w, fp16);
           reinterpret_cast<uint2*>(y16 + (long long)r * D)[c4] = u;
+        }
+        if (y16_alt) {   // second copy in the other 16-bit format (bf16 operand of the wgrad GEMM)
+          uint2 u;
+          u.x = pack16(o.x, o.y, !fp16);
+          u.y = pack16(o.z, o.w, !fp16);
+          reinterpret_cast<uint2*>(y16_alt + (long long)r * D)[c4] = u;
         }
       }
     }
@@ -424,8 +439,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __rest
 __global__ void __launch_bounds__(256)
 bn_relu_pos_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ pos,
-                       float* __restrict__ z32, __nv_bfloat16* __restrict__ z16, long long M, int D, int HW,
-                       int fp16) {
+                       float* __restrict__ z32, __nv_bfloat16* __restrict__ z16, __nv_bfloat16* __restrict__ z16_alt,
+                       long long M, int D, int HW, int fp16) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
   const int D4 = D >> 2;
@@ -450,6 +465,12 @@ bn_relu_pos_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
       u.x = pack16(o.x, o.y, fp16);
       u.y = pack16(o.z, o.w, fp16);
       reinterpret_cast<uint2*>(z16)[i] = u;
+    }
+    if (z16_alt) {
+      uint2 u;
+      u.x = pack16(o.x, o.y, !fp16);
+      u.y = pack16(o.z, o.w, !fp16);
+      reinterpret_cast<uint2*>(z16_alt)[i] = u;
     }
   }
 }
@@ -641,11 +662,12 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, const _
 }
 
 template <int NV>
-static int launch_ln_fwd(const float* x, const float* w, const float* b, float eps, float* y32, void* y16, float* mean,
-                         float* rstd, int rows, int D, int in_period, int in_pad, int fp16, cudaStream_t st) {
+static int launch_ln_fwd(const float* x, const float* w, const float* b, float eps, float* y32, void* y16, void* y16_alt,
+                         float* mean, float* rstd, int rows, int D, int in_period, int in_pad, int fp16, cudaStream_t st) {
   const int grid = grid_for(rows, 8, 8);
   B200_CUDA_OK(launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(256), 0, st, x, w, b, eps, y32,
-                          static_cast<__nv_bfloat16*>(y16), mean, rstd, rows, D, in_period, in_pad, fp16));
+                          static_cast<__nv_bfloat16*>(y16), static_cast<__nv_bfloat16*>(y16_alt), mean, rstd, rows, D,
+                          in_period, in_pad, fp16));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -782,17 +804,23 @@ extern "C" int b200_cast_f32_bf16(const float* x, void* y, long long n, void* st
   if (n == 0) return 0;
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "alignment");
   B200_CUDA_OK(launch_pdl(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      x, static_cast<__nv_bfloat16*>(y), n, 0));
+      x, static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(nullptr), n, 0));
   B200_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200_cast_f32_f16(const float* x, void* y, long long n, void* stream) {
-  B200_CHECK_ARG(x && y && n >= 0, "bad args");
+  return b200::cast_f32_f16_dual(x, y, nullptr, n, stream);
+}
+
+// fp32 -> fp16 and (optionally) bf16 in one pass
+int b200::cast_f32_f16_dual(const float* x, void* y_f16, void* y_bf16, long long n, void* stream) {
+  B200_CHECK_ARG(x && y_f16 && n >= 0, "bad args");
   if (n == 0) return 0;
-  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "alignment");
-  B200_CUDA_OK(launch_pdl(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      x, static_cast<__nv_bfloat16*>(y), n, 1));
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_f16) & 7) == 0 &&
+                     (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0, "alignment");
+  B200_CUDA_OK(launch_pdl(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+      x, static_cast<__nv_bfloat16*>(y_f16), static_cast<__nv_bfloat16*>(y_bf16), n, 1));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -897,14 +925,23 @@ extern "C" int b200_write_cls_rows(float* x, const float* cls, const float* pos,
 extern "C" int b200_layernorm_fwd(const float* x, const float* w, const float* b, float eps, float* y_f32,
                                   void* y_bf16, float* mean, float* rstd, int rows, int D, int in_period, int in_pad,
                                   int y16_is_fp16, void* stream) {
+  return b200::layernorm_fwd_dual(x, w, b, eps, y_f32, y_bf16, nullptr, mean, rstd, rows, D, in_period, in_pad,
+                                  y16_is_fp16, stream);
+}
+
+// y16_alt: optional second 16-bit copy of the output in the format y16 does NOT use
+int b200::layernorm_fwd_dual(const float* x, const float* w, const float* b, float eps, float* y_f32, void* y16,
+                             void* y16_alt, float* mean, float* rstd, int rows, int D, int in_period, int in_pad,
+                             int y16_is_fp16, void* stream) {
   B200_CHECK_ARG(x && w && b && rows > 0, "bad args");
   B200_CHECK_ARG(D % 4 == 0 && D > 0 && D <= LN_MAX_V4 * 128, "D must be a multiple of 4 and <= 1536");
+  B200_CHECK_ARG(y16_alt == nullptr || y16 != nullptr, "an alternate-format copy needs the primary 16-bit output");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nv = (int)cdiv(D, 128);
-  if (nv <= 3) return launch_ln_fwd<3>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
-  if (nv <= 6) return launch_ln_fwd<6>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
-  if (nv <= 8) return launch_ln_fwd<8>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
-  return launch_ln_fwd<12>(x, w, b, eps, y_f32, y_bf16, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
+  if (nv <= 3) return launch_ln_fwd<3>(x, w, b, eps, y_f32, y16, y16_alt, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
+  if (nv <= 6) return launch_ln_fwd<6>(x, w, b, eps, y_f32, y16, y16_alt, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
+  if (nv <= 8) return launch_ln_fwd<8>(x, w, b, eps, y_f32, y16, y16_alt, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
+  return launch_ln_fwd<12>(x, w, b, eps, y_f32, y16, y16_alt, mean, rstd, rows, D, in_period, in_pad, y16_is_fp16, st);
 }
 
 extern "C" int b200_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean,
@@ -945,9 +982,16 @@ extern "C" int b200_bn_finalize(const float* sums, float* mean, float* rstd, flo
 extern "C" int b200_bn_relu_pos_fwd(const float* y, const float* mean, const float* rstd, const float* w,
                                     const float* b, const float* pos, float* z_f32, void* z_bf16, int M, int D, int HW,
                                     int z16_is_fp16, void* stream) {
-  B200_CHECK_ARG(y && mean && rstd && w && b && pos && (z_f32 || z_bf16) && M > 0 && D % 4 == 0 && HW > 0, "bad args");
-  B200_CUDA_OK(launch_pdl(bn_relu_pos_fwd_kernel, dim3(grid_for((long long)M * D / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      y, mean, rstd, w, b, pos, z_f32, static_cast<__nv_bfloat16*>(z_bf16), M, D, HW, z16_is_fp16));
+  return b200::bn_relu_pos_fwd_dual(y, mean, rstd, w, b, pos, z_f32, z_bf16, nullptr, M, D, HW, z16_is_fp16, stream);
+}
+
+int b200::bn_relu_pos_fwd_dual(const float* y, const float* mean, const float* rstd, const float* w, const float* b,
+                               const float* pos, float* z_f32, void* z16, void* z16_alt, int M, int D, int HW,
+                               int z16_is_fp16, void* stream) {
+  B200_CHECK_ARG(y && mean && rstd && w && b && pos && (z_f32 || z16) && M > 0 && D % 4 == 0 && HW > 0, "bad args");
+  B200_CUDA_OK(launch_pdl(bn_relu_pos_fwd_kernel, dim3(grid_for((long long)M * D / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+      y, mean, rstd, w, b, pos, z_f32, static_cast<__nv_bfloat16*>(z16), static_cast<__nv_bfloat16*>(z16_alt), (long long)M, D, HW,
+      z16_is_fp16));
   B200_LAUNCH_OK();
   return 0;
 }

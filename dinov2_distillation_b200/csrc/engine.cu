@@ -36,6 +36,7 @@ struct Gemm {
   Gemm& out32(float* o, long long ld) { d.out_f32 = o; d.ldo32 = ld; return *this; }
   Gemm& out16(void* o, long long ld) { d.out_bf16 = o; d.ldo16 = ld; return *this; }
   Gemm& out16_pre(void* o, long long ld) { d.out_bf16_pre = o; d.ldo16_pre = ld; return *this; }
+  Gemm& out16_alt(void* o, long long ld) { d.out_bf16_pre = o; d.ldo16_pre = ld; d.out16_pre_alt = 1; return *this; }
   Gemm& row_map(int period, int pad) { d.out_row_period = period; d.out_row_pad = pad; return *this; }
   Gemm& fp16_operands() { d.a_is_fp16 = 1; d.b_is_fp16 = 1; return *this; }
   Gemm& out16_fp16() { d.out16_is_fp16 = 1; return *this; }
@@ -271,13 +272,15 @@ extern "C" int b200_vit_forward(const b200_vit_config* c, const b200_vit_block* 
 // Precision policy: the projector FORWARD runs fp16 operands with fp32 accumulation -- the reference's own
 // default is fp16 autocast (train.py:263) and fp16's 11-bit mantissa keeps the ReLU masks (BN->ReLU, FFN) in step with
 // the fp32 oracle, which bf16's 8 bits do not. Gradients have a wide dynamic range, so every BACKWARD operand is bf16:
-// saved fp16 activations are converted on the fly (cast_f16_bf16) right before the wgrad GEMM that consumes them.
+// every saved activation a wgrad GEMM needs is written in BOTH formats by the forward pass that produces it (tcgen05
+// kind::f16 cannot mix fp16 and bf16 operands in one product; a conversion pass per wgrad was 20 launches a step).
 namespace b200 {
 
 typedef __nv_bfloat16 h16;  // storage type for fp16 buffers (2 bytes; the kernels are told which format it holds)
 
 struct ProjSave {
-  h16 *z, *qsrc, *q, *kv, *o, *g, *h;   // fp16
+  h16 *z, *qsrc, *q, *kv, *o, *g, *h;   // fp16 (forward operands; q/k/v/o also feed the attention backward)
+  bf16 *zb, *qsrcb, *ob, *gb, *hb;      // bf16 copies of the wgrad operands, written by the same forward passes
   bf16* xt;                             // bf16 student tokens (only the conv wgrad reads them)
   float *y, *bn_mean, *bn_rstd, *lse, *f32, *mean1, *rstd1, *u32, *mean2, *rstd2;
 };
@@ -301,6 +304,11 @@ static void carve_proj_save(Arena& a, const b200_projector_config* c, int B, Pro
   s.h = a.take_n<h16>(M * 4 * D);
   s.u32 = a.take_n<float>(M * D);
   s.mean2 = a.take_n<float>(M); s.rstd2 = a.take_n<float>(M);
+  s.zb = a.take_n<bf16>(M * D);
+  s.qsrcb = a.take_n<bf16>(M * D);
+  s.ob = a.take_n<bf16>(M * D);
+  s.gb = a.take_n<bf16>(M * D);
+  s.hb = a.take_n<bf16>(M * 4 * D);
 }
 
 struct ProjFwdWs {
@@ -328,7 +336,7 @@ static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, P
 
 struct ProjBwdWs {
   bf16 *w2T, *w1T, *wpT, *wkvT, *wqT, *wcT;
-  bf16 *du16, *dh16, *df16, *do16, *dq16, *dkv16, *dqs16, *dy16, *act16;
+  bf16 *du16, *dh16, *df16, *do16, *dq16, *dkv16, *dqs16, *dy16;
   float *du32, *dg32, *df32, *dz32, *dqs32, *sums2, *dpos_t, *delta, *dxt32;
 };
 static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, ProjBwdWs& w) {
@@ -348,7 +356,6 @@ static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, P
   w.dkv16 = a.take_n<bf16>(M * 2 * D);
   w.dqs16 = a.take_n<bf16>((long long)c->HW * D);
   w.dy16 = a.take_n<bf16>(M * D);
-  w.act16 = a.take_n<bf16>(M * (4 * D > c->Cs ? 4 * D : c->Cs));
   w.du32 = a.take_n<float>(M * D);
   w.dg32 = a.take_n<float>(M * D);
   w.df32 = a.take_n<float>(M * D);
@@ -384,11 +391,10 @@ static void proj_attn_desc(b200_attn_desc& ad, const b200_projector_config* c, c
   ad.qkvo_is_fp16 = 1;
 }
 
-// dW[N_, K_] += dY^T X with X a saved fp16 activation: convert X to bf16 into scratch, then the token-major wgrad GEMM.
-static int wgrad_from_fp16(const bf16* dY, long long ld_dy, const h16* X, long long rows, int x_cols, bf16* scratch,
-                           float* dW, int n_out, void* stream) {
-  B200_TRY(b200_cast_f16_bf16(X, scratch, rows * x_cols, stream));
-  return Gemm(dY, ld_dy, scratch, x_cols, n_out, x_cols, (int)rows).out32(dW, x_cols).wgrad().run(stream);
+// dW[n_out, x_cols] += dY^T X: token-major bf16 gradient times the bf16 copy of a saved activation
+static int wgrad_tok(const bf16* dY, long long ld_dy, const bf16* X, long long rows, int x_cols, float* dW, int n_out,
+                     void* stream) {
+  return Gemm(dY, ld_dy, X, x_cols, n_out, x_cols, (int)rows).out32(dW, x_cols).wgrad().run(stream);
 }
 
 }  // namespace b200
@@ -491,21 +497,22 @@ static int projector_fwd_impl(const b200_projector_config* c, const b200_project
     B200_TRY(b200_bn_finalize(nullptr, s.bn_mean, s.bn_rstd, p->bn_running_mean, p->bn_running_var, c->bn_momentum,
                               c->bn_eps, Mi, D, stream));
   }
-  B200_TRY(b200_bn_relu_pos_fwd(s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.pos_t, w.z32, s.z, Mi, D, HW, 1, stream));
+  B200_TRY(bn_relu_pos_fwd_dual(s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.pos_t, w.z32, s.z, s.zb, Mi, D, HW, 1, stream));
 
   // cross attention: q from the query tokens, k/v from the student tokens      (losses/scalekd.py:299-316)
   const int Mq = ext ? Mi : HW;
-  B200_TRY(b200_cast_f32_f16(ext ? query : p->query_w, s.qsrc, (long long)Mq * D, stream));
+  B200_TRY(cast_f32_f16_dual(ext ? query : p->query_w, s.qsrc, s.qsrcb, (long long)Mq * D, stream));
   B200_TRY(Gemm(s.qsrc, D, w.wq, D, Mq, D, D).fp16_operands().bias(p->q_b).out16(s.q, D).out16_fp16().run(stream));
   B200_TRY(Gemm(s.z, D, w.wkv, D, Mi, 2 * D, D).fp16_operands().bias(w.bkv).out16(s.kv, 2 * D).out16_fp16().run(stream));
   b200_attn_desc ad;
   proj_attn_desc(ad, c, s, ext, B);
+  ad.o_alt = s.ob;
   B200_TRY(b200_attention_fwd(&ad, stream));
   B200_TRY(Gemm(s.o, D, w.wp, D, Mi, D, D).fp16_operands().bias(p->p_b).residual(w.z32, D).out32(s.f32, D).run(stream));
 
   // norm -> FFN(ReLU) + residual -> norm_2                                      (losses/scalekd.py:243-245)
-  B200_TRY(b200_layernorm_fwd(s.f32, p->ln1_w, p->ln1_b, c->ln_eps, w.g32, s.g, s.mean1, s.rstd1, Mi, D, 0, 0, 1, stream));
-  B200_TRY(Gemm(s.g, D, w.w1, D, Mi, 4 * D, D).fp16_operands().bias(p->ffn1_b).act(B200_ACT_RELU).out16(s.h, 4 * D).out16_fp16().run(stream));
+  B200_TRY(layernorm_fwd_dual(s.f32, p->ln1_w, p->ln1_b, c->ln_eps, w.g32, s.g, s.gb, s.mean1, s.rstd1, Mi, D, 0, 0, 1, stream));
+  B200_TRY(Gemm(s.g, D, w.w1, D, Mi, 4 * D, D).fp16_operands().bias(p->ffn1_b).act(B200_ACT_RELU).out16(s.h, 4 * D).out16_fp16().out16_alt(s.hb, 4 * D).run(stream));
   B200_TRY(Gemm(s.h, 4 * D, w.w2, 4 * D, Mi, D, 4 * D).fp16_operands().bias(p->ffn2_b).residual(w.g32, D).out32(s.u32, D).run(stream));
   B200_TRY(b200_layernorm_fwd(s.u32, p->ln2_w, p->ln2_b, c->ln_eps, out, nullptr, s.mean2, s.rstd2, Mi, D, 0, 0, 0, stream));
   return 0;
@@ -561,16 +568,16 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   B200_TRY(b200_layernorm_bwd_colsum(dout, s.u32, p->ln2_w, s.mean2, s.rstd2, nullptr, w.du32, w.du16, g->ln2_w, g->ln2_b,
                                      g->ffn2_b, Mi, D, stream));
   // FFN: u = g + W2 relu(W1 g + b1) + b2
-  B200_TRY(wgrad_from_fp16(w.du16, D, s.h, M, 4 * D, w.act16, g->ffn2_w, D, stream));
+  B200_TRY(wgrad_tok(w.du16, D, s.hb, M, 4 * D, g->ffn2_w, D, stream));
   B200_TRY(Gemm(w.du16, D, w.w2T, D, Mi, 4 * D, D).aux(s.h, 4 * D, B200_AUX_DRELU).aux_fp16().out16(w.dh16, 4 * D).run(stream));
   B200_TRY(b200_colsum(w.dh16, 1, 4 * D, g->ffn1_b, Mi, 4 * D, stream));
-  B200_TRY(wgrad_from_fp16(w.dh16, 4 * D, s.g, M, D, w.act16, g->ffn1_w, 4 * D, stream));
+  B200_TRY(wgrad_tok(w.dh16, 4 * D, s.gb, M, D, g->ffn1_w, 4 * D, stream));
   B200_TRY(Gemm(w.dh16, 4 * D, w.w1T, 4 * D, Mi, D, 4 * D).residual(w.du32, D).out32(w.dg32, D).run(stream));
   // norm
   B200_TRY(b200_layernorm_bwd_colsum(w.dg32, s.f32, p->ln1_w, s.mean1, s.rstd1, nullptr, w.df32, w.df16, g->ln1_w, g->ln1_b,
                                      g->p_b, Mi, D, stream));
   // attention output projection: f = Wp o + bp + z   (p_b gradient = column sums of df, fused above)
-  B200_TRY(wgrad_from_fp16(w.df16, D, s.o, M, D, w.act16, g->p_w, D, stream));
+  B200_TRY(wgrad_tok(w.df16, D, s.ob, M, D, g->p_w, D, stream));
   B200_TRY(Gemm(w.df16, D, w.wpT, D, Mi, D, D).out16(w.do16, D).run(stream));
   // attention core (q/k/v/o fp16 from the forward; gradients bf16)
   b200_attn_desc ad;
@@ -586,17 +593,17 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   B200_TRY(b200_attention_bwd(&ad, stream));
   // q path
   if (ext) {
-    B200_TRY(wgrad_from_fp16(w.dq16, D, s.qsrc, M, D, w.act16, g->q_w, D, stream));
+    B200_TRY(wgrad_tok(w.dq16, D, s.qsrcb, M, D, g->q_w, D, stream));
     if (dquery) B200_TRY(Gemm(w.dq16, D, w.wqT, D, Mi, D, D).out32(dquery, D).run(stream));
   } else {
     B200_TRY(b200_batch_sum_bf16(w.dq16, w.dqs32, w.dqs16, B, (long long)HW * D, stream));
-    B200_TRY(wgrad_from_fp16(w.dqs16, D, s.qsrc, HW, D, w.act16, g->q_w, D, stream));
+    B200_TRY(wgrad_tok(w.dqs16, D, s.qsrcb, HW, D, g->q_w, D, stream));
     if (g->query_w)
       B200_TRY(Gemm(w.dqs16, D, w.wqT, D, HW, D, D).residual(g->query_w, D).out32(g->query_w, D).run(stream));
   }
   // k / v path
-  B200_TRY(wgrad_from_fp16(w.dkv16, 2 * D, s.z, M, D, w.act16, g->k_w, D, stream));
-  B200_TRY(Gemm(w.dkv16 + D, 2 * D, w.act16, D, D, D, Mi).out32(g->v_w, D).wgrad().run(stream));  // act16 still holds z
+  B200_TRY(wgrad_tok(w.dkv16, 2 * D, s.zb, M, D, g->k_w, D, stream));
+  B200_TRY(wgrad_tok(w.dkv16 + D, 2 * D, s.zb, M, D, g->v_w, D, stream));
   B200_TRY(Gemm(w.dkv16, 2 * D, w.wkvT, 2 * D, Mi, D, 2 * D).residual(w.df32, D).out32(w.dz32, D).run(stream));
   // BN + ReLU + pos_embed
   B200_TRY(zero_f32(w.sums2, 2 * D, st));

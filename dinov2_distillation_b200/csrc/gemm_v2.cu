@@ -257,7 +257,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
         else v2_bulk_wait_read<1>();
       }
       __syncwarp();
-      if (has_pre) {
+      if (has_pre && !p.pre_alt) {   // copy of (acc + bias) before the activation, same format
         const uint32_t bp = stage_smem + 2048u + row_off;
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
@@ -300,6 +300,16 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
           }
+        }
+      }
+      if (has_pre && p.pre_alt) {    // copy of the FINAL value in the other 16-bit format
+        const uint32_t bp = stage_smem + 2048u + row_off;
+        const int alt = !p.out16_fp16;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int j = c * 8;
+          v2_sts128(bp + ((c ^ sw) << 4), pack16(v[j], v[j + 1], alt), pack16(v[j + 2], v[j + 3], alt),
+                    pack16(v[j + 4], v[j + 5], alt), pack16(v[j + 6], v[j + 7], alt));
         }
       }
       const uint32_t bo = buf_o + row_off;
@@ -714,6 +724,7 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   if (d->bias && !al16(d->bias)) return 1;
   if (d->col_scale && !al16(d->col_scale)) return 1;
   if (d->N % 32 != 0) return 1;   // ragged N: first-generation kernel (per-column tail handling)
+  p.pre_alt = (d->out16_pre_alt && d->out_bf16_pre) ? 1 : 0;
 
   static const int pair_mode = gemm_env_int("B200_GEMM_2CTA", -1);   // -1 auto, 0 never, 1 whenever possible
   bool pair = false;

@@ -42,7 +42,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
          aux_mode: str = "none", col_scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          res_row_period: int = 0, out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None,
          atomic_add: bool = False, split_k: int = 1, out_pre: bool = False, out_row_period: int = 0,
-         out_row_pad: int = 0, out_batch_period: int = 0):
+         out_row_pad: int = 0, out_batch_period: int = 0, out_alt: bool = False):
     """C = epilogue(A @ B^T). K-major: a [M,K], b [N,K]. MN-major: a [K,M], b [K,N] (contraction over rows)."""
     _need_cuda(a, b, bias, aux, col_scale, residual, out)
     assert a.dtype in (torch.bfloat16, torch.float16) and b.dtype in (torch.bfloat16, torch.float16)
@@ -92,9 +92,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if out_pre:
         pre = torch.empty(out_rows, N, device=a.device, dtype=out.dtype if out.dtype != torch.float32 else torch.bfloat16)
         d.out_bf16_pre, d.ldo16_pre = pre.data_ptr(), pre.stride(0)
+    if out_alt:   # second copy of the final value in the other 16-bit format (shares the pre-activation slot)
+        assert not out_pre and out.dtype in (torch.bfloat16, torch.float16)
+        pre = torch.empty(out_rows, N, device=a.device,
+                          dtype=torch.bfloat16 if out.dtype == torch.float16 else torch.float16)
+        d.out_bf16_pre, d.ldo16_pre, d.out16_pre_alt = pre.data_ptr(), pre.stride(0), 1
     d.out_row_period, d.out_row_pad = out_row_period, out_row_pad
     L.check(L.load().b200_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
-    return (out, pre) if out_pre else out
+    return (out, pre) if (out_pre or out_alt) else out
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:

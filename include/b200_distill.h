@@ -76,6 +76,10 @@ typedef struct b200_gemm_desc {
    * n % P] -- with the operand roles swapped (A = W^T, B = token-major dY) the input gradient of the 1x1 conv lands
    * directly in NCHW (P = H*W, ldo32 = H*W, stride = C*H*W) with no transpose pass. P % 32 == 0, N % P == 0. */
   int out_batch_period; long long out_batch_stride;
+  /* 1: out_bf16_pre receives the value AFTER the activation, in the 16-bit format out_bf16 does not use -- the ScaleKD
+   * FFN saves relu(W1 g + b1) as fp16 (forward operand of W2) and as bf16 (operand of the W2 wgrad GEMM) from one
+   * epilogue (tcgen05 kind::f16 cannot mix the formats in one product). Needs N % 32 == 0 and no aux operand. */
+  int out16_pre_alt;
 } b200_gemm_desc;
 
 int b200_gemm_bf16(const b200_gemm_desc* d, void* stream);
@@ -179,6 +183,8 @@ typedef struct b200_attn_desc {
   /* backward only, optional (all three or none): fp32 [heads*hd], ACCUMULATED column sums of dq / dk / dv over
    * (batch, tokens) -- the bias gradients of the q / k / v projections (losses/scalekd.py:277-279) */
   float* dq_colsum; float* dk_colsum; float* dv_colsum;
+  /* forward only, optional: a second copy of o (same strides) in the 16-bit format o does not use */
+  void* o_alt;
 } b200_attn_desc;
 int b200_attention_fwd(const b200_attn_desc* d, void* stream);
 int b200_attention_bwd(const b200_attn_desc* d, void* stream);

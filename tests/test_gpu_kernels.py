@@ -142,6 +142,12 @@ def test_gemm_tma_epilogue_paths(M, N, K):
     ah, bh = a.to(torch.float16), b.to(torch.float16)
     o16 = ops.gemm(ah, bh, bias=bias, out_dtype=torch.float16)
     assert o16.dtype == torch.float16 and rel_err(o16, ah.float() @ bh.float().t() + bias) < 2e-3
+    # final value in both 16-bit formats from one epilogue (the projector FFN saves relu(.) as fp16 and bf16)
+    if N % 32 == 0:
+        ref16 = torch.relu(ah.float() @ bh.float().t() + bias)
+        o16, alt = ops.gemm(ah, bh, bias=bias, act="relu", out_dtype=torch.float16, out_alt=True)
+        assert o16.dtype == torch.float16 and alt.dtype == torch.bfloat16
+        assert rel_err(o16, ref16) < 2e-3 and rel_err(alt, ref16) < 6e-3
     # 16-bit output x f(aux): dGELU (bf16 aux) and dReLU (fp16 aux)
     aux = bf(torch.randn(M, N, device="cuda"))
     xa = aux.float()
