@@ -37,11 +37,14 @@ WORKLOADS = {
     "cfg1": dict(desc="dinov2_vits14 + resnet_18, ScaleKD res5 only, B=2 @224", teacher="dinov2_vits14", size=224, batch=2,
                  losses=[("scalekd_res5", 512, 24, True)]),
     "cfg2": dict(desc="dinov2_vits14 -> stdc_2, config.yaml ScaleKD res4+res5, B=64/GPU @224", teacher="dinov2_vits14",
-                 size=224, batch=64, losses=[("scalekd_res4", 512, 16, True), ("scalekd_res5", 1024, 24, False)]),
+                 size=224, batch=64, losses=[("scalekd_res4", 512, 16, True), ("scalekd_res5", 1024, 24, False)],
+                 raw={"res4": 14, "res5": 7}),
     "cfg3": dict(desc="dinov2_vitb14 -> convnext_tiny, ScaleKD res4+res5, B=32/GPU @224", teacher="dinov2_vitb14",
-                 size=224, batch=32, losses=[("scalekd_res4", 384, 16, True), ("scalekd_res5", 768, 24, False)]),
+                 size=224, batch=32, losses=[("scalekd_res4", 384, 16, True), ("scalekd_res5", 768, 24, False)],
+                 raw={"res4": 14, "res5": 7}),
     "cfg4": dict(desc="dinov2_vitl14 -> swin_tiny, ScaleKD res4+res5 (heads 16), B=32/GPU @518", teacher="dinov2_vitl14",
-                 size=518, batch=32, losses=[("scalekd_res4", 384, 16, True), ("scalekd_res5", 768, 16, False)]),
+                 size=518, batch=32, losses=[("scalekd_res4", 384, 16, True), ("scalekd_res5", 768, 16, False)],
+                 raw={"res4": 33, "res5": 17}),
     "cfg5": dict(desc="dinov2_vitg14 teacher forward only, B=64/GPU @224", teacher="dinov2_vitg14", size=224, batch=64,
                  losses=[]),
 }
@@ -215,7 +218,9 @@ def build_gpu_step(wl, device):
     B = wl["batch"]
     host = {"img": torch.randn(B, 3, wl["size"], wl["size"], generator=gen).pin_memory()}
     for name, cs, _, _ in wl["losses"]:
-        host[name.split("_")[1]] = torch.randn(B, cs, g, g, generator=gen).pin_memory()
+        layer = name.split("_")[1]
+        r = wl.get("raw", {}).get(layer, g) if wl.get("raw_student") else g   # --raw-student: the backbone's own tap size
+        host[layer] = torch.randn(B, cs, r, r, generator=gen).pin_memory()
     params = [p for p in step.losses.parameters()]
     arena = D.FlatGradArena(params) if params else None
     if arena is not None:
@@ -236,10 +241,14 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--raw-student", action="store_true",
+                    help="feed the student's RAW tap maps (e.g. 14x14 / 7x7 at 224) and fuse ModelWrapper's bilinear resize "
+                         "into the projector (SURVEY 8 f1) instead of the already-resized maps the metric is quoted on")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
         wl["batch"] = args.batch
+    wl["raw_student"] = bool(args.raw_student)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -457,7 +466,9 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": wl["batch"],
                        "global_batch": wl["batch"] * world, "image_size": wl["size"],
-                       "student_features": "synthetic (student network out of scope)", "parallelism": f"dp{world}",
+                       "student_features": ("synthetic (student network out of scope)" if not wl.get("raw_student") else
+                                            f"synthetic RAW backbone maps {wl.get('raw')}, bilinear resize fused into the projector"),
+                       "parallelism": f"dp{world}",
                        "precision": "teacher bf16 operands / fp32 accum+residual; projector fwd fp16 operands, bwd bf16",
                        "l2": "per-step working set (activations >> 126 MB L2) ; no explicit flush",
                        "launch": "eager" if graphed is None else "one CUDA graph replay per step",

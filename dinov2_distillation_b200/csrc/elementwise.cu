@@ -701,6 +701,109 @@ static int launch_colreduce(const T* x, long long ldx, float* out, int rows, int
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ bilinear resize (tokens)
+// F.interpolate(mode='bilinear', align_corners=False) of models/model_zoo.py:121-126, applied to TOKEN-major maps
+// [B, h*w, D] -> [B, H*W, D]. ModelWrapper resizes the student map and ScaleKD's proj_student starts with a 1x1 conv
+// (losses/scalekd.py:199): both are linear and act on different axes, so conv1x1(resize(x)) == resize(conv1x1(x)) (the
+// four tap weights sum to one, so the bias commutes too). The projector runs the conv GEMM on the raw map and resizes
+// its D-channel token output with this kernel.
+// PyTorch's source index: src = max(0, (dst + 0.5) * in / out - 0.5); i0 = floor(src); i1 = i0 + (i0 < in - 1); l = src - i0.
+struct BilinearTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ BilinearTap bilinear_tap(int dst, int in, int out) {
+  const float scale = (float)in / (float)out;
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  BilinearTap t;
+  t.i0 = (int)src;
+  if (t.i0 > in - 1) t.i0 = in - 1;
+  t.i1 = t.i0 + (t.i0 < in - 1 ? 1 : 0);
+  t.l1 = src - (float)t.i0;
+  t.l0 = 1.0f - t.l1;
+  return t;
+}
+
+__global__ void __launch_bounds__(256) bilinear_tokens_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                 int B, int h, int w, int H, int W, int D) {
+  pdl_trigger();
+  pdl_wait();
+  const int D4 = D >> 2;
+  const long long n = (long long)B * H * W * D4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % D4);
+    long long r = i / D4;
+    const int ox = (int)(r % W); r /= W;
+    const int oy = (int)(r % H);
+    const int b = (int)(r / H);
+    const BilinearTap ty = bilinear_tap(oy, h, H), tx = bilinear_tap(ox, w, W);
+    const float4* s = reinterpret_cast<const float4*>(src + (long long)b * h * w * D) + c4;
+    const float4 a = __ldg(s + (long long)(ty.i0 * w + tx.i0) * D4), bq = __ldg(s + (long long)(ty.i0 * w + tx.i1) * D4);
+    const float4 c = __ldg(s + (long long)(ty.i1 * w + tx.i0) * D4), d = __ldg(s + (long long)(ty.i1 * w + tx.i1) * D4);
+    float4 o;
+    o.x = ty.l0 * (tx.l0 * a.x + tx.l1 * bq.x) + ty.l1 * (tx.l0 * c.x + tx.l1 * d.x);
+    o.y = ty.l0 * (tx.l0 * a.y + tx.l1 * bq.y) + ty.l1 * (tx.l0 * c.y + tx.l1 * d.y);
+    o.z = ty.l0 * (tx.l0 * a.z + tx.l1 * bq.z) + ty.l1 * (tx.l0 * c.z + tx.l1 * d.z);
+    o.w = ty.l0 * (tx.l0 * a.w + tx.l1 * bq.w) + ty.l1 * (tx.l0 * c.w + tx.l1 * d.w);
+    reinterpret_cast<float4*>(dst)[i] = o;
+  }
+}
+
+// adjoint: d_src[b, (i,j), :] = sum over output pixels of weight((oy,ox) -> (i,j)) * d_dst[b, (oy,ox), :]. One block per
+// (image, source pixel): the row / column weights of every output coordinate onto (i, j) go to shared memory first
+// (each source pixel is touched by a short contiguous range of outputs), then each thread gathers its 4 channels.
+// bf16 in (the BN backward's output), fp32 accumulation, bf16 out (operand of the conv wgrad / dgrad GEMMs).
+constexpr int BILINEAR_MAX_OUT = 256;
+__global__ void __launch_bounds__(128) bilinear_tokens_bwd_kernel(const __nv_bfloat16* __restrict__ d_dst,
+                                                                 __nv_bfloat16* __restrict__ d_src, int h, int w, int H,
+                                                                 int W, int D) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float wy[BILINEAR_MAX_OUT], wx[BILINEAR_MAX_OUT];
+  __shared__ int range[4];
+  const int q = blockIdx.x, b = blockIdx.y;
+  const int i = q / w, j = q - i * w;
+  for (int o = threadIdx.x; o < H; o += blockDim.x) {
+    const BilinearTap t = bilinear_tap(o, h, H);
+    wy[o] = (t.i0 == i ? t.l0 : 0.f) + (t.i1 == i ? t.l1 : 0.f);
+  }
+  for (int o = threadIdx.x; o < W; o += blockDim.x) {
+    const BilinearTap t = bilinear_tap(o, w, W);
+    wx[o] = (t.i0 == j ? t.l0 : 0.f) + (t.i1 == j ? t.l1 : 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int lo = H, hi = -1;
+    for (int o = 0; o < H; ++o) if (wy[o] != 0.f) { lo = o < lo ? o : lo; hi = o; }
+    range[0] = lo; range[1] = hi;
+    lo = W; hi = -1;
+    for (int o = 0; o < W; ++o) if (wx[o] != 0.f) { lo = o < lo ? o : lo; hi = o; }
+    range[2] = lo; range[3] = hi;
+  }
+  __syncthreads();
+  const int y0 = range[0], y1 = range[1], x0 = range[2], x1 = range[3];
+  const int D4 = D >> 2;
+  const __nv_bfloat16* g = d_dst + (long long)b * H * W * D;
+  for (int c4 = threadIdx.x; c4 < D4; c4 += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oy = y0; oy <= y1; ++oy) {
+      const float a = wy[oy];
+      if (a == 0.f) continue;
+      for (int ox = x0; ox <= x1; ++ox) {
+        const float wgt = a * wx[ox];
+        if (wgt == 0.f) continue;
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(g + (long long)(oy * W + ox) * D) + c4);
+        const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+        acc.x = fmaf(wgt, f0.x, acc.x); acc.y = fmaf(wgt, f0.y, acc.y);
+        acc.z = fmaf(wgt, f1.x, acc.z); acc.w = fmaf(wgt, f1.y, acc.w);
+      }
+    }
+    uint2 o;
+    o.x = pack_bf16(acc.x, acc.y);
+    o.y = pack_bf16(acc.z, acc.w);
+    reinterpret_cast<uint2*>(d_src + ((long long)b * h * w + q) * D)[c4] = o;
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------ parameter prep
 // One launch for all the per-step working copies of a projector's fp32 master parameters (casts, the 3-term split of
 // the conv weight, transposed bf16 copies for the dgrad GEMMs, bias concatenation, pos_embed to token-major): these were
@@ -891,6 +994,26 @@ extern "C" int b200_tokens_to_nchw(const float* tok, float* x, int B, int C, int
     B200_CUDA_OK(launch_pdl(transpose_kernel<float, false>, dim3(grid), dim3(dim3(32, 8)), 0, st, tok, x, HW, C, nullptr, (long long)C * HW,
                                                                   (long long)C * HW, nullptr, HW, 0));
   }
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_bilinear_tokens_fwd(const float* src, float* dst, int B, int h, int w, int H, int W, int D,
+                                        void* stream) {
+  B200_CHECK_ARG(src && dst && B > 0 && h > 0 && w > 0 && H > 0 && W > 0 && D > 0 && D % 4 == 0, "bad args");
+  B200_CUDA_OK(launch_pdl(bilinear_tokens_fwd_kernel, dim3(grid_for((long long)B * H * W * D / 4, 256)), dim3(256), 0,
+                          static_cast<cudaStream_t>(stream), src, dst, B, h, w, H, W, D));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_bilinear_tokens_bwd(const void* d_dst_bf16, void* d_src_bf16, int B, int h, int w, int H, int W,
+                                        int D, void* stream) {
+  B200_CHECK_ARG(d_dst_bf16 && d_src_bf16 && B > 0 && h > 0 && w > 0 && H > 0 && W > 0 && D > 0 && D % 4 == 0, "bad args");
+  B200_CHECK_ARG(H <= BILINEAR_MAX_OUT && W <= BILINEAR_MAX_OUT, "output grid larger than 256 per side");
+  B200_CUDA_OK(launch_pdl(bilinear_tokens_bwd_kernel, dim3((unsigned)(h * w), (unsigned)B), dim3(128), 0,
+                          static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(d_dst_bf16),
+                          static_cast<__nv_bfloat16*>(d_src_bf16), h, w, H, W, D));
   B200_LAUNCH_OK();
   return 0;
 }

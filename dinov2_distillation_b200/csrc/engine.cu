@@ -278,6 +278,13 @@ namespace b200 {
 
 typedef __nv_bfloat16 h16;  // storage type for fp16 buffers (2 bytes; the kernels are told which format it holds)
 
+// token count per image of the conv input: the raw student map when the resize is fused, else the teacher grid
+static inline int proj_hw_in(const b200_projector_config* c) { return c->raw_h > 0 ? c->raw_h * c->raw_w : c->HW; }
+static inline long long proj_rows_max(const b200_projector_config* c, int B) {
+  const int a = proj_hw_in(c);
+  return (long long)B * (a > c->HW ? a : c->HW);
+}
+
 struct ProjSave {
   h16 *z, *qsrc, *q, *kv, *o, *g, *h;   // fp16 (forward operands; q/k/v/o also feed the attention backward)
   bf16 *zb, *qsrcb, *ob, *gb, *hb;      // bf16 copies of the wgrad operands, written by the same forward passes
@@ -288,7 +295,7 @@ struct ProjSave {
 static void carve_proj_save(Arena& a, const b200_projector_config* c, int B, ProjSave& s) {
   const long long M = (long long)B * c->HW;
   const int D = c->D;
-  s.xt = a.take_n<bf16>(M * c->Cs);
+  s.xt = a.take_n<bf16>((long long)B * proj_hw_in(c) * c->Cs);
   s.y = a.take_n<float>(M * D);
   s.bn_mean = a.take_n<float>(D);
   s.bn_rstd = a.take_n<float>(D);
@@ -313,15 +320,18 @@ static void carve_proj_save(Arena& a, const b200_projector_config* c, int B, Pro
 
 struct ProjFwdWs {
   h16 *wc3, *wq, *wkv, *wp, *w1, *w2;   // fp16 working copies of the fp32 master weights (wc3: 3-term split)
-  h16* xt3;                             // 3-term split of the student tokens [M, 3Cs]
+  h16* xt3;                             // 3-term split of the student tokens [M_in, 3Cs]
   float *bkv, *sums, *pos_t, *z32, *g32, *xt32;
+  float* yraw;                          // conv output at the raw resolution [M_in, D] (fused resize only)
 };
 static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, ProjFwdWs& w) {
   const long long M = (long long)B * c->HW;
   const long long D = c->D;
+  const long long M_in = (long long)B * proj_hw_in(c);
   w.wc3 = a.take_n<h16>(3 * D * c->Cs);
-  w.xt3 = a.take_n<h16>(M * 3 * c->Cs);
-  w.xt32 = a.take_n<float>(M * c->Cs);
+  w.xt3 = a.take_n<h16>(M_in * 3 * c->Cs);
+  w.xt32 = a.take_n<float>(M_in * c->Cs);
+  w.yraw = c->raw_h > 0 ? a.take_n<float>(M_in * D) : nullptr;
   w.wq = a.take_n<h16>(D * D);
   w.wkv = a.take_n<h16>(2 * D * D);
   w.wp = a.take_n<h16>(D * D);
@@ -337,6 +347,7 @@ static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, P
 struct ProjBwdWs {
   bf16 *w2T, *w1T, *wpT, *wkvT, *wqT, *wcT;
   bf16 *du16, *dh16, *df16, *do16, *dq16, *dkv16, *dqs16, *dy16;
+  bf16* dyraw16;                        // adjoint-resized dy [M_in, D] (fused resize only)
   float *du32, *dg32, *df32, *dz32, *dqs32, *sums2, *dpos_t, *delta, *dxt32;
 };
 static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, ProjBwdWs& w) {
@@ -364,12 +375,17 @@ static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, P
   w.sums2 = a.take_n<float>(2 * D);
   w.dpos_t = a.take_n<float>((long long)c->HW * D);
   w.delta = a.take_n<float>((long long)B * c->heads * c->HW);
-  w.dxt32 = a.take_n<float>(M * c->Cs);
+  w.dxt32 = a.take_n<float>(proj_rows_max(c, B) * c->Cs);
+  w.dyraw16 = c->raw_h > 0 ? a.take_n<bf16>((long long)B * proj_hw_in(c) * D) : nullptr;
 }
 
 static int check_proj_cfg(const b200_projector_config* c, int B) {
   B200_CHECK_ARG(c != nullptr && B > 0, "bad args");
   B200_CHECK_ARG(c->D > 0 && c->Cs > 0 && c->HW > 0 && c->heads > 0, "bad config");
+  if (c->raw_h > 0)
+    B200_CHECK_ARG(c->raw_w > 0 && c->grid_h > 0 && c->grid_w > 0 && c->grid_h * c->grid_w == c->HW &&
+                       c->grid_h <= 256 && c->grid_w <= 256,
+                   "fused resize needs raw_h x raw_w and grid_h x grid_w with grid_h * grid_w == HW (<= 256 per side)");
   B200_CHECK_ARG(c->D % c->heads == 0, "teacher_dims must be divisible by num_heads");
   const int hd = c->D / c->heads;
   B200_CHECK_ARG(hd % 8 == 0 && hd <= 96, "head_dim (teacher_dims / num_heads) must be a multiple of 8 and <= 96");
@@ -419,25 +435,25 @@ extern "C" size_t b200_projector_save_bytes(const b200_projector_config* c, int 
 
 // shared student tokens of one ScaleKD (both projectors read the same preds_S): [xt bf16 [M,Cs] | xt3 fp16 [M,3Cs]]
 static size_t proj_tokens_xt3_offset(const b200_projector_config* c, int B) {
-  const size_t xt = (size_t)B * c->HW * c->Cs * 2;
+  const size_t xt = (size_t)B * proj_hw_in(c) * c->Cs * 2;
   return (xt + 255) & ~size_t(255);
 }
 
 extern "C" size_t b200_projector_tokens_bytes(const b200_projector_config* c, int B) {
   if (!c || B <= 0) return 0;
-  return proj_tokens_xt3_offset(c, B) + (size_t)B * c->HW * c->Cs * 3 * 2 + 256;
+  return proj_tokens_xt3_offset(c, B) + (size_t)B * proj_hw_in(c) * c->Cs * 3 * 2 + 256;
 }
 
 extern "C" int b200_projector_tokenize(const b200_projector_config* c, const float* x, int B, void* tokens, void* ws,
                                        size_t ws_bytes, void* stream) {
   B200_TRY(check_proj_cfg(c, B));
   B200_CHECK_ARG(x && tokens && ws, "null argument");
-  const long long M = (long long)B * c->HW;
+  const long long M = (long long)B * proj_hw_in(c);
   B200_CHECK_ARG(ws_bytes >= (size_t)M * c->Cs * 4, "workspace too small");
   bf16* xt = static_cast<bf16*>(tokens);
   h16* xt3 = reinterpret_cast<h16*>(static_cast<uint8_t*>(tokens) + proj_tokens_xt3_offset(c, B));
   float* xt32 = static_cast<float*>(ws);
-  B200_TRY(b200_nchw_to_tokens(x, xt, xt32, B, c->Cs, c->HW, 0, stream));
+  B200_TRY(b200_nchw_to_tokens(x, xt, xt32, B, c->Cs, proj_hw_in(c), 0, stream));
   B200_TRY(b200_split3_16(xt32, xt3, M, c->Cs, 0, 1, stream));
   return 0;
 }
@@ -451,6 +467,9 @@ static int projector_fwd_impl(const b200_projector_config* c, const b200_project
   const int D = c->D, Cs = c->Cs, HW = c->HW;
   const long long M = (long long)B * HW;
   const int Mi = (int)M;
+  const bool raw = c->raw_h > 0;
+  const int hw_in = proj_hw_in(c);
+  const long long M_in = (long long)B * hw_in;
   const bool ext = query != nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena sa(save, size_t(-1) >> 1);
@@ -484,10 +503,12 @@ static int projector_fwd_impl(const b200_projector_config* c, const b200_project
   if (tokens != nullptr) {
     xt3 = reinterpret_cast<const h16*>(static_cast<const uint8_t*>(tokens) + proj_tokens_xt3_offset(c, B));
   } else {
-    B200_TRY(b200_nchw_to_tokens(x, s.xt, w.xt32, B, Cs, HW, 0, stream));
-    B200_TRY(b200_split3_16(w.xt32, w.xt3, M, Cs, 0, 1, stream));
+    B200_TRY(b200_nchw_to_tokens(x, s.xt, w.xt32, B, Cs, hw_in, 0, stream));
+    B200_TRY(b200_split3_16(w.xt32, w.xt3, M_in, Cs, 0, 1, stream));
   }
-  B200_TRY(Gemm(xt3, 3 * Cs, w.wc3, 3 * Cs, Mi, D, 3 * Cs).fp16_operands().algo_scale(1.f / 3.f).bias(p->conv_b).out32(s.y, D).run(stream));
+  // fused ModelWrapper resize (models/model_zoo.py:121-126): conv at the raw resolution, then resize its output
+  B200_TRY(Gemm(xt3, 3 * Cs, w.wc3, 3 * Cs, (int)M_in, D, 3 * Cs).fp16_operands().algo_scale(1.f / 3.f).bias(p->conv_b).out32(raw ? w.yraw : s.y, D).run(stream));
+  if (raw) B200_TRY(b200_bilinear_tokens_fwd(w.yraw, s.y, B, c->raw_h, c->raw_w, c->grid_h, c->grid_w, D, stream));
   if (c->training) {
     B200_TRY(zero_f32(w.sums, 2 * D, st));
     B200_TRY(b200_bn_stats(s.y, w.sums, Mi, D, stream));
@@ -617,15 +638,23 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   // with batch statistics the column sums of dy vanish identically (sum_r yhat = 0): BN cancels the conv bias
   // (losses/scalekd.py:199-200), so its gradient is exactly zero; only the running-statistics (eval) path needs the sum.
   if (!c->training) B200_TRY(b200_colsum(w.dy16, 1, D, g->conv_b, Mi, D, stream));
-  B200_TRY(Gemm(w.dy16, D, tokens ? static_cast<const bf16*>(tokens) : s.xt, Cs, D, Cs, Mi).out32(g->conv_w, Cs).wgrad().run(stream));
+  // fused resize: the conv saw the raw map, so its gradients need R^T dy (adjoint of the bilinear resize)
+  const bf16* dyc = w.dy16;
+  const int hw_in = proj_hw_in(c);
+  const long long M_in = (long long)B * hw_in;
+  if (c->raw_h > 0) {
+    B200_TRY(b200_bilinear_tokens_bwd(w.dy16, w.dyraw16, B, c->raw_h, c->raw_w, c->grid_h, c->grid_w, D, stream));
+    dyc = w.dyraw16;
+  }
+  B200_TRY(Gemm(dyc, D, tokens ? static_cast<const bf16*>(tokens) : s.xt, Cs, D, Cs, (int)M_in).out32(g->conv_w, Cs).wgrad().run(stream));
   if (dx) {
-    if (HW % 32 == 0 && Cs % 8 == 0) {
+    if (hw_in % 32 == 0 && Cs % 8 == 0) {
       // dX in NCHW straight out of the GEMM: dx[b] [Cs, HW] = Wc^T [Cs, D] . dy_b^T -- operand roles swapped, columns
       // (b, hw) batched with period HW through a 3-D output tensor map; no token-major intermediate, no transpose
-      B200_TRY(Gemm(w.wcT, D, w.dy16, D, Cs, Mi, D).out32(dx, HW).out_batched(HW, (long long)Cs * HW).accumulate(dx_accumulate ? 1 : 0).run(stream));
+      B200_TRY(Gemm(w.wcT, D, dyc, D, Cs, (int)M_in, D).out32(dx, hw_in).out_batched(hw_in, (long long)Cs * hw_in).accumulate(dx_accumulate ? 1 : 0).run(stream));
     } else {
-      B200_TRY(Gemm(w.dy16, D, w.wcT, D, Mi, Cs, D).out32(w.dxt32, Cs).run(stream));
-      B200_TRY(b200_tokens_to_nchw(w.dxt32, dx, B, Cs, HW, dx_accumulate, stream));
+      B200_TRY(Gemm(dyc, D, w.wcT, D, (int)M_in, Cs, D).out32(w.dxt32, Cs).run(stream));
+      B200_TRY(b200_tokens_to_nchw(w.dxt32, dx, B, Cs, hw_in, dx_accumulate, stream));
     }
   }
   return 0;

@@ -102,6 +102,31 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     return (out, pre) if (out_pre or out_alt) else out
 
 
+def bilinear_tokens(src: torch.Tensor, hw, HW) -> torch.Tensor:
+    """fp32 tokens [B, h*w, D] -> [B, H*W, D]: F.interpolate(mode='bilinear', align_corners=False) on token-major maps."""
+    _need_cuda(src)
+    (h, w), (H, W) = hw, HW
+    src = src.contiguous().float()
+    B, n, D = src.shape
+    assert n == h * w
+    dst = torch.empty(B, H * W, D, device=src.device, dtype=torch.float32)
+    L.check(L.load().b200_bilinear_tokens_fwd(src.data_ptr(), dst.data_ptr(), B, h, w, H, W, D, _stream()), "bilinear_fwd")
+    return dst
+
+
+def bilinear_tokens_adjoint(d_dst: torch.Tensor, hw, HW) -> torch.Tensor:
+    """bf16 gradient tokens [B, H*W, D] -> [B, h*w, D] (transpose of `bilinear_tokens`)."""
+    _need_cuda(d_dst)
+    (h, w), (H, W) = hw, HW
+    d_dst = d_dst.contiguous()
+    assert d_dst.dtype == torch.bfloat16
+    B, n, D = d_dst.shape
+    assert n == H * W
+    out = torch.empty(B, h * w, D, device=d_dst.device, dtype=torch.bfloat16)
+    L.check(L.load().b200_bilinear_tokens_bwd(d_dst.data_ptr(), out.data_ptr(), B, h, w, H, W, D, _stream()), "bilinear_bwd")
+    return out
+
+
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     x = x.contiguous()

@@ -1,5 +1,8 @@
 """Drop-in for the reference's `ScaleKD` loss (losses/scalekd.py:12-127) and its `AttentionProjector` (:177-245).
 
+Extension: `preds_S` may also be the RAW backbone map [B, Cs, h, w]; the bilinear resize of
+`ModelWrapper.forward` (models/model_zoo.py:121-126) is then applied inside, after the 1x1 conv it commutes with.
+
 Same constructor kwargs (the `loss.losses[*].kwargs` schema of config/config.yaml:40-59 plus the keys train.py injects),
 same parameter / buffer names and shapes (so checkpoints and scripts/convert_to_anyma.py keep working), same methods
 (`forward`, `project_feat_spat/freq`, `get_spat_loss`, `get_freq_loss`) and the same 5-key output dict. Forward and
@@ -74,7 +77,7 @@ class _ProjectorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, proj, tokens, x, query, *params):
         lib = L.load()
-        cfg = proj._cfg(training=proj.training)
+        cfg = proj._cfg(training=proj.training, in_hw=tuple(x.shape[2:]))
         B = x.shape[0]
         x = x.contiguous()
         if query is not None:
@@ -182,12 +185,17 @@ class AttentionProjector(nn.Module):
             # the reference fails later, inside .reshape (losses/scalekd.py:299); fail at construction instead
             raise ValueError(f"teacher_dims={self.teacher_dims} is not divisible by num_heads={num_heads}")
 
-    def _cfg(self, training: bool) -> L.ProjectorConfig:
+    def _cfg(self, training: bool, in_hw=None) -> L.ProjectorConfig:
+        """`in_hw`: spatial size of the student map handed in. When it differs from the teacher grid the map is taken to
+        be the RAW backbone feature (before ModelWrapper's bilinear resize, models/model_zoo.py:121-126) and the resize
+        is fused behind the 1x1 conv (include/b200_distill.h: b200_projector_config.raw_h)."""
         bn = self.proj_student[1]
-        return L.ProjectorConfig(self.student_dims, self.teacher_dims, self.hw_dims[0] * self.hw_dims[1],
+        H, W = self.hw_dims
+        raw = (0, 0) if in_hw is None or tuple(int(v) for v in in_hw) == (H, W) else tuple(int(v) for v in in_hw)
+        return L.ProjectorConfig(self.student_dims, self.teacher_dims, H * W,
                                  self.pos_attention.num_heads, float(self.pos_attention.softmax_scale), float(bn.eps),
                                  float(bn.momentum if bn.momentum is not None else 0.1), float(self.norm.eps),
-                                 int(training))
+                                 int(training), raw[0], raw[1], H, W)
 
     def _params(self):
         out = []
@@ -206,7 +214,7 @@ class AttentionProjector(nn.Module):
         """Token-major working copies of the student features (bf16 tokens + 3-term fp16 split), to be shared by the
         two projectors of a ScaleKD via `forward(x, tokens=...)`."""
         lib = L.load()
-        cfg = self._cfg(training=self.training)
+        cfg = self._cfg(training=self.training, in_hw=tuple(x.shape[2:]))
         B = x.shape[0]
         x = x.contiguous().float()
         tok = torch.empty(lib.b200_projector_tokens_bytes(C.byref(cfg), B), dtype=torch.uint8, device=x.device)
@@ -224,8 +232,9 @@ class AttentionProjector(nn.Module):
         if not x.is_cuda:
             raise L.B200Error("AttentionProjector needs CUDA tensors: there is no CPU fallback")
         H, W = self.hw_dims
-        if tuple(x.shape[1:]) != (self.student_dims, H, W):
-            raise ValueError(f"expected student features [B,{self.student_dims},{H},{W}], got {tuple(x.shape)}")
+        if x.dim() != 4 or x.shape[1] != self.student_dims or x.shape[2] < 1 or x.shape[3] < 1:
+            raise ValueError(f"expected student features [B,{self.student_dims},{H},{W}] (or the raw backbone map "
+                             f"[B,{self.student_dims},h,w], resized to {H}x{W} inside), got {tuple(x.shape)}")
         return _ProjectorFn.apply(self, tokens, x.float(), None if query is None else query.float(), *self._params())
 
 
@@ -336,9 +345,8 @@ class ScaleKD(nn.Module):
                 "frequency_similarity": frequency_similarity, "loss": spat_loss + freq_loss}
 
     def _tokenize(self, preds_S: torch.Tensor):
-        H, W = self.projector_0.hw_dims
-        if not (preds_S.is_cuda and preds_S.dtype == torch.float32 and preds_S.is_contiguous()
-                and tuple(preds_S.shape[1:]) == (self.projector_0.student_dims, H, W)):
+        if not (preds_S.is_cuda and preds_S.dtype == torch.float32 and preds_S.is_contiguous() and preds_S.dim() == 4
+                and preds_S.shape[1] == self.projector_0.student_dims):
             return None   # the projector's own checks / conversions apply
         return self.projector_0.tokenize(preds_S.detach())
 

@@ -104,6 +104,13 @@ int b200_nchw_to_tokens(const float* x, void* tok_bf16, float* tok_f32, int B, i
                         void* stream);
 int b200_tokens_to_nchw(const float* tok, float* x, int B, int C, int HW, int accumulate, void* stream);
 
+/* Bilinear resize (align_corners = False: F.interpolate of models/model_zoo.py:121-126) of token-major maps
+ * fp32 [B, h*w, D] -> [B, H*W, D], and its adjoint on bf16 gradients [B, H*W, D] -> [B, h*w, D]. The projector uses
+ * them to run proj_student's 1x1 conv on the RAW student map and resize afterwards (see b200_projector_config). */
+int b200_bilinear_tokens_fwd(const float* src, float* dst, int B, int h, int w, int H, int W, int D, void* stream);
+int b200_bilinear_tokens_bwd(const void* d_dst_bf16, void* d_src_bf16, int B, int h, int w, int H, int W, int D,
+                             void* stream);
+
 /* patch-embed im2col: images fp32 [B,3,H,W] -> bf16 [B*(H/14)*(W/14), Kp], column = c*196 + i*14 + j, zero padded to
  * Kp (>= 588, multiple of 8).  (hub PatchEmbed.proj, Conv2d(3,D,14,14), reached via models/backbones/dinov2.py:32) */
 int b200_patch_im2col(const float* img, void* out, int B, int H, int W, int Kp, void* stream);
@@ -269,6 +276,12 @@ typedef struct b200_projector_config {
   float softmax_scale;   /* logits *= head_dim^-0.5 * softmax_scale */
   float bn_eps, bn_momentum, ln_eps;
   int training;          /* BN: batch statistics (1) or running statistics (0) */
+  /* Fused ModelWrapper resize (models/model_zoo.py:118-128). raw_h > 0: x (and dx) are the student map
+   * BEFORE the bilinear resize, fp32 NCHW [B, Cs, raw_h, raw_w]; the 1x1 conv runs at that resolution and its
+   * D-channel output is resized to the teacher grid grid_h x grid_w (grid_h * grid_w == HW) -- equal to resizing first
+   * (both maps are linear and the tap weights sum to one) at raw_h*raw_w / HW of the conv FLOPs and token traffic.
+   * raw_h == 0: x is already [B, Cs, HW]. */
+  int raw_h, raw_w, grid_h, grid_w;
 } b200_projector_config;
 
 size_t b200_projector_ws_bytes(const b200_projector_config* c, int B);

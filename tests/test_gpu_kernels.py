@@ -452,3 +452,30 @@ def test_arena_adamw_matches_torch_adamw_with_global_norm_clip(clip):
     for p, r in zip(ours, ref):
         assert rel_err(p.data, r.data) < 1e-6, rel_err(p.data, r.data)
         assert p.data.data_ptr() >= opt.flat_params.data_ptr()
+
+
+@pytest.mark.parametrize("hw,HW", [((7, 7), (16, 16)), ((14, 14), (16, 16)), ((17, 17), (37, 37)), ((33, 33), (37, 37)),
+                                   ((5, 9), (8, 8)), ((20, 20), (9, 9))])
+def test_bilinear_token_resize_and_adjoint(hw, HW):
+    """Token-major bilinear resize (align_corners=False, models/model_zoo.py:121-126) against oracle/resize_ref.py, and
+    its adjoint both against the oracle's transpose and through the inner-product identity <R x, g> == <x, R^T g>."""
+    from oracle import resize_ref
+    ops = _ops()
+    (h, w), (H, W) = hw, HW
+    B, D = 3, 72
+    g0 = torch.Generator().manual_seed(h * 1000 + H)
+    x = torch.randn(B, D, h, w, generator=g0)
+    ref = resize_ref.resize_bilinear(x.double(), HW).float()                       # [B, D, H, W]
+    src = x.flatten(2).transpose(1, 2).contiguous().cuda()                          # [B, h*w, D]
+    got = ops.bilinear_tokens(src, hw, HW)
+    assert rel_err(got.cpu(), ref.flatten(2).transpose(1, 2)) < 1e-5     # fp32 source coordinates, like aten
+    g = bf(torch.randn(B, H * W, D, generator=g0).cuda())
+    adj = ops.bilinear_tokens_adjoint(g, hw, HW)
+    Ry = resize_ref.resize_matrix(h, H).float()
+    Rx = resize_ref.resize_matrix(w, W).float()
+    gm = g.float().cpu().transpose(1, 2).reshape(B, D, H, W)
+    adj_ref = torch.einsum("yh,bcyx,xw->bchw", Ry, gm, Rx).flatten(2).transpose(1, 2)
+    assert rel_err(adj.cpu(), adj_ref) < 4e-3                                       # bf16 output rounding
+    lhs = (got.double() * g.double()).sum().item()
+    rhs = (src.double() * adj.double()).sum().item()
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), (got.double().norm() * g.double().norm()).item() * 1e-2)

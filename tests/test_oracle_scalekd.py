@@ -155,3 +155,33 @@ def test_b200_module_state_dict_matches_reference():
     assert list(a.keys()) == list(b.keys())
     for k in a:
         assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("n_in,n_out", [(7, 16), (14, 16), (17, 37), (33, 37), (16, 37), (32, 37), (16, 16), (20, 9)])
+def test_resize_ref_matches_interpolate(n_in, n_out):
+    """oracle/resize_ref.py against F.interpolate(bilinear, align_corners=False) -- the call ModelWrapper.forward makes
+    (models/model_zoo.py:121-126) -- on the reference's own size pairs, forward and adjoint (through autograd)."""
+    from oracle import resize_ref
+    torch.manual_seed(n_in * 100 + n_out)
+    x = torch.randn(2, 5, n_in, n_in + 1, dtype=torch.float64, requires_grad=True)
+    size = (n_out, n_out + 2)
+    ref = torch.nn.functional.interpolate(x, size=size, mode="bilinear", align_corners=False)
+    got = resize_ref.resize_bilinear(x, size)
+    assert torch.allclose(got, ref, atol=1e-12, rtol=0)
+    g = torch.randn_like(ref)
+    (gx_ref,) = torch.autograd.grad(ref, x, g, retain_graph=True)
+    (gx,) = torch.autograd.grad(got, x, g)
+    assert torch.allclose(gx, gx_ref, atol=1e-12, rtol=0)
+    # rows of the 1-D operator sum to one: a 1x1 conv's bias commutes with the resize (DESIGN.md, f1)
+    assert torch.allclose(resize_ref.resize_matrix(n_in, n_out).sum(1), torch.ones(n_out, dtype=torch.float64))
+
+
+def test_resize_commutes_with_conv1x1():
+    """The identity the fused path rests on: conv1x1(resize(x)) == resize(conv1x1(x)), bias included."""
+    from oracle import resize_ref
+    torch.manual_seed(0)
+    x = torch.randn(2, 12, 7, 7, dtype=torch.float64)
+    conv = torch.nn.Conv2d(12, 20, 1).double()
+    a = conv(torch.nn.functional.interpolate(x, size=(16, 16), mode="bilinear", align_corners=False))
+    b = resize_ref.resize_bilinear(conv(x), (16, 16))
+    assert torch.allclose(a, b, atol=1e-12, rtol=0)
