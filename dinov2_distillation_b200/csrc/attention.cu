@@ -709,6 +709,7 @@ attn_bwd_fused_kernel(const AttnParams p) {
       float dq[NBW][4];
 #pragma unroll
       for (int i = 0; i < NBW; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+#pragma unroll 4
       for (int ks = 0; ks < ksteps; ++ks) {
         uint32_t a[4];
         // A = dS (row = query, k = key), read transposed from the key-major staging tile

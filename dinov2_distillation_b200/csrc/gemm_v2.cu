@@ -150,6 +150,18 @@ __device__ __forceinline__ float v2_gelu(float x) {
   const float a = fabsf(x);
   return fmaf(-a, v2_phi_neg(a), fmaxf(x, 0.0f));
 }
+// two elements per instruction where the ISA allows it (FFMA2: one issue slot for two fp32 FMAs -- the GELU epilogue is
+// issue bound): the five Horner steps and the final fma run packed, abs / max / ex2 stay scalar
+__device__ __forceinline__ float2 v2_gelu2(float x0, float x1) {
+  const float2 a = make_float2(fabsf(x0), fabsf(x1));
+  float2 q = __ffma2_rn(make_float2(-3.046068783e-04f, -3.046068783e-04f), a, make_float2(5.602596781e-03f, 5.602596781e-03f));
+  q = __ffma2_rn(q, a, make_float2(-4.712946504e-02f, -4.712946504e-02f));
+  q = __ffma2_rn(q, a, make_float2(-4.664196592e-01f, -4.664196592e-01f));
+  q = __ffma2_rn(q, a, make_float2(-1.147315491e+00f, -1.147315491e+00f));
+  q = __ffma2_rn(q, a, make_float2(-1.000508484e+00f, -1.000508484e+00f));
+  const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+  return __ffma2_rn(make_float2(-a.x, -a.y), e, make_float2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+}
 __device__ __forceinline__ float v2_dgelu(float x) {
   const float e = v2_phi_neg(fabsf(x));
   const float cdf = x > 0.0f ? 1.0f - e : e;
@@ -268,7 +280,10 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
       }
       if constexpr (EPI == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v2_gelu(v[j]);
+        for (int j = 0; j < 32; j += 2) {
+          const float2 r = v2_gelu2(v[j], v[j + 1]);
+          v[j] = r.x; v[j + 1] = r.y;
+        }
       } else {
         if (p.act == B200_ACT_RELU) {
 #pragma unroll
