@@ -97,7 +97,8 @@ class ProjectorConfig(C.Structure):
     _fields_ = [("Cs", C.c_int), ("D", C.c_int), ("HW", C.c_int), ("heads", C.c_int),
                 ("softmax_scale", C.c_float), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
                 ("ln_eps", C.c_float), ("training", C.c_int),
-                ("raw_h", C.c_int), ("raw_w", C.c_int), ("grid_h", C.c_int), ("grid_w", C.c_int)]
+                ("raw_h", C.c_int), ("raw_w", C.c_int), ("grid_h", C.c_int), ("grid_w", C.c_int),
+                ("win_h", C.c_int), ("win_w", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/b200_distill.h declares
@@ -118,6 +119,7 @@ SIGNATURES = {
     "b200_transpose_f32_bf16_ld": (_i, [c_fp, c_vp, _i, _i, c_ll, c_fp, c_vp]),
     "b200_nchw_to_tokens": (_i, [c_fp, c_vp, c_fp, _i, _i, _i, _i, c_vp]),
     "b200_tokens_to_nchw": (_i, [c_fp, c_fp, _i, _i, _i, _i, c_vp]),
+    "b200_window_rows16": (_i, [c_vp, c_vp, c_ll, _i, _i, _i, _i, _i, c_ll, _i, c_vp]),
     "b200_bilinear_tokens_fwd": (_i, [c_fp, c_fp, _i, _i, _i, _i, _i, _i, c_vp]),
     "b200_bilinear_tokens_bwd": (_i, [c_vp, c_vp, _i, _i, _i, _i, _i, _i, c_vp]),
     "b200_patch_im2col": (_i, [c_fp, c_vp, _i, _i, _i, _i, c_vp]),

@@ -804,6 +804,31 @@ __global__ void __launch_bounds__(128) bilinear_tokens_bwd_kernel(const __nv_bfl
 }
 
 
+// ------------------------------------------------------------------------------------------------ window token order
+// WindowMultiheadPosAttention.separate_tokens (losses/scalekd.py:326-335) cuts the H x W token grid into win_h x win_w
+// windows. Rows of a token-major 16-bit matrix [B*H*W, ld] are moved between raster order and WINDOW-major order
+// (window index row-major over the windows, then row-major inside the window), so that each window's tokens are a
+// contiguous run of rows and the attention kernels can take a window as one sequence. One warp per row, 16-byte copies.
+__global__ void __launch_bounds__(256) window_rows16_kernel(const __nv_bfloat16* __restrict__ src,
+                                                           __nv_bfloat16* __restrict__ dst, long long rows, int H, int W,
+                                                           int win_h, int win_w, int cols, long long ld, int to_raster) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int hh = H / win_h, ww = W / win_w, HW = H * W;
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long b = r / HW;
+    const int t = (int)(r - b * HW);            // window-major index: win * (hh*ww) + ly * ww + lx
+    const int win = t / (hh * ww), l = t - win * (hh * ww);
+    const int wy = win / win_w, wx = win - wy * win_w, ly = l / ww, lx = l - ly * ww;
+    const long long raster = b * HW + (long long)(wy * hh + ly) * W + wx * ww + lx;
+    const uint4* s = reinterpret_cast<const uint4*>(src + (to_raster ? r : raster) * ld);
+    uint4* d = reinterpret_cast<uint4*>(dst + (to_raster ? raster : r) * ld);
+    for (int c = lane; c < cols / 8; c += 32) d[c] = s[c];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ parameter prep
 // One launch for all the per-step working copies of a projector's fp32 master parameters (casts, the 3-term split of
 // the conv weight, transposed bf16 copies for the dgrad GEMMs, bias concatenation, pos_embed to token-major): these were
@@ -1014,6 +1039,19 @@ extern "C" int b200_bilinear_tokens_bwd(const void* d_dst_bf16, void* d_src_bf16
   B200_CUDA_OK(launch_pdl(bilinear_tokens_bwd_kernel, dim3((unsigned)(h * w), (unsigned)B), dim3(128), 0,
                           static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(d_dst_bf16),
                           static_cast<__nv_bfloat16*>(d_src_bf16), h, w, H, W, D));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200_window_rows16(const void* src, void* dst, long long rows, int H, int W, int win_h, int win_w,
+                                  int cols, long long ld, int to_raster, void* stream) {
+  B200_CHECK_ARG(src && dst && src != dst && rows > 0 && H > 0 && W > 0 && win_h > 0 && win_w > 0, "bad args");
+  B200_CHECK_ARG(H % win_h == 0 && W % win_w == 0 && rows % ((long long)H * W) == 0, "windows must tile the grid");
+  B200_CHECK_ARG(cols > 0 && cols % 8 == 0 && ld % 8 == 0 && cols <= ld, "cols and ld must be multiples of 8");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "alignment");
+  B200_CUDA_OK(launch_pdl(window_rows16_kernel, dim3(grid_for(rows, 8, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                          static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, H, W, win_h, win_w,
+                          cols, ld, to_raster));
   B200_LAUNCH_OK();
   return 0;
 }

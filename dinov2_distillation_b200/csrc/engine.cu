@@ -280,6 +280,9 @@ typedef __nv_bfloat16 h16;  // storage type for fp16 buffers (2 bytes; the kerne
 
 // token count per image of the conv input: the raw student map when the resize is fused, else the teacher grid
 static inline int proj_hw_in(const b200_projector_config* c) { return c->raw_h > 0 ? c->raw_h * c->raw_w : c->HW; }
+static inline int proj_windows(const b200_projector_config* c) {
+  return (c->win_h > 1 || c->win_w > 1) ? (c->win_h > 0 ? c->win_h : 1) * (c->win_w > 0 ? c->win_w : 1) : 1;
+}
 static inline long long proj_rows_max(const b200_projector_config* c, int B) {
   const int a = proj_hw_in(c);
   return (long long)B * (a > c->HW ? a : c->HW);
@@ -323,6 +326,7 @@ struct ProjFwdWs {
   h16* xt3;                             // 3-term split of the student tokens [M_in, 3Cs]
   float *bkv, *sums, *pos_t, *z32, *g32, *xt32;
   float* yraw;                          // conv output at the raw resolution [M_in, D] (fused resize only)
+  h16 *qtmp, *kvtmp;                    // raster-order q / [k|v] before the move to window-major rows (windows only)
 };
 static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, ProjFwdWs& w) {
   const long long M = (long long)B * c->HW;
@@ -332,6 +336,8 @@ static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, P
   w.xt3 = a.take_n<h16>(M_in * 3 * c->Cs);
   w.xt32 = a.take_n<float>(M_in * c->Cs);
   w.yraw = c->raw_h > 0 ? a.take_n<float>(M_in * D) : nullptr;
+  w.qtmp = proj_windows(c) > 1 ? a.take_n<h16>(M * D) : nullptr;
+  w.kvtmp = proj_windows(c) > 1 ? a.take_n<h16>(M * 2 * D) : nullptr;
   w.wq = a.take_n<h16>(D * D);
   w.wkv = a.take_n<h16>(2 * D * D);
   w.wp = a.take_n<h16>(D * D);
@@ -348,6 +354,7 @@ struct ProjBwdWs {
   bf16 *w2T, *w1T, *wpT, *wkvT, *wqT, *wcT;
   bf16 *du16, *dh16, *df16, *do16, *dq16, *dkv16, *dqs16, *dy16;
   bf16* dyraw16;                        // adjoint-resized dy [M_in, D] (fused resize only)
+  bf16 *dq16r, *dkv16r;                 // dq / [dk|dv] moved back to raster order (windows only)
   float *du32, *dg32, *df32, *dz32, *dqs32, *sums2, *dpos_t, *delta, *dxt32;
 };
 static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, ProjBwdWs& w) {
@@ -377,11 +384,17 @@ static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, P
   w.delta = a.take_n<float>((long long)B * c->heads * c->HW);
   w.dxt32 = a.take_n<float>(proj_rows_max(c, B) * c->Cs);
   w.dyraw16 = c->raw_h > 0 ? a.take_n<bf16>((long long)B * proj_hw_in(c) * D) : nullptr;
+  w.dq16r = proj_windows(c) > 1 ? a.take_n<bf16>(M * D) : nullptr;
+  w.dkv16r = proj_windows(c) > 1 ? a.take_n<bf16>(M * 2 * D) : nullptr;
 }
 
 static int check_proj_cfg(const b200_projector_config* c, int B) {
   B200_CHECK_ARG(c != nullptr && B > 0, "bad args");
   B200_CHECK_ARG(c->D > 0 && c->Cs > 0 && c->HW > 0 && c->heads > 0, "bad config");
+  if (proj_windows(c) > 1)
+    B200_CHECK_ARG(c->grid_h > 0 && c->grid_w > 0 && c->grid_h * c->grid_w == c->HW && c->grid_h % c->win_h == 0 &&
+                       c->grid_w % c->win_w == 0,
+                   "window_shapes must tile the grid_h x grid_w token grid (grid_h * grid_w == HW)");
   if (c->raw_h > 0)
     B200_CHECK_ARG(c->raw_w > 0 && c->grid_h > 0 && c->grid_w > 0 && c->grid_h * c->grid_w == c->HW &&
                        c->grid_h <= 256 && c->grid_w <= 256,
@@ -393,16 +406,20 @@ static int check_proj_cfg(const b200_projector_config* c, int B) {
   return 0;
 }
 
+// Attention descriptor of window `win` (of n_win; one window = the whole grid when there are none). q / k / v / o are
+// window-major, so a window's tokens are `tpw` consecutive rows of every image; lse of launch `win` is [B, heads, tpw].
 static void proj_attn_desc(b200_attn_desc& ad, const b200_projector_config* c, const ProjSave& s, bool ext_query,
-                           int B) {
+                           int B, int win = 0) {
   const int D = c->D, HW = c->HW;
+  const int tpw = HW / proj_windows(c);
+  const long long r0 = (long long)win * tpw;
   memset(&ad, 0, sizeof ad);
-  ad.q = s.q; ad.q_bs = ext_query ? (long long)HW * D : 0; ad.q_ts = D;
-  ad.k = s.kv; ad.v = s.kv + D;
+  ad.q = s.q + r0 * D; ad.q_bs = ext_query ? (long long)HW * D : 0; ad.q_ts = D;
+  ad.k = s.kv + r0 * 2 * D; ad.v = s.kv + r0 * 2 * D + D;
   ad.k_bs = ad.v_bs = (long long)HW * 2 * D; ad.k_ts = ad.v_ts = 2 * D;
-  ad.o = s.o; ad.o_bs = (long long)HW * D; ad.o_ts = D;
-  ad.lse = s.lse;
-  ad.B = B; ad.heads = c->heads; ad.Nq = HW; ad.Nk = HW; ad.hd = D / c->heads;
+  ad.o = s.o + r0 * D; ad.o_bs = (long long)HW * D; ad.o_ts = D;
+  ad.lse = s.lse + (long long)win * B * c->heads * tpw;
+  ad.B = B; ad.heads = c->heads; ad.Nq = tpw; ad.Nk = tpw; ad.hd = D / c->heads;
   ad.scale = c->softmax_scale / sqrtf((float)ad.hd);
   ad.qkvo_is_fp16 = 1;
 }
@@ -523,12 +540,19 @@ static int projector_fwd_impl(const b200_projector_config* c, const b200_project
   // cross attention: q from the query tokens, k/v from the student tokens      (losses/scalekd.py:299-316)
   const int Mq = ext ? Mi : HW;
   B200_TRY(cast_f32_f16_dual(ext ? query : p->query_w, s.qsrc, s.qsrcb, (long long)Mq * D, stream));
-  B200_TRY(Gemm(s.qsrc, D, w.wq, D, Mq, D, D).fp16_operands().bias(p->q_b).out16(s.q, D).out16_fp16().run(stream));
-  B200_TRY(Gemm(s.z, D, w.wkv, D, Mi, 2 * D, D).fp16_operands().bias(w.bkv).out16(s.kv, 2 * D).out16_fp16().run(stream));
-  b200_attn_desc ad;
-  proj_attn_desc(ad, c, s, ext, B);
-  ad.o_alt = s.ob;
-  B200_TRY(b200_attention_fwd(&ad, stream));
+  const int n_win = proj_windows(c);
+  B200_TRY(Gemm(s.qsrc, D, w.wq, D, Mq, D, D).fp16_operands().bias(p->q_b).out16(n_win > 1 ? w.qtmp : s.q, D).out16_fp16().run(stream));
+  B200_TRY(Gemm(s.z, D, w.wkv, D, Mi, 2 * D, D).fp16_operands().bias(w.bkv).out16(n_win > 1 ? w.kvtmp : s.kv, 2 * D).out16_fp16().run(stream));
+  if (n_win > 1) {   // separate_tokens (losses/scalekd.py:305-308): each window's tokens become consecutive rows
+    B200_TRY(b200_window_rows16(w.qtmp, s.q, Mq, c->grid_h, c->grid_w, c->win_h, c->win_w, D, D, 0, stream));
+    B200_TRY(b200_window_rows16(w.kvtmp, s.kv, M, c->grid_h, c->grid_w, c->win_h, c->win_w, 2 * D, 2 * D, 0, stream));
+  }
+  for (int win = 0; win < n_win; ++win) {   // (the output stays window-major, as in the reference: scalekd.py:313-314)
+    b200_attn_desc ad;
+    proj_attn_desc(ad, c, s, ext, B, win);
+    ad.o_alt = s.ob + (long long)win * (HW / n_win) * D;
+    B200_TRY(b200_attention_fwd(&ad, stream));
+  }
   B200_TRY(Gemm(s.o, D, w.wp, D, Mi, D, D).fp16_operands().bias(p->p_b).residual(w.z32, D).out32(s.f32, D).run(stream));
 
   // norm -> FFN(ReLU) + residual -> norm_2                                      (losses/scalekd.py:243-245)
@@ -600,32 +624,45 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   // attention output projection: f = Wp o + bp + z   (p_b gradient = column sums of df, fused above)
   B200_TRY(wgrad_tok(w.df16, D, s.ob, M, D, g->p_w, D, stream));
   B200_TRY(Gemm(w.df16, D, w.wpT, D, Mi, D, D).out16(w.do16, D).run(stream));
-  // attention core (q/k/v/o fp16 from the forward; gradients bf16)
-  b200_attn_desc ad;
-  proj_attn_desc(ad, c, s, ext, B);
-  ad.d_o = w.do16; ad.do_bs = (long long)HW * D; ad.do_ts = D;
-  ad.delta = w.delta;
-  ad.dq = w.dq16; ad.dq_bs = (long long)HW * D; ad.dq_ts = D;
-  ad.dk = w.dkv16; ad.dv = w.dkv16 + D;
-  ad.dk_bs = ad.dv_bs = (long long)HW * 2 * D; ad.dk_ts = ad.dv_ts = 2 * D;
+  // attention core (q/k/v/o fp16 from the forward; gradients bf16), one launch per window
   // q / k / v bias gradients = column sums of dq / dk / dv over every (image, token): produced inside the attention
   // backward (for a batch-invariant self query the sum over images of dq is the same quantity)
-  ad.dq_colsum = g->q_b; ad.dk_colsum = g->k_b; ad.dv_colsum = g->v_b;
-  B200_TRY(b200_attention_bwd(&ad, stream));
+  const int n_win = proj_windows(c);
+  for (int win = 0; win < n_win; ++win) {
+    const int tpw = HW / n_win;
+    const long long r0 = (long long)win * tpw;
+    b200_attn_desc ad;
+    proj_attn_desc(ad, c, s, ext, B, win);
+    ad.d_o = w.do16 + r0 * D; ad.do_bs = (long long)HW * D; ad.do_ts = D;
+    ad.delta = w.delta + (long long)win * B * c->heads * tpw;
+    ad.dq = w.dq16 + r0 * D; ad.dq_bs = (long long)HW * D; ad.dq_ts = D;
+    ad.dk = w.dkv16 + r0 * 2 * D; ad.dv = w.dkv16 + r0 * 2 * D + D;
+    ad.dk_bs = ad.dv_bs = (long long)HW * 2 * D; ad.dk_ts = ad.dv_ts = 2 * D;
+    ad.dq_colsum = g->q_b; ad.dk_colsum = g->k_b; ad.dv_colsum = g->v_b;
+    B200_TRY(b200_attention_bwd(&ad, stream));
+  }
+  const bf16* dq16 = w.dq16;
+  const bf16* dkv16 = w.dkv16;
+  if (n_win > 1) {   // gradients of the window-major q / k / v back to the raster order their projections produced
+    B200_TRY(b200_window_rows16(w.dq16, w.dq16r, M, c->grid_h, c->grid_w, c->win_h, c->win_w, D, D, 1, stream));
+    B200_TRY(b200_window_rows16(w.dkv16, w.dkv16r, M, c->grid_h, c->grid_w, c->win_h, c->win_w, 2 * D, 2 * D, 1, stream));
+    dq16 = w.dq16r;
+    dkv16 = w.dkv16r;
+  }
   // q path
   if (ext) {
-    B200_TRY(wgrad_tok(w.dq16, D, s.qsrcb, M, D, g->q_w, D, stream));
-    if (dquery) B200_TRY(Gemm(w.dq16, D, w.wqT, D, Mi, D, D).out32(dquery, D).run(stream));
+    B200_TRY(wgrad_tok(dq16, D, s.qsrcb, M, D, g->q_w, D, stream));
+    if (dquery) B200_TRY(Gemm(dq16, D, w.wqT, D, Mi, D, D).out32(dquery, D).run(stream));
   } else {
-    B200_TRY(b200_batch_sum_bf16(w.dq16, w.dqs32, w.dqs16, B, (long long)HW * D, stream));
+    B200_TRY(b200_batch_sum_bf16(dq16, w.dqs32, w.dqs16, B, (long long)HW * D, stream));
     B200_TRY(wgrad_tok(w.dqs16, D, s.qsrcb, HW, D, g->q_w, D, stream));
     if (g->query_w)
       B200_TRY(Gemm(w.dqs16, D, w.wqT, D, HW, D, D).residual(g->query_w, D).out32(g->query_w, D).run(stream));
   }
   // k / v path
-  B200_TRY(wgrad_tok(w.dkv16, 2 * D, s.zb, M, D, g->k_w, D, stream));
-  B200_TRY(wgrad_tok(w.dkv16 + D, 2 * D, s.zb, M, D, g->v_w, D, stream));
-  B200_TRY(Gemm(w.dkv16, 2 * D, w.wkvT, 2 * D, Mi, D, 2 * D).residual(w.df32, D).out32(w.dz32, D).run(stream));
+  B200_TRY(wgrad_tok(dkv16, 2 * D, s.zb, M, D, g->k_w, D, stream));
+  B200_TRY(wgrad_tok(dkv16 + D, 2 * D, s.zb, M, D, g->v_w, D, stream));
+  B200_TRY(Gemm(dkv16, 2 * D, w.wkvT, 2 * D, Mi, D, 2 * D).residual(w.df32, D).out32(w.dz32, D).run(stream));
   // BN + ReLU + pos_embed
   B200_TRY(zero_f32(w.sums2, 2 * D, st));
   B200_TRY(zero_f32(w.dpos_t, (long long)HW * D, st));

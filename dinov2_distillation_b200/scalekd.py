@@ -195,7 +195,7 @@ class AttentionProjector(nn.Module):
         return L.ProjectorConfig(self.student_dims, self.teacher_dims, H * W,
                                  self.pos_attention.num_heads, float(self.pos_attention.softmax_scale), float(bn.eps),
                                  float(bn.momentum if bn.momentum is not None else 0.1), float(self.norm.eps),
-                                 int(training), raw[0], raw[1], H, W)
+                                 int(training), raw[0], raw[1], H, W, *self.pos_attention.window_shapes)
 
     def _params(self):
         out = []
@@ -227,8 +227,10 @@ class AttentionProjector(nn.Module):
     def forward(self, x, query=None, tokens=None):
         if query is None and self.query is None:
             raise NotImplementedError("There is no query!")
-        if self.pos_attention.window_shapes != (1, 1):
-            raise NotImplementedError("window_shapes other than [1, 1] are not on the B200 path yet")
+        wh, ww = self.pos_attention.window_shapes
+        if wh * ww > 1 and (self.hw_dims[0] != self.hw_dims[1] or self.hw_dims[0] % wh or self.hw_dims[1] % ww):
+            # the reference takes the grid as sqrt(N) x sqrt(N) and .view()s it into windows (losses/scalekd.py:326-333)
+            raise ValueError(f"window_shapes {wh}x{ww} need a square token grid they divide, got {self.hw_dims}")
         if not x.is_cuda:
             raise L.B200Error("AttentionProjector needs CUDA tensors: there is no CPU fallback")
         H, W = self.hw_dims

@@ -111,6 +111,12 @@ int b200_bilinear_tokens_fwd(const float* src, float* dst, int B, int h, int w, 
 int b200_bilinear_tokens_bwd(const void* d_dst_bf16, void* d_src_bf16, int B, int h, int w, int H, int W, int D,
                              void* stream);
 
+/* Token order of windowed attention (WindowMultiheadPosAttention.separate_tokens, losses/scalekd.py:326-335): rows of a
+ * 16-bit token-major matrix [rows = B*H*W, ld] (cols <= ld copied) between raster order and window-major order
+ * (to_raster = 0: raster -> window-major; 1: back). src != dst. */
+int b200_window_rows16(const void* src, void* dst, long long rows, int H, int W, int win_h, int win_w, int cols,
+                       long long ld, int to_raster, void* stream);
+
 /* patch-embed im2col: images fp32 [B,3,H,W] -> bf16 [B*(H/14)*(W/14), Kp], column = c*196 + i*14 + j, zero padded to
  * Kp (>= 588, multiple of 8).  (hub PatchEmbed.proj, Conv2d(3,D,14,14), reached via models/backbones/dinov2.py:32) */
 int b200_patch_im2col(const float* img, void* out, int B, int H, int W, int Kp, void* stream);
@@ -282,6 +288,10 @@ typedef struct b200_projector_config {
    * (both maps are linear and the tap weights sum to one) at raw_h*raw_w / HW of the conv FLOPs and token traffic.
    * raw_h == 0: x is already [B, Cs, HW]. */
   int raw_h, raw_w, grid_h, grid_w;
+  /* window_shapes of WindowMultiheadPosAttention (losses/scalekd.py:286, :305-314): win_h * win_w > 1 cuts the
+   * grid_h x grid_w token grid into windows, attention runs inside each window, and -- as in the reference -- the
+   * attention output STAYS in window-major token order. 0 or 1: no windows. Needs grid_h % win_h == 0 etc. */
+  int win_h, win_w;
 } b200_projector_config;
 
 size_t b200_projector_ws_bytes(const b200_projector_config* c, int B);

@@ -52,6 +52,35 @@ def scalekd_tiny(sk):
     print("scalekd_tiny:", {k: float(v) for k, v in out.items()})
 
 
+def scalekd_windows(sk):
+    """window_shapes = [2, 2] (losses/scalekd.py:305-308, :326-335) on an 8x8 grid: windowed cross attention whose
+    output stays window-major. One self-query ScaleKD and one with external queries."""
+    for tag, self_query in (("self", True), ("ext", False)):
+        torch.manual_seed(31)
+        kw = dict(name="scalekd_res5", alpha=[0.08, 0.06], student_dims=24, teacher_dims=64, query_hw=[8, 8],
+                  pos_hw=[8, 8], pos_dims=64, window_shapes=[2, 2], self_query=self_query, softmax_scale=[5.0, 3.0],
+                  num_heads=4)
+        m = sk.ScaleKD(**kw)
+        g = torch.Generator().manual_seed(32)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if p.dim() == 1:
+                    p.add_(0.1 * torch.randn(p.shape, generator=g))
+        B = 3
+        S = torch.randn(B, 24, 8, 8, generator=g, requires_grad=True)
+        T = torch.randn(B, 64, 8, 8, generator=g) + 0.2
+        qs = None if self_query else torch.randn(B, 64, 64, generator=g)
+        qf = None if self_query else torch.randn(B, 64, 64, generator=g)
+        sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        m.train()
+        out = m(S, T, query_s=qs, query_f=qf)
+        out["loss"].backward()
+        torch.save({"kwargs": kw, "state_dict": sd0, "preds_S": S.detach(), "preds_T": T, "query_s": qs, "query_f": qf,
+                    "out": {k: v.detach() for k, v in out.items()}, "grad_S": S.grad.detach(), "grads": _grads(m)},
+                   os.path.join(GOLDEN, f"scalekd_win_{tag}.pt"))
+        print(f"scalekd_win_{tag}:", {k: float(v) for k, v in out.items()})
+
+
 def scalekd_cfg1(sk):
     """BASELINE.json configs[0] loss shapes: vits14 (D=384) + resnet_18 res5 (Cs=512), 16x16 grid, B=2, heads 24.
     Weights are NOT stored (35 MB): both sides rebuild them from torch.manual_seed(3) -- the constructor consumes the RNG
@@ -121,6 +150,7 @@ def main():
     sk, dm = ref_shims.import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     scalekd_tiny(sk)
+    scalekd_windows(sk)
     scalekd_cfg1(sk)
     if dm is not None:
         pipeline_tiny(sk, dm)

@@ -479,3 +479,20 @@ def test_bilinear_token_resize_and_adjoint(hw, HW):
     lhs = (got.double() * g.double()).sum().item()
     rhs = (src.double() * adj.double()).sum().item()
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), (got.double().norm() * g.double().norm()).item() * 1e-2)
+
+
+def test_window_row_order_round_trip():
+    """b200_window_rows16 against separate_tokens' view/permute (losses/scalekd.py:326-335) and back."""
+    import ctypes as C
+    from dinov2_distillation_b200 import _lib as L
+    lib = L.load()
+    B, H, W, D, wh, ww = 3, 8, 12, 40, 2, 3
+    x = bf(torch.randn(B, H * W, D, device="cuda"))
+    y = torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b200_window_rows16(x.data_ptr(), y.data_ptr(), B * H * W, H, W, wh, ww, D, D, 0, st), "window_rows16")
+    ref = x.view(B, wh, H // wh, ww, W // ww, D).permute(0, 1, 3, 2, 4, 5).reshape(B, H * W, D)
+    assert torch.equal(y, ref)
+    z = torch.zeros_like(x)
+    L.check(lib.b200_window_rows16(y.data_ptr(), z.data_ptr(), B * H * W, H, W, wh, ww, D, D, 1, st), "window_rows16")
+    assert torch.equal(z, x)

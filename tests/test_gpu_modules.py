@@ -45,8 +45,9 @@ def check_param_grads(pairs, tol=GRAD_RTOL):
     for k, (a, b) in pairs.items():
         sib = k.replace("projector_0", "projector_X").replace("projector_1", "projector_0").replace("projector_X", "projector_1")
         scale = max(b.norm().item(), pairs[sib][1].norm().item() if sib in pairs else 0.0)
-        if scale < 1e-4 * max_norm:  # analytically zero (conv bias under BatchNorm): fp32 round-off in the reference
-            assert a.norm().item() <= 1e-4 * max_norm, (k, a.norm().item())
+        if scale < 1e-4 * max_norm:  # analytically zero (conv bias under BatchNorm, key bias under softmax): fp32
+            # round-off in the reference, bf16-gradient round-off here
+            assert a.norm().item() <= 5e-4 * max_norm, (k, a.norm().item())
             continue
         rows[k] = (a - b).norm().item() / scale
     worst = sorted(rows.items(), key=lambda kv: -kv[1])[:6]
@@ -502,3 +503,56 @@ def test_scalekd_fused_resize_matches_resize_then_scalekd(raw, self_query):
     assert rel(S.grad, S2.grad) <= GRAD_RTOL
     unfused = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
     check_param_grads({n: (fused[n], unfused[n]) for n in fused})
+
+
+@pytest.mark.parametrize("tag", ["self", "ext"])
+def test_scalekd_window_attention_golden(tag):
+    """window_shapes = [2, 2] (WindowMultiheadPosAttention.separate_tokens, losses/scalekd.py:305-314, :326-335) against
+    the outputs and gradients of the UNMODIFIED reference (tests/golden/scalekd_win_*.pt, oracle/make_golden.py)."""
+    scalekd, _, _ = _mods()
+    g = torch.load(os.path.join(GOLDEN, f"scalekd_win_{tag}.pt"))
+    m = scalekd.ScaleKD(**g["kwargs"])
+    m.load_state_dict(g["state_dict"])
+    m = m.cuda().train()
+    S = g["preds_S"].cuda().requires_grad_(True)
+    cq = lambda q: None if q is None else q.cuda().requires_grad_(True)  # noqa: E731
+    qs, qf = cq(g["query_s"]), cq(g["query_f"])
+    out = m(S, g["preds_T"].cuda(), query_s=qs, query_f=qf)
+    _check_out(out, g["out"])
+    out["loss"].backward()
+    assert rel(S.grad, g["grad_S"]) <= GRAD_RTOL, rel(S.grad, g["grad_S"])
+    pairs = {n: (p.grad, g["grads"][n]) for n, p in m.named_parameters() if n in g["grads"]}
+    assert flat_rel(list(pairs.values())) <= GRAD_RTOL          # north-star gate on the projector gradient
+    check_param_grads(pairs, tol=2e-2)                          # per tensor: toy widths (D = 64, B = 3), see f1 test
+
+
+@pytest.mark.parametrize("win", [(2, 2), (4, 2), (1, 4)])
+def test_scalekd_window_attention_vs_oracle(win):
+    """Other window shapes (incl. non-square window counts) on a 16x16 grid with config.yaml-like widths, against the
+    oracle port (itself pinned to the reference by the golden files above)."""
+    scalekd, _, _ = _mods()
+    from oracle import scalekd_ref
+    kw = dict(name="scalekd_res5", alpha=[0.08, 0.06], student_dims=64, teacher_dims=192, query_hw=[16, 16],
+              pos_hw=[16, 16], pos_dims=192, window_shapes=list(win), self_query=True, softmax_scale=[5.0, 5.0],
+              num_heads=12)
+    torch.manual_seed(41)
+    m = scalekd.ScaleKD(**kw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    gen = torch.Generator().manual_seed(42)
+    B = 8
+    S0 = torch.randn(B, 64, 16, 16, generator=gen)
+    T = torch.randn(B, 192, 16, 16, generator=gen)
+    sd_ref = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    S_ref = S0.clone().requires_grad_(True)
+    ref = scalekd_ref.scalekd_forward(sd_ref, S_ref, T, alpha=kw["alpha"], hw=(16, 16), num_heads=12,
+                                      softmax_scale=kw["softmax_scale"], window_shapes=win)
+    ref["loss"].backward()
+    S = S0.cuda().requires_grad_(True)
+    out = m(S, T.cuda())
+    _check_out(out, ref)
+    out["loss"].backward()
+    assert rel(S.grad, S_ref.grad) <= GRAD_RTOL, rel(S.grad, S_ref.grad)
+    pairs = {n: (p.grad, sd_ref[n].grad) for n, p in m.named_parameters() if sd_ref[n].grad is not None}
+    assert flat_rel(list(pairs.values())) <= GRAD_RTOL
+    check_param_grads(pairs, tol=2e-2)

@@ -51,7 +51,7 @@ def test_scalekd_errors_like_the_reference_and_never_falls_back_to_cpu():
         m.get_spat_loss(torch.randn(1, 9, 32), torch.randn(1, 32, 3, 3))
     with pytest.raises(ValueError):
         ScaleKD(**_kw(teacher_dims=30, pos_dims=30, num_heads=4))   # reference: RuntimeError inside reshape
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="window_shapes"):   # 2x2 windows do not tile a 3x3 grid (reference: .view fails)
         ScaleKD(**_kw(window_shapes=[2, 2])).cpu().projector_0(torch.randn(1, 16, 3, 3))
 
 

@@ -185,3 +185,29 @@ def test_resize_commutes_with_conv1x1():
     a = conv(torch.nn.functional.interpolate(x, size=(16, 16), mode="bilinear", align_corners=False))
     b = resize_ref.resize_bilinear(conv(x), (16, 16))
     assert torch.allclose(a, b, atol=1e-12, rtol=0)
+
+
+@pytest.mark.parametrize("tag", ["self", "ext"])
+def test_port_matches_golden_scalekd_windows(tag):
+    """window_shapes = [2, 2]: the port's separate_tokens / window-major output (losses/scalekd.py:305-314, :326-335)
+    against the unmodified reference's outputs and gradients (oracle/make_golden.py: scalekd_windows)."""
+    g = torch.load(os.path.join(GOLDEN, f"scalekd_win_{tag}.pt"))
+    kw = g["kwargs"]
+    sd = _grad_sd(g["state_dict"])
+    S = g["preds_S"].clone().requires_grad_(True)
+    out = scalekd_ref.scalekd_forward(sd, S, g["preds_T"], g["query_s"], g["query_f"], alpha=kw["alpha"],
+                                      hw=kw["query_hw"], num_heads=kw["num_heads"], softmax_scale=kw["softmax_scale"],
+                                      window_shapes=kw["window_shapes"])
+    for k, v in g["out"].items():
+        assert abs(out[k].item() - v.item()) <= 1e-5 * max(1.0, abs(v.item())), k
+    out["loss"].backward()
+    assert rel(S.grad, g["grad_S"]) < 1e-4
+    for k, ref in g["grads"].items():
+        if ref.norm() < 1e-6:
+            continue
+        assert rel(sd[k].grad, ref) < 2e-4, (k, rel(sd[k].grad, ref))
+    # and the windows matter: the same weights without windows give a different loss
+    out1 = scalekd_ref.scalekd_forward(_grad_sd(g["state_dict"]), g["preds_S"], g["preds_T"], g["query_s"], g["query_f"],
+                                       alpha=kw["alpha"], hw=kw["query_hw"], num_heads=kw["num_heads"],
+                                       softmax_scale=kw["softmax_scale"])
+    assert abs(out1["loss"].item() - g["out"]["loss"].item()) > 1e-4
