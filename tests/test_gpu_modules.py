@@ -556,3 +556,38 @@ def test_scalekd_window_attention_vs_oracle(win):
     pairs = {n: (p.grad, sd_ref[n].grad) for n, p in m.named_parameters() if sd_ref[n].grad is not None}
     assert flat_rel(list(pairs.values())) <= GRAD_RTOL
     check_param_grads(pairs, tol=2e-2)
+
+
+def test_scalekd_under_fp16_autocast_and_grad_scaler():
+    """The reference trains with Lightning `precision=16` (train.py:263): the loss modules are called inside
+    torch.autocast(fp16) with half student features and backward runs on a GradScaler-scaled loss. The shells keep their
+    own precision policy: same outputs, and the unscaled gradients equal the plain fp32-call gradients."""
+    scalekd, teacher, _ = _mods()
+    kw = dict(name="scalekd_res5", alpha=[0.08, 0.06], student_dims=64, teacher_dims=128, query_hw=[8, 8], pos_hw=[8, 8],
+              pos_dims=128, window_shapes=[1, 1], self_query=True, softmax_scale=[5.0, 5.0], num_heads=8)
+    torch.manual_seed(51)
+    m = scalekd.ScaleKD(**kw).cuda().train()
+    gen = torch.Generator().manual_seed(52)
+    S0 = torch.randn(4, 64, 8, 8, generator=gen).half().float().cuda()     # exactly representable in fp16
+    T = torch.randn(4, 128, 8, 8, generator=gen).cuda()
+    S = S0.clone().requires_grad_(True)
+    out = m(S, T)
+    out["loss"].backward()
+    ref_grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+    ref_dS = S.grad.clone()
+    m.zero_grad(set_to_none=True)
+    for mod in m.modules():                                               # same BN running-stat state for both calls
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.reset_running_stats()
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 14)
+    Sh = S0.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out16 = m(Sh.half(), T)
+    for k in out:
+        assert out16[k].dtype == torch.float32
+        assert abs(out16[k].item() - out[k].item()) <= 1e-5 * max(1.0, abs(out[k].item())), k
+    scaler.scale(out16["loss"]).backward()
+    inv = 1.0 / scaler.get_scale()
+    assert torch.isfinite(Sh.grad).all()
+    assert rel(Sh.grad * inv, ref_dS) <= 5e-3
+    check_param_grads({n: (p.grad * inv, ref_grads[n]) for n, p in m.named_parameters()}, tol=5e-3)
