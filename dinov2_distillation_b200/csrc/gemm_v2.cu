@@ -208,9 +208,11 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
   }
 
   uint32_t raw[PREFETCH ? 2 : 1][32];
+  // residual rows repeat with period res_row_period (pos_embed under the patch-embed GEMM): 32-row units never straddle
+  const int xrow = (F32 && p.res_row_period > 0) ? row0 % p.res_row_period : row0;
   if (use_x && lane == 0) {
     mbar_expect_tx(xbar, UNIT_BYTES);
-    v2_tma_load_2d_s(buf_x, tmX, xbar, n0 + half * 32, row0);
+    v2_tma_load_2d_s(buf_x, tmX, xbar, n0 + half * 32, xrow);
   }
   tmem_ld_32x32(taddr + half * 32, raw[0]);
 #pragma unroll
@@ -238,7 +240,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
     if (p.dbg & 1) {   // B200_GEMM_DBG=1: mainloop-only floor (drain TMEM, no epilogue math, no stores)
       if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1];
       if (use_x) { mbar_wait(xbar, xphase); xphase ^= 1; __syncwarp();
-        if (next_ok && lane == 0) { mbar_expect_tx(xbar, UNIT_BYTES); v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, row0); } }
+        if (next_ok && lane == 0) { mbar_expect_tx(xbar, UNIT_BYTES); v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, xrow); } }
       continue;
     }
     // (N is a multiple of 32 on this path -- launch_gemm_v2 sends ragged N to the first-generation kernel -- so there
@@ -306,7 +308,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
           __syncwarp();   // every lane has read the aux tile: it may be refilled
           if (next_ok && lane == 0) {
             mbar_expect_tx(xbar, UNIT_BYTES);
-            v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, row0);
+            v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, xrow);
           }
           if (p.aux_mode == B200_AUX_DGELU) {
 #pragma unroll
@@ -385,7 +387,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
         __syncwarp();
         if (next_ok && lane == 0) {
           mbar_expect_tx(xbar, UNIT_BYTES);
-          v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, row0);
+          v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, xrow);
         }
       }
       if (lane == 0) v2_bulk_wait_read<0>();
@@ -402,7 +404,10 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
       if (!(p.dbg & 8)) fence_proxy_async();
       __syncwarp();
       if (lane == 0 && !(p.dbg & 2)) {
-        if (p.out_bp > 0) {   // columns batched with period out_bp: (column in batch, row, batch)
+        if (p.out_row_period > 0) {   // rows batched with a gap (cls rows of the token buffer): (column, row in batch, batch)
+          const int bi = row0 / p.out_row_period;
+          v2_tma_store_3d(tmO, stage_smem, c0, row0 - bi * p.out_row_period, bi);
+        } else if (p.out_bp > 0) {   // columns batched with period out_bp: (column in batch, row, batch)
           const int bi = c0 / p.out_bp, cb = c0 - bi * p.out_bp;
           if (reduce_out) v2_tma_reduce_add_3d(tmO, stage_smem, cb, row0, bi);
           else v2_tma_store_3d(tmO, stage_smem, cb, row0, bi);
@@ -717,8 +722,17 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   if (!enabled) return 1;
   const bool mn = d->a_mn_major && d->b_mn_major;
   if (d->a_mn_major != d->b_mn_major) return 1;
-  if (d->out_row_period > 0 || d->res_row_period > 0) return 1;
   const bool f32 = d->out_f32 != nullptr;
+  if (d->out_row_period > 0 || d->res_row_period > 0) {
+    // row-remapped output / periodic residual (patch embed -> token buffer with cls gaps, + pos_embed): 3-D output map,
+    // when the periods are multiples of the 32-row store unit and nothing else is going on
+    const bool ok = f32 && !d->a_mn_major && !d->b_mn_major && d->split_k <= 1 && !d->atomic_add && d->out_batch_period <= 0 &&
+                    (d->out_row_period <= 0 || (d->out_row_period % 32 == 0 && d->M % d->out_row_period == 0)) &&
+                    (d->res_row_period <= 0 || (d->res_row_period % 32 == 0 && d->residual != nullptr)) &&
+                    (d->out_row_period <= 0 || d->residual == nullptr || d->res_row_period > 0) &&
+                    (const void*)d->residual != (const void*)d->out_f32;
+    if (!ok) return 1;
+  }
   if (d->out_batch_period > 0) {
     B200_CHECK_ARG(f32 && !d->residual && d->out_batch_period % 32 == 0 && d->N % d->out_batch_period == 0 &&
                        d->N % 32 == 0 && d->out_batch_stride % 4 == 0 && d->ldo32 % 4 == 0 && !d->a_mn_major && !d->b_mn_major,
@@ -783,8 +797,15 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
                                 (uint64_t)d->ldo32, (uint64_t)d->out_batch_stride, 32, 32, 1, 128));
     tx = to;
   } else if (f32) {
-    B200_TRY(make_tensor_map_ex(&to, d->out_f32, 4, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo32, 32, 32, 128));
-    if (use_x) B200_TRY(make_tensor_map_ex(&tx, d->residual, 4, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldres, 32, 32, 128));
+    if (d->out_row_period > 0) {
+      const long long rp = d->out_row_period, pad = d->out_row_pad;
+      B200_TRY(make_tensor_map_3d(&to, d->out_f32 + pad * d->ldo32, 4, (uint64_t)d->N, (uint64_t)rp, (uint64_t)(d->M / rp),
+                                  (uint64_t)d->ldo32, (uint64_t)((rp + pad) * d->ldo32), 32, 32, 1, 128));
+    } else {
+      B200_TRY(make_tensor_map_ex(&to, d->out_f32, 4, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo32, 32, 32, 128));
+    }
+    const uint64_t res_rows = d->res_row_period > 0 ? (uint64_t)d->res_row_period : (uint64_t)d->M;
+    if (use_x) B200_TRY(make_tensor_map_ex(&tx, d->residual, 4, (uint64_t)d->N, res_rows, (uint64_t)d->ldres, 32, 32, 128));
     else tx = to;
   } else {
     B200_TRY(make_tensor_map_ex(&to, d->out_bf16, 2, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo16, 32, 32, 64));

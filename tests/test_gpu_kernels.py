@@ -496,3 +496,21 @@ def test_window_row_order_round_trip():
     z = torch.zeros_like(x)
     L.check(lib.b200_window_rows16(y.data_ptr(), z.data_ptr(), B * H * W, H, W, wh, ww, D, D, 1, st), "window_rows16")
     assert torch.equal(z, x)
+
+
+@pytest.mark.parametrize("B,period,N,K", [(5, 256, 384, 608), (3, 64, 160, 96)])
+def test_gemm_row_remap_aligned_period_bulk_store(B, period, N, K):
+    """Patch-embed form on the bulk-store kernel: token rows written around the cls gap through a 3-D output tensor map,
+    pos_embed added as a residual that repeats every `period` rows (period a multiple of the 32-row store unit)."""
+    ops = _ops()
+    M, pad = B * period, 1
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    bias = torch.randn(N, device="cuda")
+    pos = torch.randn(period, N, device="cuda")
+    out = torch.full((B * (period + pad), N), 7.0, device="cuda")
+    ops.gemm(a, b, bias=bias, residual=pos, res_row_period=period, out=out, out_row_period=period, out_row_pad=pad)
+    ref = (a.float() @ b.float().t() + bias).view(B, period, N) + pos
+    o3 = out.view(B, period + pad, N)
+    assert rel_err(o3[:, pad:, :], ref) < 2e-3
+    assert (o3[:, 0, :] == 7.0).all()        # cls rows untouched
