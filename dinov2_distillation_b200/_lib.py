@@ -35,6 +35,7 @@ class GemmDesc(C.Structure):
         ("algo_flops_scale", C.c_float),
         ("out_batch_period", C.c_int), ("out_batch_stride", c_ll),
         ("out16_pre_alt", C.c_int),
+        ("out16_colsum", c_fp),
     ]
 
 
@@ -77,6 +78,7 @@ PROJ_PARAM_FIELDS = [
     "conv_w", "conv_b", "bn_w", "bn_b", "bn_running_mean", "bn_running_var", "pos_embed",
     "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "p_w", "p_b",
     "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b", "ln1_w", "ln1_b", "ln2_w", "ln2_b", "query_w",
+    "bn_num_batches_tracked",
 ]
 PROJ_GRAD_FIELDS = [
     "conv_w", "conv_b", "bn_w", "bn_b", "pos_embed",
@@ -143,6 +145,7 @@ SIGNATURES = {
     "b200_kd_loss_ws_floats": (c_ll, [_i, _i, _i]),
     "b200_kd_loss_fwd": (_i, [c_fp, c_fp, _i, _i, _i, _i, _i, _i, _f, c_fp, c_fp, c_vp]),
     "b200_kd_loss_bwd": (_i, [c_fp, c_fp, _i, _i, _i, _i, _i, _i, _f, c_fp, c_fp, _i, c_fp, c_vp]),
+    "b200_kd_loss_bwd_split": (_i, [c_fp, c_fp, _i, _i, _i, _i, _i, _i, _f, c_fp, c_fp, c_fp, _i, c_fp, c_vp]),
     "b200_dct_zero_dc_idct": (_i, [c_fp, c_fp, _i, _i, _i, c_ll, c_ll, c_vp]),
     "b200_vit_forward_ws_bytes": (_sz, [C.POINTER(VitConfig), _i, _i, _i]),
     "b200_vit_forward": (_i, [C.POINTER(VitConfig), C.POINTER(VitBlock), c_vp, _i, c_fp, c_fp, c_fp, c_fp, c_fp,

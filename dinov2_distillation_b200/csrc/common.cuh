@@ -175,6 +175,13 @@ int cast_f32_f16_dual(const float* x, void* y_f16, void* y_bf16, long long n, vo
 int layernorm_fwd_dual(const float* x, const float* w, const float* b, float eps, float* y_f32, void* y16, void* y16_alt,
                        float* mean, float* rstd, int rows, int D, int in_period, int in_pad, int y16_is_fp16,
                        void* stream);
+// b200_bn_finalize that also bumps nn.BatchNorm2d.num_batches_tracked (int64 device scalar, may be NULL)
+int bn_finalize_counted(const float* sums, float* mean, float* rstd, float* running_mean, float* running_var,
+                        float momentum, float eps, int M, int D, long long* num_batches_tracked, void* stream);
+// b200_bn_relu_pos_bwd_apply that also adds sums2 (d beta | d gamma) into the BN affine gradient buffers
+int bn_relu_pos_bwd_apply_acc(const float* dz, const float* y, const float* mean, const float* rstd, const float* w,
+                              const float* b, const float* sums2, void* dy_bf16, int use_batch_stats, int M, int D,
+                              float* acc_bn_b, float* acc_bn_w, void* stream);
 int bn_relu_pos_fwd_dual(const float* y, const float* mean, const float* rstd, const float* w, const float* b,
                          const float* pos, float* z_f32, void* z16, void* z16_alt, int M, int D, int HW,
                          int z16_is_fp16, void* stream);

@@ -2,6 +2,7 @@
 // BatchNorm(+ReLU+pos) fwd/bwd, column reductions, SwiGLU gate.  All vectorised (128-bit) and coalesced on the
 // contiguous channel dimension; reductions use warp shuffles + one atomic per block column.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/b200_distill.h"
 
 namespace b200 {
@@ -414,10 +415,11 @@ __global__ void zero_kernel(float* __restrict__ p, long long n) {
 
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
-                                   int M, int D) {
+                                   int M, int D, long long* __restrict__ num_batches_tracked) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;   // nn.BatchNorm2d's step counter
   if (c >= D) return;
   if (sums != nullptr) {
     const float mu = sums[c] / (float)M;
@@ -526,9 +528,13 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
                     const float* __restrict__ sums2, __nv_bfloat16* __restrict__ dy16, int batch_stats, long long M,
-                    int D) {
+                    int D, float* __restrict__ acc_b, float* __restrict__ acc_w) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
+  // optional: the BN affine gradients are the two column sums this pass already reads (d beta = sums2[0:D],
+  // d gamma = sums2[D:2D]): block 0 adds them to the gradient buffers (was two axpy launches)
+  if (acc_b != nullptr && blockIdx.x == 0)
+    for (int c = threadIdx.x; c < D; c += blockDim.x) { acc_b[c] += sums2[c]; acc_w[c] += sums2[D + c]; }
   const int D4 = D >> 2;
   const long long n4 = M * D4;
   const float invM = 1.0f / (float)M;
@@ -664,8 +670,10 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, const _
 template <int NV>
 static int launch_ln_fwd(const float* x, const float* w, const float* b, float eps, float* y32, void* y16, void* y16_alt,
                          float* mean, float* rstd, int rows, int D, int in_period, int in_pad, int fp16, cudaStream_t st) {
-  const int grid = grid_for(rows, 8, 8);
-  B200_CUDA_OK(launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(256), 0, st, x, w, b, eps, y32,
+  static const int bps = [] { const char* e = getenv("B200_LN_BPS"); return e ? atoi(e) : 12; }();    // blocks per SM cap (12: best of a 4..32 scan at the teacher shape)
+  static const int wpb = [] { const char* e = getenv("B200_LN_WPB"); return e ? atoi(e) : 8; }();     // warps per block
+  const int grid = grid_for(rows, wpb, bps);
+  B200_CUDA_OK(launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(32 * wpb), 0, st, x, w, b, eps, y32,
                           static_cast<__nv_bfloat16*>(y16), static_cast<__nv_bfloat16*>(y16_alt), mean, rstd, rows, D,
                           in_period, in_pad, fp16));
   B200_LAUNCH_OK();
@@ -1132,10 +1140,15 @@ extern "C" int b200_bn_stats(const float* y, float* sums, int M, int D, void* st
 
 extern "C" int b200_bn_finalize(const float* sums, float* mean, float* rstd, float* running_mean, float* running_var,
                                 float momentum, float eps, int M, int D, void* stream) {
+  return b200::bn_finalize_counted(sums, mean, rstd, running_mean, running_var, momentum, eps, M, D, nullptr, stream);
+}
+
+int b200::bn_finalize_counted(const float* sums, float* mean, float* rstd, float* running_mean, float* running_var,
+                              float momentum, float eps, int M, int D, long long* num_batches_tracked, void* stream) {
   B200_CHECK_ARG(mean && rstd && D > 0, "bad args");
   B200_CHECK_ARG(sums || (running_mean && running_var), "need batch sums or running statistics");
-  B200_CUDA_OK(launch_pdl(bn_finalize_kernel, dim3((unsigned)cdiv(D, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      sums, mean, rstd, running_mean, running_var, momentum, eps, M, D));
+  B200_CUDA_OK(launch_pdl(bn_finalize_kernel, dim3((unsigned)cdiv(D, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+      sums, mean, rstd, running_mean, running_var, momentum, eps, M, D, num_batches_tracked));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -1179,10 +1192,18 @@ extern "C" int b200_bn_relu_pos_bwd_reduce(const float* dz, const float* y, cons
 extern "C" int b200_bn_relu_pos_bwd_apply(const float* dz, const float* y, const float* mean, const float* rstd,
                                           const float* w, const float* b, const float* sums2, void* dy_bf16,
                                           int use_batch_stats, int M, int D, void* stream) {
+  return b200::bn_relu_pos_bwd_apply_acc(dz, y, mean, rstd, w, b, sums2, dy_bf16, use_batch_stats, M, D, nullptr, nullptr,
+                                         stream);
+}
+
+int b200::bn_relu_pos_bwd_apply_acc(const float* dz, const float* y, const float* mean, const float* rstd, const float* w,
+                                    const float* b, const float* sums2, void* dy_bf16, int use_batch_stats, int M, int D,
+                                    float* acc_bn_b, float* acc_bn_w, void* stream) {
   B200_CHECK_ARG(dz && y && mean && rstd && w && b && dy_bf16 && M > 0 && D % 4 == 0, "bad args");
   B200_CHECK_ARG(!use_batch_stats || sums2, "batch statistics need sums2");
-  B200_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for((long long)M * D / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      dz, y, mean, rstd, w, b, sums2, static_cast<__nv_bfloat16*>(dy_bf16), use_batch_stats, M, D));
+  B200_CHECK_ARG((acc_bn_b == nullptr) == (acc_bn_w == nullptr) && (acc_bn_b == nullptr || sums2 != nullptr), "bad accumulators");
+  B200_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for((long long)M * D / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+      dz, y, mean, rstd, w, b, sums2, static_cast<__nv_bfloat16*>(dy_bf16), use_batch_stats, (long long)M, D, acc_bn_b, acc_bn_w));
   B200_LAUNCH_OK();
   return 0;
 }

@@ -36,6 +36,7 @@ struct Gemm {
   Gemm& out32(float* o, long long ld) { d.out_f32 = o; d.ldo32 = ld; return *this; }
   Gemm& out16(void* o, long long ld) { d.out_bf16 = o; d.ldo16 = ld; return *this; }
   Gemm& out16_pre(void* o, long long ld) { d.out_bf16_pre = o; d.ldo16_pre = ld; return *this; }
+  Gemm& colsum16(float* cs) { d.out16_colsum = cs; return *this; }
   Gemm& out16_alt(void* o, long long ld) { d.out_bf16_pre = o; d.ldo16_pre = ld; d.out16_pre_alt = 1; return *this; }
   Gemm& row_map(int period, int pad) { d.out_row_period = period; d.out_row_pad = pad; return *this; }
   Gemm& fp16_operands() { d.a_is_fp16 = 1; d.b_is_fp16 = 1; return *this; }
@@ -379,8 +380,8 @@ static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, P
   w.df32 = a.take_n<float>(M * D);
   w.dz32 = a.take_n<float>(M * D);
   w.dqs32 = a.take_n<float>((long long)c->HW * D);
-  w.sums2 = a.take_n<float>(2 * D);
-  w.dpos_t = a.take_n<float>((long long)c->HW * D);
+  w.sums2 = a.take_n<float>(2 * D + (long long)c->HW * D);   // [sums2 | dpos_t]: adjacent, zeroed by one launch
+  w.dpos_t = w.sums2 ? w.sums2 + 2 * D : nullptr;
   w.delta = a.take_n<float>((long long)B * c->heads * c->HW);
   w.dxt32 = a.take_n<float>(proj_rows_max(c, B) * c->Cs);
   w.dyraw16 = c->raw_h > 0 ? a.take_n<bf16>((long long)B * proj_hw_in(c) * D) : nullptr;
@@ -529,8 +530,8 @@ static int projector_fwd_impl(const b200_projector_config* c, const b200_project
   if (c->training) {
     B200_TRY(zero_f32(w.sums, 2 * D, st));
     B200_TRY(b200_bn_stats(s.y, w.sums, Mi, D, stream));
-    B200_TRY(b200_bn_finalize(w.sums, s.bn_mean, s.bn_rstd, p->bn_running_mean, p->bn_running_var, c->bn_momentum,
-                              c->bn_eps, Mi, D, stream));
+    B200_TRY(bn_finalize_counted(w.sums, s.bn_mean, s.bn_rstd, p->bn_running_mean, p->bn_running_var, c->bn_momentum,
+                                 c->bn_eps, Mi, D, p->bn_num_batches_tracked, stream));
   } else {
     B200_TRY(b200_bn_finalize(nullptr, s.bn_mean, s.bn_rstd, p->bn_running_mean, p->bn_running_var, c->bn_momentum,
                               c->bn_eps, Mi, D, stream));
@@ -614,8 +615,8 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
                                      g->ffn2_b, Mi, D, stream));
   // FFN: u = g + W2 relu(W1 g + b1) + b2
   B200_TRY(wgrad_tok(w.du16, D, s.hb, M, 4 * D, g->ffn2_w, D, stream));
-  B200_TRY(Gemm(w.du16, D, w.w2T, D, Mi, 4 * D, D).aux(s.h, 4 * D, B200_AUX_DRELU).aux_fp16().out16(w.dh16, 4 * D).run(stream));
-  B200_TRY(b200_colsum(w.dh16, 1, 4 * D, g->ffn1_b, Mi, 4 * D, stream));
+  // (ffn1's bias gradient = column sums of dh: accumulated by the same epilogue)
+  B200_TRY(Gemm(w.du16, D, w.w2T, D, Mi, 4 * D, D).aux(s.h, 4 * D, B200_AUX_DRELU).aux_fp16().out16(w.dh16, 4 * D).colsum16(g->ffn1_b).run(stream));
   B200_TRY(wgrad_tok(w.dh16, 4 * D, s.gb, M, D, g->ffn1_w, 4 * D, stream));
   B200_TRY(Gemm(w.dh16, 4 * D, w.w1T, 4 * D, Mi, D, 4 * D).residual(w.du32, D).out32(w.dg32, D).run(stream));
   // norm
@@ -664,13 +665,12 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   B200_TRY(wgrad_tok(dkv16 + D, 2 * D, s.zb, M, D, g->v_w, D, stream));
   B200_TRY(Gemm(dkv16, 2 * D, w.wkvT, 2 * D, Mi, D, 2 * D).residual(w.df32, D).out32(w.dz32, D).run(stream));
   // BN + ReLU + pos_embed
-  B200_TRY(zero_f32(w.sums2, 2 * D, st));
-  B200_TRY(zero_f32(w.dpos_t, (long long)HW * D, st));
+  B200_TRY(zero_f32(w.sums2, 2 * D + (long long)HW * D, st));   // sums2 and dpos_t
   B200_TRY(b200_bn_relu_pos_bwd_reduce(w.dz32, s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.sums2, w.dpos_t, Mi, D, HW, stream));
   B200_TRY(b200_tokens_to_nchw(w.dpos_t, g->pos_embed, 1, D, HW, 1, stream));
-  B200_TRY(b200_axpy(w.sums2, g->bn_b, 1.0f, D, stream));
-  B200_TRY(b200_axpy(w.sums2 + D, g->bn_w, 1.0f, D, stream));
-  B200_TRY(b200_bn_relu_pos_bwd_apply(w.dz32, s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.sums2, w.dy16, c->training ? 1 : 0, Mi, D, stream));
+  // (BN affine gradients = sums2: added to g->bn_b / g->bn_w by the apply pass)
+  B200_TRY(bn_relu_pos_bwd_apply_acc(w.dz32, s.y, s.bn_mean, s.bn_rstd, p->bn_w, p->bn_b, w.sums2, w.dy16, c->training ? 1 : 0, Mi, D,
+                                     g->bn_b, g->bn_w, stream));
   // conv1x1
   // with batch statistics the column sums of dy vanish identically (sum_r yhat = 0): BN cancels the conv bias
   // (losses/scalekd.py:199-200), so its gradient is exactly zero; only the running-statistics (eval) path needs the sum.

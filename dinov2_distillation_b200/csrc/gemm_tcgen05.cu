@@ -413,6 +413,7 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   p.dbg = dbg;
   p.dbg_buf = nullptr;
   p.pre_alt = 0;
+  p.colsum = nullptr;
   p.out16_fp16 = d->out16_is_fp16 ? 1 : 0;
   p.aux_fp16 = d->aux_is_fp16 ? 1 : 0;
   // a_format / b_format: 0 = F16, 1 = BF16 (bits 7-9 / 10-12)
@@ -427,6 +428,7 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
     if (rv <= 0) return rv;
   }
   B200_CHECK_ARG(d->out_batch_period <= 0, "out_batch_period is only implemented by the bulk-store kernel (see launch_gemm_v2)");
+  B200_CHECK_ARG(d->out16_colsum == nullptr, "out16_colsum is only implemented by the bulk-store kernel (16-bit output, N % 32 == 0, no split-K)");
   B200_CHECK_ARG(!(d->out16_pre_alt && d->out_bf16_pre), "out16_pre_alt is only implemented by the bulk-store kernel (N % 32 == 0, no aux, 16-byte aligned outputs)");
   if (!d->a_mn_major && !d->b_mn_major && split == 1) {
     const int r2 = launch_gemm_2cta(d, p, st);

@@ -346,6 +346,22 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
                     pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
         }
       }
+      if (p.colsum != nullptr) {
+        // column sums of the 16-bit output exactly as stored (a bias gradient: dW1's bias = column sums of dh): lane j
+        // walks column j of the staged 32 x 32 tile (64-byte rows, 16-byte chunks swizzled by (row >> 1) & 3)
+        __syncwarp();
+        const int nrow = min(32, p.M - row0);
+        const uint32_t cbase = buf_o + (lane & 7) * 2;
+        const uint32_t chunk = lane >> 3;
+        float cs = 0.0f;
+#pragma unroll 8
+        for (int r = 0; r < nrow; ++r) {
+          uint16_t h;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(cbase + r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4)));
+          cs += p.out16_fp16 ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
+        }
+        atomicAdd(p.colsum + c0 + lane, cs);
+      }
       if (!(p.dbg & 8)) fence_proxy_async();
       __syncwarp();
       if (lane == 0 && !(p.dbg & 2)) {
@@ -754,6 +770,8 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   if (d->col_scale && !al16(d->col_scale)) return 1;
   if (d->N % 32 != 0) return 1;   // ragged N: first-generation kernel (per-column tail handling)
   p.pre_alt = (d->out16_pre_alt && d->out_bf16_pre) ? 1 : 0;
+  p.colsum = (!f32 && p.split_k == 1) ? d->out16_colsum : nullptr;
+  if (d->out16_colsum != nullptr && p.colsum == nullptr) return 1;
 
   static const int pair_mode = gemm_env_int("B200_GEMM_2CTA", -1);   // -1 auto, 0 never, 1 whenever possible
   bool pair = false;

@@ -109,11 +109,12 @@ __global__ void kd_loss_finalize_kernel(const float* __restrict__ acc, float* __
 __global__ void __launch_bounds__(256)
 kd_loss_bwd_kernel(const float* __restrict__ S, const float* __restrict__ T, int rows, int HW, int D, int Nt,
                    int t_skip, const float* __restrict__ ms, const float* __restrict__ mt,
-                   const float* __restrict__ g_out, float loss_scale, float sim_scale, float* __restrict__ dS) {
+                   const float* __restrict__ g_loss, const float* __restrict__ g_sim, float loss_scale, float sim_scale,
+                   float* __restrict__ dS) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const float gl = g_out[0] * loss_scale, gs = g_out[1] * sim_scale;
+  const float gl = g_loss[0] * loss_scale, gs = (g_sim != nullptr ? g_sim[0] : 0.0f) * sim_scale;
   for (int r = blockIdx.x * wpb + wid; r < rows; r += gridDim.x * wpb) {
     const int b = r / HW, p = r - b * HW;
     const float* s = S + (long long)r * D;
@@ -262,7 +263,14 @@ extern "C" int b200_kd_loss_fwd(const float* S, const float* T, int B, int HW, i
 
 extern "C" int b200_kd_loss_bwd(const float* S, const float* T, int B, int HW, int D, int Nt, int t_skip, int freq,
                                 float alpha, const float* g_out, float* dS, int accumulate, float* ws, void* stream) {
-  B200_CHECK_ARG(S && T && g_out && dS && ws && B > 0 && HW > 0 && D > 0 && D % 4 == 0, "bad args");
+  B200_CHECK_ARG(g_out != nullptr, "bad args");
+  return b200_kd_loss_bwd_split(S, T, B, HW, D, Nt, t_skip, freq, alpha, g_out, g_out + 1, dS, accumulate, ws, stream);
+}
+
+extern "C" int b200_kd_loss_bwd_split(const float* S, const float* T, int B, int HW, int D, int Nt, int t_skip, int freq,
+                                      float alpha, const float* g_loss, const float* g_sim, float* dS, int accumulate,
+                                      float* ws, void* stream) {
+  B200_CHECK_ARG(S && T && g_loss && dS && ws && B > 0 && HW > 0 && D > 0 && D % 4 == 0, "bad args");
   B200_CHECK_ARG(!accumulate, "accumulate is not supported (autograd sums the branches)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* ms = ws + ws_acc_floats();
@@ -272,7 +280,7 @@ extern "C" int b200_kd_loss_bwd(const float* S, const float* T, int B, int HW, i
   long long g = cdiv(rows, 8);
   if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
   B200_CUDA_OK(launch_pdl(kd_loss_bwd_kernel, dim3((unsigned)g), dim3(256), 0, st, S, T, rows, HW, D, Nt, t_skip, freq ? ms : nullptr,
-                                                  freq ? mt : nullptr, g_out, alpha / (float)B, 1.0f / (float)rows, dS));
+                                                  freq ? mt : nullptr, g_loss, g_sim, alpha / (float)B, 1.0f / (float)rows, dS));
   B200_LAUNCH_OK();
   if (freq) {
     dim3 grid((unsigned)cdiv(D, 128), (unsigned)B);

@@ -16,6 +16,32 @@ from .scalekd import LOSS_REGISTRY
 _STAGE_FRACTION = {"res2": 0.25, "res3": 0.50, "res4": 0.75}
 
 
+class _CombineLosses(torch.autograd.Function):
+    """Every weighted entry of the loss dict and the total from the raw (spatial, frequency) terms of the processed
+    stages: out = A @ stack(terms) -- one concat and one matrix-vector product instead of ~13 scalar add / mul kernels,
+    and one kernel in backward (A[row] * g) instead of a mul / select chain per term. A is a small constant matrix
+    ([3 * stages + 1, 2 * stages]: per stage (s + f) * w, f * w, s * w; last row the total, train/distillation_module.py
+    :225-246); the outputs are views of one buffer."""
+
+    @staticmethod
+    def forward(ctx, A, *terms):
+        out = torch.mv(A, torch.stack(terms))
+        ctx.save_for_backward(A)
+        ctx.set_materialize_grads(False)
+        return out.unbind(0)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (A,) = ctx.saved_tensors
+        gx = None
+        for i, g in enumerate(grads):
+            if g is not None:
+                gx = A[i] * g if gx is None else torch.addcmul(gx, A[i], g)
+        if gx is None:
+            return (None,) * (1 + A.shape[1])
+        return (None, *gx.unbind(0))
+
+
 class DistillationStep(nn.Module):
     """student: callable images -> {'res4': [B,C,H,W], ...} (already resized to the teacher grid, as ModelWrapper does,
     models/model_zoo.py:118-128) or None when features are supplied directly; teacher: DINOv2ViT-like;
@@ -88,14 +114,29 @@ class DistillationStep(nn.Module):
         if ready is not None:
             torch.cuda.current_stream().wait_event(ready)
 
+    def _combine_matrix(self, names, device):
+        key = (tuple(names), tuple(float(self.loss_weights[n]) for n in names), str(device))
+        cache = getattr(self, "_combine_cache", None)
+        if cache is None or cache[0] != key:
+            n = len(names)
+            A = torch.zeros(3 * n + 1, 2 * n)
+            for i, nm in enumerate(names):
+                w = float(self.loss_weights[nm])
+                A[3 * i, 2 * i] = A[3 * i, 2 * i + 1] = w      # total = (spatial + frequency) * weight
+                A[3 * i + 1, 2 * i + 1] = w                    # frequency * weight
+                A[3 * i + 2, 2 * i] = w                        # spatial * weight
+                A[3 * n, 2 * i] = A[3 * n, 2 * i + 1] = w      # 'loss'
+            self._combine_cache = cache = (key, A.to(device))
+        return cache[1]
+
     def _compute_losses(self, features):
-        total_loss = 0
         loss_dict = {}
         spatial_query = frequency_query = None
         ready = features.get("teacher_ready")
+        done, terms = [], []
         for name in sorted(self.losses.keys()):
             layer = name.split("_")[1]
-            loss_fn, weight = self.losses[name], self.loss_weights[name]
+            loss_fn = self.losses[name]
             s_feat = features["student"][layer]
             main, side = self._branch_streams(s_feat)
             if side is not None and ready is not None:
@@ -107,12 +148,10 @@ class DistillationStep(nn.Module):
                 else:
                     self._await(ready)
                     loss = loss_fn(s_feat, features["teacher"], query_s=spatial_query, query_f=frequency_query)
-                loss_dict[f"{name}_total_loss"] = loss["loss"] * weight
-                loss_dict[f"{name}_frequency_loss"] = loss["frequency_loss"] * weight
-                loss_dict[f"{name}_spatial_loss"] = loss["spatial_loss"] * weight
+                done.append(name)
+                terms += [loss["spatial_loss"], loss["frequency_loss"]]
                 loss_dict[f"{name}_spatial_similarity"] = loss["spatial_similarity"]
                 loss_dict[f"{name}_frequency_similarity"] = loss["frequency_similarity"]
-                total_loss = total_loss + loss["loss"] * weight
                 break
             if side is None or not hasattr(loss_fn, "tokenize_for_both"):
                 feat_spat = loss_fn.project_feat_spat(s_feat, query=spatial_query)
@@ -139,14 +178,24 @@ class DistillationStep(nn.Module):
                 for t in (feat_freq, frequency_loss, frequency_similarity):   # allocated on `side`, read on `main`
                     t.record_stream(main)
             spatial_query, frequency_query = feat_spat, feat_freq
-            loss_dict[f"{name}_total_loss"] = (spatial_loss + frequency_loss) * weight
-            loss_dict[f"{name}_frequency_loss"] = frequency_loss * weight
-            loss_dict[f"{name}_spatial_loss"] = spatial_loss * weight
+            done.append(name)
+            terms += [spatial_loss, frequency_loss]
             loss_dict[f"{name}_spatial_similarity"] = spatial_similarity
             loss_dict[f"{name}_frequency_similarity"] = frequency_similarity
-            total_loss = total_loss + (spatial_loss + frequency_loss) * weight
-        loss_dict["loss"] = total_loss
-        return loss_dict
+        if not done:
+            loss_dict["loss"] = 0
+            return loss_dict
+        # weighted entries and the total (train/distillation_module.py:225-246) in one fused combine
+        outs = _CombineLosses.apply(self._combine_matrix(done, terms[0].device), *terms)
+        ordered = {}                                   # key order of the reference's dict (:225-246)
+        for i, name in enumerate(done):
+            ordered[f"{name}_total_loss"] = outs[3 * i]
+            ordered[f"{name}_frequency_loss"] = outs[3 * i + 1]
+            ordered[f"{name}_spatial_loss"] = outs[3 * i + 2]
+            ordered[f"{name}_spatial_similarity"] = loss_dict[f"{name}_spatial_similarity"]
+            ordered[f"{name}_frequency_similarity"] = loss_dict[f"{name}_frequency_similarity"]
+        ordered["loss"] = outs[3 * len(done)]
+        return ordered
 
     def _extract_features(self, batch):
         if batch.is_cuda and self.two_streams:

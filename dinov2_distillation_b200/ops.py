@@ -42,7 +42,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
          aux_mode: str = "none", col_scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          res_row_period: int = 0, out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None,
          atomic_add: bool = False, split_k: int = 1, out_pre: bool = False, out_row_period: int = 0,
-         out_row_pad: int = 0, out_batch_period: int = 0, out_alt: bool = False):
+         out_row_pad: int = 0, out_batch_period: int = 0, out_alt: bool = False,
+         out_colsum: Optional[torch.Tensor] = None):
     """C = epilogue(A @ B^T). K-major: a [M,K], b [N,K]. MN-major: a [K,M], b [K,N] (contraction over rows)."""
     _need_cuda(a, b, bias, aux, col_scale, residual, out)
     assert a.dtype in (torch.bfloat16, torch.float16) and b.dtype in (torch.bfloat16, torch.float16)
@@ -98,6 +99,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
                           dtype=torch.bfloat16 if out.dtype == torch.float16 else torch.float16)
         d.out_bf16_pre, d.ldo16_pre, d.out16_pre_alt = pre.data_ptr(), pre.stride(0), 1
     d.out_row_period, d.out_row_pad = out_row_period, out_row_pad
+    if out_colsum is not None:   # fp32 [N], += column sums of the 16-bit output as stored
+        assert out_colsum.dtype == torch.float32 and out_colsum.numel() == N and out_colsum.is_contiguous()
+        d.out16_colsum = out_colsum.data_ptr()
     L.check(L.load().b200_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
     return (out, pre) if (out_pre or out_alt) else out
 

@@ -88,6 +88,10 @@ class _ProjectorFn(torch.autograd.Function):
         bn = proj.proj_student[1]
         pstruct.bn_running_mean = bn.running_mean.data_ptr()
         pstruct.bn_running_var = bn.running_var.data_ptr()
+        # nn.BatchNorm2d's step counter is bumped by the BN kernel itself (one launch less than `+= 1`)
+        nbt = bn.num_batches_tracked
+        counted = proj.training and nbt is not None and nbt.is_cuda and nbt.dtype == torch.int64
+        pstruct.bn_num_batches_tracked = nbt.data_ptr() if counted else None
         out = torch.empty(B, cfg.HW, cfg.D, device=x.device, dtype=torch.float32)
         save = torch.empty(lib.b200_projector_save_bytes(C.byref(cfg), B), dtype=torch.uint8, device=x.device)
         ws_bytes = lib.b200_projector_ws_bytes(C.byref(cfg), B)
@@ -97,7 +101,7 @@ class _ProjectorFn(torch.autograd.Function):
                                            save.data_ptr(), ws.data_ptr(), ws_bytes,
                                            None if tokens is None else tokens.data_ptr(), _stream()), "projector_fwd")
         ctx.tokens = tokens   # shared student tokens (ScaleKD tokenises preds_S once for both projectors)
-        if proj.training:
+        if proj.training and not counted and nbt is not None:
             bn.num_batches_tracked += 1
         ctx.proj, ctx.cfg, ctx.pstruct = proj, cfg, pstruct
         ctx.has_query = query is not None
@@ -259,6 +263,10 @@ def _teacher_tokens(preds_T: torch.Tensor) -> Tuple[torch.Tensor, int]:
 
 
 class _KdLossFn(torch.autograd.Function):
+    """(loss, similarity) of one ScaleKD term as TWO 0-dim autograd outputs (views of one 2-float buffer), so neither
+    the forward (`out[0]`, `out[1]`) nor the backward (SelectBackward: zeros + copy per output) launches glue kernels:
+    the backward kernel reads the two upstream gradients through separate pointers."""
+
     @staticmethod
     def forward(ctx, S, T_tok, nt, freq, alpha):
         S = S.contiguous()
@@ -270,17 +278,25 @@ class _KdLossFn(torch.autograd.Function):
                                      out.data_ptr(), ws.data_ptr(), _stream()), "kd_loss_fwd")
         ctx.save_for_backward(S, T_tok, ws)
         ctx.meta = (nt, int(freq), float(alpha))
-        return out
+        ctx.set_materialize_grads(False)
+        loss, sim = out.unbind(0)
+        return loss, sim
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_loss, g_sim):
         S, T_tok, ws = ctx.saved_tensors
         nt, freq, alpha = ctx.meta
         B, HW, D = S.shape
-        g_out = g_out.contiguous().float()
+        if g_loss is None and g_sim is None:
+            return None, None, None, None, None
+        if g_loss is None:
+            g_loss = torch.zeros((), device=S.device, dtype=torch.float32)
+        g_loss = g_loss.contiguous().float()
+        g_sim = None if g_sim is None else g_sim.contiguous().float()
         dS = torch.empty_like(S)
-        L.check(L.load().b200_kd_loss_bwd(S.data_ptr(), T_tok.data_ptr(), B, HW, D, nt, 0, freq, alpha, g_out.data_ptr(),
-                                          dS.data_ptr(), 0, ws.data_ptr(), _stream()), "kd_loss_bwd")
+        L.check(L.load().b200_kd_loss_bwd_split(S.data_ptr(), T_tok.data_ptr(), B, HW, D, nt, 0, freq, alpha,
+                                                g_loss.data_ptr(), None if g_sim is None else g_sim.data_ptr(),
+                                                dS.data_ptr(), 0, ws.data_ptr(), _stream()), "kd_loss_bwd")
         return dS, None, None, None, None
 
 
@@ -293,8 +309,7 @@ def _kd_term(preds_S: torch.Tensor, preds_T: torch.Tensor, alpha: float, freq: b
     if tuple(preds_S.shape) != (N, H * W, Cc):
         raise ValueError(f"expected projected tokens [{N},{H * W},{Cc}], got {tuple(preds_S.shape)}")
     T_tok, nt = _teacher_tokens(preds_T.detach())
-    out = _KdLossFn.apply(preds_S.float(), T_tok, nt, freq, alpha)
-    return out[0], out[1]
+    return _KdLossFn.apply(preds_S.float(), T_tok, nt, freq, alpha)
 
 
 class ScaleKD(nn.Module):

@@ -80,6 +80,10 @@ typedef struct b200_gemm_desc {
    * FFN saves relu(W1 g + b1) as fp16 (forward operand of W2) and as bf16 (operand of the W2 wgrad GEMM) from one
    * epilogue (tcgen05 kind::f16 cannot mix the formats in one product). Needs N % 32 == 0 and no aux operand. */
   int out16_pre_alt;
+  /* optional fp32 [N]: += the column sums (over the M rows) of the 16-bit output exactly as stored -- the bias gradient
+   * that belongs to an input-gradient GEMM (dh = (du W2) * relu'(h): ffn1's bias gradient is colsum(dh)), produced in
+   * the epilogue instead of a second pass over the output. 16-bit output, N % 32 == 0, split_k == 1. */
+  float* out16_colsum;
 } b200_gemm_desc;
 
 int b200_gemm_bf16(const b200_gemm_desc* d, void* stream);
@@ -214,6 +218,11 @@ int b200_kd_loss_fwd(const float* S, const float* T, int B, int HW, int D, int N
  * DESIGN.md -- g_sim is supported for completeness). */
 int b200_kd_loss_bwd(const float* S, const float* T, int B, int HW, int D, int Nt, int t_skip, int freq, float alpha,
                      const float* g_out /* device [2] */, float* dS, int accumulate, float* ws, void* stream);
+/* Same with the two upstream gradients as separate device scalars (g_sim may be NULL = 0): lets the Python shell hand
+ * out the loss and the similarity as two autograd outputs without select / stack kernels in between. */
+int b200_kd_loss_bwd_split(const float* S, const float* T, int B, int HW, int D, int Nt, int t_skip, int freq,
+                           float alpha, const float* g_loss, const float* g_sim, float* dS, int accumulate, float* ws,
+                           void* stream);
 /* explicit separable 2-D DCT-II -> zero DC -> inverse, per (b, channel) plane, token-major in/out. Cross-check for the
  * mean-subtraction identity (losses/scalekd.py:337-428). R = H = W <= 64. */
 int b200_dct_zero_dc_idct(const float* x, float* y, int B, int R, int D, long long x_bs, long long x_ts, void* stream);
@@ -269,6 +278,7 @@ typedef struct b200_projector_params {
   const float *ffn1_w, *ffn1_b, *ffn2_w, *ffn2_b; /* [4D,D],[4D],[D,4D],[D] */
   const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;     /* norm, norm_2 */
   const float* query_w;                  /* [HW, D] or NULL (self_query=False) */
+  long long* bn_num_batches_tracked;     /* int64 device scalar or NULL: += 1 per training forward (nn.BatchNorm2d) */
 } b200_projector_params;
 
 typedef struct b200_projector_grads {

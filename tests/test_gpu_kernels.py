@@ -514,3 +514,21 @@ def test_gemm_row_remap_aligned_period_bulk_store(B, period, N, K):
     o3 = out.view(B, period + pad, N)
     assert rel_err(o3[:, pad:, :], ref) < 2e-3
     assert (o3[:, 0, :] == 7.0).all()        # cls rows untouched
+
+
+@pytest.mark.parametrize("M,N,K", [(16384, 1536, 384), (1000, 96, 64)])
+def test_gemm_epilogue_column_sums_of_16bit_output(M, N, K):
+    """out16_colsum: the bias gradient that belongs to an input-gradient GEMM (ffn1: colsum((du W2) * relu'(h))),
+    accumulated from the staged 16-bit tile -- equals the column sums of the stored output, rows past M excluded."""
+    ops = _ops()
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    aux = torch.randn(M, N, device="cuda").to(torch.float16)
+    acc0 = torch.randn(N, device="cuda")
+    cs = acc0.clone()
+    out = ops.gemm(a, b, aux=aux, aux_mode="drelu", out_dtype=torch.bfloat16, out_colsum=cs)
+    assert rel_err(out, (a.float() @ b.float().t()) * (aux.float() > 0)) < 6e-3
+    assert rel_err(cs - acc0, out.float().sum(0)) < 1e-4
+    cs2 = torch.zeros(N, device="cuda")
+    o2 = ops.gemm(a, b, out_dtype=torch.float16, out_colsum=cs2)
+    assert rel_err(cs2, o2.float().sum(0)) < 1e-4
