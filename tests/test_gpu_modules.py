@@ -591,3 +591,37 @@ def test_scalekd_under_fp16_autocast_and_grad_scaler():
     assert torch.isfinite(Sh.grad).all()
     assert rel(Sh.grad * inv, ref_dS) <= 5e-3
     check_param_grads({n: (p.grad * inv, ref_grads[n]) for n, p in m.named_parameters()}, tol=5e-3)
+
+
+@pytest.mark.parametrize("heads,raw", [(16, None), (4, (17, 17))])
+def test_scalekd_odd_grid_37x37_long_sequence_paths(heads, raw):
+    """The 518-pixel configurations (cfg4): a 37 x 37 teacher grid, HW = 1369 tokens -- not a multiple of any tile size,
+    longer than one attention key pass (two-kernel backward, multi-block forward), NCHW gradients through the transpose
+    fallback; head_dim 16 and 64; with and without the fused 17 -> 37 resize. Against the oracle port."""
+    scalekd, _, _ = _mods()
+    from oracle import resize_ref, scalekd_ref
+    H = W = 37
+    D, Cs, B = 256, 64, 2
+    kw = dict(name="scalekd_res5", alpha=[0.08, 0.06], student_dims=Cs, teacher_dims=D, query_hw=[H, W], pos_hw=[H, W],
+              pos_dims=D, window_shapes=[1, 1], self_query=True, softmax_scale=[5.0, 5.0], num_heads=heads)
+    torch.manual_seed(61)
+    m = scalekd.ScaleKD(**kw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    gen = torch.Generator().manual_seed(62)
+    S0 = torch.randn(B, Cs, *(raw or (H, W)), generator=gen)
+    T = torch.randn(B, D, H, W, generator=gen)
+    sd_ref = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    S_ref = S0.clone().requires_grad_(True)
+    S_in = resize_ref.resize_bilinear(S_ref, (H, W)) if raw else S_ref
+    ref = scalekd_ref.scalekd_forward(sd_ref, S_in, T, alpha=kw["alpha"], hw=(H, W), num_heads=heads,
+                                      softmax_scale=kw["softmax_scale"])
+    ref["loss"].backward()
+    S = S0.cuda().requires_grad_(True)
+    out = m(S, T.cuda())
+    _check_out(out, ref)
+    out["loss"].backward()
+    assert rel(S.grad, S_ref.grad) <= GRAD_RTOL, rel(S.grad, S_ref.grad)
+    pairs = {n: (p.grad, sd_ref[n].grad) for n, p in m.named_parameters() if sd_ref[n].grad is not None}
+    assert flat_rel(list(pairs.values())) <= GRAD_RTOL
+    check_param_grads(pairs, tol=2e-2)
