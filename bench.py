@@ -89,15 +89,16 @@ def algorithmic_gflop_per_image(wl):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """`nvidia-smi -lms 50` on this rank's GPU, started BEFORE the warm-up (the tool needs up to a second to produce its
+    first line -- longer with 8 GPUs in the box) and kept running; `with sampler:` marks a timed window, and the summary
+    covers only the lines that arrived inside the marked windows."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.windows, self._t0 = [], None, index, [], None
 
-    def __enter__(self):
-        if self.proc is not None and self.proc.poll() is None:
-            return self
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
@@ -110,9 +111,16 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def __enter__(self):
+        self._t0 = time.perf_counter()
+        return self
 
     def __exit__(self, *a):
+        self.windows.append((self._t0, time.perf_counter()))
+
+    def stop(self):
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -123,7 +131,9 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not any(a - 0.05 <= ts <= b + 0.05 for a, b in self.windows):   # a line reports the 50 ms before it
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for nm, v in zip(names, r[3:7]):
@@ -306,6 +316,7 @@ def main():
             torch.cuda.synchronize()
 
     res_img, res_feats = (None, None) if graphed is not None else (dev["img"], feats)
+    clocks = ClockSampler(local).start()       # streaming before the warm-up; windows are marked below
     for _ in range(args.warmup):
         hot_path(res_img, res_feats)
     sync_all()
@@ -313,7 +324,7 @@ def main():
     # ---- timed region: device-resident inputs, CUDA events, max over ranks
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lib.b200_reset_launch_count()
-    with ClockSampler(local) as clocks:
+    with clocks:
         sync_all()
         e0.record()
         for _ in range(args.steps):
@@ -387,6 +398,9 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_value = wl["batch"] * world * args.steps / (float(t.item()) / 1e3)
+
+    clocks.stop()
+    clocks_summary = clocks.summary()
 
     # ---- roofline leg: per-launch CUDA-event timing of the dense kernels over the same steps (rank 0 reports)
     roofline, extra = None, {}
@@ -475,7 +489,7 @@ def main():
                        "algorithmic_gflop_per_image": gf},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "clocks": clocks.summary(),
+            "clocks": clocks_summary,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "model_tflops": value * gf["total"] / 1e3 / world,
