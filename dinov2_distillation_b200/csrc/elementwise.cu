@@ -251,8 +251,11 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(256)
+// WG: the launch needs column partials (dgamma / dbeta and / or the column sums of the output). The plain form (re-used
+// teacher blocks: no parameter gradients) drops those 9 * NV accumulator registers: 89 -> ~56 registers, four blocks per
+// SM instead of two, i.e. twice the loads in flight for a kernel that is pure HBM traffic (3.1 -> ... TB/s, profiles/).
+template <int NV, bool WG>
+__global__ void __launch_bounds__(256, WG ? 2 : 4)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dw,
@@ -262,27 +265,57 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_d = 1.0f / (float)D;
-  float4 aw[NV], ab[NV], ao[NV];   // column partials: dw, db and (dx_colsum) the output itself
+  float4 aw[WG ? NV : 1], ab[WG ? NV : 1], ao[WG ? NV : 1];   // column partials: dw, db and (dx_colsum) the output itself
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { aw[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ao[i] = make_float4(0, 0, 0, 0); }
-  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+  for (int i = 0; i < (WG ? NV : 1); ++i) { aw[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ao[i] = make_float4(0, 0, 0, 0); }
+  // The accumulating form keeps two blocks per SM (one atomic per column per block), so each warp keeps its NEXT row's
+  // loads in flight while it reduces the current one (register double buffer); the plain form has the occupancy instead.
+  const int r_first = blockIdx.x * warps_per_block + (threadIdx.x >> 5), r_step = gridDim.x * warps_per_block;
+  float4 nd[WG ? NV : 1], nx[WG ? NV : 1];
+  if (WG && r_first < rows) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) {
+        nd[i] = reinterpret_cast<const float4*>(dy + (long long)r_first * D)[c4];
+        nx[i] = reinterpret_cast<const float4*>(x + (long long)r_first * D)[c4];
+      }
+    }
+  }
+  for (int r = r_first; r < rows; r += r_step) {
     const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)r * D);
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)r * D);
     const float mu = mean[r], rs = rstd[r];
     float4 g[NV], xh[NV];
+    float4 cd[WG ? NV : 1], cx[WG ? NV : 1];
+    if (WG) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { cd[i] = nd[i]; cx[i] = nx[i]; }
+      const int rn = r + r_step;
+      if (rn < rows) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c4 = i * 32 + lane;
+          if (c4 * 4 < D) {
+            nd[i] = reinterpret_cast<const float4*>(dy + (long long)rn * D)[c4];
+            nx[i] = reinterpret_cast<const float4*>(x + (long long)rn * D)[c4];
+          }
+        }
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = i * 32 + lane;
       if (c4 * 4 < D) {
-        const float4 d4 = dyr[c4];
-        const float4 x4 = xr[c4];
+        const float4 d4 = WG ? cd[i] : dyr[c4];
+        const float4 x4 = WG ? cx[i] : xr[c4];
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + c4);
         xh[i] = make_float4((x4.x - mu) * rs, (x4.y - mu) * rs, (x4.z - mu) * rs, (x4.w - mu) * rs);
         g[i] = make_float4(d4.x * w4.x, d4.y * w4.y, d4.z * w4.z, d4.w * w4.w);
         s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
         s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-        if (dw) {
+        if (WG && dw) {
           aw[i].x += d4.x * xh[i].x; aw[i].y += d4.y * xh[i].y; aw[i].z += d4.z * xh[i].z; aw[i].w += d4.w * xh[i].w;
           ab[i].x += d4.x; ab[i].y += d4.y; ab[i].z += d4.z; ab[i].w += d4.w;
         }
@@ -303,7 +336,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
           const float4 rr = reinterpret_cast<const float4*>(dres + (long long)r * D)[c4];
           o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
         }
-        if (dx_colsum) { ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w; }
+        if (WG && dx_colsum) { ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w; }
         if (dx) reinterpret_cast<float4*>(dx + (long long)r * D)[c4] = o;
         if (dx16) {
           uint2 u;
@@ -314,6 +347,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       }
     }
   }
+  if constexpr (!WG) return;
   if (dw) {
     // block reduction over warps through shared memory, then one atomic per column per block
     extern __shared__ float red[];  // [warps][2][D]  (D <= 1536, warps = 8 -> 96 KB max; sized by the launcher)
@@ -684,13 +718,16 @@ template <int NV>
 static int launch_ln_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                          const float* dres, float* dx, void* dx16, float* dw, float* db, float* dx_colsum, int rows,
                          int D, cudaStream_t st) {
-  auto kern = layernorm_bwd_kernel<NV>;
+  const bool wg = dw != nullptr || dx_colsum != nullptr;
+  auto kern = wg ? layernorm_bwd_kernel<NV, true> : layernorm_bwd_kernel<NV, false>;
   size_t smem = dw ? size_t(8) * 2 * D * sizeof(float) : (dx_colsum ? size_t(8) * D * sizeof(float) : 0);
   if (smem > 48 * 1024) {
     static bool set = false;
     if (!set) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
   }
-  const int grid = grid_for(rows, 8 * 4, (dw || dx_colsum) ? 2 : 8);
+  static const int rpb = [] { const char* e = getenv("B200_LNB_RPB"); return e ? atoi(e) : 8; }();    // rows per block (plain form)
+  static const int bps = [] { const char* e = getenv("B200_LNB_BPS"); return e ? atoi(e) : 8; }();    // blocks per SM cap
+  const int grid = wg ? grid_for(rows, 32, 2) : grid_for(rows, rpb, bps);
   B200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(256), smem, st, dy, x, w, mean, rstd, dres, dx,
                           static_cast<__nv_bfloat16*>(dx16), dw, db, dx_colsum, rows, D));
   B200_LAUNCH_OK();
