@@ -133,37 +133,34 @@ __global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict_
 __global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W,
                                     int Kp) {
   pdl_wait();   // PDL: launched through launch_pdl(); multi-wave grid, no early trigger
-  extern __shared__ float srow[];  // [3*14][W]
+  extern __shared__ float srow[];  // [3*14][W + 1]  (odd pitch: the column-segment reads below hit distinct banks)
   const int Wp = W / 14, Hp = H / 14;
   const int b = blockIdx.x / Hp, ph = blockIdx.x % Hp;
-  const int W4 = W >> 2;  // W % 14 == 0 and even; use float2 to stay safe on alignment
-  (void)W4;
-  const int W2 = W >> 1;
+  const int W2 = W >> 1;   // W % 14 == 0, so W is even: float2 loads stay aligned
+  const int WP = W + 1;
+#pragma unroll 6
   for (int idx = threadIdx.x; idx < 42 * W2; idx += blockDim.x) {
     const int rr = idx / W2, x2 = idx - rr * W2;
     const int c = rr / 14, i = rr - c * 14;
     const float2 v = __ldg(reinterpret_cast<const float2*>(img + (((long long)b * 3 + c) * H + (ph * 14 + i)) * W) + x2);
-    srow[rr * W + 2 * x2] = v.x;
-    srow[rr * W + 2 * x2 + 1] = v.y;
+    srow[rr * WP + 2 * x2] = v.x;
+    srow[rr * WP + 2 * x2 + 1] = v.y;
   }
   __syncthreads();
-  const int Kp2 = Kp >> 1;
   __nv_bfloat16* obase = out + ((long long)(b * Hp + ph) * Wp) * Kp;
-  for (int idx = threadIdx.x; idx < Wp * Kp2; idx += blockDim.x) {
-    const int pw = idx / Kp2, k2 = idx - pw * Kp2;
-    float v[2];
+  // output column = c*196 + i*14 + j = (c*14 + i)*14 + j: one task = the 14 contiguous pixels of (patch pw, row ci)
+  // -> 14 contiguous bf16 of the output row (28 bytes, 4-byte aligned): no per-element div / mod
+  for (int t = threadIdx.x; t < Wp * 42; t += blockDim.x) {
+    const int pw = t / 42, ci = t - pw * 42;
+    const float* src = srow + ci * WP + pw * 14;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(obase + (long long)pw * Kp + ci * 14);
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = 2 * k2 + e;
-      if (col < 588) {
-        const int c = col / 196, rem = col - c * 196;
-        const int i = rem / 14, j = rem - i * 14;
-        v[e] = srow[(c * 14 + i) * W + pw * 14 + j];
-      } else {
-        v[e] = 0.f;
-      }
-    }
-    reinterpret_cast<uint32_t*>(obase + (long long)pw * Kp)[k2] = pack_bf16(v[0], v[1]);
+    for (int j = 0; j < 7; ++j) dst[j] = pack_bf16(src[2 * j], src[2 * j + 1]);
+  }
+  const int pad2 = (Kp - 588) >> 1;   // zero padding of the contraction dimension (Kp % 8 == 0, 588 % 4 == 0)
+  for (int t = threadIdx.x; t < Wp * pad2; t += blockDim.x) {
+    const int pw = t / pad2, k2 = t - pw * pad2;
+    reinterpret_cast<uint32_t*>(obase + (long long)pw * Kp + 588)[k2] = 0u;
   }
 }
 
@@ -406,7 +403,8 @@ colreduce_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out
   const int r1 = min(rows, r0 + rows_per_block);
   float4 a = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
   if (c < cols) {
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+#pragma unroll 4
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {   // (independent loads: four rows in flight per thread)
       float4 v;
       if constexpr (sizeof(T) == 4) {
         v = *reinterpret_cast<const float4*>(x + (long long)r * ldx + c);
@@ -511,6 +509,70 @@ bn_relu_pos_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
   }
 }
 
+// Same column sums, with the pos_embed gradient in the same pass: dpos[p, :] += sum over images of dz[(b, p), :]
+// (pos_embed is added after the ReLU, so dz reaches it unmasked). A block owns 8 positions x 128 columns for EVERY image
+// -- thread (x, y): 4 columns of position p0 + y -- so the per-position sums need no atomics and dz is read once (the
+// separate batch-sum pass read it a second time: 25 MB and a launch per projector).
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_pos_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
+                         float* __restrict__ sums2, float* __restrict__ dpos, int B, int HW, int D) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float4 sh[8][32];
+  __shared__ float4 sh2[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int p = blockIdx.y * 8 + threadIdx.y;
+  // the images are split over gridDim.z blocks (more loads in flight than one block per position group gives); the
+  // per-position sums of the z-slices meet in dpos through atomics (dpos is an accumulator, zeroed by the caller)
+  const int per_z = (B + gridDim.z - 1) / gridDim.z;
+  const int b0 = blockIdx.z * per_z, b1 = min(B, b0 + per_z);
+  float4 a = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0), dp = make_float4(0, 0, 0, 0);
+  if (c < D && p < HW) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(w + c);
+    const float4 be = *reinterpret_cast<const float4*>(b + c);
+#pragma unroll 4
+    for (int i = b0; i < b1; ++i) {
+      const long long off = ((long long)i * HW + p) * D + c;
+      const float4 d4 = *reinterpret_cast<const float4*>(dz + off);
+      const float4 y4 = *reinterpret_cast<const float4*>(y + off);
+      const float4 yh = make_float4((y4.x - mu.x) * rs.x, (y4.y - mu.y) * rs.y, (y4.z - mu.z) * rs.z, (y4.w - mu.w) * rs.w);
+      float4 dr;
+      dr.x = (yh.x * g.x + be.x > 0.f) ? d4.x : 0.f;
+      dr.y = (yh.y * g.y + be.y > 0.f) ? d4.y : 0.f;
+      dr.z = (yh.z * g.z + be.z > 0.f) ? d4.z : 0.f;
+      dr.w = (yh.w * g.w + be.w > 0.f) ? d4.w : 0.f;
+      a.x += dr.x; a.y += dr.y; a.z += dr.z; a.w += dr.w;
+      q.x += dr.x * yh.x; q.y += dr.y * yh.y; q.z += dr.z * yh.z; q.w += dr.w * yh.w;
+      dp.x += d4.x; dp.y += d4.y; dp.z += d4.z; dp.w += d4.w;
+    }
+    float* o = dpos + (long long)p * D + c;
+    if (gridDim.z == 1) {
+      float4 old = *reinterpret_cast<float4*>(o);
+      old.x += dp.x; old.y += dp.y; old.z += dp.z; old.w += dp.w;
+      *reinterpret_cast<float4*>(o) = old;
+    } else {
+      atomicAdd(o, dp.x); atomicAdd(o + 1, dp.y); atomicAdd(o + 2, dp.z); atomicAdd(o + 3, dp.w);
+    }
+  }
+  sh[threadIdx.y][threadIdx.x] = a;
+  sh2[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 t = sh[k][threadIdx.x], u = sh2[k][threadIdx.x];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      q.x += u.x; q.y += u.y; q.z += u.z; q.w += u.w;
+    }
+    atomicAdd(sums2 + c, a.x); atomicAdd(sums2 + c + 1, a.y); atomicAdd(sums2 + c + 2, a.z); atomicAdd(sums2 + c + 3, a.w);
+    float* o2 = sums2 + D;
+    atomicAdd(o2 + c, q.x); atomicAdd(o2 + c + 1, q.y); atomicAdd(o2 + c + 2, q.z); atomicAdd(o2 + c + 3, q.w);
+  }
+}
+
 // sums2[0:D] += sum_r dr ; sums2[D:2D] += sum_r dr * yhat ; dr = dz * (yhat*w+b > 0)
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float* __restrict__ mean,
@@ -529,6 +591,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, 
     const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
     const float4 g = *reinterpret_cast<const float4*>(w + c);
     const float4 be = *reinterpret_cast<const float4*>(b + c);
+#pragma unroll 4
     for (int r = r0 + threadIdx.y; r < r1; r += 8) {
       const float4 d4 = *reinterpret_cast<const float4*>(dz + (long long)r * D + c);
       const float4 y4 = *reinterpret_cast<const float4*>(y + (long long)r * D + c);
@@ -1105,7 +1168,7 @@ extern "C" int b200_patch_im2col(const float* img, void* out, int B, int H, int 
   B200_CHECK_ARG(img && out && B > 0, "bad args");
   B200_CHECK_ARG(H % 14 == 0 && W % 14 == 0 && H > 0 && W > 0, "image size must be a multiple of the 14-pixel patch");
   B200_CHECK_ARG(Kp >= 588 && Kp % 8 == 0, "Kp must be >= 588 and a multiple of 8");
-  const size_t smem = size_t(42) * W * sizeof(float);
+  const size_t smem = size_t(42) * (W + 1) * sizeof(float);
   B200_CHECK_ARG(smem <= 200 * 1024, "image too wide");
   if (smem > 48 * 1024) {
     static size_t set_to = 0;
@@ -1213,6 +1276,17 @@ extern "C" int b200_bn_relu_pos_bwd_reduce(const float* dz, const float* y, cons
   B200_CHECK_ARG(dz && y && mean && rstd && w && b && sums2 && M > 0 && D % 4 == 0, "bad args");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int gx = (int)cdiv(D, 128);
+  if (dpos != nullptr && HW > 0 && M % HW == 0 && M / HW >= 8) {   // enough images per position to keep a thread busy
+    const int nb = M / HW;
+    const long long blocks_xy = (long long)gx * cdiv(HW, 8);
+    int gz = (int)cdiv((long long)sm_count() * 4, blocks_xy);    // ~4 blocks per SM, at least 8 images per block
+    if (gz > nb / 8) gz = nb / 8;
+    if (gz < 1) gz = 1;
+    B200_CUDA_OK(launch_pdl(bn_bwd_reduce_pos_kernel, dim3(dim3(gx, (unsigned)cdiv(HW, 8), (unsigned)gz)), dim3(dim3(32, 8)), 0, st,
+                            dz, y, mean, rstd, w, b, sums2, dpos, nb, HW, D));
+    B200_LAUNCH_OK();
+    return 0;
+  }
   int gy = (int)cdiv((long long)sm_count() * 4, gx);
   int rpb = (int)cdiv(M, gy);
   if (rpb < 64) rpb = 64;

@@ -25,6 +25,7 @@ token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int HW, 
   float4 a = make_float4(0, 0, 0, 0);
   if (c < D) {
     const float* base = x + (long long)b * bstride + (long long)skip * D + c;
+#pragma unroll 4
     for (int p = threadIdx.y; p < HW; p += 8) {
       const float4 v = *reinterpret_cast<const float4*>(base + (long long)p * D);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
@@ -76,16 +77,28 @@ kd_loss_fwd_kernel(const float* __restrict__ S, const float* __restrict__ T, int
   pdl_wait();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float loss = 0.f, sim = 0.f;
-  for (int r = blockIdx.x * wpb + wid; r < rows; r += gridDim.x * wpb) {
-    const int b = r / HW, p = r - b * HW;
-    const float* s = S + (long long)r * D;
-    const float* t = T + ((long long)b * Nt + t_skip + p) * D;
-    const RowStats q = row_stats(s, t, ms ? ms + (long long)b * D : nullptr, ms ? mt + (long long)b * D : nullptr, D, lane);
-    // F.normalize(eps=1e-12) then MSE(sum) and cosine_similarity(eps=1e-8) on the normalised vectors
-    const float ns = fmaxf(sqrtf(q.ss), 1e-12f), nt = fmaxf(sqrtf(q.tt), 1e-12f);
-    const float hs2 = q.ss / (ns * ns), ht2 = q.tt / (nt * nt), hst = q.st / (ns * nt);
-    loss += hs2 + ht2 - 2.f * hst;
-    sim += hst / (fmaxf(sqrtf(hs2), 1e-8f) * fmaxf(sqrtf(ht2), 1e-8f));
+  // two rows per trip: the loads of both are issued before either row's three warp reductions
+  const int step = gridDim.x * wpb;
+  for (int r = blockIdx.x * wpb + wid; r < rows; r += 2 * step) {
+    RowStats q[2];
+    const int r2 = r + step;
+    const bool two = r2 < rows;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int rr = (k == 0 || two) ? (k == 0 ? r : r2) : r;
+      const int b = rr / HW, p = rr - b * HW;
+      q[k] = row_stats(S + (long long)rr * D, T + ((long long)b * Nt + t_skip + p) * D, ms ? ms + (long long)b * D : nullptr,
+                       ms ? mt + (long long)b * D : nullptr, D, lane);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !two) break;
+      // F.normalize(eps=1e-12) then MSE(sum) and cosine_similarity(eps=1e-8) on the normalised vectors
+      const float ns = fmaxf(sqrtf(q[k].ss), 1e-12f), nt = fmaxf(sqrtf(q[k].tt), 1e-12f);
+      const float hs2 = q[k].ss / (ns * ns), ht2 = q[k].tt / (nt * nt), hst = q[k].st / (ns * nt);
+      loss += hs2 + ht2 - 2.f * hst;
+      sim += hst / (fmaxf(sqrtf(hs2), 1e-8f) * fmaxf(sqrtf(ht2), 1e-8f));
+    }
   }
   __shared__ float sl[8], sm[8];
   if (lane == 0) { sl[wid] = loss; sm[wid] = sim; }
