@@ -430,10 +430,15 @@ colreduce_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out
         q.x += u.x; q.y += u.y; q.z += u.z; q.w += u.w;
       }
     }
-    atomicAdd(out + c, a.x); atomicAdd(out + c + 1, a.y); atomicAdd(out + c + 2, a.z); atomicAdd(out + c + 3, a.w);
+    // one 16-byte reduction per accumulator (a few hundred blocks meet on cols / 4 addresses) when `out` allows it
+    // (gradient views of a flat arena are only 4-byte aligned)
+    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (al16) atomicAdd(reinterpret_cast<float4*>(out + c), a);
+    else { atomicAdd(out + c, a.x); atomicAdd(out + c + 1, a.y); atomicAdd(out + c + 2, a.z); atomicAdd(out + c + 3, a.w); }
     if (SQ) {
       float* o2 = out + cols;
-      atomicAdd(o2 + c, q.x); atomicAdd(o2 + c + 1, q.y); atomicAdd(o2 + c + 2, q.z); atomicAdd(o2 + c + 3, q.w);
+      if (al16) atomicAdd(reinterpret_cast<float4*>(o2 + c), q);
+      else { atomicAdd(o2 + c, q.x); atomicAdd(o2 + c + 1, q.y); atomicAdd(o2 + c + 2, q.z); atomicAdd(o2 + c + 3, q.w); }
     }
   }
 }
@@ -554,7 +559,7 @@ bn_bwd_reduce_pos_kernel(const float* __restrict__ dz, const float* __restrict__
       old.x += dp.x; old.y += dp.y; old.z += dp.z; old.w += dp.w;
       *reinterpret_cast<float4*>(o) = old;
     } else {
-      atomicAdd(o, dp.x); atomicAdd(o + 1, dp.y); atomicAdd(o + 2, dp.z); atomicAdd(o + 3, dp.w);
+      atomicAdd(reinterpret_cast<float4*>(o), dp);
     }
   }
   sh[threadIdx.y][threadIdx.x] = a;
@@ -567,9 +572,8 @@ bn_bwd_reduce_pos_kernel(const float* __restrict__ dz, const float* __restrict__
       a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
       q.x += u.x; q.y += u.y; q.z += u.z; q.w += u.w;
     }
-    atomicAdd(sums2 + c, a.x); atomicAdd(sums2 + c + 1, a.y); atomicAdd(sums2 + c + 2, a.z); atomicAdd(sums2 + c + 3, a.w);
-    float* o2 = sums2 + D;
-    atomicAdd(o2 + c, q.x); atomicAdd(o2 + c + 1, q.y); atomicAdd(o2 + c + 2, q.z); atomicAdd(o2 + c + 3, q.w);
+    atomicAdd(reinterpret_cast<float4*>(sums2 + c), a);
+    atomicAdd(reinterpret_cast<float4*>(sums2 + D + c), q);
   }
 }
 
@@ -615,9 +619,8 @@ bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, 
       a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
       q.x += u.x; q.y += u.y; q.z += u.z; q.w += u.w;
     }
-    atomicAdd(sums2 + c, a.x); atomicAdd(sums2 + c + 1, a.y); atomicAdd(sums2 + c + 2, a.z); atomicAdd(sums2 + c + 3, a.w);
-    float* o2 = sums2 + D;
-    atomicAdd(o2 + c, q.x); atomicAdd(o2 + c + 1, q.y); atomicAdd(o2 + c + 2, q.z); atomicAdd(o2 + c + 3, q.w);
+    atomicAdd(reinterpret_cast<float4*>(sums2 + c), a);
+    atomicAdd(reinterpret_cast<float4*>(sums2 + D + c), q);
   }
 }
 

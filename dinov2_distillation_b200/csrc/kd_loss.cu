@@ -15,18 +15,19 @@ int zero_f32(float* p, long long n, cudaStream_t st);
 static inline long long ws_acc_floats() { return 4; }
 
 // mean over the HW tokens of each image: out[b, c] = 1/HW sum_p x[b, skip + p, c]
-__global__ void __launch_bounds__(256)
+// (32 x 16 threads, eight rows in flight per thread: one block per (image, 128 columns) has to cover the latency itself)
+__global__ void __launch_bounds__(512)
 token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int HW, int D, long long bstride, int skip) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
-  __shared__ float4 sh[8][32];
+  __shared__ float4 sh[16][32];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int b = blockIdx.y;
   float4 a = make_float4(0, 0, 0, 0);
   if (c < D) {
     const float* base = x + (long long)b * bstride + (long long)skip * D + c;
-#pragma unroll 4
-    for (int p = threadIdx.y; p < HW; p += 8) {
+#pragma unroll 8
+    for (int p = threadIdx.y; p < HW; p += 16) {
       const float4 v = *reinterpret_cast<const float4*>(base + (long long)p * D);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
@@ -35,7 +36,7 @@ token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int HW, 
   __syncthreads();
   if (threadIdx.y == 0 && c < D) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
+    for (int k = 1; k < 16; ++k) {
       const float4 t = sh[k][threadIdx.x];
       a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
     }
@@ -258,9 +259,9 @@ extern "C" int b200_kd_loss_fwd(const float* S, const float* T, int B, int HW, i
   float* mt = ms + (long long)B * D;
   if (freq) {
     dim3 grid((unsigned)cdiv(D, 128), (unsigned)B);
-    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 8)), 0, st, S, ms, HW, D, (long long)HW * D, 0));
+    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 16)), 0, st, S, ms, HW, D, (long long)HW * D, 0));
     B200_LAUNCH_OK();
-    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 8)), 0, st, T, mt, HW, D, (long long)Nt * D, t_skip));
+    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 16)), 0, st, T, mt, HW, D, (long long)Nt * D, t_skip));
     B200_LAUNCH_OK();
   }
   const int rows = B * HW;
@@ -297,7 +298,7 @@ extern "C" int b200_kd_loss_bwd_split(const float* S, const float* T, int B, int
   B200_LAUNCH_OK();
   if (freq) {
     dim3 grid((unsigned)cdiv(D, 128), (unsigned)B);
-    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 8)), 0, st, dS, md, HW, D, (long long)HW * D, 0));
+    B200_CUDA_OK(launch_pdl(token_mean_kernel, dim3(grid), dim3(dim3(32, 16)), 0, st, dS, md, HW, D, (long long)HW * D, 0));
     B200_LAUNCH_OK();
     long long n4 = (long long)rows * D / 4;
     long long gg = cdiv(n4, 256);
