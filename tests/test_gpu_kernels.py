@@ -532,3 +532,49 @@ def test_gemm_epilogue_column_sums_of_16bit_output(M, N, K):
     cs2 = torch.zeros(N, device="cuda")
     o2 = ops.gemm(a, b, out_dtype=torch.float16, out_colsum=cs2)
     assert rel_err(cs2, o2.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("B,HW,D", [(16, 256, 384), (8, 1369, 256), (2, 49, 128)])
+def test_batchnorm_relu_pos_kernels_vs_autograd(B, HW, D):
+    """proj_student's BatchNorm2d -> ReLU, + pos_embed (losses/scalekd.py:199-201, :238) on token-major data: forward
+    (stats, finalize, apply) and backward (reduce -- incl. the path that owns all images of a position and emits the
+    pos_embed gradient from the same pass, and the fallback for few images -- and apply) against torch autograd."""
+    import ctypes as C
+    from dinov2_distillation_b200 import _lib as L
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    M = B * HW
+    gen = torch.Generator(device="cuda").manual_seed(B * 1000 + HW)
+    y = torch.randn(M, D, device="cuda", generator=gen)
+    w = torch.rand(D, device="cuda", generator=gen) + 0.5
+    b = torch.randn(D, device="cuda", generator=gen) * 0.3
+    pos = torch.randn(HW, D, device="cuda", generator=gen)
+    dz = torch.randn(M, D, device="cuda", generator=gen)
+    eps = 1e-5
+    # reference: autograd through batch-statistics BN
+    yr, wr, br, pr = (t.clone().double().requires_grad_(True) for t in (y, w, b, pos))
+    mu, var = yr.mean(0), yr.var(0, unbiased=False)
+    z_ref = torch.relu((yr - mu) / torch.sqrt(var + eps) * wr + br) + pr.repeat(B, 1)
+    z_ref.backward(dz.double())
+    # ours
+    sums = torch.zeros(2 * D, device="cuda")
+    mean, rstd = torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
+    rm, rv = torch.zeros(D, device="cuda"), torch.ones(D, device="cuda")
+    L.check(lib.b200_bn_stats(y.data_ptr(), sums.data_ptr(), M, D, st), "bn_stats")
+    L.check(lib.b200_bn_finalize(sums.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rm.data_ptr(), rv.data_ptr(), 0.1, eps, M, D, st), "fin")
+    z = torch.empty(M, D, device="cuda")
+    L.check(lib.b200_bn_relu_pos_fwd(y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), w.data_ptr(), b.data_ptr(), pos.data_ptr(),
+                                     z.data_ptr(), None, M, D, HW, 0, st), "fwd")
+    assert rel_err(z, z_ref.float()) < 1e-5
+    assert rel_err(rm, 0.1 * mu.float()) < 1e-4
+    sums2 = torch.zeros(2 * D, device="cuda")
+    dpos = torch.zeros(HW, D, device="cuda")
+    L.check(lib.b200_bn_relu_pos_bwd_reduce(dz.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                            sums2.data_ptr(), dpos.data_ptr(), M, D, HW, st), "reduce")
+    assert rel_err(dpos, pr.grad.float()) < 1e-5
+    assert rel_err(sums2[:D], br.grad.float()) < 1e-4          # d beta
+    assert rel_err(sums2[D:], wr.grad.float()) < 1e-4          # d gamma
+    dy16 = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.b200_bn_relu_pos_bwd_apply(dz.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                           sums2.data_ptr(), dy16.data_ptr(), 1, M, D, st), "apply")
+    assert rel_err(dy16, yr.grad.float()) < 4e-3               # bf16 output
