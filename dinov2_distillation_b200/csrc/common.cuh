@@ -175,6 +175,8 @@ int cast_f32_f16_dual(const float* x, void* y_f16, void* y_bf16, long long n, vo
 int layernorm_fwd_dual(const float* x, const float* w, const float* b, float eps, float* y_f32, void* y16, void* y16_alt,
                        float* mean, float* rstd, int rows, int D, int in_period, int in_pad, int y16_is_fp16,
                        void* stream);
+// NCHW fp32 -> bf16 tokens [B*HW, C] + 3-term fp16 split [B*HW, 3C] ([hi|hi|lo]) in one pass (elementwise.cu)
+int tokenize_split3(const float* x, void* xt_bf16, void* xt3_fp16, int B, int C, int HW, void* stream);
 // b200_bn_finalize that also bumps nn.BatchNorm2d.num_batches_tracked (int64 device scalar, may be NULL)
 int bn_finalize_counted(const float* sums, float* mean, float* rstd, float* running_mean, float* running_var,
                         float momentum, float eps, int M, int D, long long* num_batches_tracked, void* stream);

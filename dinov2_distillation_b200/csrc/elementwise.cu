@@ -129,6 +129,41 @@ __global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ student tokenisation
+// NCHW fp32 [B, C, HW] -> token-major working copies of the projector input in ONE pass: xt bf16 [B*HW, C] (operand of
+// the conv wgrad) and the 3-term fp16 split xt3 [B*HW, 3C] = [hi | hi | lo] (left operand of the split conv GEMM, see
+// split3_kernel). Replaces transpose (bf16 + fp32 token copies) followed by split3 over the fp32 copy: 12 instead of
+// 20 bytes of traffic per element. 64 channels x 32 positions per block; every store is a full 128-byte row segment.
+__global__ void __launch_bounds__(256) tokenize_split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xt,
+                                                             __nv_bfloat16* __restrict__ xt3, int C, int HW) {
+  pdl_wait();   // multi-wave grid: no early trigger
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const float* src = x + (long long)b * C * HW;
+#pragma unroll
+  for (int j = threadIdx.y; j < 64; j += 8) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? src[(long long)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  const int c = c0 + 2 * threadIdx.x;
+  if (c >= C) return;
+#pragma unroll
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int p = p0 + j;
+    if (p >= HW) continue;
+    const float v0 = tile[2 * threadIdx.x][j], v1 = tile[2 * threadIdx.x + 1][j];
+    const long long row = (long long)b * HW + p;
+    *reinterpret_cast<uint32_t*>(xt + row * C + c) = pack_bf16(v0, v1);
+    const float h0 = __half2float(__float2half_rn(v0)), h1 = __half2float(__float2half_rn(v1));
+    const uint32_t hi = pack16(h0, h1, 1), lo = pack16(v0 - h0, v1 - h1, 1);
+    __nv_bfloat16* o = xt3 + row * 3 * C + c;
+    *reinterpret_cast<uint32_t*>(o) = hi;
+    *reinterpret_cast<uint32_t*>(o + C) = hi;
+    *reinterpret_cast<uint32_t*>(o + 2 * C) = lo;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ patch im2col
 __global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W,
                                     int Kp) {
@@ -1163,6 +1198,15 @@ extern "C" int b200_window_rows16(const void* src, void* dst, long long rows, in
   B200_CUDA_OK(launch_pdl(window_rows16_kernel, dim3(grid_for(rows, 8, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
                           static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, H, W, win_h, win_w,
                           cols, ld, to_raster));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200::tokenize_split3(const float* x, void* xt_bf16, void* xt3_fp16, int B, int C, int HW, void* stream) {
+  B200_CHECK_ARG(x && xt_bf16 && xt3_fp16 && B > 0 && C > 0 && HW > 0 && C % 2 == 0, "bad args");
+  dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(C, 64), (unsigned)B);
+  B200_CUDA_OK(launch_pdl(tokenize_split3_kernel, grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream), x,
+                          static_cast<__nv_bfloat16*>(xt_bf16), static_cast<__nv_bfloat16*>(xt3_fp16), C, HW));
   B200_LAUNCH_OK();
   return 0;
 }

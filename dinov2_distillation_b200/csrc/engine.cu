@@ -325,7 +325,7 @@ static void carve_proj_save(Arena& a, const b200_projector_config* c, int B, Pro
 struct ProjFwdWs {
   h16 *wc3, *wq, *wkv, *wp, *w1, *w2;   // fp16 working copies of the fp32 master weights (wc3: 3-term split)
   h16* xt3;                             // 3-term split of the student tokens [M_in, 3Cs]
-  float *bkv, *sums, *pos_t, *z32, *g32, *xt32;
+  float *bkv, *sums, *pos_t, *z32, *g32;
   float* yraw;                          // conv output at the raw resolution [M_in, D] (fused resize only)
   h16 *qtmp, *kvtmp;                    // raster-order q / [k|v] before the move to window-major rows (windows only)
 };
@@ -335,7 +335,6 @@ static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, P
   const long long M_in = (long long)B * proj_hw_in(c);
   w.wc3 = a.take_n<h16>(3 * D * c->Cs);
   w.xt3 = a.take_n<h16>(M_in * 3 * c->Cs);
-  w.xt32 = a.take_n<float>(M_in * c->Cs);
   w.yraw = c->raw_h > 0 ? a.take_n<float>(M_in * D) : nullptr;
   w.qtmp = proj_windows(c) > 1 ? a.take_n<h16>(M * D) : nullptr;
   w.kvtmp = proj_windows(c) > 1 ? a.take_n<h16>(M * 2 * D) : nullptr;
@@ -465,14 +464,13 @@ extern "C" size_t b200_projector_tokens_bytes(const b200_projector_config* c, in
 extern "C" int b200_projector_tokenize(const b200_projector_config* c, const float* x, int B, void* tokens, void* ws,
                                        size_t ws_bytes, void* stream) {
   B200_TRY(check_proj_cfg(c, B));
-  B200_CHECK_ARG(x && tokens && ws, "null argument");
+  B200_CHECK_ARG(x && tokens, "null argument");
+  (void)ws; (void)ws_bytes;   // (kept in the signature: the one-pass tokenisation needs no scratch)
   const long long M = (long long)B * proj_hw_in(c);
-  B200_CHECK_ARG(ws_bytes >= (size_t)M * c->Cs * 4, "workspace too small");
   bf16* xt = static_cast<bf16*>(tokens);
   h16* xt3 = reinterpret_cast<h16*>(static_cast<uint8_t*>(tokens) + proj_tokens_xt3_offset(c, B));
-  float* xt32 = static_cast<float*>(ws);
-  B200_TRY(b200_nchw_to_tokens(x, xt, xt32, B, c->Cs, proj_hw_in(c), 0, stream));
-  B200_TRY(b200_split3_16(xt32, xt3, M, c->Cs, 0, 1, stream));
+  (void)M;
+  B200_TRY(tokenize_split3(x, xt, xt3, B, c->Cs, proj_hw_in(c), stream));
   return 0;
 }
 
@@ -521,8 +519,7 @@ static int projector_fwd_impl(const b200_projector_config* c, const b200_project
   if (tokens != nullptr) {
     xt3 = reinterpret_cast<const h16*>(static_cast<const uint8_t*>(tokens) + proj_tokens_xt3_offset(c, B));
   } else {
-    B200_TRY(b200_nchw_to_tokens(x, s.xt, w.xt32, B, Cs, hw_in, 0, stream));
-    B200_TRY(b200_split3_16(w.xt32, w.xt3, M_in, Cs, 0, 1, stream));
+    B200_TRY(tokenize_split3(x, s.xt, w.xt3, B, Cs, hw_in, stream));
   }
   // fused ModelWrapper resize (models/model_zoo.py:121-126): conv at the raw resolution, then resize its output
   B200_TRY(Gemm(xt3, 3 * Cs, w.wc3, 3 * Cs, (int)M_in, D, 3 * Cs).fp16_operands().algo_scale(1.f / 3.f).bias(p->conv_b).out32(raw ? w.yraw : s.y, D).run(stream));
