@@ -11,8 +11,10 @@ namespace b200 {
 
 int zero_f32(float* p, long long n, cudaStream_t st);
 
-// ws layout (floats): [0]=loss sum, [1]=sim sum, [2..3] pad, then ms[B*D], mt[B*D], md[B*D]
-static inline long long ws_acc_floats() { return 4; }
+// ws layout (floats): KD_SLOTS x [loss sum, sim sum] (blocks spread their atomics over the slots: a thousand blocks on
+// one address serialise for longer than the kernel reads its 50 MB), then ms[B*D], mt[B*D], md[B*D]
+constexpr int KD_SLOTS = 32;
+static inline long long ws_acc_floats() { return 2 * KD_SLOTS; }
 
 // mean over the HW tokens of each image: out[b, c] = 1/HW sum_p x[b, skip + p, c]
 // (32 x 16 threads, eight rows in flight per thread: one block per (image, 128 columns) has to cover the latency itself)
@@ -107,8 +109,9 @@ kd_loss_fwd_kernel(const float* __restrict__ S, const float* __restrict__ T, int
   if (threadIdx.x == 0) {
     float a = 0.f, c = 0.f;
     for (int k = 0; k < wpb; ++k) { a += sl[k]; c += sm[k]; }
-    atomicAdd(acc, a);
-    atomicAdd(acc + 1, c);
+    float* slot = acc + 2 * (blockIdx.x % KD_SLOTS);
+    atomicAdd(slot, a);
+    atomicAdd(slot + 1, c);
   }
 }
 
@@ -116,8 +119,10 @@ __global__ void kd_loss_finalize_kernel(const float* __restrict__ acc, float* __
                                         float sim_scale) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
-  out[0] = acc[0] * loss_scale;
-  out[1] = acc[1] * sim_scale;
+  float l = 0.f, c = 0.f;
+  for (int k = 0; k < KD_SLOTS; ++k) { l += acc[2 * k]; c += acc[2 * k + 1]; }
+  out[0] = l * loss_scale;
+  out[1] = c * sim_scale;
 }
 
 __global__ void __launch_bounds__(256)
@@ -254,7 +259,7 @@ extern "C" int b200_kd_loss_fwd(const float* S, const float* T, int B, int HW, i
   B200_CHECK_ARG(D % 4 == 0, "D must be a multiple of 4");
   B200_CHECK_ARG(Nt >= HW + t_skip, "teacher token count too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  B200_TRY(zero_f32(ws, 4, st));
+  B200_TRY(zero_f32(ws, ws_acc_floats(), st));
   float* ms = ws + ws_acc_floats();
   float* mt = ms + (long long)B * D;
   if (freq) {
