@@ -196,7 +196,8 @@ attn_fwd_kernel(const AttnParams p) {
   float o[HDP / 8][4];
 #pragma unroll
   for (int i = 0; i < HDP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // m: running max of the raw (sign-normalised) logits
+  const float sc = fabsf(p.scale_log2);
 
   for (int it = 0; it < n_tiles; ++it) {
     const int buf = it & 1;
@@ -209,24 +210,37 @@ attn_fwd_kernel(const AttnParams p) {
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (it == 0) load_a_frags<HDP>(qa, sQ, warp, lane);
+    if (it == 0) {
+      load_a_frags<HDP>(qa, sQ, warp, lane);
+      if (p.scale_log2 < 0.f) {   // s' = -s, scale' = |scale|: same softmax
+#pragma unroll
+        for (int kb = 0; kb < HDP / 16; ++kb)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) qa[kb][e] ^= 0x80008000u;
+      }
+    }
 
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
     mma_a_tT<HDP, HALF, false>(s, qa, sK + buf * TILE, lane);
 
+    // Softmax in the exp2 domain on the RAW logits: running max m (raw), p = ex2(s * sc - m * sc) as one FFMA + MUFU per
+    // element (sc = |scale| * log2 e > 0; a negative scale flips the sign of the Q fragments once, above). The key mask is
+    // applied only on the tile that needs it (warp-uniform). This loop is issue bound for head dims 16-32: per element
+    // FMNMX + FFMA + MUFU + FADD (+ half a pack), down from FMUL + ISETP + FSEL + FMNMX + FADD + MUFU + FADD.
     const int kbase = it * ATT_BK;
+    if (kbase + ATT_BK > p.Nk) {
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (kbase + nb * 8 + 2 * t4 + (e & 1) >= p.Nk) s[nb][e] = -INFINITY;
+      }
+    }
     float mx0 = m0, mx1 = m1;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = kbase + nb * 8 + 2 * t4 + (e & 1);
-        float v = s[nb][e] * p.scale_log2;
-        if (col >= p.Nk) v = -INFINITY;
-        s[nb][e] = v;
-      }
       mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
     }
@@ -234,15 +248,16 @@ attn_fwd_kernel(const AttnParams p) {
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float a0 = ex2_fast(m0 - mx0), a1 = ex2_fast(m1 - mx1);
+    const float a0 = ex2_fast((m0 - mx0) * sc), a1 = ex2_fast((m1 - mx1) * sc);
     m0 = mx0; m1 = mx1;
+    const float ms0 = mx0 * sc, ms1 = mx1 * sc;
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-      s[nb][0] = ex2_fast(s[nb][0] - mx0);
-      s[nb][1] = ex2_fast(s[nb][1] - mx0);
-      s[nb][2] = ex2_fast(s[nb][2] - mx1);
-      s[nb][3] = ex2_fast(s[nb][3] - mx1);
+      s[nb][0] = ex2_fast(fmaf(s[nb][0], sc, -ms0));
+      s[nb][1] = ex2_fast(fmaf(s[nb][1], sc, -ms0));
+      s[nb][2] = ex2_fast(fmaf(s[nb][2], sc, -ms1));
+      s[nb][3] = ex2_fast(fmaf(s[nb][3], sc, -ms1));
       rs0 += s[nb][0] + s[nb][1];
       rs1 += s[nb][2] + s[nb][3];
     }
@@ -282,8 +297,8 @@ attn_fwd_kernel(const AttnParams p) {
   if (p.lse != nullptr && t4 == 0) {
     float* lse = p.lse + ((long long)b * p.heads + h) * p.Nq;
     const float ln2 = 0.6931471805599453f;
-    if (r0 < p.Nq) lse[r0] = (m0 + log2f(l0)) * ln2;
-    if (r1 < p.Nq) lse[r1] = (m1 + log2f(l1)) * ln2;
+    if (r0 < p.Nq) lse[r0] = (m0 * sc + log2f(l0)) * ln2;
+    if (r1 < p.Nq) lse[r1] = (m1 * sc + log2f(l1)) * ln2;
   }
 }
 
@@ -809,6 +824,7 @@ static int fill_params(const b200_attn_desc* d, AttnParams& p, bool bwd) {
   B200_CHECK_ARG(d != nullptr, "null descriptor");
   B200_CHECK_ARG(d->q && d->k && d->v && d->o, "null tensor");
   B200_CHECK_ARG(d->B > 0 && d->heads > 0 && d->Nq > 0 && d->Nk > 0, "empty problem");
+  B200_CHECK_ARG(d->scale != 0.f && d->scale == d->scale, "softmax scale must be a non-zero number");
   B200_CHECK_ARG(d->hd % 8 == 0 && d->hd >= 8 && d->hd <= 96, "head_dim must be a multiple of 8 in [8, 96]");
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   B200_CHECK_ARG(al(d->q) && al(d->k) && al(d->v) && al(d->o), "tensors must be 16-byte aligned");
