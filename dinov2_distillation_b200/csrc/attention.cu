@@ -397,15 +397,23 @@ attn_bwd_dq_kernel(const AttnParams p) {
     mma_a_tT<HDP, HALF, false>(s, qa, sK + buf * TILE, lane);
     mma_a_tT<HDP, false, HALF>(dp, doa, sV + buf * TILE, lane);
     const int kbase = it * ATT_BK;
+    // P = 2^(s * scale - lse) as one FFMA + MUFU (ex2.approx, like the fused kernel); the key mask only on the tail tile
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int col = kbase + nb * 8 + 2 * t4 + (e & 1);
         const float l = (e < 2) ? lse0 : lse1;
         const float dlt = (e < 2) ? dl0 : dl1;
-        const float pv = (col < p.Nk) ? exp2f(s[nb][e] * p.scale_log2 - l) : 0.f;
+        const float pv = ex2_fast(fmaf(s[nb][e], p.scale_log2, -l));
         s[nb][e] = pv * (dp[nb][e] - dlt);
+      }
+    }
+    if (kbase + ATT_BK > p.Nk) {   // warp-uniform
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (kbase + nb * 8 + 2 * t4 + (e & 1) >= p.Nk) s[nb][e] = 0.f;
       }
     }
     mma_p_t<HDP, false, HALF>(dq, s, sK + buf * TILE, lane);
@@ -506,7 +514,7 @@ attn_bwd_dkv_kernel(const AttnParams p) {
         const float l = sLse[buf * 64 + qc];
         const float dlt = sDl[buf * 64 + qc];
         const bool ok = (e < 2) ? kok0 : kok1;
-        const float pv = ok ? exp2f(st[nb][e] * p.scale_log2 - l) : 0.f;
+        const float pv = ok ? ex2_fast(fmaf(st[nb][e], p.scale_log2, -l)) : 0.f;
         pt[nb][e] = pv;
         st[nb][e] = pv * (dpt[nb][e] - dlt);
       }
