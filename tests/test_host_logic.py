@@ -203,3 +203,72 @@ def test_plugin_install_rebinds_the_reference_plugin_points():
         import losses
         losses.ScaleKD = ref_scalekd
         dm.ScaleKD = ref_scalekd
+
+
+def test_compute_losses_dict_weights_and_gradients_with_stub_losses():
+    """`_compute_losses` (train/distillation_module.py:180-246) on CPU with stub loss modules: key set and order, the
+    res4 'frequency' term scored with get_spat_loss, the break after res5, query chaining, and the fused combine
+    (`_CombineLosses`): every weighted entry and d(loss)/d(term) equal the reference's scalar arithmetic."""
+    from dinov2_distillation_b200.distill import DistillationStep
+    from dinov2_distillation_b200.teacher import DINOv2ViT
+
+    class StubKD(torch.nn.Module):
+        def __init__(self, base):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.tensor(float(base)))
+            self.calls = []
+
+        def project_feat_spat(self, x, query=None):
+            self.calls.append(("spat", query is not None))
+            return x * self.p
+
+        def project_feat_freq(self, x, query=None):
+            self.calls.append(("freq", query is not None))
+            return x * (self.p + 1.0)
+
+        def get_spat_loss(self, s, t):
+            self.calls.append(("get_spat_loss",))
+            return (s.sum() - t.sum()) ** 2, s.mean()
+
+        def forward(self, s, t, query_s=None, query_f=None):
+            self.calls.append(("forward", query_s is not None, query_f is not None))
+            a, b = (s * self.p).sum() ** 2, (s * self.p).mean() ** 2
+            return {"spatial_loss": a, "frequency_loss": b, "spatial_similarity": s.mean(), "frequency_similarity": s.std(),
+                    "loss": a + b}
+
+    specs = [{"type": "scalekd", "weight": 2.0, "kwargs": _kw(name="scalekd_res4", teacher_dims=384, pos_dims=384, num_heads=16)},
+             {"type": "scalekd", "weight": 0.5, "kwargs": _kw(name="scalekd_res5", teacher_dims=384, pos_dims=384, num_heads=24, self_query=False)},
+             {"type": "scalekd", "weight": 9.0, "kwargs": _kw(name="scalekd_res6", teacher_dims=384, pos_dims=384, num_heads=24)}]
+    step = DistillationStep(None, DINOv2ViT("dinov2_vits14"), specs)
+    step.two_streams = False
+    step.losses = torch.nn.ModuleDict({"scalekd_res4": StubKD(1.5), "scalekd_res5": StubKD(0.7), "scalekd_res6": StubKD(3.0)})
+    step._forward_specific_stage = lambda feat, layer: feat + 1.0
+    f4 = torch.randn(2, 3, requires_grad=True)
+    f5 = torch.randn(2, 3, requires_grad=True)
+    T = torch.randn(2, 3)
+    out = step._compute_losses({"student": {"res4": f4, "res5": f5, "res6": f5}, "teacher": T})
+    assert list(out.keys()) == [
+        "scalekd_res4_total_loss", "scalekd_res4_frequency_loss", "scalekd_res4_spatial_loss",
+        "scalekd_res4_spatial_similarity", "scalekd_res4_frequency_similarity",
+        "scalekd_res5_total_loss", "scalekd_res5_frequency_loss", "scalekd_res5_spatial_loss",
+        "scalekd_res5_spatial_similarity", "scalekd_res5_frequency_similarity", "loss"]      # res6 never runs (break)
+    k4, k5 = step.losses["scalekd_res4"], step.losses["scalekd_res5"]
+    assert k4.calls == [("spat", False), ("freq", False), ("get_spat_loss",), ("get_spat_loss",)]
+    assert k5.calls == [("forward", True, True)] and step.losses["scalekd_res6"].calls == []
+    # the reference's arithmetic, written out
+    s4 = ((f4 * 1.5 + 1.0).sum() - T.sum()) ** 2
+    q4 = ((f4 * 2.5 + 1.0).sum() - T.sum()) ** 2
+    a5, b5 = (f5 * 0.7).sum() ** 2, (f5 * 0.7).mean() ** 2
+    ref = {"scalekd_res4_total_loss": (s4 + q4) * 2.0, "scalekd_res4_frequency_loss": q4 * 2.0, "scalekd_res4_spatial_loss": s4 * 2.0,
+           "scalekd_res5_total_loss": (a5 + b5) * 0.5, "scalekd_res5_frequency_loss": b5 * 0.5, "scalekd_res5_spatial_loss": a5 * 0.5}
+    ref["loss"] = ref["scalekd_res4_total_loss"] + ref["scalekd_res5_total_loss"]
+    for k, v in ref.items():
+        assert torch.allclose(out[k], v.detach(), rtol=1e-5), k
+    g_ref = torch.autograd.grad(ref["loss"], [f4, f5], retain_graph=True)
+    g = torch.autograd.grad(out["loss"], [f4, f5], retain_graph=True)
+    for a, b in zip(g, g_ref):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    # a weighted entry other than the total back-propagates too
+    (g4,) = torch.autograd.grad(out["scalekd_res4_frequency_loss"], [f4])
+    (g4_ref,) = torch.autograd.grad(ref["scalekd_res4_frequency_loss"], [f4])
+    assert torch.allclose(g4, g4_ref, rtol=1e-5, atol=1e-6)
