@@ -151,7 +151,7 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
 
 // Multi-job parameter preparation (elementwise.cu: param_prep_kernel)
 enum { PREP_CAST16 = 0, PREP_SPLIT3_RIGHT = 1, PREP_COPY32 = 2, PREP_TRANSPOSE16 = 3, PREP_TRANSPOSE32 = 4 };
-constexpr int PREP_MAX_JOBS = 12;
+constexpr int PREP_MAX_JOBS = 20;
 struct PrepJob {
   const float* src;
   void* dst;

@@ -292,6 +292,8 @@ static inline long long proj_rows_max(const b200_projector_config* c, int B) {
 struct ProjSave {
   h16 *z, *qsrc, *q, *kv, *o, *g, *h;   // fp16 (forward operands; q/k/v/o also feed the attention backward)
   bf16 *zb, *qsrcb, *ob, *gb, *hb;      // bf16 copies of the wgrad operands, written by the same forward passes
+  bf16 *w2T, *w1T, *wpT, *wkvT, *wqT, *wcT;   // training: transposed bf16 weights for the dgrad GEMMs, made by the
+                                        // forward's parameter-prep launch (the masters do not change before backward)
   bf16* xt;                             // bf16 student tokens (only the conv wgrad reads them)
   float *y, *bn_mean, *bn_rstd, *lse, *f32, *mean1, *rstd1, *u32, *mean2, *rstd2;
 };
@@ -320,6 +322,13 @@ static void carve_proj_save(Arena& a, const b200_projector_config* c, int B, Pro
   s.ob = a.take_n<bf16>(M * D);
   s.gb = a.take_n<bf16>(M * D);
   s.hb = a.take_n<bf16>(M * 4 * D);
+  const long long Dl = D;
+  s.w2T = a.take_n<bf16>(4 * Dl * Dl);
+  s.w1T = a.take_n<bf16>(4 * Dl * Dl);
+  s.wpT = a.take_n<bf16>(Dl * Dl);
+  s.wkvT = a.take_n<bf16>(2 * Dl * Dl);
+  s.wqT = a.take_n<bf16>(Dl * Dl);
+  s.wcT = a.take_n<bf16>(Dl * c->Cs);
 }
 
 struct ProjFwdWs {
@@ -510,6 +519,15 @@ static int projector_fwd_impl(const b200_projector_config* c, const b200_project
     jobs.add(PREP_COPY32, p->k_b, w.bkv, 1, D);
     jobs.add(PREP_COPY32, p->v_b, w.bkv + D, 1, D);
     jobs.add(PREP_TRANSPOSE32, p->pos_embed, w.pos_t, D, HW, 0, D);   // [D, HW] -> [HW, D]
+    if (c->training) {   // the backward's transposed bf16 weights ride along (one launch less per projector and step)
+      jobs.add(PREP_TRANSPOSE16, p->ffn2_w, s.w2T, D, 4 * D, 0, D);        // [D,4D] -> [4D, D]
+      jobs.add(PREP_TRANSPOSE16, p->ffn1_w, s.w1T, 4 * D, D, 0, 4 * D);    // [4D,D] -> [D, 4D]
+      jobs.add(PREP_TRANSPOSE16, p->p_w, s.wpT, D, D, 0, D);
+      jobs.add(PREP_TRANSPOSE16, p->k_w, s.wkvT, D, D, 0, 2 * D);          // [D, 2D]: [Wk^T | Wv^T]
+      jobs.add(PREP_TRANSPOSE16, p->v_w, s.wkvT + D, D, D, 0, 2 * D);
+      jobs.add(PREP_TRANSPOSE16, p->q_w, s.wqT, D, D, 0, D);
+      jobs.add(PREP_TRANSPOSE16, p->conv_w, s.wcT, D, Cs, 0, D);           // [D,Cs] -> [Cs, D]
+    }
     B200_TRY(launch_param_prep(jobs, st));
   }
 
@@ -593,8 +611,10 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
   carve_proj_bwd_ws(wa, c, B, w);
   B200_CHECK_ARG(wa.ok(), "workspace too small");
 
-  // transposed bf16 weights for the dgrad GEMMs, one launch
-  {
+  // transposed bf16 weights for the dgrad GEMMs: made by the forward's prep launch when training, else here
+  if (c->training) {
+    w.w2T = s.w2T; w.w1T = s.w1T; w.wpT = s.wpT; w.wkvT = s.wkvT; w.wqT = s.wqT; w.wcT = s.wcT;
+  } else {
     PrepJobs jobs{};
     jobs.add(PREP_TRANSPOSE16, p->ffn2_w, w.w2T, D, 4 * D, 0, D);        // [D,4D] -> [4D, D]
     jobs.add(PREP_TRANSPOSE16, p->ffn1_w, w.w1T, 4 * D, D, 0, 4 * D);    // [4D,D] -> [D, 4D]
