@@ -663,44 +663,49 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
                     const float* __restrict__ sums2, __nv_bfloat16* __restrict__ dy16, int batch_stats, long long M,
-                    int D, float* __restrict__ acc_b, float* __restrict__ acc_w) {
+                    int D, float* __restrict__ acc_b, float* __restrict__ acc_w, int rows_per_block) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
   // optional: the BN affine gradients are the two column sums this pass already reads (d beta = sums2[0:D],
-  // d gamma = sums2[D:2D]): block 0 adds them to the gradient buffers (was two axpy launches)
-  if (acc_b != nullptr && blockIdx.x == 0)
-    for (int c = threadIdx.x; c < D; c += blockDim.x) { acc_b[c] += sums2[c]; acc_w[c] += sums2[D + c]; }
-  const int D4 = D >> 2;
-  const long long n4 = M * D4;
+  // d gamma = sums2[D:2D]): block (0, 0) adds them to the gradient buffers (was two axpy launches)
+  if (acc_b != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
+    for (int c = threadIdx.y * 32 + threadIdx.x; c < D; c += 256) { acc_b[c] += sums2[c]; acc_w[c] += sums2[D + c]; }
+  // thread (x, y): 4 columns, every 8th row of this block's row range -- the per-column constants are loaded once and
+  // there is no per-element index division
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  if (c >= D) return;
   const float invM = 1.0f / (float)M;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / D4;
-    const int c4 = (int)(i - r * D4);
-    const float4 d4 = reinterpret_cast<const float4*>(dz)[i];
-    const float4 y4 = reinterpret_cast<const float4*>(y)[i];
-    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
-    const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c4);
-    const float4 be = __ldg(reinterpret_cast<const float4*>(b) + c4);
-    float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
-    if (batch_stats) {
-      s1 = __ldg(reinterpret_cast<const float4*>(sums2) + c4);
-      s2 = __ldg(reinterpret_cast<const float4*>(sums2 + D) + c4);
-    }
-    const float yh[4] = {(y4.x - mu.x) * rs.x, (y4.y - mu.y) * rs.y, (y4.z - mu.z) * rs.z, (y4.w - mu.w) * rs.w};
-    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-    const float rr[4] = {rs.x, rs.y, rs.z, rs.w};
-    const float a1[4] = {s1.x, s1.y, s1.z, s1.w}, a2[4] = {s2.x, s2.y, s2.z, s2.w};
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+  const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+  const float4 g = *reinterpret_cast<const float4*>(w + c);
+  const float4 be = *reinterpret_cast<const float4*>(b + c);
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+  if (batch_stats) {
+    s1 = *reinterpret_cast<const float4*>(sums2 + c);
+    s2 = *reinterpret_cast<const float4*>(sums2 + D + c);
+  }
+  const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
+  const float mm[4] = {mu.x, mu.y, mu.z, mu.w};
+  const float a1[4] = {s1.x * invM, s1.y * invM, s1.z * invM, s1.w * invM};
+  const float a2[4] = {s2.x * invM, s2.y * invM, s2.z * invM, s2.w * invM};
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+#pragma unroll 4
+  for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+    const float4 d4 = *reinterpret_cast<const float4*>(dz + r * D + c);
+    const float4 y4 = *reinterpret_cast<const float4*>(y + r * D + c);
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, yy[4] = {y4.x, y4.y, y4.z, y4.w};
     float o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float dr = (yh[e] * gg[e] + bb[e] > 0.f) ? dd[e] : 0.f;
-      o[e] = gg[e] * rr[e] * (dr - a1[e] * invM - yh[e] * a2[e] * invM);
+      const float yh = (yy[e] - mm[e]) * rr[e];
+      const float dr = (yh * gg[e] + bb[e] > 0.f) ? dd[e] : 0.f;
+      o[e] = gg[e] * rr[e] * (dr - a1[e] - yh * a2[e]);
     }
     uint2 u;
     u.x = pack_bf16(o[0], o[1]);
     u.y = pack_bf16(o[2], o[3]);
-    reinterpret_cast<uint2*>(dy16)[i] = u;
+    *reinterpret_cast<uint2*>(dy16 + r * D + c) = u;
   }
 }
 
@@ -1360,8 +1365,14 @@ int b200::bn_relu_pos_bwd_apply_acc(const float* dz, const float* y, const float
   B200_CHECK_ARG(dz && y && mean && rstd && w && b && dy_bf16 && M > 0 && D % 4 == 0, "bad args");
   B200_CHECK_ARG(!use_batch_stats || sums2, "batch statistics need sums2");
   B200_CHECK_ARG((acc_bn_b == nullptr) == (acc_bn_w == nullptr) && (acc_bn_b == nullptr || sums2 != nullptr), "bad accumulators");
-  B200_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for((long long)M * D / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-      dz, y, mean, rstd, w, b, sums2, static_cast<__nv_bfloat16*>(dy_bf16), use_batch_stats, (long long)M, D, acc_bn_b, acc_bn_w));
+  const int gx = (int)cdiv(D, 128);
+  int gy = (int)cdiv((long long)sm_count() * 6, gx);
+  int rpb = (int)cdiv(M, gy);
+  if (rpb < 32) rpb = 32;
+  gy = (int)cdiv(M, rpb);
+  B200_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(gx, gy), dim3(32, 8), 0, static_cast<cudaStream_t>(stream),
+      dz, y, mean, rstd, w, b, sums2, static_cast<__nv_bfloat16*>(dy_bf16), use_batch_stats, (long long)M, D, acc_bn_b, acc_bn_w,
+      rpb));
   B200_LAUNCH_OK();
   return 0;
 }
