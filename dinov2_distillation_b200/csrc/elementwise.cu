@@ -757,7 +757,8 @@ __global__ void batch_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 a = make_float4(0, 0, 0, 0);
-    for (int b = 0; b < B; ++b) {
+#pragma unroll 8
+    for (int b = 0; b < B; ++b) {   // (few threads -- n / 4 -- so each keeps eight images' loads in flight)
       const uint2 u = reinterpret_cast<const uint2*>(x + (long long)b * n)[i];
       const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
       a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
@@ -1401,7 +1402,7 @@ extern "C" int b200_swiglu(const void* x12, void* out, int rows, int H, void* st
 
 extern "C" int b200_batch_sum_bf16(const void* x, float* out_f32, void* out_bf16, int B, long long n, void* stream) {
   B200_CHECK_ARG(x && (out_f32 || out_bf16) && B > 0 && n > 0 && n % 4 == 0, "bad args");
-  B200_CUDA_OK(launch_pdl(batch_sum_bf16_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+  B200_CUDA_OK(launch_pdl(batch_sum_bf16_kernel, dim3(grid_for(n / 4, 64, 16)), dim3(64), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), out_f32, static_cast<__nv_bfloat16*>(out_bf16), B, n));
   B200_LAUNCH_OK();
   return 0;
