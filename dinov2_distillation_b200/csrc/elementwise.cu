@@ -183,19 +183,24 @@ __global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16
   }
   __syncthreads();
   __nv_bfloat16* obase = out + ((long long)(b * Hp + ph) * Wp) * Kp;
-  // output column = c*196 + i*14 + j = (c*14 + i)*14 + j: one task = the 14 contiguous pixels of (patch pw, row ci)
-  // -> 14 contiguous bf16 of the output row (28 bytes, 4-byte aligned): no per-element div / mod
-  for (int t = threadIdx.x; t < Wp * 42; t += blockDim.x) {
-    const int pw = t / 42, ci = t - pw * 42;
-    const float* src = srow + ci * WP + pw * 14;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(obase + (long long)pw * Kp + ci * 14);
-#pragma unroll
-    for (int j = 0; j < 7; ++j) dst[j] = pack_bf16(src[2 * j], src[2 * j + 1]);
-  }
-  const int pad2 = (Kp - 588) >> 1;   // zero padding of the contraction dimension (Kp % 8 == 0, 588 % 4 == 0)
-  for (int t = threadIdx.x; t < Wp * pad2; t += blockDim.x) {
-    const int pw = t / pad2, k2 = t - pw * pad2;
-    reinterpret_cast<uint32_t*>(obase + (long long)pw * Kp + 588)[k2] = 0u;
+  // output column = c*196 + i*14 + j = (c*14 + i)*14 + j =: ci*14 + j. One warp writes one patch's row of the output
+  // (Kp bf16, contiguous): lanes take consecutive column pairs -> 128-byte coalesced stores, consecutive shared-memory
+  // reads (14 columns share a ci), and the only division is by the constant 14.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int Kp2 = Kp >> 1;
+  for (int pw = warp; pw < Wp; pw += nwarp) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(obase + (long long)pw * Kp);
+    const float* src = srow + pw * 14;
+    for (int k2 = lane; k2 < Kp2; k2 += 32) {
+      const int col = 2 * k2;
+      uint32_t v = 0u;
+      if (col < 588) {   // 588 is even: a pair never straddles the padding
+        const int ci0 = col / 14, j0 = col - ci0 * 14;
+        const int ci1 = (col + 1) / 14, j1 = col + 1 - ci1 * 14;
+        v = pack_bf16(src[ci0 * WP + j0], src[ci1 * WP + j1]);
+      }
+      dst[k2] = v;
+    }
   }
 }
 
