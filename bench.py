@@ -221,7 +221,7 @@ def build_gpu_step(wl, device):
     from dinov2_distillation_b200.distill import DistillationStep
     from dinov2_distillation_b200.teacher import DINOv2ViT
     torch.manual_seed(3)
-    teacher = DINOv2ViT(wl["teacher"])
+    teacher = DINOv2ViT(wl["teacher"], weights="synthetic")
     step = DistillationStep(None, teacher, loss_specs(wl)).to(device).train()
     g = wl["size"] // 14
     gen = torch.Generator().manual_seed(0)

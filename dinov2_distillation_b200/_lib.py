@@ -56,6 +56,7 @@ class AttnDesc(C.Structure):
         ("qkvo_is_fp16", C.c_int),
         ("dq_colsum", c_fp), ("dk_colsum", c_fp), ("dv_colsum", c_fp),
         ("o_alt", c_vp),
+        ("q_alt", c_vp), ("k_alt", c_vp), ("v_alt", c_vp),
     ]
 
 
@@ -111,6 +112,8 @@ SIGNATURES = {
     "b200_launch_count": (c_ll, []),
     "b200_reset_launch_count": (None, []),
     "b200_profile_enable": (None, [_i]),
+    "b200_set_option": (_i, [C.c_char_p, _i]),
+    "b200_get_option": (_i, [C.c_char_p]),
     "b200_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll)]),
     "b200_gemm_bf16": (_i, [C.POINTER(GemmDesc), c_vp]),
     "b200_cast_f32_bf16": (_i, [c_fp, c_vp, c_ll, c_vp]),
@@ -172,7 +175,7 @@ SIGNATURES = {
                                     c_fp, c_fp, c_fp, _i, c_fp, _i, c_fp, c_vp, c_vp, _sz, c_vp, c_vp]),
 }
 
-ABI_VERSION = 2   # include/b200_distill.h: B200_ABI_VERSION
+ABI_VERSION = 3   # include/b200_distill.h: B200_ABI_VERSION
 
 _lib = None
 

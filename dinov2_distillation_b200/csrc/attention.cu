@@ -888,6 +888,17 @@ static int launch_fwd(const AttnParams& p, cudaStream_t st) {
   return p.half ? launch_fwd_t<HDP, true>(p, st) : launch_fwd_t<HDP, false>(p, st);
 }
 
+// delta = rowsum(dO o O): shared by the tcgen05 and the mma.sync backward
+static int launch_delta(const AttnParams& p, cudaStream_t st) {
+  const long long n = (long long)p.B * p.Nq * p.heads;
+  long long gd = cdiv(n, 256);
+  if (gd > (long long)sm_count() * 16) gd = (long long)sm_count() * 16;
+  if (p.half) B200_CUDA_OK(launch_pdl(attn_delta_kernel<true>, dim3((unsigned)gd), dim3(256), 0, st, p));
+  else B200_CUDA_OK(launch_pdl(attn_delta_kernel<false>, dim3((unsigned)gd), dim3(256), 0, st, p));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 template <int HDP, bool HALF>
 static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
   constexpr size_t smem_dq = size_t(6) * 64 * (HDP + ATT_PAD) * 2;
@@ -898,16 +909,9 @@ static int launch_bwd_t(const AttnParams& p, cudaStream_t st) {
     B200_TRY(set_smem(attn_bwd_dkv_kernel<HDP, HALF>, smem_dkv));
     once = true;
   }
-  const long long n = (long long)p.B * p.Nq * p.heads;
-  long long gd = cdiv(n, 256);
-  if (gd > (long long)sm_count() * 16) gd = (long long)sm_count() * 16;
   const int prof = prof_begin(st);
-  B200_CUDA_OK(launch_pdl(attn_delta_kernel<HALF>, dim3((unsigned)gd), dim3(256), 0, st, p));
-  B200_LAUNCH_OK();
   if constexpr (HDP == 16 || HDP == 32 || HDP == 64) {
-    static int fused_on = -1;
-    if (fused_on < 0) { const char* e = getenv("B200_ATTN_BWD_FUSED"); fused_on = (e && e[0] == '0') ? 0 : 1; }
-    if (fused_on && p.Nk <= ATTF_KEYS) {
+    if (option(OPT_ATTN_BWD_FUSED) && p.Nk <= ATTF_KEYS) {
       constexpr size_t smem_f = size_t(2 * ATTF_KEYS + 4 * 64) * (HDP + ATT_PAD) * 2 + size_t(ATTF_KEYS) * ATTF_DS_PITCH * 2 +
                                 7 * 64 * sizeof(float) + (HALF ? size_t(ATTF_KEYS + 64) * (HDP + ATT_PAD) * 2 : 0);
       static bool once_f = false;
@@ -947,6 +951,7 @@ using namespace b200;
 
 namespace b200 {
 int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st);   // attention_tc.cu (tcgen05, head_dim 64)
+int launch_attention_tc_bwd(const b200_attn_desc* d, cudaStream_t st);   // attention_bwd_tc.cu (tcgen05, Nq / Nk <= 256)
 }
 
 extern "C" int b200_attention_fwd(const b200_attn_desc* d, void* stream) {
@@ -955,8 +960,10 @@ extern "C" int b200_attention_fwd(const b200_attn_desc* d, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d->o_alt == nullptr) {   // (the tcgen05 kernel writes one output format)
     const int r = launch_attention_tc_fwd(d, st);
+    if (r == 0) bump_stat(STAT_ATTN_TC_FWD);
     if (r <= 0) return r;
   }
+  bump_stat(STAT_ATTN_MMA_FWD);
   if (p.hd <= 16) return launch_fwd<16>(p, st);
   if (p.hd <= 32) return launch_fwd<32>(p, st);
   if (p.hd <= 48) return launch_fwd<48>(p, st);
@@ -968,6 +975,13 @@ extern "C" int b200_attention_bwd(const b200_attn_desc* d, void* stream) {
   AttnParams p{};
   B200_TRY(fill_params(d, p, true));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200_TRY(launch_delta(p, st));
+  {
+    const int r = launch_attention_tc_bwd(d, st);
+    if (r == 0) bump_stat(STAT_ATTN_TC_BWD);
+    if (r <= 0) return r;
+  }
+  bump_stat(STAT_ATTN_MMA_BWD);
   if (p.hd <= 16) return launch_bwd<16>(p, st);
   if (p.hd <= 32) return launch_bwd<32>(p, st);
   if (p.hd <= 48) return launch_bwd<48>(p, st);

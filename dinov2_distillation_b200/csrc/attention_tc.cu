@@ -30,6 +30,12 @@ namespace b200 {
 int make_tensor_map_3d(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
                        uint64_t ld2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle);
 
+// per-phase clock stamps of CTA 0 are compiled in only with -DB200_ATTN_PROBES
+#ifdef B200_ATTN_PROBES
+constexpr bool kAttnProbes = true;
+#else
+constexpr bool kAttnProbes = false;
+#endif
 constexpr int ATC_THREADS = 384;
 constexpr int ATC_SM_WARPS = 8;
 constexpr int ATC_NKP_MAX = 272;                 // keys, padded to a multiple of 16
@@ -89,7 +95,7 @@ __device__ __forceinline__ void atc_tma_store_3d(const CUtensorMap* m, uint32_t 
 }
 #define ATC_STAMP(slot)                                                                        \
   do {                                                                                          \
-    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item < 8) p.dbg[item * 16 + (slot)] = clock64(); \
+    if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item < 8) p.dbg[item * 16 + (slot)] = clock64(); \
   } while (0)
 
 __device__ __forceinline__ void atc_ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -213,10 +219,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t v_addr = smem_u32(smem + ATC_OFF_V + kb * ATC_KV_BYTES);
             const bool last_blk = j == p.nblk - 1;
             const int nkp = last_blk ? p.nkp_last : 256;
-            if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 8] = clock64();
+            if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 8] = clock64();
             if (item > 0) mbar_wait(s_free, (item - 1) & 1);   // the previous block's S row is in registers
             tc_fence_after();
-            if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 9] = clock64();
+            if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 9] = clock64();
             // S = Q K_j^T
             const uint32_t id1 = last_blk ? p.idesc_qk1 : p.idesc_qk_full;
 #pragma unroll
@@ -243,14 +249,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
                 atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, ks > 0 ? 1u : 0u);
               }
-              if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 10] = clock64();
+              if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 10] = clock64();
               mbar_wait(&p_full[1], item & 1);
               tc_fence_after();
               for (int ks = split; ks < ksteps; ++ks) {
                 const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);
                 atc_mma_ts(tmem_base + ATC_TMEM_O, tmem_base + ATC_TMEM_P + ks * 8, db, p.idesc_pv, 1u);
               }
-              if (p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 11] = clock64();
+              if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && item < 8) p.dbg[item * 16 + 11] = clock64();
             }
             tc_commit(o_full);
             if (p.nblk > 1 || qt == p.n_qt - 1) tc_commit(&kv_empty[kb]);
@@ -275,7 +281,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint8_t* sK = smem + ATC_OFF_K + kb * ATC_KV_BYTES;
         const uint8_t* sV = smem + ATC_OFF_V + kb * ATC_KV_BYTES;
         mbar_wait(&kv_full[kb], (uc >> 1) & 1);
-        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && uc < 4) p.dbg[uc * 16 + 12] = clock64();
+        if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && uc < 4) p.dbg[uc * 16 + 12] = clock64();
         // A fragments of the tail queries: fragment rows 0..7 = tail rows (zero beyond tail_n), rows 8..15 unused
         uint32_t qa[4][2];
         {
@@ -349,7 +355,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             *reinterpret_cast<uint32_t*>(orow + nb * 8 + 2 * t) = pack_bf16(oc[nb][0] * inv, oc[nb][1] * inv);
         }
         __syncwarp();
-        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && uc < 4) p.dbg[uc * 16 + 13] = clock64();
+        if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && uc < 4) p.dbg[uc * 16 + 13] = clock64();
         if (lane == 0) mbar_arrive(&kv_empty[kb]);
       }
     }
@@ -434,7 +440,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           m_run = m_new;
           const float ms = m_new * p.scale_log2;
           if (ew == 0) ATC_STAMP(3);
-          if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2] = clock64();
+          if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2] = clock64();
           // P = exp2(scale * S - max) as bf16 pairs (tcgen05.st), published in two groups; partial row sum in fp32
           sum *= alpha;
 #pragma unroll
@@ -476,7 +482,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             __syncwarp();
             if (lane == 0) { mbar_arrive(&p_full[0]); mbar_arrive(&p_full[1]); }
           }
-          if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2 + 1] = clock64();
+          if (kAttnProbes && p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && item == 4) p.dbg[128 + ew * 2 + 1] = clock64();
           if (ew == 0) ATC_STAMP(4);
           // this block's contribution to the warp's 32 output columns: o = alpha * o + P V_j
           mbar_wait(o_full, item & 1);
@@ -535,16 +541,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 // Returns 1 when the problem is outside this kernel's envelope (the caller falls back to the mma.sync kernel).
 int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("B200_ATTN_TC");
-    enabled = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!enabled) return 1;
+  if (!option(OPT_ATTN_TC_FWD)) return 1;
   if (d->hd != 64 || d->qkvo_is_fp16 || d->Nk < 33 || d->q_bs == 0) return 1;
-  static int long_on = -1;
-  if (long_on < 0) { const char* e = getenv("B200_ATTN_TC_LONG"); long_on = (e && e[0] == '0') ? 0 : 1; }
-  if (d->Nk > ATC_NKP_MAX && !long_on) return 1;
+  if (d->Nk > ATC_NKP_MAX && !option(OPT_ATTN_TC_FWD_LONG)) return 1;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(d->q) || !al16(d->k) || !al16(d->v) || !al16(d->o)) return 1;
   if (d->q_ts % 8 || d->k_ts % 8 || d->v_ts % 8 || d->o_ts % 8 || d->q_bs % 8 || d->k_bs % 8 || d->v_bs % 8 || d->o_bs % 8)
@@ -591,8 +590,7 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   const int grid = units < sm_count() ? units : sm_count();
   const int prof = prof_begin(st);
   static long long* dbg_buf = nullptr;
-  static int dbg_on = -1;
-  if (dbg_on < 0) { const char* e = getenv("B200_ATTN_DBG"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
+  const bool dbg_on = kAttnProbes;
   if (dbg_on && dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 9 * 16 * sizeof(long long)); }
   if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 9 * 16 * sizeof(long long), st);
   p.dbg = dbg_on ? dbg_buf : nullptr;

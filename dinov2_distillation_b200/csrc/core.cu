@@ -3,6 +3,7 @@
 #include "../../include/b200_distill.h"
 
 #include <stdlib.h>
+#include <string.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -27,14 +28,39 @@ int sm_count() {
   return sms;
 }
 
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("B200_PDL");
-    on = (e && e[0] == '0') ? 0 : 1;
+// ---- dispatch options: a table of ints the launchers read (no getenv on any launch path). Defaults = the production
+// path; the environment is consulted ONCE, when the library is loaded, so that A/B runs of a tool need no rebuild, and
+// tests flip entries through b200_set_option().
+struct OptDef { const char* name; const char* env; int value; };
+static OptDef g_opts[OPT_COUNT] = {
+    {"pdl", "B200_PDL", 1},                          // programmatic dependent launch attribute on every launch
+    {"attn_tc_fwd", "B200_ATTN_TC", 1},              // tcgen05 attention forward (head_dim 64)
+    {"attn_tc_fwd_long", "B200_ATTN_TC_LONG", 1},    // ... also for key ranges > 272 (online softmax)
+    {"attn_tc_bwd", "B200_ATTN_TC_BWD", 1},          // tcgen05 attention backward (Nq, Nk <= 256)
+    {"attn_bwd_fused", "B200_ATTN_BWD_FUSED", 1},    // mma.sync fallback: one-kernel backward when Nk <= 256
+    {"gemm_v2", "B200_GEMM_V2", 1},                  // bulk-store GEMM kernel (0: first-generation kernel everywhere)
+    {"gemm_bn", "B200_GEMM_BN", 0},                  // force the tile width (128 / 192 / 256; 0 = cost model)
+    {"gemm_2cta", "B200_GEMM_2CTA", -1},             // cta_group::2: -1 by K, 0 never, 1 whenever possible
+    {"gemm_inplace_red", "B200_GEMM_INPLACE_RED", 1},
+    {"gemm_ew", "B200_GEMM_EW", 16},                 // epilogue warps where the epilogue stages no operand tile
+    {"gemm_dbg", "B200_GEMM_DBG", 0},                // probe mask (only in -DB200_GEMM_PROBES builds)
+    {"attn_probe_skip", "B200_ATTN_PROBE_SKIP", 0},  // work-skipping mask (only in -DB200_ATTN_PROBES builds)
+    {"stat_attn_tc_bwd", "", 0},                     // counters (read with b200_get_option, reset with b200_set_option):
+    {"stat_attn_mma_bwd", "", 0},                    //   attention backward launches per path
+    {"stat_attn_tc_fwd", "", 0},
+    {"stat_attn_mma_fwd", "", 0},
+};
+static const bool g_opts_init = [] {
+  for (auto& o : g_opts) {
+    const char* e = o.env[0] ? getenv(o.env) : nullptr;
+    if (e && ((e[0] >= '0' && e[0] <= '9') || e[0] == '-')) o.value = atoi(e);
   }
-  return on != 0;
-}
+  return true;
+}();
+int option(int id) { return g_opts[id].value; }
+void bump_stat(int id) { ++g_opts[id].value; }
+
+bool pdl_enabled() { return g_opts[OPT_PDL].value != 0; }
 
 // ---- optional per-launch timing of the dense kernels (bench.py's roofline leg): CUDA events on the launch stream
 struct ProfRec { cudaEvent_t a, b; double flops; int cat; };
@@ -87,6 +113,20 @@ extern "C" int b200_profile_read(int n_cat, double* ms, double* flops, long long
   }
   g_recs.clear();
   return 0;
+}
+
+extern "C" int b200_set_option(const char* name, int value) {
+  using namespace b200;
+  for (auto& o : g_opts)
+    if (name && strcmp(name, o.name) == 0) { o.value = value; return 0; }
+  set_error(std::string("b200_set_option: unknown option '") + (name ? name : "(null)") + "'");
+  return -1;
+}
+extern "C" int b200_get_option(const char* name) {
+  using namespace b200;
+  for (auto& o : g_opts)
+    if (name && strcmp(name, o.name) == 0) return o.value;
+  return -1;
 }
 
 extern "C" const char* b200_last_error(void) { return b200::g_last_error.c_str(); }

@@ -816,8 +816,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, const _
 template <int NV>
 static int launch_ln_fwd(const float* x, const float* w, const float* b, float eps, float* y32, void* y16, void* y16_alt,
                          float* mean, float* rstd, int rows, int D, int in_period, int in_pad, int fp16, cudaStream_t st) {
-  static const int bps = [] { const char* e = getenv("B200_LN_BPS"); return e ? atoi(e) : 12; }();    // blocks per SM cap (12: best of a 4..32 scan at the teacher shape)
-  static const int wpb = [] { const char* e = getenv("B200_LN_WPB"); return e ? atoi(e) : 8; }();     // warps per block
+  constexpr int bps = 12;    // blocks per SM cap (12: best of a 4..32 scan at the teacher shape)
+  constexpr int wpb = 8;     // warps per block
   const int grid = grid_for(rows, wpb, bps);
   B200_CUDA_OK(launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(32 * wpb), 0, st, x, w, b, eps, y32,
                           static_cast<__nv_bfloat16*>(y16), static_cast<__nv_bfloat16*>(y16_alt), mean, rstd, rows, D,
@@ -837,8 +837,8 @@ static int launch_ln_bwd(const float* dy, const float* x, const float* w, const 
     static bool set = false;
     if (!set) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
   }
-  static const int rpb = [] { const char* e = getenv("B200_LNB_RPB"); return e ? atoi(e) : 8; }();    // rows per block (plain form)
-  static const int bps = [] { const char* e = getenv("B200_LNB_BPS"); return e ? atoi(e) : 8; }();    // blocks per SM cap
+  constexpr int rpb = 8;    // rows per block (plain form)
+  constexpr int bps = 8;    // blocks per SM cap
   const int grid = wg ? grid_for(rows, 32, 2) : grid_for(rows, rpb, bps);
   B200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(256), smem, st, dy, x, w, mean, rstd, dres, dx,
                           static_cast<__nv_bfloat16*>(dx16), dw, db, dx_colsum, rows, D));

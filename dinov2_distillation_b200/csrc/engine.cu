@@ -292,6 +292,7 @@ static inline long long proj_rows_max(const b200_projector_config* c, int B) {
 struct ProjSave {
   h16 *z, *qsrc, *q, *kv, *o, *g, *h;   // fp16 (forward operands; q/k/v/o also feed the attention backward)
   bf16 *zb, *qsrcb, *ob, *gb, *hb;      // bf16 copies of the wgrad operands, written by the same forward passes
+  bf16 *qb, *kvb;                       // bf16 copies of q / [k|v]: gradient-product operands of the tcgen05 attention backward
   bf16 *w2T, *w1T, *wpT, *wkvT, *wqT, *wcT;   // training: transposed bf16 weights for the dgrad GEMMs, made by the
                                         // forward's parameter-prep launch (the masters do not change before backward)
   bf16* xt;                             // bf16 student tokens (only the conv wgrad reads them)
@@ -329,6 +330,8 @@ static void carve_proj_save(Arena& a, const b200_projector_config* c, int B, Pro
   s.wkvT = a.take_n<bf16>(2 * Dl * Dl);
   s.wqT = a.take_n<bf16>(Dl * Dl);
   s.wcT = a.take_n<bf16>(Dl * c->Cs);
+  s.qb = a.take_n<bf16>(M * D);
+  s.kvb = a.take_n<bf16>(M * 2 * D);
 }
 
 struct ProjFwdWs {
@@ -337,6 +340,7 @@ struct ProjFwdWs {
   float *bkv, *sums, *pos_t, *z32, *g32;
   float* yraw;                          // conv output at the raw resolution [M_in, D] (fused resize only)
   h16 *qtmp, *kvtmp;                    // raster-order q / [k|v] before the move to window-major rows (windows only)
+  bf16 *qtmpb, *kvtmpb;                 // ... and their bf16 copies
 };
 static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, ProjFwdWs& w) {
   const long long M = (long long)B * c->HW;
@@ -347,6 +351,8 @@ static void carve_proj_fwd_ws(Arena& a, const b200_projector_config* c, int B, P
   w.yraw = c->raw_h > 0 ? a.take_n<float>(M_in * D) : nullptr;
   w.qtmp = proj_windows(c) > 1 ? a.take_n<h16>(M * D) : nullptr;
   w.kvtmp = proj_windows(c) > 1 ? a.take_n<h16>(M * 2 * D) : nullptr;
+  w.qtmpb = proj_windows(c) > 1 ? a.take_n<bf16>(M * D) : nullptr;
+  w.kvtmpb = proj_windows(c) > 1 ? a.take_n<bf16>(M * 2 * D) : nullptr;
   w.wq = a.take_n<h16>(D * D);
   w.wkv = a.take_n<h16>(2 * D * D);
   w.wp = a.take_n<h16>(D * D);
@@ -557,11 +563,22 @@ static int projector_fwd_impl(const b200_projector_config* c, const b200_project
   const int Mq = ext ? Mi : HW;
   B200_TRY(cast_f32_f16_dual(ext ? query : p->query_w, s.qsrc, s.qsrcb, (long long)Mq * D, stream));
   const int n_win = proj_windows(c);
-  B200_TRY(Gemm(s.qsrc, D, w.wq, D, Mq, D, D).fp16_operands().bias(p->q_b).out16(n_win > 1 ? w.qtmp : s.q, D).out16_fp16().run(stream));
-  B200_TRY(Gemm(s.z, D, w.wkv, D, Mi, 2 * D, D).fp16_operands().bias(w.bkv).out16(n_win > 1 ? w.kvtmp : s.kv, 2 * D).out16_fp16().run(stream));
+  // (q and [k|v] are also stored as bf16 -- the gradient products of the attention backward read those)
+  {
+    Gemm gq(s.qsrc, D, w.wq, D, Mq, D, D);
+    gq.fp16_operands().bias(p->q_b).out16(n_win > 1 ? w.qtmp : s.q, D).out16_fp16();
+    gq.out16_alt(n_win > 1 ? w.qtmpb : s.qb, D);
+    B200_TRY(gq.run(stream));
+    Gemm gkv(s.z, D, w.wkv, D, Mi, 2 * D, D);
+    gkv.fp16_operands().bias(w.bkv).out16(n_win > 1 ? w.kvtmp : s.kv, 2 * D).out16_fp16();
+    gkv.out16_alt(n_win > 1 ? w.kvtmpb : s.kvb, 2 * D);
+    B200_TRY(gkv.run(stream));
+  }
   if (n_win > 1) {   // separate_tokens (losses/scalekd.py:305-308): each window's tokens become consecutive rows
     B200_TRY(b200_window_rows16(w.qtmp, s.q, Mq, c->grid_h, c->grid_w, c->win_h, c->win_w, D, D, 0, stream));
     B200_TRY(b200_window_rows16(w.kvtmp, s.kv, M, c->grid_h, c->grid_w, c->win_h, c->win_w, 2 * D, 2 * D, 0, stream));
+    B200_TRY(b200_window_rows16(w.qtmpb, s.qb, Mq, c->grid_h, c->grid_w, c->win_h, c->win_w, D, D, 0, stream));
+    B200_TRY(b200_window_rows16(w.kvtmpb, s.kvb, M, c->grid_h, c->grid_w, c->win_h, c->win_w, 2 * D, 2 * D, 0, stream));
   }
   for (int win = 0; win < n_win; ++win) {   // (the output stays window-major, as in the reference: scalekd.py:313-314)
     b200_attn_desc ad;
@@ -657,6 +674,7 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
     ad.dk = w.dkv16 + r0 * 2 * D; ad.dv = w.dkv16 + r0 * 2 * D + D;
     ad.dk_bs = ad.dv_bs = (long long)HW * 2 * D; ad.dk_ts = ad.dv_ts = 2 * D;
     ad.dq_colsum = g->q_b; ad.dk_colsum = g->k_b; ad.dv_colsum = g->v_b;
+    ad.q_alt = s.qb + r0 * D; ad.k_alt = s.kvb + r0 * 2 * D; ad.v_alt = s.kvb + r0 * 2 * D + D;
     B200_TRY(b200_attention_bwd(&ad, stream));
   }
   const bf16* dq16 = w.dq16;

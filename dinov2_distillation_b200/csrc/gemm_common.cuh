@@ -181,15 +181,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, bool row_ok,
 
 int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
                        uint32_t b1);
-// CTA-pair (cta_group::2) kernel for K-major operands; returns 1 when the shape is not handled (caller falls through
-// to the 1-CTA kernel), 0 on success, negative on error.
-int launch_gemm_2cta(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st);
-int gemm_env_int(const char* name, int dflt);
+// Kernel-internal measurement probes (mainloop-only / epilogue-only floors, wait-cycle counters: DESIGN.md section 4) are
+// compiled in only with -DB200_GEMM_PROBES; the production build carries none of their branches.
+#ifdef B200_GEMM_PROBES
+constexpr bool kGemmProbes = true;
+#else
+constexpr bool kGemmProbes = false;
+#endif
 int make_tensor_map_ex(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
                        uint32_t b1, int swizzle);
 int make_tensor_map_3d(CUtensorMap* out, const void* ptr, int esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
                        uint64_t ld2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle);
-// second-generation kernel (gemm_v2.cu); same return convention as launch_gemm_2cta
+// second-generation kernel (gemm_v2.cu): returns 1 when the shape is not handled (the caller falls through to the
+// first-generation kernel), 0 on success, negative on error
 int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st);
 
 }  // namespace b200

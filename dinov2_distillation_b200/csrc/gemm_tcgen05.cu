@@ -157,7 +157,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[EPI_W];
 #pragma unroll
         for (int j = 0; j < EPI_W; ++j) v[j] = __uint_as_float(raw[j]);
-        if (p.dbg & 1) {
+        if (kGemmProbes && (p.dbg & 1)) {
           if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1];
           continue;
         }
@@ -305,6 +305,66 @@ int make_tensor_map_3d(CUtensorMap* out, const void* ptr, int esize, uint64_t d0
   return 0;
 }
 
+// Rank-4 tensor map over 16-bit elements (attention backward: head_dim x heads x tokens x batch, so that a box wider than
+// head_dim is zero-filled past the head instead of reading into the next one). ld[i]: element pitch of dim i+1.
+// Returns -4 with the error text set when the driver rejects the encoding.
+int make_tensor_map_4d(CUtensorMap* out, const void* ptr, const uint64_t (&dims)[4], const uint64_t (&ld)[3],
+                       const uint32_t (&box)[4], int swizzle) {
+  struct Key4 {
+    const void* ptr; uint64_t d[4], l[3]; uint32_t b[4], sw;
+    bool operator==(const Key4& o) const {
+      if (ptr != o.ptr || sw != o.sw) return false;
+      for (int i = 0; i < 4; ++i) if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
+      for (int i = 0; i < 3; ++i) if (l[i] != o.l[i]) return false;
+      return true;
+    }
+  };
+  struct Key4Hash {
+    size_t operator()(const Key4& k) const {
+      size_t h = reinterpret_cast<size_t>(k.ptr) ^ k.sw;
+      for (int i = 0; i < 4; ++i) h ^= (k.d[i] * 0x9E3779B97F4A7C15ull + k.b[i]) + (h << 6) + (h >> 2);
+      for (int i = 0; i < 3; ++i) h ^= k.l[i] * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+      return h;
+    }
+  };
+  static std::mutex mu;
+  static std::unordered_map<Key4, CUtensorMap, Key4Hash> cache;
+  Key4 key{};
+  key.ptr = ptr; key.sw = (uint32_t)swizzle;
+  for (int i = 0; i < 4; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+  for (int i = 0; i < 3; ++i) key.l[i] = ld[i];
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -4; }
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstride[3] = {ld[0] * 2, ld[1] * 2, ld[2] * 2};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[384];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled(4d) failed (%d) ptr=%p dims=(%llu,%llu,%llu,%llu) ld=(%llu,%llu,%llu) box=(%u,%u,%u,%u) sw=%d",
+             (int)r, ptr, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+             (unsigned long long)dims[3], (unsigned long long)ld[0], (unsigned long long)ld[1], (unsigned long long)ld[2],
+             box[0], box[1], box[2], box[3], swizzle);
+    set_error(buf);
+    return -4;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
 // operand maps: 16-bit elements, 128-byte swizzle
 int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
                        uint32_t b1) {
@@ -337,13 +397,8 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
   return launch_gemm<BN, false, true>(ta, tb, p, st);
 }
 
-int gemm_env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && e[0]) ? atoi(e) : dflt;
-}
-
 static int pick_bn(int N, int m_tiles) {
-  static const int forced = gemm_env_int("B200_GEMM_BN", 0);
+  const int forced = option(OPT_GEMM_BN);
   if (forced == 128 || forced == 192 || forced == 256) return forced;
   // fewest wasted columns first; among equals prefer the widest tile (less smem traffic per MMA).
   const int cands[3] = {256, 192, 128};
@@ -409,8 +464,7 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   if (p.out_bf16_pre) vec = vec && al16(p.out_bf16_pre) && p.ldo16_pre % 8 == 0;
   p.vec_ok = vec ? 1 : 0;
   p.algo_scale = d->algo_flops_scale > 0.f ? d->algo_flops_scale : 1.0f;
-  static const int dbg = gemm_env_int("B200_GEMM_DBG", 0);
-  p.dbg = dbg;
+  p.dbg = kGemmProbes ? option(OPT_GEMM_DBG) : 0;
   p.dbg_buf = nullptr;
   p.pre_alt = 0;
   p.colsum = nullptr;
@@ -430,10 +484,6 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   B200_CHECK_ARG(d->out_batch_period <= 0, "out_batch_period is only implemented by the bulk-store kernel (see launch_gemm_v2)");
   B200_CHECK_ARG(d->out16_colsum == nullptr, "out16_colsum is only implemented by the bulk-store kernel (16-bit output, N % 32 == 0, no split-K)");
   B200_CHECK_ARG(!(d->out16_pre_alt && d->out_bf16_pre), "out16_pre_alt is only implemented by the bulk-store kernel (N % 32 == 0, no aux, 16-byte aligned outputs)");
-  if (!d->a_mn_major && !d->b_mn_major && split == 1) {
-    const int r2 = launch_gemm_2cta(d, p, st);
-    if (r2 <= 0) return r2;
-  }
   CUtensorMap ta, tb;
   if (!d->a_mn_major) {
     B200_TRY(make_tensor_map_2d(&ta, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM));

@@ -237,7 +237,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[PREFETCH ? (i & 1) : 0][j]);
     if (!PREFETCH && next_ok) tmem_ld_32x32(taddr + (u + NG) * 32, raw[0]);   // values copied out: refill
-    if (p.dbg & 1) {   // B200_GEMM_DBG=1: mainloop-only floor (drain TMEM, no epilogue math, no stores)
+    if (kGemmProbes && (p.dbg & 1)) {   // B200_GEMM_DBG=1: mainloop-only floor (drain TMEM, no epilogue math, no stores)
       if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1];
       if (use_x) { mbar_wait(xbar, xphase); xphase ^= 1; __syncwarp();
         if (next_ok && lane == 0) { mbar_expect_tx(xbar, UNIT_BYTES); v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, xrow); } }
@@ -330,7 +330,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
         }
       }
       const uint32_t bo = buf_o + row_off;
-      if (p.dbg & 16) {
+      if (kGemmProbes && (p.dbg & 16)) {
       } else if (p.out16_fp16) {
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
@@ -362,9 +362,9 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
         }
         atomicAdd(p.colsum + c0 + lane, cs);
       }
-      if (!(p.dbg & 8)) fence_proxy_async();
+      if (!(kGemmProbes && (p.dbg & 8))) fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && !(p.dbg & 2)) {
+      if (lane == 0 && !(kGemmProbes && (p.dbg & 2))) {
         v2_tma_store_2d(tmO, buf_o, c0, row0);
         if (has_pre)
           v2_tma_store_2d(tmX, stage_smem + 2048u, c0, row0);
@@ -409,7 +409,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
       if (lane == 0) v2_bulk_wait_read<0>();
       __syncwarp();
       const uint32_t bo = stage_smem + row_off;
-      if (!(p.dbg & 16)) {
+      if (!(kGemmProbes && (p.dbg & 16))) {
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
           const int j = c * 4;
@@ -417,9 +417,9 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
                     __float_as_uint(v[j + 3]));
         }
       } else if (v[3] == 123.456f) p.out_f32[1] = v[5];
-      if (!(p.dbg & 8)) fence_proxy_async();
+      if (!(kGemmProbes && (p.dbg & 8))) fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && !(p.dbg & 2)) {
+      if (lane == 0 && !(kGemmProbes && (p.dbg & 2))) {
         if (p.out_row_period > 0) {   // rows batched with a gap (cls rows of the token buffer): (column, row in batch, batch)
           const int bi = row0 / p.out_row_period;
           v2_tma_store_3d(tmO, stage_smem, c0, row0 - bi * p.out_row_period, bi);
@@ -509,9 +509,9 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m0 = (r / p.n_tiles) * TILE_M + (int)rank * 128;
         const int n0 = (r % p.n_tiles) * BN + (int)rank * Cfg::B_ROWS * (PAIR ? 1 : 0);
         const int kb0 = ks * p.kb_per_split;
-        const int kb1 = (p.dbg & 4) ? kb0 : min(p.num_kb, kb0 + p.kb_per_split);   // B200_GEMM_DBG=4: epilogue-only floor
+        const int kb1 = (kGemmProbes && (p.dbg & 4)) ? kb0 : min(p.num_kb, kb0 + p.kb_per_split);   // B200_GEMM_DBG=4: epilogue-only floor
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (p.dbg_buf) { const long long c = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - c; }
+          if (kGemmProbes && p.dbg_buf) { const long long c = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - c; }
           else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + A_TILE_BYTES;
@@ -534,7 +534,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.dbg_buf && blockIdx.x == 0) { p.dbg_buf[0] = clock64() - t_begin; p.dbg_buf[1] = w_empty; }
+      if (kGemmProbes && p.dbg_buf && blockIdx.x == 0) { p.dbg_buf[0] = clock64() - t_begin; p.dbg_buf[1] = w_empty; }
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
@@ -548,14 +548,14 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = worker; t < p.total_tiles; t += workers) {
         const int ks = t / tiles_mn;
         const int kb0 = ks * p.kb_per_split;
-        const int kb1 = (p.dbg & 4) ? kb0 : min(p.num_kb, kb0 + p.kb_per_split);
+        const int kb1 = (kGemmProbes && (p.dbg & 4)) ? kb0 : min(p.num_kb, kb0 + p.kb_per_split);
         ++n_t;
-        if (p.dbg_buf) { const long long c = clock64(); mbar_wait(&tempty_bar[as], aphase ^ 1); w_tempty += clock64() - c; }
+        if (kGemmProbes && p.dbg_buf) { const long long c = clock64(); mbar_wait(&tempty_bar[as], aphase ^ 1); w_tempty += clock64() - c; }
         else mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::TMEM_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (p.dbg_buf) { const long long c = clock64(); mbar_wait(&full_bar[stage], phase); w_full += clock64() - c; }
+          if (kGemmProbes && p.dbg_buf) { const long long c = clock64(); mbar_wait(&full_bar[stage], phase); w_full += clock64() - c; }
           else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -578,7 +578,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else tc_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      if (p.dbg_buf && blockIdx.x == 0) {
+      if (kGemmProbes && p.dbg_buf && blockIdx.x == 0) {
         p.dbg_buf[2] = clock64() - t_begin; p.dbg_buf[3] = w_full; p.dbg_buf[4] = w_tempty; p.dbg_buf[5] = n_t;
       }
     }
@@ -618,7 +618,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
-      if (p.dbg_buf) { const long long c = clock64(); mbar_wait(&tfull_bar[as], aphase); w_tfull += clock64() - c; }
+      if (kGemmProbes && p.dbg_buf) { const long long c = clock64(); mbar_wait(&tfull_bar[as], aphase); w_tfull += clock64() - c; }
       else mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
@@ -630,7 +630,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // bulk stores read shared memory asynchronously: the CTA must not exit before they are done
     if (lane == 0) v2_bulk_wait_all();
     __syncwarp();
-    if (p.dbg_buf && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == EW - 1)) {
+    if (kGemmProbes && p.dbg_buf && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == EW - 1)) {
       const int o = ew == 0 ? 6 : 9;
       p.dbg_buf[o] = t_loop; p.dbg_buf[o + 1] = w_tfull; p.dbg_buf[o + 2] = clock64() - t_begin;
     }
@@ -673,7 +673,7 @@ static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
   const int prof = prof_begin(st);
-  if (p.dbg & 32) {   // wait-cycle counters of CTA 0 (eager launches only: synchronises and prints)
+  if (kGemmProbes && (p.dbg & 32)) {   // wait-cycle counters of CTA 0 (eager launches only: synchronises and prints)
     static long long* buf = nullptr;
     if (!buf) cudaMalloc(&buf, 16 * sizeof(long long));
     cudaMemsetAsync(buf, 0, 16 * sizeof(long long), st);
@@ -717,7 +717,7 @@ static int v2_dispatch_bn(int bn, int epi, const CUtensorMap& ta, const CUtensor
 
 // tile width: fewest (waves x tile cost); wide tiles amortise the A traffic, narrow ones the wave quantisation
 static int v2_pick_bn(int N, long long row_tiles, int workers) {
-  static const int forced = gemm_env_int("B200_GEMM_BN", 0);
+  const int forced = option(OPT_GEMM_BN);
   if (forced == 128 || forced == 192 || forced == 256) return forced;
   const int cands[3] = {256, 192, 128};
   int best = 128;
@@ -734,8 +734,7 @@ static int v2_pick_bn(int N, long long row_tiles, int workers) {
 // Returns 1 when the problem is outside what this kernel handles (the caller falls back to the first-generation
 // kernels), 0 on success, negative on error.
 int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
-  static const int enabled = gemm_env_int("B200_GEMM_V2", 1);
-  if (!enabled) return 1;
+  if (!option(OPT_GEMM_V2)) return 1;
   const bool mn = d->a_mn_major && d->b_mn_major;
   if (d->a_mn_major != d->b_mn_major) return 1;
   const bool f32 = d->out_f32 != nullptr;
@@ -773,7 +772,7 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   p.colsum = (!f32 && p.split_k == 1) ? d->out16_colsum : nullptr;
   if (d->out16_colsum != nullptr && p.colsum == nullptr) return 1;
 
-  static const int pair_mode = gemm_env_int("B200_GEMM_2CTA", -1);   // -1 auto, 0 never, 1 whenever possible
+  const int pair_mode = option(OPT_GEMM_2CTA);   // -1 auto, 0 never, 1 whenever possible
   bool pair = false;
   if (!mn && p.split_k == 1 && d->M >= 1024 && d->N >= 128) {
     // the CTA pair halves the B traffic per SM; it pays once the mainloop is long enough to be operand bound
@@ -790,7 +789,7 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   if (d->b_is_fp16) p.idesc &= ~(7u << 10);
 
   const bool inplace = f32 && d->residual && (const void*)d->residual == (const void*)d->out_f32 && d->ldres == d->ldo32;
-  static const int inplace_red = gemm_env_int("B200_GEMM_INPLACE_RED", 1);
+  const int inplace_red = option(OPT_GEMM_INPLACE_RED);
   int reduce_out = (f32 && d->atomic_add) ? 1 : 0;
   int use_x = 0;
   if (f32 && d->residual) {
@@ -833,7 +832,7 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   }
   const int epi = f32 ? 2 : (d->act == B200_ACT_GELU ? 1 : 0);
   // 16 epilogue warps when the epilogue stages no operand tile (4 KB of staging per warp is then enough)
-  static const int ew_mode = gemm_env_int("B200_GEMM_EW", 16);
+  const int ew_mode = option(OPT_GEMM_EW);
   const bool ew16 = ew_mode == 16 && !use_x && !pair;
   if (mn) {
     if (ew16) return v2_dispatch_bn<false, true, 16>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);

@@ -74,21 +74,40 @@ class FlatGradArena:
         return n
 
     def zero(self) -> None:
+        self.wait()
         self.buffer.zero_()
         for p, v in zip(self.params, self.views):  # re-attach if an optimizer set grads to None
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v
 
-    def allreduce_mean(self, group=None):
-        """One collective per step. Returns the async work handle (None when not distributed)."""
+    def allreduce_mean(self, group=None, async_op: bool = False):
+        """One collective per step over the whole arena (mean over ranks, like DDP).
+
+        Default: stream-ordered -- when this returns, every later kernel on the CURRENT stream (optimizer step, norm,
+        zero) sees the reduced gradients; nothing on the host blocks. async_op=True (NCCL only) leaves the collective
+        running on NCCL's stream and returns its work handle; the arena remembers it and `wait()` / `zero()` /
+        `ArenaAdamW.step()` make the current stream wait for it, so a discarded handle cannot race."""
+        self.wait()
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
         if dist.get_backend(group) == "nccl":
-            return dist.all_reduce(self.buffer, op=dist.ReduceOp.AVG, group=group, async_op=True)
+            work = dist.all_reduce(self.buffer, op=dist.ReduceOp.AVG, group=group, async_op=True)
+            if async_op:
+                self._pending = work
+                return work
+            work.wait()   # NCCL: the current stream waits for the collective (no host block)
+            return None
         work = dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group, async_op=True)
         work.wait()
         self.buffer.div_(dist.get_world_size(group))
         return None
+
+    def wait(self) -> None:
+        """Order the current stream after a pending asynchronous all-reduce (no-op otherwise)."""
+        work = getattr(self, "_pending", None)
+        if work is not None:
+            work.wait()
+            self._pending = None
 
 
 def reduce_metrics(metrics: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:

@@ -232,7 +232,28 @@ def attention_fwd(q, k, v, heads: int, scale: float):
     return o, lse
 
 
-def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float):
+def set_option(name: str, value: int) -> None:
+    """Flip a dispatch option of the library (include/b200_distill.h: b200_set_option)."""
+    L.check(L.load().b200_set_option(name.encode(), int(value)), "set_option")
+
+
+def get_option(name: str) -> int:
+    return int(L.load().b200_get_option(name.encode()))
+
+
+def _bf16_copy_same_strides(t):
+    """bf16 copy of a 16-bit tensor with t's strides (the *_alt operands of b200_attn_desc), or None when t's layout is
+    not one a plain copy reproduces (the backward then runs its register-converting kernels)."""
+    if t.is_contiguous():
+        return t.to(torch.bfloat16)
+    if t.stride(0) == 0 and t[0].is_contiguous():
+        return t[:1].to(torch.bfloat16).expand_as(t)
+    return None
+
+
+def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, colsums=None, alts=None):
+    """colsums: optional (dq_sum, dk_sum, dv_sum) fp32 [heads*hd] accumulators (bias gradients).
+    alts: optional precomputed bf16 copies of fp16 (q, k, v) with the same strides (made here when omitted)."""
     _need_cuda(q, k, v, o, lse, d_o)
     B, Nq, Dm = q.shape
     Nk = k.shape[1]
@@ -246,7 +267,15 @@ def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float):
     d.dq, d.dq_bs, d.dq_ts = dq.data_ptr(), dq.stride(0), dq.stride(1)
     d.dk, d.dk_bs, d.dk_ts = dk.data_ptr(), dk.stride(0), dk.stride(1)
     d.dv, d.dv_bs, d.dv_ts = dv.data_ptr(), dv.stride(0), dv.stride(1)
+    keep = None
+    if q.dtype == torch.float16:
+        keep = list(alts) if alts is not None else [_bf16_copy_same_strides(t) for t in (q, k, v)]
+        if all(t is not None for t in keep):
+            d.q_alt, d.k_alt, d.v_alt = (t.data_ptr() for t in keep)
+    if colsums is not None:
+        d.dq_colsum, d.dk_colsum, d.dv_colsum = (_p(t) for t in colsums)
     L.check(L.load().b200_attention_bwd(C.byref(d), _stream()), "attention_bwd")
+    del keep
     return dq, dk, dv
 
 

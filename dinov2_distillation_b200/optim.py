@@ -63,6 +63,7 @@ class ArenaAdamW:
     def step(self, extra_sq_norm: Optional[torch.Tensor] = None) -> None:
         lib = L.load()
         self.steps += 1
+        self.arena.wait()   # a still-running asynchronous all-reduce of the gradients
         g = self.arena.buffer
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
         if clip:

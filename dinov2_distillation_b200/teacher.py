@@ -341,16 +341,24 @@ class DINOv2ViT(nn.Module):
         c = TEACHER_CONFIGS[model_name]
         self.model_name = model_name
         self.model = DinoVisionTransformerB200(c["dim"], c["depth"], c["heads"], c["ffn"], c["swiglu"])
-        path = weights or os.environ.get("DINOV2_WEIGHTS_DIR")
-        if path and os.path.isdir(path):
-            path = os.path.join(path, f"{model_name}_pretrain.pth")
-        if path and os.path.isfile(path):
-            self.model.load_state_dict(torch.load(path, map_location="cpu"), strict=True)
-        else:
-            # the reference downloads hub weights (dinov2.py:20); offline we fall back to seeded synthetic weights
-            warnings.warn(f"{model_name}: no pretrained weights found (set DINOV2_WEIGHTS_DIR); using seeded synthetic "
-                          "weights", stacklevel=2)
+        # The reference always loads pretrained hub weights (models/backbones/dinov2.py:20). Here: `weights` (a .pth file
+        # or a directory holding <model_name>_pretrain.pth), else $DINOV2_WEIGHTS_DIR. Seeded synthetic weights are an
+        # explicit opt-in (weights="synthetic": tests, bench.py, smoke) -- a missing or mistyped path raises instead of
+        # silently distilling from a random teacher.
+        if weights == "synthetic":
             _seeded_init_(self.model, seed)
+        else:
+            path = weights or os.environ.get("DINOV2_WEIGHTS_DIR")
+            if not path:
+                raise FileNotFoundError(
+                    f"{model_name}: no pretrained weights given. Pass weights=<file or directory> or set "
+                    "DINOV2_WEIGHTS_DIR (hub format: <model_name>_pretrain.pth); pass weights='synthetic' for seeded "
+                    "random weights (benchmarks / tests only).")
+            if os.path.isdir(path):
+                path = os.path.join(path, f"{model_name}_pretrain.pth")
+            if not os.path.isfile(path):
+                raise FileNotFoundError(f"{model_name}: pretrained weights not found at {path!r}")
+            self.model.load_state_dict(torch.load(path, map_location="cpu"), strict=True)
         self.model.eval()
         for p in self.model.parameters():
             p.requires_grad = False

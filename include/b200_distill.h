@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 
 const char* b200_last_error(void);
 int b200_abi_version(void);
@@ -38,6 +38,11 @@ void b200_reset_launch_count(void);
  * b200_profile_read synchronises the recorded events, fills sums per category and clears the records. */
 void b200_profile_enable(int on);
 int b200_profile_read(int n_cat, double* ms, double* flops, long long* launches);
+/* Dispatch options (ints; defaults select the production kernels). The launchers read this table, never the
+ * environment; tests and A/B tools flip entries. Names: "pdl", "attn_tc_fwd", "attn_tc_fwd_long", "attn_tc_bwd",
+ * "attn_bwd_fused". b200_set_option returns -1 for an unknown name; b200_get_option returns -1 likewise. */
+int b200_set_option(const char* name, int value);
+int b200_get_option(const char* name);
 
 /* ------------------------------------------------------------------------------------------------ GEMM (tcgen05)
  * C[M,N] = epilogue(A * B^T): bf16 operands staged by TMA (128B swizzle), tcgen05.mma with fp32 accumulators in TMEM.
@@ -202,6 +207,11 @@ typedef struct b200_attn_desc {
   float* dq_colsum; float* dk_colsum; float* dv_colsum;
   /* forward only, optional: a second copy of o (same strides) in the 16-bit format o does not use */
   void* o_alt;
+  /* backward only, optional (all three or none), used when qkvo_is_fp16: bf16 copies of q / k / v with the strides of
+   * the fp16 tensors. The tcgen05 backward needs them (kind::f16 cannot mix fp16 and bf16 operands in one product: the
+   * scores are recomputed from the fp16 tensors, every gradient product reads the bf16 copies); without them the
+   * mma.sync kernels run, which convert fragments in registers. */
+  const void* q_alt; const void* k_alt; const void* v_alt;
 } b200_attn_desc;
 int b200_attention_fwd(const b200_attn_desc* d, void* stream);
 int b200_attention_bwd(const b200_attn_desc* d, void* stream);

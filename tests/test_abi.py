@@ -21,7 +21,7 @@ def _declared_symbols():
 def test_library_loads_and_exports_every_declared_symbol():
     from dinov2_distillation_b200 import _lib
     lib = _lib.load()
-    assert lib.b200_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.b200_abi_version() == _lib.ABI_VERSION == 3
     declared = _declared_symbols()
     assert len(declared) >= 40
     missing = [s for s in declared if not hasattr(lib, s)]
@@ -66,7 +66,7 @@ def test_errors_are_reported_not_swallowed():
 
 def test_header_is_plain_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text(f'#include "{HEADER}"\nint main(void) {{ return B200_ABI_VERSION == 2 ? 0 : 1; }}\n')
+    src.write_text(f'#include "{HEADER}"\nint main(void) {{ return B200_ABI_VERSION == 3 ? 0 : 1; }}\n')
     subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", str(src)], check=True)
 
 

@@ -183,7 +183,7 @@ def _teacher_pair(name_or_cfg, seed, pos_grid=37):
     if isinstance(name_or_cfg, str):
         cfg = dinov2_ref.TEACHER_CFGS[name_or_cfg]
         sd = dinov2_ref.make_state_dict(cfg, seed=seed)
-        t = teacher.DINOv2ViT(name_or_cfg)
+        t = teacher.DINOv2ViT(name_or_cfg, weights="synthetic")
         t.model.load_state_dict(sd)
     else:
         cfg = name_or_cfg

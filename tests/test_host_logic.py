@@ -61,7 +61,7 @@ def test_teacher_shell_surface():
     assert sorted(TEACHER_CONFIGS) == ["dinov2_vitb14", "dinov2_vitg14", "dinov2_vitl14", "dinov2_vits14"]
     with pytest.raises(KeyError):
         DINOv2ViT("dinov2_vitx14")
-    t = DINOv2ViT("dinov2_vits14")
+    t = DINOv2ViT("dinov2_vits14", weights="synthetic")
     assert all(not p.requires_grad for p in t.parameters())
     assert len(t.model.blocks) == 12 and not t.model.training
     keys = set(t.model.state_dict().keys())
@@ -73,9 +73,28 @@ def test_teacher_shell_surface():
         t(torch.randn(1, 3, 224, 224))
     with pytest.raises(_lib.B200Error, match="no CPU fallback"):
         t.model.blocks[9](torch.randn(1, 256, 384))
-    g = DINOv2ViT("dinov2_vitg14")
+    g = DINOv2ViT("dinov2_vitg14", weights="synthetic")
     assert "blocks.0.mlp.w12.weight" in g.model.state_dict() and g.model.blocks[0].mlp.w12.weight.shape == (8192, 1536)
     assert abs(sum(p.numel() for p in g.parameters()) - 1136.5e6) / 1136.5e6 < 0.005
+
+
+def test_teacher_requires_real_weights_unless_synthetic_is_requested(tmp_path, monkeypatch):
+    """models/backbones/dinov2.py:20 always loads pretrained weights: a missing / mistyped path must raise, never fall
+    back to a random teacher; a hub-format checkpoint on disk loads strictly (file or directory form)."""
+    from dinov2_distillation_b200.teacher import DINOv2ViT
+    monkeypatch.delenv("DINOV2_WEIGHTS_DIR", raising=False)
+    with pytest.raises(FileNotFoundError, match="no pretrained weights"):
+        DINOv2ViT("dinov2_vits14")
+    with pytest.raises(FileNotFoundError, match="not found"):
+        DINOv2ViT("dinov2_vits14", weights=str(tmp_path / "nope.pth"))
+    monkeypatch.setenv("DINOV2_WEIGHTS_DIR", str(tmp_path))
+    with pytest.raises(FileNotFoundError, match="not found"):
+        DINOv2ViT("dinov2_vits14")
+    src = DINOv2ViT("dinov2_vits14", weights="synthetic", seed=7)
+    torch.save(src.model.state_dict(), tmp_path / "dinov2_vits14_pretrain.pth")
+    for t in (DINOv2ViT("dinov2_vits14"), DINOv2ViT("dinov2_vits14", weights=str(tmp_path / "dinov2_vits14_pretrain.pth"))):
+        for k, v in src.model.state_dict().items():
+            assert torch.equal(t.model.state_dict()[k], v), k
 
 
 def test_distillation_step_mirrors_reference_orchestration():
@@ -83,7 +102,7 @@ def test_distillation_step_mirrors_reference_orchestration():
     from dinov2_distillation_b200.teacher import DINOv2ViT
     specs = [{"type": "scalekd", "weight": 1.0, "kwargs": _kw(name="scalekd_res4", teacher_dims=384, pos_dims=384, num_heads=16)},
              {"type": "scalekd", "weight": 0.5, "kwargs": _kw(name="scalekd_res5", teacher_dims=384, pos_dims=384, num_heads=24, self_query=False)}]
-    step = DistillationStep(None, DINOv2ViT("dinov2_vits14"), specs)
+    step = DistillationStep(None, DINOv2ViT("dinov2_vits14", weights="synthetic"), specs)
     assert sorted(step.losses.keys()) == ["scalekd_res4", "scalekd_res5"]
     assert step.loss_weights == {"scalekd_res4": 1.0, "scalekd_res5": 0.5}
     step.train()
@@ -239,7 +258,7 @@ def test_compute_losses_dict_weights_and_gradients_with_stub_losses():
     specs = [{"type": "scalekd", "weight": 2.0, "kwargs": _kw(name="scalekd_res4", teacher_dims=384, pos_dims=384, num_heads=16)},
              {"type": "scalekd", "weight": 0.5, "kwargs": _kw(name="scalekd_res5", teacher_dims=384, pos_dims=384, num_heads=24, self_query=False)},
              {"type": "scalekd", "weight": 9.0, "kwargs": _kw(name="scalekd_res6", teacher_dims=384, pos_dims=384, num_heads=24)}]
-    step = DistillationStep(None, DINOv2ViT("dinov2_vits14"), specs)
+    step = DistillationStep(None, DINOv2ViT("dinov2_vits14", weights="synthetic"), specs)
     step.two_streams = False
     step.losses = torch.nn.ModuleDict({"scalekd_res4": StubKD(1.5), "scalekd_res5": StubKD(0.7), "scalekd_res6": StubKD(3.0)})
     step._forward_specific_stage = lambda feat, layer: feat + 1.0
