@@ -130,6 +130,48 @@ def test_port_matches_live_reference_scalekd():
 
 
 @needs_reference
+def test_module_level_orchestration_matches_live_reference_compute_losses():
+    """oracle compute_losses_modules (the loop the GPU tests drive over the B200 shells) against the reference's own
+    DistillationModule._compute_losses, both over the reference's ScaleKD modules and a reference-shaped teacher."""
+    import torch.nn as nn
+    from oracle import dinov2_ref
+    sk, dm = ref_shims.import_reference()
+    if dm is None:
+        pytest.skip("train.distillation_module not importable")
+    cfg = dinov2_ref.VitCfg(64, 8, 4, 256)
+    teacher = dinov2_ref.RefTeacher(cfg, dinov2_ref.make_state_dict(cfg, seed=21, pos_grid=4))
+    common = dict(alpha=[0.08, 0.06], teacher_dims=64, query_hw=[4, 4], pos_hw=[4, 4], pos_dims=64,
+                  window_shapes=[1, 1], softmax_scale=[5.0, 5.0])
+    torch.manual_seed(31)
+    mods = nn.ModuleDict({
+        "scalekd_res4": sk.ScaleKD(**dict(common, name="scalekd_res4", student_dims=32, self_query=True, num_heads=4)),
+        "scalekd_res5": sk.ScaleKD(**dict(common, name="scalekd_res5", student_dims=48, self_query=False, num_heads=8))}).train()
+    weights = {"scalekd_res4": 2.0, "scalekd_res5": 0.5}
+    mod = dm.DistillationModule.__new__(dm.DistillationModule)
+    nn.Module.__init__(mod)
+    mod.teacher, mod.losses, mod.loss_weights = teacher, mods, weights
+    g = torch.Generator().manual_seed(32)
+    T = teacher(torch.randn(2, 3, 56, 56, generator=g))["feature_map"]
+    base = {"res4": torch.randn(2, 32, 4, 4, generator=g), "res5": torch.randn(2, 48, 4, 4, generator=g)}
+    f1 = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+    ref = mod._compute_losses({"student": f1, "teacher": T})
+    ref["loss"].backward()
+    g1 = {k: p.grad.clone() for k, p in mods.named_parameters() if p.grad is not None}
+    mods.zero_grad(set_to_none=True)
+    f2 = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+    out = scalekd_ref.compute_losses_modules(mods, weights, f2, T, teacher)
+    out["loss"].backward()
+    assert list(out.keys()) == list(ref.keys())
+    for k in ref:
+        assert torch.allclose(out[k].detach(), ref[k].detach(), rtol=1e-6, atol=1e-7), k
+    for k in f1:
+        assert torch.allclose(f2[k].grad, f1[k].grad, rtol=1e-5, atol=1e-8), k
+    for k, p in mods.named_parameters():
+        if k in g1:
+            assert torch.allclose(p.grad, g1[k], rtol=1e-5, atol=1e-8), k
+
+
+@needs_reference
 def test_closed_form_dct_matches_reference_fft_construction():
     sk, _ = ref_shims.import_reference()
     for R in (4, 16, 37):
