@@ -57,6 +57,7 @@ class AttnDesc(C.Structure):
         ("dq_colsum", c_fp), ("dk_colsum", c_fp), ("dv_colsum", c_fp),
         ("o_alt", c_vp),
         ("q_alt", c_vp), ("k_alt", c_vp), ("v_alt", c_vp),
+        ("dq_accum", c_fp),
     ]
 
 

@@ -13,7 +13,11 @@
 //   dV_j += P^T  dO_i                      tcgen05.mma TS (A from TMEM, B = dO_i MN-major)   -> TMEM accumulator
 //   dK_j += dS^T Q_i                       tcgen05.mma TS (B = Q_i MN-major)
 //   dQ_m += dS   K_j   (per query pair m)  tcgen05.mma SS (A = staged dS^T read MN-major, B = K_j MN-major)
-// dQ of the whole unit (<= 256 x hd) stays in TMEM across the key blocks, so nothing is reduced through memory.
+// Resident mode (Nq, Nk <= 256: every 224-pixel configuration): dQ of the whole unit (<= 256 x hd) stays in TMEM across
+// the key blocks, nothing is reduced through memory. Streaming mode (longer sequences: the 518-pixel configurations, 1369
+// tokens): one unit per (batch, head, key block); dV_j / dK_j stay in TMEM over all query items, the dQ contribution of
+// every query pair is drained from one of two TMEM slots and added into an fp32 accumulator [B, Nq, heads*hd] with
+// cp.reduce.async.bulk.tensor (.add.f32), and a small pass scales / converts it to bf16 afterwards.
 // Operands arrive by TMA through 4-D maps (head_dim, heads, tokens, batch): boxes wider than the head (24 -> 32,
 // 48 -> 64) and rows past the sequence are zero-filled by the hardware; outputs leave through swizzled staging tiles and
 // bulk tensor stores (clipped the same way). fp16 forward operands (DUAL): S^T is recomputed from the fp16 q / k so that
@@ -30,7 +34,7 @@
 namespace b200 {
 
 int make_tensor_map_4d(CUtensorMap* out, const void* ptr, const uint64_t (&dims)[4], const uint64_t (&ld)[3],
-                       const uint32_t (&box)[4], int swizzle);
+                       const uint32_t (&box)[4], int swizzle, int esize);
 
 constexpr int ABT_THREADS = 512;
 constexpr int ABT_SM_WARPS = 8;
@@ -49,8 +53,8 @@ struct AbtCfg {
   static constexpr int OFF_KV = 0;
   static constexpr int OFF_Q = OFF_KV + KVB * NT * KTILE;
   static constexpr int OFF_DS = OFF_Q + QST * NT * QTILE;
-  static constexpr int OFF_OUT = OFF_DS + 4 * ABT_DS_BLOCK;       // [4 epilogue warps][32 rows x ROWB]
-  static constexpr int OFF_X = OFF_OUT + 4 * 32 * ROWB;           // [8 softmax warps][lse2 64 | delta 64] fp32
+  static constexpr int OFF_OUT = OFF_DS + 4 * ABT_DS_BLOCK;       // [4 epilogue warps][4 KB: 32 rows x ROWB 16-bit, or 32 x 32 fp32]
+  static constexpr int OFF_X = OFF_OUT + 4 * 4096;           // [8 softmax warps][lse2 64 | delta 64] fp32
   static constexpr int OFF_BAR = OFF_X + ABT_SM_WARPS * 512;
   static constexpr int SMEM = OFF_BAR + 256 + 1024;
   static constexpr uint32_t LAYOUT = HDP == 64 ? 2u : 4u;         // SWIZZLE_128B / SWIZZLE_64B
@@ -60,6 +64,7 @@ struct AbtCfg {
 struct AbtParams {
   int B, heads, Nq, Nk, hd;
   int n_kb, n_items;             // 128-key blocks, 64-query items per unit
+  int stream, kb_total;          // streaming mode: unit = (batch, head, key block), n_kb = 1, kb_total blocks per (b, h)
   int q_batched;                 // 0: q (and its copies) are batch invariant
   float scale, scale_log2;
   const float* lse;
@@ -164,6 +169,44 @@ __device__ __forceinline__ void abt_store_slice(uint32_t taddr, float scale, con
   }
 }
 
+__device__ __forceinline__ void abt_tma_reduce_add_4d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+// Streaming mode: one [32 rows x HDP] fp32 slice of a query pair's dQ contribution, TMEM -> registers -> swizzled fp32
+// staging tile (32 columns at a time) -> bulk tensor reduce-add into the fp32 accumulator (rows / columns past the
+// tensor are clipped by the map).
+template <int HDP>
+__device__ __forceinline__ void abt_reduce_slice(uint32_t taddr, const CUtensorMap* tm, uint32_t stage, int h, int row0,
+                                                 int b, int lane, uint64_t* free_bar) {
+  uint32_t raw[HDP];
+#pragma unroll
+  for (int c = 0; c < HDP / 32; ++c) tmem_ld_32x32(taddr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[c * 32]));
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(free_bar);
+#pragma unroll
+  for (int t = 0; t < HDP / 32; ++t) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t addr = stage + lane * 128 + ((c ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(raw[t * 32 + 4 * c]), "r"(raw[t * 32 + 4 * c + 1]),
+                   "r"(raw[t * 32 + 4 * c + 2]), "r"(raw[t * 32 + 4 * c + 3]) : "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      abt_tma_reduce_add_4d(tm, stage, t * 32, h, row0, b);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+}
+
 template <int HDP, bool DUAL>
 __global__ void __launch_bounds__(ABT_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_constant__ CUtensorMap tmKs,
@@ -185,8 +228,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
   uint64_t* ds_free = bars + 16;       // [2] staged dS^T pair consumed by the dQ product
   uint64_t* dkv_full = bars + 18;      // dV / dK of a key block complete
   uint64_t* dkv_free = bars + 19;      // ... and drained (4 epilogue warps)
-  uint64_t* dq_full = bars + 20;
-  uint64_t* dq_free = bars + 21;
+  uint64_t* dq_full = bars + 20;       // [2] (streaming mode: one per dQ slot; resident mode uses [0])
+  uint64_t* dq_free = bars + 22;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -205,7 +248,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
     }
     for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(dkv_full, 1); mbar_init(dkv_free, 4);
-    mbar_init(dq_full, 1); mbar_init(dq_free, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&dq_full[i], 1); mbar_init(&dq_free[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -216,22 +259,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
   pdl_trigger();
   pdl_wait();
 
-  AbtIter it0{(int)blockIdx.x, 0, 0, p.B * p.heads, p.n_kb, p.n_items, (int)gridDim.x};
+  AbtIter it0{(int)blockIdx.x, 0, 0, p.B * p.heads * (p.stream ? p.kb_total : 1), p.n_kb, p.n_items, (int)gridDim.x};
+  // unit -> (batch, head) index and the key block an iterator position works on
+  auto unit_bh = [&](int u) { return p.stream ? u / p.kb_total : u; };
+  auto key_block = [&](const AbtIter& t) { return p.stream ? t.u % p.kb_total : t.j; };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int kvc = 0, ic = 0;
       for (AbtIter it = it0; it.valid(); it.next()) {
-        const int b = it.u / p.heads, h = it.u - b * p.heads;
+        const int bh = unit_bh(it.u), b = bh / p.heads, h = bh - b * p.heads;
         if (it.i == 0) {
-          const int kb = kvc % KVB;
+          const int kb = kvc % KVB, jg = key_block(it);
           mbar_wait(&kv_empty[kb], ((kvc / KVB) & 1) ^ 1);
           mbar_expect_tx(&kv_full[kb], NT * C::KTILE);
           uint8_t* dst = smem + C::OFF_KV + kb * NT * C::KTILE;
-          tma_load_4d(dst, &tmKs, &kv_full[kb], 0, h, it.j * 128, b);
-          if (DUAL) tma_load_4d(dst + C::KTILE, &tmKg, &kv_full[kb], 0, h, it.j * 128, b);
-          tma_load_4d(dst + (NT - 1) * C::KTILE, &tmV, &kv_full[kb], 0, h, it.j * 128, b);
+          tma_load_4d(dst, &tmKs, &kv_full[kb], 0, h, jg * 128, b);
+          if (DUAL) tma_load_4d(dst + C::KTILE, &tmKg, &kv_full[kb], 0, h, jg * 128, b);
+          tma_load_4d(dst + (NT - 1) * C::KTILE, &tmV, &kv_full[kb], 0, h, jg * 128, b);
           ++kvc;
         }
         const int st = ic % QST;
@@ -316,16 +362,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
           const bool last_item = cur.i == p.n_items - 1;
           if ((cur.i & 1) || last_item) {
             // dQ_m += dS_pair K_j over the 128 keys of the block (A: two staged blocks of 64 queries, MN-major)
+            // resident: slot m accumulates over the unit's key blocks; streaming: slot = pair parity, drained per pair
             const int m = cur.i >> 1;
-            if (cur.j == 0 && m == 0 && g_uc > 0) { mbar_wait(dq_free, (g_uc - 1) & 1); tc_fence_after(); }
+            const int slot = p.stream ? (g_pc & 1) : m;
+            if (p.stream) {
+              if (g_pc >= 2) { mbar_wait(&dq_free[slot], ((g_pc >> 1) - 1) & 1); tc_fence_after(); }
+            } else if (cur.j == 0 && m == 0 && g_uc > 0) {
+              mbar_wait(&dq_free[0], (g_uc - 1) & 1);
+              tc_fence_after();
+            }
+            const bool dq_acc = !p.stream && cur.j > 0;
             const uint32_t a_addr = ds_base + (g_pc & 1) * 2 * ABT_DS_BLOCK;
             const uint32_t kg_addr = kv_addr + (DUAL ? C::KTILE : 0);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
               const uint64_t da = make_smem_desc(a_addr + ks * 2048, ABT_DS_BLOCK, 1024, 2u);
               const uint64_t db = make_smem_desc(kg_addr + ks * 16 * ROWB, 8 * ROWB, 8 * ROWB, C::LAYOUT);
-              if (!ABT_SKIP(1)) tc_mma_bf16(tmem_base + ABT_T_DQ + m * 64, da, db, p.idesc_dq, (cur.j > 0 || ks > 0) ? 1u : 0u);
+              if (!ABT_SKIP(1)) tc_mma_bf16(tmem_base + ABT_T_DQ + slot * 64, da, db, p.idesc_dq, (dq_acc || ks > 0) ? 1u : 0u);
             }
+            if (p.stream) tc_commit(&dq_full[slot]);
             tc_commit(&ds_free[g_pc & 1]);
             ++g_pc;
           }
@@ -333,7 +388,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
             tc_commit(&kv_empty[kb]);
             tc_commit(dkv_full);
             ++g_jc;
-            if (cur.j == p.n_kb - 1) { tc_commit(dq_full); ++g_uc; }
+            if (cur.j == p.n_kb - 1) {
+              if (!p.stream) tc_commit(&dq_full[0]);
+              ++g_uc;
+            }
           }
           ABT_STAMP(g_ic, 13);
           ++g_ic; ++graded;
@@ -359,8 +417,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
     float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
     auto ld_stats = [&](const AbtIter& t) {
       if (!t.valid()) return;
-      const int b = t.u / p.heads, h = t.u - b * p.heads;
-      const long long o = ((long long)b * p.heads + h) * p.Nq;
+      const long long o = (long long)unit_bh(t.u) * p.Nq;
       const int q0 = t.i * 64 + lane, q1 = q0 + 32;
       l0 = q0 < p.Nq ? __ldg(p.lse + o + q0) * 1.4426950408889634f : INFINITY;   // +inf: P = 0 past the last query
       l1 = q1 < p.Nq ? __ldg(p.lse + o + q1) * 1.4426950408889634f : INFINITY;
@@ -389,7 +446,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
       mbar_wait(&ds_free[pc & 1], ((pc >> 1) & 1) ^ 1);
       tc_fence_after();
       if (quad == 0 && lane == 0) ABT_STAMP(ic, 2);
-      const bool row_dead = it.j * 128 + row >= p.Nk;   // rows past the last key (zero-filled K / V) take no part
+      const bool row_dead = key_block(it) * 128 + row >= p.Nk;   // rows past the last key (zero-filled K / V) take no part
       const uint32_t blk = ds_base + ((pc & 1) * 2 + (it.i & 1)) * ABT_DS_BLOCK + row * 128;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -447,12 +504,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
     // ------------------------------------------------------------------ epilogue warps (thread = output row)
     const int quad = warp & 3;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t stage = smem_u32(smem + C::OFF_OUT + quad * 32 * ROWB);
-    int jc = 0, uc = 0;
+    const uint32_t stage = smem_u32(smem + C::OFF_OUT + quad * 4096);
+    int jc = 0, uc = 0, pc = 0;
     for (AbtIter it = it0; it.valid(); it.next()) {
-      if (it.i != p.n_items - 1) continue;   // one visit per (unit, key block)
-      const int b = it.u / p.heads, h = it.u - b * p.heads;
-      const int row0 = it.j * 128 + quad * 32;
+      const int bh = unit_bh(it.u), b = bh / p.heads, h = bh - b * p.heads;
+      const bool pair_end = (it.i & 1) || it.i == p.n_items - 1;
+      if (pair_end) {
+        if (p.stream) {   // this pair's dQ contribution: TMEM slot -> fp32 reduce-add into the accumulator
+          const int slot = pc & 1;
+          mbar_wait(&dq_full[slot], (pc >> 1) & 1);
+          tc_fence_after();
+          abt_reduce_slice<HDP>(tmem_base + lane_base + ABT_T_DQ + slot * 64, &tmdQ, stage, h, (it.i >> 1) * 128 + quad * 32,
+                                b, lane, &dq_free[slot]);
+        }
+        ++pc;
+      }
+      if (it.i != p.n_items - 1) continue;   // below: one visit per (unit, key block)
+      const int row0 = key_block(it) * 128 + quad * 32;
       mbar_wait(dkv_full, jc & 1);
       tc_fence_after();
       if (quad == 0 && lane == 0) ABT_STAMP(jc, 14);
@@ -462,14 +530,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQs, const __grid_consta
                            p.Nk - row0, dkv_free);
       if (quad == 0 && lane == 0) ABT_STAMP(jc, 15);
       ++jc;
-      if (it.j == p.n_kb - 1) {
-        mbar_wait(dq_full, uc & 1);
+      if (!p.stream && it.j == p.n_kb - 1) {
+        mbar_wait(&dq_full[0], uc & 1);
         tc_fence_after();
         const int n_pairs = (p.n_items + 1) >> 1;
         for (int m = 0; m < n_pairs; ++m) {
           const int qrow0 = m * 128 + quad * 32;
           abt_store_slice<HDP>(tmem_base + lane_base + ABT_T_DQ + m * 64, p.scale, &tmdQ, stage, h, qrow0, b, lane,
-                               p.dq_colsum, p.hd, p.Nq - qrow0, m == n_pairs - 1 ? dq_free : nullptr);
+                               p.dq_colsum, p.hd, p.Nq - qrow0, m == n_pairs - 1 ? &dq_free[0] : nullptr);
         }
         ++uc;
       }
@@ -497,32 +565,72 @@ static int abt_launch(const CUtensorMap (&tm)[9], const AbtParams& p, int grid, 
   return 0;
 }
 
+// Streaming mode, last pass: dq = bf16(scale * accumulator), with the optional column sums (q-bias gradient).
+// Thread = one 8-column group, walking the rows of its block: 32-byte loads / 16-byte stores, column partials in registers.
+constexpr int ABT_FIN_ROWS = 64;
+__global__ void __launch_bounds__(256)
+attn_dq_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long dq_bs, long long dq_ts,
+                      int Nq, int cols, float scale, float* __restrict__ colsum) {
+  pdl_wait();
+  const int ngroups = cols >> 3;
+  const int ry = 256 / ngroups > 0 ? 256 / ngroups : 1;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * ABT_FIN_ROWS, r_end = min(Nq, r_begin + ABT_FIN_ROWS);
+  for (int cg = threadIdx.x % ngroups + (threadIdx.x / (ngroups * ry)) * ngroups; cg < ngroups; cg += ngroups) {
+    // (ngroups <= 256 on this path: every column group has exactly one owner column of threads)
+    const int ty = (threadIdx.x / ngroups) % ry;
+    if (threadIdx.x >= ngroups * ry) break;
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = r_begin + ty; r < r_end; r += ry) {
+      const float* src = acc + ((long long)b * Nq + r) * cols + cg * 8;
+      const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+      const float v[8] = {a0.x * scale, a0.y * scale, a0.z * scale, a0.w * scale, a1.x * scale, a1.y * scale, a1.z * scale, a1.w * scale};
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dq + (long long)b * dq_bs + (long long)r * dq_ts + cg * 8) = o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cs[e] += v[e];
+    }
+    if (colsum != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(colsum + cg * 8 + e, cs[e]);
+    }
+  }
+}
+
 // Returns 1 when the problem is outside this kernel's envelope (the caller falls back to the mma.sync kernels), 0 when
 // the backward was launched, negative on error. delta must already be in d->delta.
 int launch_attention_tc_bwd(const b200_attn_desc* d, cudaStream_t st) {
   if (!option(OPT_ATTN_TC_BWD)) return 1;
   const bool dual = d->qkvo_is_fp16 != 0;
-  if (d->hd < 16 || d->hd > 64 || d->hd % 8 != 0 || d->Nq > 256 || d->Nk > 256) return 1;
+  const bool stream = d->Nq > 256 || d->Nk > 256;
+  if (d->hd < 16 || d->hd > 64 || d->hd % 8 != 0) return 1;
+  if (stream && (d->dq_accum == nullptr || !option(OPT_ATTN_TC_BWD_LONG) || d->heads * d->hd > 2048)) return 1;
   if (dual && (d->q_alt == nullptr || d->k_alt == nullptr || d->v_alt == nullptr)) return 1;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(d->q) || !al16(d->k) || !al16(d->v) || !al16(d->d_o) || !al16(d->dq) || !al16(d->dk) || !al16(d->dv)) return 1;
   if (dual && (!al16(d->q_alt) || !al16(d->k_alt) || !al16(d->v_alt))) return 1;
+  if (stream && !al16(d->dq_accum)) return 1;
   const long long strides[] = {d->q_ts, d->k_ts, d->v_ts, d->do_ts, d->dq_ts, d->dk_ts, d->dv_ts,
                                d->q_bs, d->k_bs, d->v_bs, d->do_bs, d->dq_bs, d->dk_bs, d->dv_bs};
   for (long long s : strides)
     if (s % 8 != 0 || s < 0) return 1;
   if (d->k_bs == 0 || d->v_bs == 0 || d->do_bs == 0 || d->dq_bs == 0 || d->dk_bs == 0 || d->dv_bs == 0) return 1;
   const int hdp = d->hd <= 32 ? 32 : 64;
+  const int cols = d->heads * d->hd;
 
   AbtParams p{};
   p.B = d->B; p.heads = d->heads; p.Nq = d->Nq; p.Nk = d->Nk; p.hd = d->hd;
-  p.n_kb = (d->Nk + 127) / 128;
+  p.kb_total = (d->Nk + 127) / 128;
+  p.stream = stream ? 1 : 0;
+  p.n_kb = stream ? 1 : p.kb_total;
   p.n_items = (d->Nq + 63) / 64;
   p.q_batched = d->q_bs != 0 ? 1 : 0;
   p.scale = d->scale;
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.lse = d->lse; p.delta = d->delta;
-  p.dq_colsum = d->dq_colsum; p.dk_colsum = d->dk_colsum; p.dv_colsum = d->dv_colsum;
+  p.dq_colsum = stream ? nullptr : d->dq_colsum;   // (streaming: summed by the finishing pass)
+  p.dk_colsum = d->dk_colsum; p.dv_colsum = d->dv_colsum;
   p.idesc_s = make_idesc_16(128, 64, false, false, dual ? 0 : 1);
   p.idesc_dp = make_idesc_16(128, 64, false, false, 1);
   p.idesc_g = make_idesc_16(128, hdp, false, true, 1);
@@ -534,23 +642,33 @@ int launch_attention_tc_bwd(const b200_attn_desc* d, cudaStream_t st) {
     const uint64_t dims[4] = {(uint64_t)d->hd, (uint64_t)d->heads, (uint64_t)N, (uint64_t)(batched ? d->B : 1)};
     const uint64_t ld[3] = {(uint64_t)d->hd, (uint64_t)ts, (uint64_t)(batched ? bs : (long long)N * ts)};
     const uint32_t box[4] = {(uint32_t)hdp, 1u, (uint32_t)box_rows, 1u};
-    return make_tensor_map_4d(out, ptr, dims, ld, box, sw);
+    return make_tensor_map_4d(out, ptr, dims, ld, box, sw, 2);
   };
   CUtensorMap tm[9];
   // a tensor-map encoding the driver rejects is not an error of the caller: use the fallback kernels
   const void* qg = dual ? d->q_alt : d->q;
   const void* kg = dual ? d->k_alt : d->k;
   const void* vg = dual ? d->v_alt : d->v;
-  if (mk(&tm[0], d->q, d->Nq, d->q_ts, d->q_bs, 64) || mk(&tm[1], d->k, d->Nk, d->k_ts, d->k_bs, 128) ||
-      mk(&tm[2], qg, d->Nq, d->q_ts, d->q_bs, 64) || mk(&tm[3], kg, d->Nk, d->k_ts, d->k_bs, 128) ||
-      mk(&tm[4], vg, d->Nk, d->v_ts, d->v_bs, 128) || mk(&tm[5], d->d_o, d->Nq, d->do_ts, d->do_bs, 64) ||
-      mk(&tm[6], d->dq, d->Nq, d->dq_ts, d->dq_bs, 32) || mk(&tm[7], d->dk, d->Nk, d->dk_ts, d->dk_bs, 32) ||
-      mk(&tm[8], d->dv, d->Nk, d->dv_ts, d->dv_bs, 32)) {
+  int bad = mk(&tm[0], d->q, d->Nq, d->q_ts, d->q_bs, 64) || mk(&tm[1], d->k, d->Nk, d->k_ts, d->k_bs, 128) ||
+            mk(&tm[2], qg, d->Nq, d->q_ts, d->q_bs, 64) || mk(&tm[3], kg, d->Nk, d->k_ts, d->k_bs, 128) ||
+            mk(&tm[4], vg, d->Nk, d->v_ts, d->v_bs, 128) || mk(&tm[5], d->d_o, d->Nq, d->do_ts, d->do_bs, 64) ||
+            mk(&tm[7], d->dk, d->Nk, d->dk_ts, d->dk_bs, 32) || mk(&tm[8], d->dv, d->Nk, d->dv_ts, d->dv_bs, 32);
+  if (!bad) {
+    if (stream) {   // fp32 accumulator [B, Nq, heads*hd]: boxes of 32 columns x 32 rows
+      const uint64_t dims[4] = {(uint64_t)d->hd, (uint64_t)d->heads, (uint64_t)d->Nq, (uint64_t)d->B};
+      const uint64_t ld[3] = {(uint64_t)d->hd, (uint64_t)cols, (uint64_t)d->Nq * cols};
+      const uint32_t box[4] = {32u, 1u, 32u, 1u};
+      bad = make_tensor_map_4d(&tm[6], d->dq_accum, dims, ld, box, 128, 4);
+    } else {
+      bad = mk(&tm[6], d->dq, d->Nq, d->dq_ts, d->dq_bs, 32);
+    }
+  }
+  if (bad) {
     static bool warned = false;
     if (!warned) { fprintf(stderr, "[b200] attention backward: tensor map rejected, using the mma.sync path\n"); warned = true; }
     return 1;
   }
-  const int units = d->B * d->heads;
+  const int units = d->B * d->heads * (stream ? p.kb_total : 1);
   const int grid = units < sm_count() ? units : sm_count();
   static long long* dbg_buf = nullptr;
   if (kAbtProbes) {
@@ -559,6 +677,7 @@ int launch_attention_tc_bwd(const b200_attn_desc* d, cudaStream_t st) {
     p.dbg = dbg_buf;
     p.skip = option(OPT_ATTN_PROBE_SKIP);
   }
+  if (stream) B200_CUDA_OK(cudaMemsetAsync(d->dq_accum, 0, (size_t)d->B * d->Nq * cols * sizeof(float), st));
   const int prof = prof_begin(st);
   int r;
   if (hdp == 64) r = dual ? abt_launch<64, true>(tm, p, grid, st) : abt_launch<64, false>(tm, p, grid, st);
@@ -566,6 +685,13 @@ int launch_attention_tc_bwd(const b200_attn_desc* d, cudaStream_t st) {
   if (r != 0) return r;
   prof_end(prof, st, 8.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 2);
   B200_LAUNCH_OK();
+  if (stream) {
+    dim3 g((unsigned)cdiv(d->Nq, ABT_FIN_ROWS), (unsigned)d->B);
+    B200_CUDA_OK(launch_pdl(attn_dq_finish_kernel, g, dim3(256), 0, st, (const float*)d->dq_accum,
+                            static_cast<__nv_bfloat16*>(d->dq), (long long)d->dq_bs, (long long)d->dq_ts, d->Nq, cols, d->scale,
+                            d->dq_colsum));
+    B200_LAUNCH_OK();
+  }
   if (kAbtProbes) {
     static int printed = 0;
     cudaStreamSynchronize(st);

@@ -38,6 +38,7 @@ static OptDef g_opts[OPT_COUNT] = {
     {"attn_tc_fwd_long", "B200_ATTN_TC_LONG", 1},    // ... also for key ranges > 272 (online softmax)
     {"attn_tc_bwd", "B200_ATTN_TC_BWD", 1},          // tcgen05 attention backward (Nq, Nk <= 256)
     {"attn_bwd_fused", "B200_ATTN_BWD_FUSED", 1},    // mma.sync fallback: one-kernel backward when Nk <= 256
+    {"attn_tc_bwd_long", "B200_ATTN_TC_BWD_LONG", 1},   // tcgen05 backward also for Nq / Nk > 256 (fp32 dQ accumulator)
     {"gemm_v2", "B200_GEMM_V2", 1},                  // bulk-store GEMM kernel (0: first-generation kernel everywhere)
     {"gemm_bn", "B200_GEMM_BN", 0},                  // force the tile width (128 / 192 / 256; 0 = cost model)
     {"gemm_2cta", "B200_GEMM_2CTA", -1},             // cta_group::2: -1 by K, 0 never, 1 whenever possible

@@ -58,6 +58,7 @@ struct Gemm {
 struct VitWs {
   bf16 *xn, *qkv, *attn, *h, *h12, *d16, *dh, *dqkv, *dattn, *dh12;
   float *t32, *dmid, *delta, *lse;
+  float* dq_acc;   // fp32 dQ accumulator of the long-sequence attention backward (N > 256)
 };
 
 static void carve_block_ws(Arena& a, const b200_vit_config* c, long long M, int B, int N, bool bwd, VitWs& w) {
@@ -80,6 +81,7 @@ static void carve_block_ws(Arena& a, const b200_vit_config* c, long long M, int 
     w.dqkv = a.take_n<bf16>(M * 3 * D);
     w.delta = a.take_n<float>((long long)B * c->heads * N);
     if (c->swiglu) w.h = a.take_n<bf16>(M * F);
+    w.dq_acc = N > 256 ? a.take_n<float>(M * D) : nullptr;
   }
 }
 
@@ -223,6 +225,7 @@ extern "C" int b200_vit_block_bwd_input(const b200_vit_config* c, const b200_vit
   ad.dq = w.dqkv; ad.dk = w.dqkv + D; ad.dv = w.dqkv + 2 * D;
   ad.dq_bs = ad.dk_bs = ad.dv_bs = (long long)N * 3 * D;
   ad.dq_ts = ad.dk_ts = ad.dv_ts = 3 * D;
+  ad.dq_accum = w.dq_acc;
   B200_TRY(b200_attention_bwd(&ad, stream));
   B200_TRY(Gemm(w.dqkv, 3 * D, k->qkv_wT, 3 * D, Mi, D, 3 * D).out32(w.t32, D).run(stream));
   B200_TRY(b200_layernorm_bwd(w.t32, x, k->ln1_w, sv.mean1, sv.rstd1, w.dmid, dx, nullptr, nullptr, nullptr, Mi, D,
@@ -371,6 +374,7 @@ struct ProjBwdWs {
   bf16* dyraw16;                        // adjoint-resized dy [M_in, D] (fused resize only)
   bf16 *dq16r, *dkv16r;                 // dq / [dk|dv] moved back to raster order (windows only)
   float *du32, *dg32, *df32, *dz32, *dqs32, *sums2, *dpos_t, *delta, *dxt32;
+  float* dq_acc;                        // fp32 dQ accumulator of the long-sequence attention backward (> 256 tokens)
 };
 static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, ProjBwdWs& w) {
   const long long M = (long long)B * c->HW;
@@ -401,6 +405,7 @@ static void carve_proj_bwd_ws(Arena& a, const b200_projector_config* c, int B, P
   w.dyraw16 = c->raw_h > 0 ? a.take_n<bf16>((long long)B * proj_hw_in(c) * D) : nullptr;
   w.dq16r = proj_windows(c) > 1 ? a.take_n<bf16>(M * D) : nullptr;
   w.dkv16r = proj_windows(c) > 1 ? a.take_n<bf16>(M * 2 * D) : nullptr;
+  w.dq_acc = c->HW / proj_windows(c) > 256 ? a.take_n<float>((long long)B * (c->HW / proj_windows(c)) * D) : nullptr;
 }
 
 static int check_proj_cfg(const b200_projector_config* c, int B) {
@@ -675,6 +680,7 @@ static int projector_bwd_impl(const b200_projector_config* c, const b200_project
     ad.dk_bs = ad.dv_bs = (long long)HW * 2 * D; ad.dk_ts = ad.dv_ts = 2 * D;
     ad.dq_colsum = g->q_b; ad.dk_colsum = g->k_b; ad.dv_colsum = g->v_b;
     ad.q_alt = s.qb + r0 * D; ad.k_alt = s.kvb + r0 * 2 * D; ad.v_alt = s.kvb + r0 * 2 * D + D;
+    ad.dq_accum = w.dq_acc;
     B200_TRY(b200_attention_bwd(&ad, stream));
   }
   const bf16* dq16 = w.dq16;

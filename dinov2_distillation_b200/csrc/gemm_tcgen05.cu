@@ -305,11 +305,11 @@ int make_tensor_map_3d(CUtensorMap* out, const void* ptr, int esize, uint64_t d0
   return 0;
 }
 
-// Rank-4 tensor map over 16-bit elements (attention backward: head_dim x heads x tokens x batch, so that a box wider than
+// Rank-4 tensor map over 16-bit (esize 2) or fp32 (esize 4) elements (attention backward: head_dim x heads x tokens x batch, so that a box wider than
 // head_dim is zero-filled past the head instead of reading into the next one). ld[i]: element pitch of dim i+1.
 // Returns -4 with the error text set when the driver rejects the encoding.
 int make_tensor_map_4d(CUtensorMap* out, const void* ptr, const uint64_t (&dims)[4], const uint64_t (&ld)[3],
-                       const uint32_t (&box)[4], int swizzle) {
+                       const uint32_t (&box)[4], int swizzle, int esize) {
   struct Key4 {
     const void* ptr; uint64_t d[4], l[3]; uint32_t b[4], sw;
     bool operator==(const Key4& o) const {
@@ -330,7 +330,7 @@ int make_tensor_map_4d(CUtensorMap* out, const void* ptr, const uint64_t (&dims)
   static std::mutex mu;
   static std::unordered_map<Key4, CUtensorMap, Key4Hash> cache;
   Key4 key{};
-  key.ptr = ptr; key.sw = (uint32_t)swizzle;
+  key.ptr = ptr; key.sw = (uint32_t)(swizzle + 1000 * esize);
   for (int i = 0; i < 4; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
   for (int i = 0; i < 3; ++i) key.l[i] = ld[i];
   {
@@ -341,13 +341,14 @@ int make_tensor_map_4d(CUtensorMap* out, const void* ptr, const uint64_t (&dims)
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -4; }
   cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
-  cuuint64_t gstride[3] = {ld[0] * 2, ld[1] * 2, ld[2] * 2};
+  cuuint64_t gstride[3] = {ld[0] * (uint64_t)esize, ld[1] * (uint64_t)esize, ld[2] * (uint64_t)esize};
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, bx, estr,
+  CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                  const_cast<void*>(ptr), gdim, gstride, bx, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[384];

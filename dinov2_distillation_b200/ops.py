@@ -274,8 +274,12 @@ def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, colsums=None, 
             d.q_alt, d.k_alt, d.v_alt = (t.data_ptr() for t in keep)
     if colsums is not None:
         d.dq_colsum, d.dk_colsum, d.dv_colsum = (_p(t) for t in colsums)
+    acc = None
+    if max(Nq, Nk) > 256:   # long sequences: fp32 dQ accumulator of the tcgen05 backward
+        acc = torch.empty(B, Nq, Dm, device=q.device, dtype=torch.float32)
+        d.dq_accum = acc.data_ptr()
     L.check(L.load().b200_attention_bwd(C.byref(d), _stream()), "attention_bwd")
-    del keep
+    del keep, acc
     return dq, dk, dv
 
 

@@ -40,7 +40,7 @@ void b200_profile_enable(int on);
 int b200_profile_read(int n_cat, double* ms, double* flops, long long* launches);
 /* Dispatch options (ints; defaults select the production kernels). The launchers read this table, never the
  * environment; tests and A/B tools flip entries. Names: "pdl", "attn_tc_fwd", "attn_tc_fwd_long", "attn_tc_bwd",
- * "attn_bwd_fused". b200_set_option returns -1 for an unknown name; b200_get_option returns -1 likewise. */
+ * "attn_bwd_fused", "attn_tc_bwd_long". b200_set_option returns -1 for an unknown name; b200_get_option returns -1 likewise. */
 int b200_set_option(const char* name, int value);
 int b200_get_option(const char* name);
 
@@ -212,6 +212,10 @@ typedef struct b200_attn_desc {
    * scores are recomputed from the fp16 tensors, every gradient product reads the bf16 copies); without them the
    * mma.sync kernels run, which convert fragments in registers. */
   const void* q_alt; const void* k_alt; const void* v_alt;
+  /* backward only, optional: fp32 workspace [B, Nq, heads*hd]. Sequences longer than 256 tokens run the tcgen05
+   * backward one key block per work unit and add each unit's dQ contribution into this accumulator (bulk tensor
+   * reduce-add); without it they run the two-kernel mma.sync backward. */
+  float* dq_accum;
 } b200_attn_desc;
 int b200_attention_fwd(const b200_attn_desc* d, void* stream);
 int b200_attention_bwd(const b200_attn_desc* d, void* stream);

@@ -140,6 +140,14 @@ if __name__ == "__main__":
         dict(B=2, heads=4, hd=64, Nq=150, Nk=150, half=True, colsum=True),
         dict(B=3, heads=24, hd=32, Nq=100, Nk=77, half=True, colsum=True),
         dict(B=2, heads=16, hd=24, Nq=64, Nk=64, half=True, colsum=True),
+        # streaming mode (fp32 dQ accumulator)
+        dict(B=1, heads=1, hd=64, Nq=384, Nk=384, half=False),
+        dict(B=2, heads=3, hd=64, Nq=300, Nk=257, half=False),
+        dict(B=2, heads=16, hd=64, Nq=1369, Nk=1369, half=False, fused_qkv=True),
+        dict(B=2, heads=16, hd=64, Nq=1369, Nk=1369, half=True, colsum=True, do_scale=1e-4),
+        dict(B=2, heads=16, hd=64, Nq=1369, Nk=1369, half=True, shared_q=True, colsum=True),
+        dict(B=1, heads=4, hd=32, Nq=1024, Nk=520, half=True, colsum=True),
+        dict(B=1, heads=2, hd=48, Nq=200, Nk=600, half=False),
     ]
     for c in cases:
         try:
@@ -154,3 +162,5 @@ if __name__ == "__main__":
         timeit(64, 24, 16, 256, True)
         timeit(64, 16, 24, 256, True)
         timeit(32, 16, 48, 256, True)
+        timeit(32, 16, 64, 1369, False, iters=5)
+        timeit(32, 16, 64, 1369, True, iters=5)
