@@ -35,16 +35,16 @@ UNIT = "images/s"
 # BASELINE.json configs. per-GPU batch is fixed as N grows (weak scaling, like `batch_size ... #per gpu`, config.yaml:75)
 WORKLOADS = {
     "cfg1": dict(desc="dinov2_vits14 + resnet_18, ScaleKD res5 only, B=2 @224", teacher="dinov2_vits14", size=224, batch=2,
-                 losses=[("scalekd_res5", 512, 24, True)]),
+                 losses=[("scalekd_res5", 512, 24, True)], student_params=11_180_000),
     "cfg2": dict(desc="dinov2_vits14 -> stdc_2, config.yaml ScaleKD res4+res5, B=64/GPU @224", teacher="dinov2_vits14",
                  size=224, batch=64, losses=[("scalekd_res4", 512, 16, True), ("scalekd_res5", 1024, 24, False)],
-                 raw={"res4": 14, "res5": 7}),
+                 raw={"res4": 14, "res5": 7}, student_params=9_350_000),
     "cfg3": dict(desc="dinov2_vitb14 -> convnext_tiny, ScaleKD res4+res5, B=32/GPU @224", teacher="dinov2_vitb14",
                  size=224, batch=32, losses=[("scalekd_res4", 384, 16, True), ("scalekd_res5", 768, 24, False)],
-                 raw={"res4": 14, "res5": 7}),
+                 raw={"res4": 14, "res5": 7}, student_params=27_860_000),
     "cfg4": dict(desc="dinov2_vitl14 -> swin_tiny, ScaleKD res4+res5 (heads 16), B=32/GPU @518", teacher="dinov2_vitl14",
                  size=518, batch=32, losses=[("scalekd_res4", 384, 16, True), ("scalekd_res5", 768, 16, False)],
-                 raw={"res4": 33, "res5": 17}),
+                 raw={"res4": 33, "res5": 17}, student_params=27_550_000),
     "cfg5": dict(desc="dinov2_vitg14 teacher forward only, B=64/GPU @224", teacher="dinov2_vitg14", size=224, batch=64,
                  losses=[]),
 }
@@ -295,7 +295,10 @@ def build_gpu_step(wl, device):
         r = wl.get("raw", {}).get(layer, g) if wl.get("raw_student") else g   # --raw-student: the backbone's own tap size
         host[layer] = torch.randn(B, cs, r, r, generator=gen).pin_memory()
     params = [p for p in step.losses.parameters()]
-    arena = D.FlatGradArena(params) if params else None
+    # data parallel: the arena also carries a student-sized tail, so the ONE all-reduce per step has the size SURVEY.md
+    # section 8(e) gives it (student + ScaleKD gradients; the student's own backward is stock PyTorch and out of scope)
+    extra = int(wl.get("student_params", 0)) if wl.get("dp_student_tail") else 0
+    arena = D.FlatGradArena(params, extra_numel=extra) if params else None
     if arena is not None:
         arena.enable_direct_accumulation(step.losses)   # backward kernels add straight into the arena views
     return step, host, arena
@@ -315,6 +318,11 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--no-student-tail", action="store_true",
+                    help="N > 1: all-reduce only the ScaleKD gradients (default: plus a student-sized tail, SURVEY 8e)")
+    ap.add_argument("--serial-allreduce", action="store_true",
+                    help="N > 1: wait for the all-reduce right after the step instead of overlapping it with the next "
+                         "step's teacher forward")
     ap.add_argument("--raw-student", action="store_true",
                     help="feed the student's RAW tap maps (e.g. 14x14 / 7x7 at 224) and fuse ModelWrapper's bilinear resize "
                          "into the projector (SURVEY 8 f1) instead of the already-resized maps the metric is quoted on")
@@ -341,6 +349,8 @@ def main():
     torch.cuda.set_device(device)
     lib = L.load()
 
+    wl["dp_student_tail"] = world > 1 and not args.no_student_tail
+    overlap = world > 1 and not args.serial_allreduce and not args.no_graph and bool(wl["losses"])
     step, host, arena = build_gpu_step(wl, device)
     dev = {k: v.to(device) for k, v in host.items()}
     layers = [n.split("_")[1] for n, *_ in wl["losses"]]
@@ -349,10 +359,18 @@ def main():
     graphed = None
     if not args.no_graph:
         from dinov2_distillation_b200.distill import GraphedDistillStep
-        graphed = GraphedDistillStep(step, dev["img"], {k: dev[k] for k in layers}, arena)
+        graphed = GraphedDistillStep(step, dev["img"], {k: dev[k] for k in layers}, arena, split_teacher=overlap)
 
     def hot_path(img, feats):
         """One step with inputs resident in HBM (img / feats=None: reuse the graph's static input buffers)."""
+        if overlap:
+            # data parallel: the all-reduce of the PREVIOUS step stays in flight under this step's frozen-teacher forward
+            # (nothing a step changes feeds it) and is joined before anything reads trainable state or the arena
+            graphed.run_teacher(img)
+            arena.wait()
+            out, _ = graphed.run_losses(feats)
+            arena.allreduce_mean(async_op=True)
+            return out
         if graphed is not None:
             out, _ = graphed(img, feats)
             if not layers:
@@ -368,12 +386,12 @@ def main():
             out = step._compute_losses({"student": feats, "teacher": T})
             out["loss"].backward()
         if arena is not None and world > 1:
-            w = arena.allreduce_mean()
-            if w is not None:
-                w.wait()
+            arena.allreduce_mean()
         return out
 
     def sync_all():
+        if arena is not None:
+            arena.wait()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -393,6 +411,8 @@ def main():
         e0.record()
         for _ in range(args.steps):
             hot_path(res_img, res_feats)
+        if arena is not None:
+            arena.wait()           # the last step's all-reduce ends inside the timed region
         e1.record()
         sync_all()
     launches = int(lib.b200_launch_count())
@@ -431,13 +451,18 @@ def main():
         if graphed is not None:
             # this step's inputs were staged H2D (side stream) while the previous step computed; stage the next
             # step's inputs now so that its copy overlaps this step -- every step still copies its own batch
-            out, _ = graphed.run_staged()
+            if overlap:
+                graphed.consume_staged()
+                graphed.run_teacher()
+                arena.wait()
+                out, _ = graphed.run_losses()
+                arena.allreduce_mean(async_op=True)
+            else:
+                out, _ = graphed.run_staged()
             if not layers:
                 out = out["teacher"]
-            if arena is not None and world > 1:
-                w = arena.allreduce_mean()
-                if w is not None:
-                    w.wait()
+            if arena is not None and world > 1 and not overlap:
+                arena.allreduce_mean()
             if not last:
                 graphed.stage_inputs(host["img"], {k: host[k] for k in layers})
         else:
@@ -473,6 +498,8 @@ def main():
                 graphed.stage_inputs(host["img"], {k: host[k] for k in layers})   # step 0's copy is inside the region
             for i in range(args.steps):
                 e2e_step(last=(i == args.steps - 1))
+            if arena is not None:
+                arena.wait()
             e1.record()
             sync_all()
         t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -571,6 +598,12 @@ def main():
                        "student_features": ("synthetic (student network out of scope)" if not wl.get("raw_student") else
                                             f"synthetic RAW backbone maps {wl.get('raw')}, bilinear resize fused into the projector"),
                        "parallelism": f"dp{world}",
+                       "allreduce": (None if world == 1 else
+                                     {"bytes": int(arena.numel * 4) if arena is not None else 0,
+                                      "student_tail_params": int(wl.get("student_params", 0)) if wl.get("dp_student_tail") else 0,
+                                      "overlap": ("in flight under the next step's teacher forward (two graphs: teacher / "
+                                                  "projectors+losses+backward), joined before the second graph" if overlap
+                                                  else "stream-ordered right after the step")}),
                        "precision": "teacher bf16 operands / fp32 accum+residual; projector fwd fp16 operands, bwd bf16",
                        "l2": "per-step working set (activations >> 126 MB L2) ; no explicit flush",
                        "launch": "eager" if graphed is None else "one CUDA graph replay per step",

@@ -117,6 +117,7 @@ SIGNATURES = {
     "b200_get_option": (_i, [C.c_char_p]),
     "b200_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll)]),
     "b200_gemm_bf16": (_i, [C.POINTER(GemmDesc), c_vp]),
+    "b200_ln_gemm_bf16": (_i, [c_fp, c_fp, c_fp, C.c_float, c_fp, c_fp, c_vp, C.POINTER(GemmDesc), c_vp]),
     "b200_cast_f32_bf16": (_i, [c_fp, c_vp, c_ll, c_vp]),
     "b200_split3_16": (_i, [c_fp, c_vp, c_ll, _i, _i, _i, c_vp]),
     "b200_cast_f32_f16": (_i, [c_fp, c_vp, c_ll, c_vp]),

@@ -46,6 +46,7 @@ static OptDef g_opts[OPT_COUNT] = {
     {"gemm_ew", "B200_GEMM_EW", 16},                 // epilogue warps where the epilogue stages no operand tile
     {"gemm_dbg", "B200_GEMM_DBG", 0},                // probe mask (only in -DB200_GEMM_PROBES builds)
     {"attn_probe_skip", "B200_ATTN_PROBE_SKIP", 0},  // work-skipping mask (only in -DB200_ATTN_PROBES builds)
+    {"gemm_ln", "B200_GEMM_LN", 1},                  // LayerNorm-prologue GEMM (K <= 384) instead of layernorm_fwd + GEMM
     {"stat_attn_tc_bwd", "", 0},                     // counters (read with b200_get_option, reset with b200_set_option):
     {"stat_attn_mma_bwd", "", 0},                    //   attention backward launches per path
     {"stat_attn_tc_fwd", "", 0},

@@ -52,6 +52,10 @@ struct Gemm {
     return *this;
   }
   int run(void* stream) { return b200_gemm_bf16(&d, stream); }
+  // C = epilogue(LayerNorm(x) W^T): one kernel for K <= 384, else LayerNorm into xn_ws + this GEMM (b200_ln_gemm_bf16)
+  int run_ln(const float* x, const float* w, const float* b, float eps, float* mean, float* rstd, void* xn_ws, void* stream) {
+    return b200_ln_gemm_bf16(x, w, b, eps, mean, rstd, xn_ws, &d, stream);
+  }
 };
 
 // ================================================================================================ teacher
@@ -125,24 +129,24 @@ static int vit_block_fwd_impl(const b200_vit_config* c, const b200_vit_block* k,
   float* lse = sv ? sv->lse : w.lse;
   float* x_mid = sv ? sv->x_mid : y;
   // attention half
-  B200_TRY(b200_layernorm_fwd(x, k->ln1_w, k->ln1_b, c->ln_eps, nullptr, w.xn, sv ? sv->mean1 : nullptr,
-                              sv ? sv->rstd1 : nullptr, Mi, D, 0, 0, 0, stream));
-  B200_TRY(Gemm(w.xn, D, k->qkv_w, D, Mi, 3 * D, D).bias(k->qkv_b).out16(qkv, 3 * D).run(stream));
+  B200_TRY(Gemm(w.xn, D, k->qkv_w, D, Mi, 3 * D, D).bias(k->qkv_b).out16(qkv, 3 * D)
+               .run_ln(x, k->ln1_w, k->ln1_b, c->ln_eps, sv ? sv->mean1 : nullptr, sv ? sv->rstd1 : nullptr, w.xn, stream));
   b200_attn_desc ad;
   attn_desc_self(ad, c, qkv, attn, lse, B, N);
   B200_TRY(b200_attention_fwd(&ad, stream));
   B200_TRY(Gemm(attn, D, k->proj_w, D, Mi, D, D).bias(k->proj_b).col_scale(k->ls1).residual(x, D).out32(x_mid, D).run(stream));
   // MLP half
-  B200_TRY(b200_layernorm_fwd(x_mid, k->ln2_w, k->ln2_b, c->ln_eps, nullptr, w.xn, sv ? sv->mean2 : nullptr,
-                              sv ? sv->rstd2 : nullptr, Mi, D, 0, 0, 0, stream));
+  float* mean2 = sv ? sv->mean2 : nullptr;
+  float* rstd2 = sv ? sv->rstd2 : nullptr;
   if (!c->swiglu) {
     Gemm g1(w.xn, D, k->fc1_w, D, Mi, F, D);
     g1.bias(k->fc1_b).act(B200_ACT_GELU).out16(w.h, F);
     if (sv) g1.out16_pre(sv->h_pre, F);
-    B200_TRY(g1.run(stream));
+    B200_TRY(g1.run_ln(x_mid, k->ln2_w, k->ln2_b, c->ln_eps, mean2, rstd2, w.xn, stream));
   } else {
     bf16* h12 = sv ? sv->h_pre : w.h12;
-    B200_TRY(Gemm(w.xn, D, k->fc1_w, D, Mi, 2 * F, D).bias(k->fc1_b).out16(h12, 2 * F).run(stream));
+    B200_TRY(Gemm(w.xn, D, k->fc1_w, D, Mi, 2 * F, D).bias(k->fc1_b).out16(h12, 2 * F)
+                 .run_ln(x_mid, k->ln2_w, k->ln2_b, c->ln_eps, mean2, rstd2, w.xn, stream));
     B200_TRY(b200_swiglu(h12, w.h, Mi, F, stream));
   }
   B200_TRY(Gemm(w.h, F, k->fc2_w, F, Mi, D, F).bias(k->fc2_b).col_scale(k->ls2).residual(x_mid, D).out32(y, D).run(stream));

@@ -501,3 +501,24 @@ extern "C" int b200_gemm_bf16(const b200_gemm_desc* d, void* stream) {
   if (bn == 192) return dispatch_major<192>(amn, bmn, ta, tb, p, st);
   return dispatch_major<128>(amn, bmn, ta, tb, p, st);
 }
+
+namespace b200 {
+int launch_gemm_ln(const b200_gemm_desc* d, const float* x, long long ldx, const float* ln_w, const float* ln_b, float eps,
+                   float* mean, float* rstd, cudaStream_t st);   // gemm_v2.cu
+}
+
+extern "C" int b200_ln_gemm_bf16(const float* x, const float* ln_w, const float* ln_b, float eps, float* mean, float* rstd,
+                                 void* xn_ws, const b200_gemm_desc* d, void* stream) {
+  B200_CHECK_ARG(d != nullptr && x != nullptr && ln_w != nullptr && ln_b != nullptr, "null argument");
+  B200_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0 && d->B, "empty problem");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int r = launch_gemm_ln(d, x, d->K, ln_w, ln_b, eps, mean, rstd, st);
+  if (r <= 0) return r;
+  // outside the fused kernel's envelope: LayerNorm pass into the caller's bf16 workspace, then the plain GEMM
+  B200_CHECK_ARG(xn_ws != nullptr, "the unfused path needs the [M, K] bf16 workspace");
+  B200_TRY(b200_layernorm_fwd(x, ln_w, ln_b, eps, nullptr, xn_ws, mean, rstd, d->M, d->K, 0, 0, 0, stream));
+  b200_gemm_desc g = *d;
+  g.A = xn_ws;
+  g.lda = d->K;
+  return b200_gemm_bf16(&g, stream);
+}

@@ -81,6 +81,16 @@ __device__ __forceinline__ void v2_mbar_arrive_cta(uint64_t* bar, uint32_t cta) 
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// accumulator hand-back: the TMEM reads were ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync; a release
+// at cluster scope would add a MEMBAR.ALL.CTA + ERRBAR per tile and warp (18 % of the stall samples, profiles/r02)
+__device__ __forceinline__ void v2_mbar_arrive_cta_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
 template <int kCols>
 __device__ __forceinline__ void v2_tmem_alloc_pair(uint32_t* smem_slot) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols)
@@ -176,7 +186,8 @@ template <int BN, int EPI, int EW>
 __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUtensorMap* tmO, const CUtensorMap* tmX,
                                                  uint32_t taddr, int row0, int n0, uint32_t stage_smem, uint64_t* xbar,
                                                  uint32_t& xphase, int half, int lane, bool first_split, bool use_x_arg,
-                                                 bool reduce_out, uint64_t* tempty, bool pair, uint32_t* out_toggle, uint32_t vec_smem) {
+                                                 bool reduce_out, uint64_t* tempty, bool pair, uint32_t* out_toggle, uint32_t vec_smem,
+                                                 uint32_t bias_row_smem = 0) {
   constexpr int NG = EW / 4;                             // warps per TMEM quadrant
   constexpr int UNITS = (BN / 32 + NG - 1) / NG;         // units per warp (the last may be absent: BN = 192, NG = 4)
   constexpr bool PREFETCH = EW == 8;                     // 8 warps: next unit's tcgen05.ld in flight during this one
@@ -201,7 +212,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      if (pair) v2_mbar_arrive_cta(tempty, 0);
+      if (pair) v2_mbar_arrive_cta_relaxed(tempty, 0);
       else mbar_arrive(tempty);
     }
     return;
@@ -229,7 +240,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (pair) v2_mbar_arrive_cta(tempty, 0);
+        if (pair) v2_mbar_arrive_cta_relaxed(tempty, 0);
         else mbar_arrive(tempty);
       }
     }
@@ -246,7 +257,14 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
     // (N is a multiple of 32 on this path -- launch_gemm_v2 sends ragged N to the first-generation kernel -- so there
     // is no per-column tail code: the if-converted tail branches were ~170 predicated-off issue slots per unit)
     if (p.bias != nullptr && first_split) {
-      if (vec_smem != 0) {   // staged in this warp's spare shared memory before the accumulator wait (broadcast reads)
+      if (bias_row_smem != 0) {   // the whole bias vector sits in shared memory (row-panel kernels: every column tile passes)
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const uint4 q = v2_lds128(bias_row_smem + (c0 + j) * 4);
+          v[j] += __uint_as_float(q.x); v[j + 1] += __uint_as_float(q.y);
+          v[j + 2] += __uint_as_float(q.z); v[j + 3] += __uint_as_float(q.w);
+        }
+      } else if (vec_smem != 0) {   // staged in this warp's spare shared memory before the accumulator wait (broadcast reads)
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const uint4 q = v2_lds128(vec_smem + i * 128 + j * 4);
@@ -645,6 +663,253 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LayerNorm-prologue GEMM
+// C[M, N] = epilogue(LN(x)[M, K] W[N, K]^T) for K = D <= 384 (the ViT-S teacher's LN1 -> qkv and LN2 -> fc1: hub Block.forward,
+// called via models/backbones/dinov2.py:32 and train/distillation_module.py:177). One CTA owns a 128-row panel:
+//   * its epilogue warps read the panel's fp32 rows ONCE (one warp per row, row in registers, the arithmetic of
+//     layernorm_fwd_kernel), normalise, and write the bf16 operand straight into shared memory in the 128-byte-swizzled
+//     K-major layout the MMA descriptors expect -- the [M, D] bf16 round trip through HBM and the LayerNorm launch are gone,
+//     and the A operand is staged once instead of once per column tile;
+//   * the panel then stays resident while W streams through a TMA ring; CTAs run as pairs (cta_group::2: each CTA stages
+//     half of every W tile, the leader issues 256 x BN MMAs for both), so each W tile leaves L2 once per 256 rows;
+//   * accumulators double-buffered in TMEM, epilogue = v2_epilogue_tile (bias / GELU / pre-activation copy, bulk stores).
+struct LnPrologue {
+  const float* x; long long ldx;
+  const float* w; const float* b; float eps;
+  float* mean; float* rstd;   // optional outputs [M] (saved for the block's input-gradient pass)
+};
+
+constexpr int LNG_KB_MAX = 6;   // K <= 384
+
+template <int BN>
+struct LnCfg {
+  static constexpr int A_BYTES = LNG_KB_MAX * A_TILE_BYTES;        // resident panel: 128 rows x 384 bf16
+  static constexpr int B_STAGE = (BN / 2) * BK * 2;                // this CTA's half of a W tile (BN/2 rows x 64)
+  static constexpr int BIAS_BYTES = 8192;                          // the bias vector of every column tile (N <= 2048)
+  static constexpr int RING = 232448 - 1024 - 512 - V2_EPI_BYTES - A_BYTES - BIAS_BYTES;
+  static constexpr int STAGES = (RING / B_STAGE) > 8 ? 8 : (RING / B_STAGE);
+  static constexpr int TMEM_STRIDE = (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * TMEM_STRIDE;
+  static constexpr int SMEM_BYTES = A_BYTES + STAGES * B_STAGE + V2_EPI_BYTES + BIAS_BYTES + 1024 + 512;
+  static_assert(STAGES >= 3, "W ring too shallow");
+};
+
+template <int BN, int EPI, int EW>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+               const __grid_constant__ CUtensorMap tmX, const GemmParams p, const LnPrologue ln) {
+  using Cfg = LnCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::A_BYTES;
+  uint8_t* epi_smem = sB + STAGES * Cfg::B_STAGE;
+  float* s_bias = reinterpret_cast<float*>(epi_smem + V2_EPI_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + V2_EPI_BYTES + Cfg::BIAS_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* x_bar = tempty_bar + 2;                      // one per epilogue warp
+  uint64_t* a_bar = x_bar + V2_MAX_EPI_WARPS;            // both CTAs' panels are normalised and staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = v2_cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (p.out_bf16_pre != nullptr) tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * EW);
+    }
+    for (int s = 0; s < EW; ++s) mbar_init(&x_bar[s], 1);
+    mbar_init(a_bar, 2 * EW);
+    fence_barrier_init();
+  }
+  if (warp == 2) v2_tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  v2_cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  const int m0 = (int)(blockIdx.x >> 1) * 256 + (int)rank * 128;
+  const int kblocks = p.K / BK;
+#define LNG_STAMP(slot) do { if (kGemmProbes && p.dbg_buf && blockIdx.x == 0) p.dbg_buf[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) LNG_STAMP(0);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nt = 0; nt < p.n_tiles; ++nt) {
+        const int n0 = nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_STAGE);
+          v2_tma_load_2d_pair(sB + stage * Cfg::B_STAGE, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      mbar_wait(a_bar, 0);
+      tc_fence_after();
+      LNG_STAMP(2);
+      const uint32_t a_addr = smem_u32(sA);
+      for (int nt = 0; nt < p.n_tiles; ++nt) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        if (nt < 8) LNG_STAMP(8 + nt);
+        const uint32_t d_tmem = tmem_base + as * Cfg::TMEM_STRIDE;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + kb * A_TILE_BYTES + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            v2_mma_pair(d_tmem, da, db, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          v2_commit_pair(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        v2_commit_pair(&tfull_bar[as]);
+        if (nt < 8) LNG_STAMP(16 + nt);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    // ---- LayerNorm prologue: rows ew, ew + EW, ... of this CTA's panel (layernorm_fwd_kernel's arithmetic, row in registers)
+    {
+      constexpr int NV = (LNG_KB_MAX * BK) / 128;   // float4 per lane: 3 at K = 384
+      constexpr int RB = 2;                         // rows per batch; the next batch's loads are in flight while this one is
+      constexpr int NB = 128 / (EW * RB);           // normalised and stored (the prologue is load latency otherwise)
+      const float inv_d = 1.0f / (float)p.K;
+      const uint32_t a_base = smem_u32(sA);
+      // the bias of every column tile -> shared memory (each epilogue unit would pay an L2 round trip for it otherwise)
+      if (p.bias != nullptr) {
+        for (int i = (ew * 32 + lane) * 4; i < p.N; i += EW * 32 * 4)
+          *reinterpret_cast<float4*>(s_bias + i) = __ldg(reinterpret_cast<const float4*>(p.bias + i));
+      }
+      float4 v[2][RB][NV];
+      auto load_batch = [&](int bi, float4 (&dst)[RB][NV]) {
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          const int row = m0 + ew + (bi * RB + j) * EW;
+          const bool live = row < p.M;
+          const float4* xr = reinterpret_cast<const float4*>(ln.x + (long long)row * ln.ldx);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c4 = i * 32 + lane;
+            dst[j][i] = (live && c4 * 4 < p.K) ? xr[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      load_batch(0, v[0]);
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi) {
+        if (bi + 1 < NB) load_batch(bi + 1, v[(bi + 1) & 1]);
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          const float4 (&vr)[NV] = v[bi & 1][j];
+          const int r = ew + (bi * RB + j) * EW;
+          const int row = m0 + r;
+          const bool live = row < p.M;
+          float sm = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) sm += (vr[i].x + vr[i].y) + (vr[i].z + vr[i].w);
+          const float mean = warp_sum(sm) * inv_d;
+          float q = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c4 = i * 32 + lane;
+            if (c4 * 4 < p.K) {
+              const float a = vr[i].x - mean, bq = vr[i].y - mean, c = vr[i].z - mean, d = vr[i].w - mean;
+              q += (a * a + bq * bq) + (c * c + d * d);
+            }
+          }
+          const float rstd = rsqrtf(warp_sum(q) * inv_d + ln.eps);
+          if (lane == 0 && live) {
+            if (ln.mean) ln.mean[row] = mean;
+            if (ln.rstd) ln.rstd[row] = rstd;
+          }
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c4 = i * 32 + lane;
+            const int c = c4 * 4;
+            if (c < p.K) {
+              uint32_t u0 = 0u, u1 = 0u;
+              if (live) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(ln.w) + c4);
+                const float4 be = __ldg(reinterpret_cast<const float4*>(ln.b) + c4);
+                u0 = pack_bf16((vr[i].x - mean) * rstd * g.x + be.x, (vr[i].y - mean) * rstd * g.y + be.y);
+                u1 = pack_bf16((vr[i].z - mean) * rstd * g.z + be.z, (vr[i].w - mean) * rstd * g.w + be.w);
+              }
+              // element (r, c) of the K-major panel: k-block c / 64, 128-byte row r, 16-byte chunk swizzled by r & 7
+              const uint32_t addr = a_base + (c >> 6) * A_TILE_BYTES + r * 128 + (((((uint32_t)c & 63u) >> 3) ^ ((uint32_t)r & 7u)) << 4) +
+                                    ((uint32_t)c & 7u) * 2;
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(u0), "r"(u1) : "memory");
+            }
+          }
+        }
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor-core (async proxy) reads, of either CTA
+      __syncwarp();
+      if (lane == 0) v2_mbar_arrive_cta(a_bar, 0);
+      if (ew == 0 && lane == 0) LNG_STAMP(1);
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");   // the bias row is staged by all epilogue warps
+    }
+    const uint32_t bias_row = p.bias != nullptr ? smem_u32(s_bias) : 0u;
+    // ---- epilogue over the column tiles
+    const uint32_t stage_smem = smem_u32(epi_smem + ew * (V2_EPI_BYTES / EW));
+    uint64_t* xbar = &x_bar[ew];
+    uint32_t xphase = 0;
+    uint32_t out_toggle = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int nt = 0; nt < p.n_tiles; ++nt) {
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
+      if (ew == 0 && lane == 0 && nt < 8) LNG_STAMP(24 + nt);
+      v2_epilogue_tile<BN, EPI, EW>(p, &tmO, &tmX, taddr, m0 + quad * 32, nt * BN, stage_smem, xbar, xphase, half, lane, true,
+                                    false, false, &tempty_bar[as], true, &out_toggle, 0u, bias_row);
+      if (ew == 0 && lane == 0 && nt < 8) LNG_STAMP(32 + nt);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) v2_bulk_wait_all();
+    __syncwarp();
+    if (ew == 0 && lane == 0) LNG_STAMP(3);
+  }
+
+  tc_fence_before();
+  v2_cluster_sync();
+  if (warp == 2) v2_tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+  if (threadIdx.x == 0) LNG_STAMP(4);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 template <int BN, bool PAIR, bool MN, int EPI, int EW>
 static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
@@ -841,6 +1106,110 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   if (pair) return v2_dispatch_bn<true, false, 8>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
   if (ew16) return v2_dispatch_bn<false, false, 16>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
   return v2_dispatch_bn<false, false, 8>(bn, epi, ta, tb, to, tx, p, use_x, reduce_out, st);
+}
+
+template <int BN, int EPI, int EW>
+static int lng_launch(const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx, const GemmParams& p,
+                      const LnPrologue& ln, cudaStream_t st) {
+  using Cfg = LnCfg<BN>;
+  auto kern = gemm_ln_kernel<BN, EPI, EW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (unsigned)cdiv(p.M, 256));
+  cfg.blockDim = dim3(128 + EW * 32);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  const int prof = prof_begin(st);
+  if (kGemmProbes && option(OPT_GEMM_DBG)) {   // clock stamps of CTA 0 (eager launches only: synchronises and prints)
+    static long long* buf = nullptr;
+    if (!buf) cudaMalloc(&buf, 48 * sizeof(long long));
+    cudaMemsetAsync(buf, 0, 48 * sizeof(long long), st);
+    GemmParams q = p;
+    q.dbg_buf = buf;
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tb, to, tx, q, ln));
+    cudaStreamSynchronize(st);
+    long long h[48];
+    cudaMemcpy(h, buf, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[gemm_ln dbg] BN=%d epi=%d: ln_done %lld a_bar %lld epi_done %lld exit %lld |", BN, EPI, h[1] - h[0], h[2] - h[0],
+            h[3] - h[0], h[4] - h[0]);
+    for (int t = 0; t < p.n_tiles && t < 8; ++t)
+      fprintf(stderr, " tile%d mma %lld-%lld epi %lld-%lld |", t, h[8 + t] - h[0], h[16 + t] - h[0], h[24 + t] - h[0], h[32 + t] - h[0]);
+    fprintf(stderr, "\n");
+    B200_LAUNCH_OK();
+    return 0;
+  }
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tb, to, tx, p, ln));
+  prof_end(prof, st, 2.0 * p.M * p.N * p.K, 0);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <int BN>
+static int lng_dispatch(int epi, bool has_pre, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                        const GemmParams& p, const LnPrologue& ln, cudaStream_t st) {
+  (void)has_pre;
+  if (epi == 1) return lng_launch<BN, 1, 16>(tb, to, tx, p, ln, st);
+  return lng_launch<BN, 0, 16>(tb, to, tx, p, ln, st);
+}
+
+// Returns 1 when the problem is outside the kernel's envelope (the caller runs layernorm_fwd + the plain GEMM).
+int launch_gemm_ln(const b200_gemm_desc* d, const float* x, long long ldx, const float* ln_w, const float* ln_b, float eps,
+                   float* mean, float* rstd, cudaStream_t st) {
+  if (!option(OPT_GEMM_LN)) return 1;
+  if (d->K % BK != 0 || d->K > LNG_KB_MAX * BK || d->K % 128 != 0 || d->N % 32 != 0 || d->N > 2048 || d->M < 256) return 1;
+  if (d->a_mn_major || d->b_mn_major || d->a_is_fp16 || d->b_is_fp16 || d->split_k > 1 || d->atomic_add) return 1;
+  if (d->out_f32 || d->residual || d->col_scale || d->aux || d->out16_colsum || d->out16_pre_alt || d->out16_is_fp16) return 1;
+  if (d->out_row_period > 0 || d->res_row_period > 0 || d->out_batch_period > 0) return 1;
+  if (d->out_bf16 == nullptr || (d->act != B200_ACT_NONE && d->act != B200_ACT_GELU)) return 1;
+  if (d->act == B200_ACT_GELU && false) return 1;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(x) || ldx % 4 != 0 || !al16(ln_w) || !al16(ln_b) || !al16(d->B) || d->ldb % 8 != 0) return 1;
+  if (!al16(d->out_bf16) || d->ldo16 % 8 != 0 || (d->bias && !al16(d->bias))) return 1;
+  if (d->out_bf16_pre && (!al16(d->out_bf16_pre) || d->ldo16_pre % 8 != 0)) return 1;
+  // column tile: the kernel is paced by its epilogue (32-column units, EW / 4 warps per TMEM quadrant): fewest unit rounds
+  // per warp first (256 columns = two full rounds per tile), least padded MMA work on ties
+  int bn = 256;
+  long long best = -1;
+  for (int c : {256, 192, 128}) {
+    const long long tiles = cdiv(d->N, c), rounds_per_tile = cdiv(c / 32, 4);
+    long long rounds = (tiles - 1) * rounds_per_tile + cdiv(cdiv(d->N - (tiles - 1) * c, 32), 4);
+    const long long cost = rounds * 1000 + tiles * c;
+    if (best < 0 || cost < best) { best = cost; bn = c; }
+  }
+  GemmParams p{};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.m_tiles = (int)cdiv(d->M, 256); p.n_tiles = (int)cdiv(d->N, bn); p.num_kb = d->K / BK; p.kb_per_split = p.num_kb; p.split_k = 1;
+  p.total_tiles = p.m_tiles * p.n_tiles;
+  p.bias = d->bias; p.act = d->act;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16); p.ldo16 = d->ldo16;
+  p.out_bf16_pre = static_cast<__nv_bfloat16*>(d->out_bf16_pre); p.ldo16_pre = d->ldo16_pre;
+  p.vec_ok = 1;
+  p.algo_scale = 1.0f;
+  p.idesc = make_idesc_bf16(256, bn, false, false);
+  p.dbg = kGemmProbes ? option(OPT_GEMM_DBG) : 0;
+  LnPrologue ln{x, ldx, ln_w, ln_b, eps, mean, rstd};
+  CUtensorMap tb, to, tx;
+  B200_TRY(make_tensor_map_2d(&tb, d->B, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, (uint32_t)(bn / 2)));
+  B200_TRY(make_tensor_map_ex(&to, d->out_bf16, 2, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo16, 32, 32, 64));
+  if (d->out_bf16_pre) B200_TRY(make_tensor_map_ex(&tx, d->out_bf16_pre, 2, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldo16_pre, 32, 32, 64));
+  else tx = to;
+  const int epi = d->act == B200_ACT_GELU ? 1 : 0;
+  if (bn == 256) return lng_dispatch<256>(epi, d->out_bf16_pre != nullptr, tb, to, tx, p, ln, st);
+  if (bn == 192) return lng_dispatch<192>(epi, d->out_bf16_pre != nullptr, tb, to, tx, p, ln, st);
+  return lng_dispatch<128>(epi, d->out_bf16_pre != nullptr, tb, to, tx, p, ln, st);
 }
 
 }  // namespace b200

@@ -101,6 +101,14 @@ class DistillationStep(nn.Module):
         if getattr(self, "_teacher_stream", None) is None or self._teacher_stream.device != dev:
             self._teacher_stream = torch.cuda.Stream(device=dev)
         ts = self._teacher_stream
+        # the teacher's cached bf16 weight pack (and the position embedding of this grid) are built on first use: do that
+        # on the MAIN stream, before the fork -- the re-used teacher blocks read the same buffers from the main / side
+        # streams, which only join the teacher stream at the loss terms
+        model = getattr(self.teacher, "model", None)
+        if model is not None and hasattr(model, "_ensure_pack"):
+            model._ensure_pack()
+            if hasattr(model, "_pos_for_grid") and batch.dim() == 4:
+                model._pos_for_grid(batch.shape[2] // 14, batch.shape[3] // 14)
         ts.wait_stream(main)
         with torch.cuda.stream(ts), torch.no_grad():
             T = self.teacher(batch)[self.teacher_key]
@@ -225,14 +233,23 @@ class GraphedDistillStep:
     The student network stays outside the graph (stock PyTorch, as in the reference)."""
 
     def __init__(self, step: "DistillationStep", img: torch.Tensor, feats: Dict[str, torch.Tensor], arena=None,
-                 warmup: int = 3):
+                 warmup: int = 3, split_teacher: bool = False):
+        """split_teacher: capture TWO graphs -- the frozen teacher forward, and everything that touches trainable state
+        (projectors, loss terms, backward). A data-parallel loop can then keep the gradient all-reduce of step i in
+        flight under the teacher forward of step i + 1 (which depends on nothing a step changes) and only join it
+        before the second graph: `run_teacher()` ... `arena.wait()` ... `run_losses()`."""
         if not img.is_cuda:
             raise RuntimeError("GraphedDistillStep needs CUDA tensors: there is no CPU fallback")
         self.step, self.arena = step, arena
+        self.split_teacher = bool(split_teacher) and bool(feats)
         if arena is not None:
             arena.enable_direct_accumulation(step.losses)
         self.img = img.detach().clone()
         self.feats = {k: v.detach().clone().requires_grad_(True) for k, v in feats.items()}
+        # module state the warm-up steps would otherwise leave behind: BatchNorm running statistics / counters advance
+        # on every training forward, and parameter gradients accumulate when no arena zeroes them
+        state = {n: b.detach().clone() for n, b in step.losses.named_buffers()}
+        grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in step.losses.named_parameters()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -240,26 +257,65 @@ class GraphedDistillStep:
                 self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = self._run()
+        if self.split_teacher:
+            self.graph_teacher = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_teacher):
+                self._T = self.step.teacher(self.img)[self.step.teacher_key]
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, pool=self.graph_teacher.pool()):
+                self.out = self._run_losses(self._T)
+        else:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._run()
         self.feat_grads = {k: v.grad for k, v in self.feats.items()}
+        # undo what warm-up and capture did to the module: the first replay is step 0, as in the reference
+        with torch.no_grad():
+            for n, b in step.losses.named_buffers():
+                b.copy_(state[n])
+            if arena is not None:
+                arena.zero()
+            else:
+                for n, p in step.losses.named_parameters():
+                    if grads[n] is None:
+                        if p.grad is not None:
+                            p.grad.zero_()   # (the captured graph accumulates into this tensor: it must stay allocated)
+                    else:
+                        p.grad.copy_(grads[n])
 
-    def _run(self):
+    def _run_losses(self, T, ready=None):
         if self.arena is not None:
             self.arena.zero()
         for f in self.feats.values():
             f.grad = None
-        if not self.feats or not self.step.two_streams:
-            T = self.step.teacher(self.img)[self.step.teacher_key]
-            if not self.feats:
-                return {"teacher": T}
-            out = self.step._compute_losses({"student": self.feats, "teacher": T})
-        else:
-            T, ready = self.step.teacher_async(self.img)
-            out = self.step._compute_losses({"student": self.feats, "teacher": T, "teacher_ready": ready})
+        feats = {"student": self.feats, "teacher": T}
+        if ready is not None:
+            feats["teacher_ready"] = ready
+        out = self.step._compute_losses(feats)
         out["loss"].backward()
         return {k: v.detach() for k, v in out.items()}
+
+    def _run(self):
+        if not self.feats:
+            return {"teacher": self.step.teacher(self.img)[self.step.teacher_key]}
+        if self.split_teacher or not self.step.two_streams:
+            return self._run_losses(self.step.teacher(self.img)[self.step.teacher_key])
+        T, ready = self.step.teacher_async(self.img)
+        return self._run_losses(T, ready)
+
+    # ---- split form (data parallel): teacher forward and the trainable part as separate replays
+    def run_teacher(self, img: Optional[torch.Tensor] = None) -> None:
+        if img is not None and img.data_ptr() != self.img.data_ptr():
+            self.img.copy_(img, non_blocking=True)
+        self.graph_teacher.replay()
+
+    def run_losses(self, feats: Optional[Dict[str, torch.Tensor]] = None):
+        if feats is not None:
+            for k, v in feats.items():
+                if v.data_ptr() != self.feats[k].data_ptr():
+                    self.feats[k].data.copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out, self.feat_grads
 
     def __call__(self, img: Optional[torch.Tensor] = None, feats: Optional[Dict[str, torch.Tensor]] = None):
         if img is not None and img.data_ptr() != self.img.data_ptr():
@@ -268,6 +324,8 @@ class GraphedDistillStep:
             for k, v in feats.items():
                 if v.data_ptr() != self.feats[k].data_ptr():
                     self.feats[k].data.copy_(v, non_blocking=True)
+        if self.split_teacher:
+            self.graph_teacher.replay()
         self.graph.replay()
         return self.out, self.feat_grads
 
@@ -291,13 +349,19 @@ class GraphedDistillStep:
                 self._stage_feats[k].copy_(v, non_blocking=True)
             self._stage_ready.record(cs)
 
-    def run_staged(self):
-        """Consume the staged inputs (see `stage_inputs`) and replay the captured step."""
+    def consume_staged(self) -> None:
+        """Move the staged inputs (see `stage_inputs`) into the graphs' static input buffers."""
         cur = torch.cuda.current_stream()
         cur.wait_event(self._stage_ready)
         self.img.copy_(self._stage_img, non_blocking=True)
         for k, v in self._stage_feats.items():
             self.feats[k].data.copy_(v, non_blocking=True)
         self._stage_free.record(cur)
+
+    def run_staged(self):
+        """Consume the staged inputs and replay the captured step."""
+        self.consume_staged()
+        if self.split_teacher:
+            self.graph_teacher.replay()
         self.graph.replay()
         return self.out, self.feat_grads

@@ -177,6 +177,33 @@ def patch_im2col(img: torch.Tensor, Kp: int = 592) -> torch.Tensor:
     return out
 
 
+def ln_gemm(x: torch.Tensor, ln_w: torch.Tensor, ln_b: torch.Tensor, eps: float, w: torch.Tensor, *,
+            bias: Optional[torch.Tensor] = None, act: str = "none", out_pre: bool = False, stats: bool = False):
+    """C = epilogue(LayerNorm(x) @ w^T): x fp32 [M, K] contiguous, w bf16 [N, K] (b200_ln_gemm_bf16: one kernel for
+    K <= 384, LayerNorm + GEMM otherwise). Returns (out bf16 [M, N], pre-activation copy or None, mean, rstd)."""
+    _need_cuda(x, ln_w, ln_b, w, bias)
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.dtype == torch.bfloat16 and w.stride(-1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    d = L.GemmDesc()
+    d.B, d.ldb = w.data_ptr(), w.stride(0)
+    d.M, d.N, d.K, d.split_k = M, N, K, 1
+    d.bias = _p(bias)
+    d.act = ACT[act]
+    out = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    d.out_bf16, d.ldo16 = out.data_ptr(), N
+    pre = None
+    if out_pre:
+        pre = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+        d.out_bf16_pre, d.ldo16_pre = pre.data_ptr(), N
+    mean = torch.empty(M, device=x.device, dtype=torch.float32) if stats else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if stats else None
+    ws = torch.empty(M, K, device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().b200_ln_gemm_bf16(x.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), float(eps), _p(mean), _p(rstd),
+                                       ws.data_ptr(), C.byref(d), _stream()), "ln_gemm_bf16")
+    return out, pre, mean, rstd
+
+
 def layernorm_fwd(x, w, b, eps, want_f32=True, want_bf16=False, want_stats=False, in_period=0, in_pad=0, rows=None):
     _need_cuda(x, w, b)
     D = x.shape[-1]

@@ -40,7 +40,7 @@ void b200_profile_enable(int on);
 int b200_profile_read(int n_cat, double* ms, double* flops, long long* launches);
 /* Dispatch options (ints; defaults select the production kernels). The launchers read this table, never the
  * environment; tests and A/B tools flip entries. Names: "pdl", "attn_tc_fwd", "attn_tc_fwd_long", "attn_tc_bwd",
- * "attn_bwd_fused", "attn_tc_bwd_long". b200_set_option returns -1 for an unknown name; b200_get_option returns -1 likewise. */
+ * "attn_bwd_fused", "attn_tc_bwd_long", "gemm_ln". b200_set_option returns -1 for an unknown name; b200_get_option returns -1 likewise. */
 int b200_set_option(const char* name, int value);
 int b200_get_option(const char* name);
 
@@ -92,6 +92,14 @@ typedef struct b200_gemm_desc {
 } b200_gemm_desc;
 
 int b200_gemm_bf16(const b200_gemm_desc* d, void* stream);
+/* LayerNorm in front of a GEMM: C = epilogue(LN(x) W^T), x fp32 [M, K] contiguous rows (K = the model width), the
+ * pre-norm linears of hub Block.forward (norm1 -> attn.qkv, norm2 -> mlp.fc1; facebookresearch/dinov2 layers/block.py,
+ * reached through models/backbones/dinov2.py:32 and train/distillation_module.py:177). d->A / d->lda are ignored.
+ * K <= 384 with a 16-bit output runs ONE kernel (the panel is normalised into shared memory, no bf16 round trip);
+ * anything else runs b200_layernorm_fwd into xn_ws (bf16 [M, K]) followed by b200_gemm_bf16. mean / rstd: optional
+ * fp32 [M] outputs. */
+int b200_ln_gemm_bf16(const float* x, const float* ln_w, const float* ln_b, float eps, float* mean, float* rstd,
+                      void* xn_ws, const b200_gemm_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ bandwidth kernels */
 /* fp32 -> bf16 / fp16 casts and fp16 -> bf16 (n elements). */

@@ -213,9 +213,8 @@ def test_reference_loop_over_b200_shells_matches_distillation_step():
         # (the two loops launch the two branches in a different stream order: atomics in the BatchNorm statistics and
         # the loss reductions re-associate (measured: 1e-4 relative), nothing else differs)
         assert abs(a - b) <= max(1e-4 * abs(b), 2e-5), (k, a, b)
+    # gradients: a handful of ReLU masks flip with the re-associated BatchNorm statistics (measured 3-4e-3, as in
+    # test_cfg2_full_size_properties): the north-star gradient gate applies
     for k in base:
-        assert rel(ours[1][k], theirs[1][k]) <= 2e-3, (k, rel(ours[1][k], theirs[1][k]))
-    big = max(v.norm().item() for v in theirs[2].values())
-    for k, v in theirs[2].items():
-        if v.norm().item() > 1e-3 * big:
-            assert rel(ours[2][k], v) <= 5e-3, (k, rel(ours[2][k], v))
+        assert rel(ours[1][k], theirs[1][k]) <= GRAD_RTOL, (k, rel(ours[1][k], theirs[1][k]))
+    check_param_grads({k: (ours[2][k], v) for k, v in theirs[2].items()})

@@ -233,6 +233,41 @@ def test_layernorm_drop_cls_rows():
     assert (y32 - ref).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("M,K,N,act,pre", [(16448, 384, 1152, "none", False), (16384, 384, 1536, "gelu", True),
+                                            (300, 384, 1536, "gelu", False), (1000, 256, 96, "none", True),
+                                            (2000, 128, 640, "gelu", False), (4112, 768, 2304, "none", False)])
+def test_ln_gemm_fused_prologue_and_fallback(M, K, N, act, pre):
+    """b200_ln_gemm_bf16: LayerNorm fused in front of the GEMM as a shared-memory prologue (K <= 384: CTA-pair kernel,
+    the panel is normalised once and stays resident; partial last pair / panel at M = 16448, 300, 1000) and the
+    LayerNorm + GEMM fallback (K = 768). Must equal the two-kernel path (same per-row arithmetic) and the fp32 reference."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    x = torch.randn(M, K, device="cuda", generator=g) * 2.0 + 0.3
+    x[:, ::37] *= 8.0          # a few large-magnitude channels, like a ViT residual stream
+    lw = 1.0 + 0.1 * torch.randn(K, device="cuda", generator=g)
+    lb = 0.1 * torch.randn(K, device="cuda", generator=g)
+    w = bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = 0.1 * torch.randn(N, device="cuda", generator=g)
+    out, p, mean, rstd = ops.ln_gemm(x, lw, lb, 1e-6, w, bias=bias, act=act, out_pre=pre, stats=True)
+    xn = torch.nn.functional.layer_norm(x, (K,), lw, lb, 1e-6)
+    z = bf(xn).float() @ w.float().t() + bias
+    ref = torch.nn.functional.gelu(z) if act == "gelu" else z
+    assert rel_err(out, ref) < 6e-3, rel_err(out, ref)
+    if pre:
+        assert rel_err(p, z) < 6e-3, rel_err(p, z)
+    assert (mean - x.mean(1)).abs().max().item() < 1e-4
+    assert rel_err(rstd, (x.var(1, unbiased=False) + 1e-6).rsqrt()) < 1e-5
+    # the unfused path (option off) runs layernorm_fwd + the plain GEMM: same operand bits, same products
+    ops.set_option("gemm_ln", 0)
+    try:
+        out2, p2, _, _ = ops.ln_gemm(x, lw, lb, 1e-6, w, bias=bias, act=act, out_pre=pre, stats=True)
+    finally:
+        ops.set_option("gemm_ln", 1)
+    assert rel_err(out, out2) < 2e-3, rel_err(out, out2)
+    if pre:
+        assert rel_err(p, p2) < 2e-3
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _attn_ref(q, k, v, heads, scale):
     B, Nq, D = q.shape

@@ -343,6 +343,61 @@ def test_graphed_step_follows_new_inputs_and_matches_eager():
     assert abs(out["loss"].item() - ref_a[0]["loss"].item()) <= 2e-3 * abs(ref_a[0]["loss"].item())
 
 
+def test_graphed_step_leaves_module_state_at_step_zero_and_split_teacher_form_matches():
+    """GraphedDistillStep's warm-up steps and capture must not leak into the module: BatchNorm running statistics /
+    num_batches_tracked and the gradients are those of step 0 afterwards (the reference's first optimizer step sees one
+    batch, not four). The split form (teacher forward and the trainable part as two graphs, for an all-reduce kept in
+    flight under the next teacher forward) replays the same numbers as the single graph."""
+    _, teacher, distill = _mods()
+    from dinov2_distillation_b200.distributed import FlatGradArena
+    from oracle import dinov2_ref
+    g = torch.load(os.path.join(GOLDEN, "pipeline_tiny.pt"))
+    cfg = dinov2_ref.VitCfg(*g["teacher_cfg"])
+    t, _, _ = _teacher_pair(cfg, seed=21, pos_grid=4)
+    t.model.load_state_dict(g["teacher_sd"])
+    step = distill.DistillationStep(None, t, g["specs"])
+    step.losses.load_state_dict(g["losses_sd"])
+    step = step.cuda().train()
+    img = g["img"].cuda()
+    feats = {k: v.cuda() for k, v in g["feats"].items()}
+    before = {n: b.detach().clone() for n, b in step.losses.named_buffers()}
+    # without an arena: gradients the captured graph accumulates into start at zero
+    graphed = distill.GraphedDistillStep(step, img, feats, None)
+    for n, b in step.losses.named_buffers():
+        assert torch.equal(b, before[n]), n
+    for n, p in step.losses.named_parameters():
+        assert p.grad is None or p.grad.abs().max().item() == 0.0, n
+    out1, fg1 = graphed(img, feats)
+    torch.cuda.synchronize()
+    nb = [b for n, b in step.losses.named_buffers() if n.endswith("num_batches_tracked")]
+    assert nb and all(int(b) == 1 for b in nb)
+    g1 = {n: p.grad.detach().clone() for n, p in step.losses.named_parameters() if p.grad is not None}
+    out1 = {k: v.clone() for k, v in out1.items()}
+    fg1 = {k: v.clone() for k, v in fg1.items()}
+    # split form with an arena
+    for p in step.losses.parameters():
+        p.grad = None
+    with torch.no_grad():
+        for n, b in step.losses.named_buffers():
+            b.copy_(before[n])
+    arena = FlatGradArena(step.losses.parameters())
+    split = distill.GraphedDistillStep(step, img, feats, arena, split_teacher=True)
+    assert arena.buffer.abs().max().item() == 0.0
+    split.run_teacher(img)
+    out2, fg2 = split.run_losses(feats)
+    torch.cuda.synchronize()
+    for k, v in out1.items():
+        assert abs(out2[k].item() - v.item()) <= 2e-3 * max(abs(v.item()), 1e-3), (k, out2[k].item(), v.item())
+    for k, v in fg1.items():
+        assert rel(fg2[k], v) <= 2e-3, (k, rel(fg2[k], v))
+    for n, p in step.losses.named_parameters():
+        if n in g1 and g1[n].norm().item() > 1e-6:
+            assert rel(p.grad, g1[n]) <= 5e-3, (n, rel(p.grad, g1[n]))
+    out3, _ = split(img, feats)          # the combined call of the split form
+    torch.cuda.synchronize()
+    assert abs(out3["loss"].item() - out1["loss"].item()) <= 2e-3 * abs(out1["loss"].item())
+
+
 def test_cfg2_shapes_vs_oracle_port():
     """config.yaml losses (res4 heads 16 self-query + res5 heads 24) on vits14 dims, B=4, against the oracle port."""
     _, teacher, distill = _mods()
