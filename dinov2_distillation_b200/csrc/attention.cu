@@ -952,12 +952,18 @@ using namespace b200;
 namespace b200 {
 int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st);   // attention_tc.cu (tcgen05, head_dim 64)
 int launch_attention_tc_bwd(const b200_attn_desc* d, cudaStream_t st);   // attention_bwd_tc.cu (tcgen05, Nq / Nk <= 256)
+int launch_attention_pp_fwd(const b200_attn_desc* d, cudaStream_t st);   // attention_pp.cu (tcgen05, two tiles in flight, Nk <= 256)
 }
 
 extern "C" int b200_attention_fwd(const b200_attn_desc* d, void* stream) {
   AttnParams p{};
   B200_TRY(fill_params(d, p, false));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const int r = launch_attention_pp_fwd(d, st);
+    if (r == 0) bump_stat(STAT_ATTN_PP_FWD);
+    if (r <= 0) return r;
+  }
   if (d->o_alt == nullptr) {   // (the tcgen05 kernel writes one output format)
     const int r = launch_attention_tc_fwd(d, st);
     if (r == 0) bump_stat(STAT_ATTN_TC_FWD);

@@ -1,0 +1,515 @@
+// tcgen05 / TMEM attention forward with TWO query tiles in flight ("ping-pong"), for key ranges that fit one TMEM
+// accumulator (Nk <= 256) and head dims 16 ... 64, fp16 or bf16:
+//   ScaleKD cross-attention : losses/scalekd.py:299-314 (fp16 operands, head_dim 16 / 24 / 32 / 48 / 64, per window or
+//                             whole grid; q may be batch invariant -- the self-query embedding, scalekd.py:232-234)
+//   re-used teacher blocks  : hub Attention.forward at N = 256, train/distillation_module.py:176-177 (bf16, head_dim 64)
+//
+// At these shapes the exponentials are the bound (one ex2 per score, 16 / clk / SM), not the tensor pipe: a 128 x 256
+// score tile needs 2 x 128-wide MMA k-steps per 16 of head_dim but 32 768 MUFU results. One tile at a time leaves the
+// MUFU pipe idle while S is loaded, the row maxima are exchanged, PV runs and O is drained (attention_tc.cu: ~2 200 of
+// ~5 500 cycles per tile); so two sets of eight softmax warps work on alternate tiles, each on its own 256-column half
+// of TMEM:
+//   S_t [128, Nk] = Q_t K^T      tcgen05.mma SS (K-major, K = head_dim padded to 32 / 64 by the TMA zero fill)
+//   pass 1: row maxima           thread = row, two warps per TMEM lane quadrant split the columns (0..127 | 128..255),
+//                                64 columns per tcgen05.ld round trip, partial maxima meet in shared memory
+//   pass 2: P = exp2(scale*S-m)  32-column chunks read again (TMEM reads are cheap; holding the row in registers would
+//                                need 128 of them for 16 warps that only get 104), 16-bit pairs written back over S
+//                                columns the warp has already consumed
+//   O_t [128, hd] = P V          tcgen05.mma TS (A = P from TMEM, B = V MN-major) into consumed S columns of half 0; for
+//                                head dims <= 32 the first half of P is published early and its products overlap the
+//                                remaining exponentials
+//   O / rowsum -> 16-bit         straight from registers: thread = row writes its contiguous 32 / 64 bytes per format
+//                                (the projector wants fp16 AND bf16 copies: the backward's gradient products read bf16)
+// K / V of a (batch, head) unit are loaded once by TMA (4-D maps (head_dim, heads, tokens, batch): rows past the sequence
+// and columns past the head are zero-filled) into a two-deep ring, Q tiles into their own.
+//
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-11: softmax set 0   warps 12-19: set 1
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/b200_distill.h"
+
+namespace b200 {
+
+int make_tensor_map_4d(CUtensorMap* out, const void* ptr, const uint64_t (&dims)[4], const uint64_t (&ld)[3],
+                       const uint32_t (&box)[4], int swizzle, int esize);
+
+#ifdef B200_ATTN_PROBES
+constexpr bool kAppProbes = true;
+#else
+constexpr bool kAppProbes = false;
+#endif
+// clock stamps of CTA 0 (only with -DB200_ATTN_PROBES): [tile][16]
+#define APP_STAMP(tile, slot)                                                                                   \
+  do {                                                                                                           \
+    if (kAppProbes && p.dbg != nullptr && blockIdx.x == 0 && (tile) < 16) p.dbg[(tile) * 16 + (slot)] = clock64(); \
+  } while (0)
+constexpr int APP_THREADS = 640;
+constexpr int APP_SET_WARPS = 8;
+
+template <int HDP>
+struct AppCfg {
+  static constexpr int ROWB = HDP * 2;               // bytes per operand row = swizzle width (64 or 128)
+  static constexpr int QTILE = 128 * ROWB;
+  static constexpr int KTILE = 256 * ROWB;
+  static constexpr int OFF_Q = 0;                    // [2][QTILE]
+  static constexpr int OFF_K = OFF_Q + 2 * QTILE;    // [2][KTILE]
+  static constexpr int OFF_V = OFF_K + 2 * KTILE;    // [2][KTILE]
+  static constexpr int OFF_X = OFF_V + 2 * KTILE;    // [2 sets][2 halves][128 rows] fp32 partial maxima, then the same for sums
+  static constexpr int OFF_BAR = OFF_X + 2 * 2 * 2 * 128 * 4;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;
+  static constexpr uint32_t LAYOUT = HDP == 64 ? 2u : 4u;   // SWIZZLE_128B / SWIZZLE_64B
+  // TMEM columns inside a warp half's 128 S columns: P of its chunks 0-1 at [0, 32), P of chunks 2-3 at P_HI, and (half 0
+  // only) the O accumulator at O_OFF. HDP = 32: O sits at [32, 64) -- S columns every warp has consumed when the FIRST P
+  // group is published, so PV of that group runs under the remaining exponentials. HDP = 64 needs 64 columns, which are
+  // only free once the whole row is consumed: O at [64, 128), both groups published together.
+  static constexpr bool SPLIT = HDP == 32;
+  static constexpr uint32_t P_HI = SPLIT ? 64u : 32u;
+  static constexpr uint32_t O_OFF = SPLIT ? 32u : 64u;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+struct AppParams {
+  int B, heads, Nq, Nk, hd;
+  int nkp;                   // keys padded to a multiple of 16 (MMA N of QK^T, K of PV)
+  int n_qt;                  // 128-row query tiles per unit
+  int q_batched;
+  float scale_log2;
+  float* lse;
+  void* o; long long o_bs, o_ts;          // same 16-bit format as q / k / v
+  void* o_alt;                            // optional: the other 16-bit format, same strides
+  uint32_t idesc_qk, idesc_pv;
+  long long* dbg;
+};
+
+__device__ __forceinline__ float app_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t app_pack_f16(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int HDP, bool FP16>
+__global__ void __launch_bounds__(APP_THREADS, 1)
+attn_pp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AppParams p) {
+  using C = AppCfg<HDP>;
+  constexpr int ROWB = C::ROWB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;           // [2]
+  uint64_t* q_empty = bars + 2;      // [2]
+  uint64_t* kv_full = bars + 4;      // [2]
+  uint64_t* kv_empty = bars + 6;     // [2]
+  uint64_t* s_full = bars + 8;       // [2] S of the tile is in TMEM half (tile & 1)
+  uint64_t* p_full = bars + 10;      // [2 sets][2] P published by the set's eight warps: first / second half of each warp's columns
+  uint64_t* o_full = bars + 14;      // [2] PV complete
+  uint64_t* o_free = bars + 16;      // [2] O drained into registers: the half may take the next S
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[2 * i], APP_SET_WARPS);
+      mbar_init(&p_full[2 * i + 1], APP_SET_WARPS);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], APP_SET_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_units = p.B * p.heads;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      if (elect_one()) {
+        int t = 0, uc = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+          const int b = u / p.heads, h = u - b * p.heads;
+          const int kb = uc & 1;
+          mbar_wait(&kv_empty[kb], ((uc >> 1) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[kb], 2 * C::KTILE);
+          tma_load_4d(smem + C::OFF_K + kb * C::KTILE, &tmK, &kv_full[kb], 0, h, 0, b);
+          tma_load_4d(smem + C::OFF_V + kb * C::KTILE, &tmV, &kv_full[kb], 0, h, 0, b);
+          for (int qt = 0; qt < p.n_qt; ++qt, ++t) {
+            const int qb = t & 1;
+            mbar_wait(&q_empty[qb], ((t >> 1) & 1) ^ 1);
+            mbar_expect_tx(&q_full[qb], C::QTILE);
+            tma_load_4d(smem + C::OFF_Q + qb * C::QTILE, &tmQ, &q_full[qb], 0, h, qt * 128, p.q_batched ? b : 0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer
+      // S of tile t+1 is issued before PV of tile t: the other set's exponentials start while this set's P is consumed.
+      if (elect_one()) {
+        int n_mine = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) ++n_mine;
+        const int T = n_mine * p.n_qt;
+        const int ksteps_pv = p.nkp >> 4;
+        auto issue_s = [&](int t) {
+          const int uc = t / p.n_qt, qt = t - uc * p.n_qt;
+          const int bf = t & 1, kb = uc & 1;
+          APP_STAMP(t, 8);
+          if (qt == 0) mbar_wait(&kv_full[kb], (uc >> 1) & 1);
+          mbar_wait(&q_full[bf], (t >> 1) & 1);
+          APP_STAMP(t, 9);
+          if (t >= 2) mbar_wait(&o_free[bf], ((t >> 1) - 1) & 1);
+          tc_fence_after();
+          APP_STAMP(t, 10);
+          const uint32_t q_addr = smem_u32(smem + C::OFF_Q + bf * C::QTILE);
+          const uint32_t k_addr = smem_u32(smem + C::OFF_K + kb * C::KTILE);
+#pragma unroll
+          for (int ks = 0; ks < HDP / 16; ++ks) {
+            const uint64_t da = make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, C::LAYOUT);
+            const uint64_t db = make_smem_desc(k_addr + ks * 32, 16, 8 * ROWB, C::LAYOUT);
+            tc_mma_bf16(tmem_base + bf * 256, da, db, p.idesc_qk, ks > 0 ? 1u : 0u);
+          }
+          tc_commit(&q_empty[bf]);
+          tc_commit(&s_full[bf]);
+        };
+        auto issue_pv = [&](int t) {
+          const int uc = t / p.n_qt, qt = t - uc * p.n_qt;
+          const int bf = t & 1, kb = uc & 1;
+          APP_STAMP(t, 11);
+          const uint32_t v_addr = smem_u32(smem + C::OFF_V + kb * C::KTILE);
+          const uint32_t t_buf = tmem_base + bf * 256;
+          const uint64_t db0 = make_smem_desc(v_addr, 8 * ROWB, 8 * ROWB, C::LAYOUT);
+          uint32_t acc = 0u;
+          // keys 16 ks .. +15 were written by warp half ks >> 3 as 8 packed columns (k-steps 0..3 of the half at [0, 32),
+          // 4..7 at P_HI); each warp publishes its k-steps 0..3 first, then 4..7
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&p_full[2 * bf + g], (t >> 1) & 1);
+            tc_fence_after();
+            if (g == 0) APP_STAMP(t, 12);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int ks = (i >> 2) * 8 + g * 4 + (i & 3);
+              if (ks < ksteps_pv) {
+                tc_mma_ts(t_buf + C::O_OFF, t_buf + 128 * (ks >> 3) + g * C::P_HI + 8 * (i & 3),
+                          db0 + (uint64_t)(ks * ((16 * ROWB) >> 4)), p.idesc_pv, acc);
+                acc = 1u;
+              }
+            }
+          }
+          tc_commit(&o_full[bf]);
+          if (qt == p.n_qt - 1) tc_commit(&kv_empty[kb]);
+          APP_STAMP(t, 13);
+        };
+        if (T > 0) issue_s(0);
+        for (int t = 0; t < T; ++t) {
+          if (t + 1 < T) issue_s(t + 1);
+          issue_pv(t);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
+    const int sw_ = warp - 4;
+    const int set = sw_ >> 3;             // tile parity / TMEM half served by this warp
+    const int ew = sw_ & 7;
+    const int quad = warp & 3;            // TMEM lanes 32*quad .. +31 (hardware: warp id % 4)
+    const int hf = ew >> 2;               // S columns [128 hf, 128 hf + 128); O columns [hf HDP/2, (hf + 1) HDP/2)
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t t_buf = tmem_base + lane_base + set * 256;
+    const uint32_t t_s = t_buf + 128 * hf;
+    const uint32_t t_o = t_buf + C::O_OFF + hf * (HDP / 2);
+    float* xmax = reinterpret_cast<float*>(smem + C::OFF_X) + set * 256;   // [2 halves][128 rows]
+    float* xsum = reinterpret_cast<float*>(smem + C::OFF_X) + 512 + set * 256;
+    const int row_in_tile = quad * 32 + lane;
+    const int bar_id = 1 + set * 4 + quad;
+    // 32-column chunks of this warp's column half that hold live keys
+    int n_ch = (p.nkp - 128 * hf + 31) >> 5;
+    n_ch = n_ch < 0 ? 0 : (n_ch > 4 ? 4 : n_ch);
+    const int nk_local = p.Nk - 128 * hf;   // live columns of this half (may be <= 0 or >= 128)
+    int t = 0, i_mine = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int b = u / p.heads, h = u - b * p.heads;
+      for (int qt = 0; qt < p.n_qt; ++qt, ++t) {
+        if ((t & 1) != set) continue;
+        const uint32_t ph = i_mine & 1;
+        ++i_mine;
+        const bool stamp = ew == 0 && lane == 0;
+        if (stamp) APP_STAMP(t, 0);
+        mbar_wait(&s_full[set], ph);
+        tc_fence_after();
+        if (stamp) APP_STAMP(t, 1);
+        // ---- pass 1: row maximum of the raw scores, 64 columns per TMEM round trip (the load latency, not the maxima,
+        // is what this pass costs)
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (2 * c < n_ch) {
+            uint32_t sv[64];
+            tmem_ld_32x64(t_s + c * 64, sv);
+            tmem_ld_wait();
+            if (c * 64 + 64 > nk_local) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j)
+                if (c * 64 + j >= nk_local) sv[j] = 0xff800000u;   // -inf: zero-filled key rows (and stale columns) take no part
+            }
+            float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
+#pragma unroll
+            for (int j = 4; j < 64; j += 4) {
+              m0 = fmaxf(m0, __uint_as_float(sv[j]));
+              m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
+              m2 = fmaxf(m2, __uint_as_float(sv[j + 2]));
+              m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
+            }
+            mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          }
+        }
+        if (stamp) APP_STAMP(t, 2);
+        xmax[hf * 128 + row_in_tile] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        if (stamp) APP_STAMP(t, 3);
+        mx = fmaxf(mx, xmax[(hf ^ 1) * 128 + row_in_tile]);
+        const float ms = mx * p.scale_log2;
+        // ---- pass 2: P = exp2(scale * S - max) as 16-bit pairs over the consumed S columns; partial row sum in fp32
+        // 32-column chunks; chunk c's 16 packed columns land on S columns this warp has already read (AppCfg). With SPLIT the
+        // warp publishes after its second and after its fourth chunk.
+        float sum = 0.f;
+        auto publish = [&](int group) {
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (!C::SPLIT) mbar_arrive(&p_full[2 * set]);
+            mbar_arrive(&p_full[2 * set + group]);
+          }
+        };
+        if (nk_local >= 128) {
+          // Full column half (every whole-grid shape): 16-column steps through three register buffers, two stages deep.
+          // While step c is summed, packed and stored, the exponentials of step c+1 are already in the MUFU pipe and the
+          // TMEM load of step c+2 is in flight. (The two warps of a quadrant share a scheduler and run in lock step after
+          // the pair barrier: without this every step ends in a bubble -- results awaited, packed, stored, next load
+          // awaited -- in which the MUFU pipe idles for both.) Step c's 8 packed columns land on S columns this warp has
+          // already read (AppCfg).
+          uint32_t buf[3][16];
+          tmem_ld_32x16(t_s, buf[0]);
+          tmem_ld_wait();
+          tmem_ld_32x16(t_s + 16, buf[1]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) buf[0][j] = __float_as_uint(app_ex2(fmaf(__uint_as_float(buf[0][j]), p.scale_log2, -ms)));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c + 1 < 8) {
+              tmem_ld_wait();
+              if (c + 2 < 8) tmem_ld_32x16(t_s + (c + 2) * 16, buf[(c + 2) % 3]);
+            }
+            // element by element: two exponentials of step c+1 enter the MUFU pipe (8 cycles of it per warp instruction),
+            // then the sum / pack work of step c issues underneath them
+            uint32_t pk[8];
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (c + 1 < 8) {
+                uint32_t (&nx)[16] = buf[(c + 1) % 3];
+                nx[2 * j] = __float_as_uint(app_ex2(fmaf(__uint_as_float(nx[2 * j]), p.scale_log2, -ms)));
+                nx[2 * j + 1] = __float_as_uint(app_ex2(fmaf(__uint_as_float(nx[2 * j + 1]), p.scale_log2, -ms)));
+              }
+              const float e0 = __uint_as_float(buf[c % 3][2 * j]), e1 = __uint_as_float(buf[c % 3][2 * j + 1]);
+              s0 += e0;
+              s1 += e1;
+              pk[j] = FP16 ? app_pack_f16(e0, e1) : pack_bf16(e0, e1);
+            }
+            sum += s0 + s1;
+            tmem_st_32x8(t_s + (c < 4 ? c * 8 : C::P_HI + (c - 4) * 8), pk);
+            if (C::SPLIT && c == 3) publish(0);
+          }
+          publish(1);
+        } else {
+          // ragged key counts and window-sized sequences: 16-column steps, masked, one at a time
+          const int n16 = n_ch * 2;
+#pragma unroll 1
+          for (int c = 0; c < n16; ++c) {
+            uint32_t sv[16];
+            tmem_ld_32x16(t_s + c * 16, sv);
+            tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float e0 = c * 16 + 2 * j < nk_local ? app_ex2(fmaf(__uint_as_float(sv[2 * j]), p.scale_log2, -ms)) : 0.f;
+              const float e1 = c * 16 + 2 * j + 1 < nk_local ? app_ex2(fmaf(__uint_as_float(sv[2 * j + 1]), p.scale_log2, -ms)) : 0.f;
+              sum += e0 + e1;
+              pk[j] = FP16 ? app_pack_f16(e0, e1) : pack_bf16(e0, e1);
+            }
+            tmem_st_32x8(t_s + (c < 4 ? c * 8 : C::P_HI + (c - 4) * 8), pk);
+          }
+          if (C::SPLIT) publish(0);
+          publish(1);
+        }
+        if (stamp) APP_STAMP(t, 4);
+        xsum[hf * 128 + row_in_tile] = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");   // (partner's sum visible; its xmax read is done too)
+        sum += xsum[(hf ^ 1) * 128 + row_in_tile];
+        const float inv = 1.f / sum;
+        const int row = qt * 128 + row_in_tile;
+        if (hf == 0 && p.lse != nullptr && row < p.Nq)
+          p.lse[((long long)b * p.heads + h) * p.Nq + row] = (ms + log2f(sum)) * 0.6931471805599453f;
+        // ---- epilogue: O / sum -> 16-bit, thread = row
+        if (stamp) APP_STAMP(t, 5);
+        mbar_wait(&o_full[set], ph);
+        tc_fence_after();
+        if (stamp) APP_STAMP(t, 6);
+        uint32_t raw[HDP / 2];
+        if constexpr (HDP == 64) tmem_ld_32x32(t_o, raw);
+        else tmem_ld_32x16(t_o, raw);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[set]);
+        if (row < p.Nq) {
+          const int col0 = hf * (HDP / 2);
+          const long long off = (long long)b * p.o_bs + (long long)row * p.o_ts + h * p.hd + col0;
+          uint16_t* o1 = static_cast<uint16_t*>(p.o) + off;
+          uint16_t* o2 = p.o_alt != nullptr ? static_cast<uint16_t*>(p.o_alt) + off : nullptr;
+#pragma unroll
+          for (int g = 0; g < HDP / 16; ++g) {
+            if (col0 + g * 8 < p.hd) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g * 8 + j]) * inv;
+              uint4 a, c;
+              a.x = FP16 ? app_pack_f16(v[0], v[1]) : pack_bf16(v[0], v[1]);
+              a.y = FP16 ? app_pack_f16(v[2], v[3]) : pack_bf16(v[2], v[3]);
+              a.z = FP16 ? app_pack_f16(v[4], v[5]) : pack_bf16(v[4], v[5]);
+              a.w = FP16 ? app_pack_f16(v[6], v[7]) : pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(o1 + g * 8) = a;
+              if (o2 != nullptr) {
+                c.x = FP16 ? pack_bf16(v[0], v[1]) : app_pack_f16(v[0], v[1]);
+                c.y = FP16 ? pack_bf16(v[2], v[3]) : app_pack_f16(v[2], v[3]);
+                c.z = FP16 ? pack_bf16(v[4], v[5]) : app_pack_f16(v[4], v[5]);
+                c.w = FP16 ? pack_bf16(v[6], v[7]) : app_pack_f16(v[6], v[7]);
+                *reinterpret_cast<uint4*>(o2 + g * 8) = c;
+              }
+            }
+          }
+        }
+        if (stamp) APP_STAMP(t, 7);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+template <int HDP, bool FP16>
+static int app_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AppParams& p, int grid,
+                      cudaStream_t st) {
+  using C = AppCfg<HDP>;
+  auto kern = attn_pp_fwd_kernel<HDP, FP16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  B200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(APP_THREADS), C::SMEM, st, tq, tk, tv, p));
+  return 0;
+}
+
+// Returns 1 when the problem is outside this kernel's envelope (the caller tries the next path), 0 when launched.
+int launch_attention_pp_fwd(const b200_attn_desc* d, cudaStream_t st) {
+  if (!option(OPT_ATTN_PP_FWD)) return 1;
+  if (d->hd < 16 || d->hd > 64 || d->hd % 8 != 0) return 1;
+  if (d->Nk < 1 || d->Nk > 256 || d->Nq < 1 || d->scale <= 0.f) return 1;
+  // small windows (scalekd.py:305-308 with window_shapes > [1,1]: 64 tokens at 2x2 on a 16x16 grid) leave most of a
+  // 128 x 256 tile empty and the per-tile barrier chain becomes the cost: measured 47 vs 22 us at 64 tokens -- those stay
+  // on the flash-style kernel unless asked for (attn_pp_fwd = 2: every shape in the envelope, used by the tests)
+  if (d->Nk < 128 && option(OPT_ATTN_PP_FWD) < 2) return 1;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(d->q) || !al16(d->k) || !al16(d->v) || !al16(d->o) || (d->o_alt != nullptr && !al16(d->o_alt))) return 1;
+  const long long strides[] = {d->q_ts, d->k_ts, d->v_ts, d->o_ts, d->q_bs, d->k_bs, d->v_bs, d->o_bs};
+  for (long long s : strides)
+    if (s % 8 != 0 || s < 0) return 1;
+  if (d->k_bs == 0 || d->v_bs == 0 || d->o_bs == 0) return 1;
+  const int hdp = d->hd <= 32 ? 32 : 64;
+  const int fmt = d->qkvo_is_fp16 ? 0 : 1;
+
+  AppParams p{};
+  p.B = d->B; p.heads = d->heads; p.Nq = d->Nq; p.Nk = d->Nk; p.hd = d->hd;
+  p.nkp = (d->Nk + 15) & ~15;
+  p.n_qt = (d->Nq + 127) / 128;
+  p.q_batched = d->q_bs != 0 ? 1 : 0;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.lse = d->lse;
+  p.o = d->o; p.o_bs = d->o_bs; p.o_ts = d->o_ts; p.o_alt = d->o_alt;
+  p.idesc_qk = make_idesc_16(128, p.nkp, false, false, fmt);
+  p.idesc_pv = make_idesc_16(128, hdp, false, true, fmt);
+
+  auto mk = [&](CUtensorMap* out, const void* ptr, int N, long long ts, long long bs, int box_rows) -> int {
+    const bool batched = bs != 0;
+    const uint64_t dims[4] = {(uint64_t)d->hd, (uint64_t)d->heads, (uint64_t)N, (uint64_t)(batched ? d->B : 1)};
+    const uint64_t ld[3] = {(uint64_t)d->hd, (uint64_t)ts, (uint64_t)(batched ? bs : (long long)N * ts)};
+    const uint32_t box[4] = {(uint32_t)hdp, 1u, (uint32_t)box_rows, 1u};
+    return make_tensor_map_4d(out, ptr, dims, ld, box, hdp * 2, 2);
+  };
+  CUtensorMap tq, tk, tv;
+  if (mk(&tq, d->q, d->Nq, d->q_ts, d->q_bs, 128) || mk(&tk, d->k, d->Nk, d->k_ts, d->k_bs, 256) ||
+      mk(&tv, d->v, d->Nk, d->v_ts, d->v_bs, 256)) {
+    static bool warned = false;
+    if (!warned) { fprintf(stderr, "[b200] attention forward: tensor map rejected, using the next path\n"); warned = true; }
+    return 1;
+  }
+  const int units = d->B * d->heads;
+  const int grid = units < sm_count() ? units : sm_count();
+  static long long* dbg_buf = nullptr;
+  if (kAppProbes) {
+    if (dbg_buf == nullptr) cudaMalloc(&dbg_buf, 16 * 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 16 * 16 * sizeof(long long), st);
+    p.dbg = dbg_buf;
+  }
+  const int prof = prof_begin(st);
+  int r;
+  if (hdp == 64) r = fmt == 0 ? app_launch<64, true>(tq, tk, tv, p, grid, st) : app_launch<64, false>(tq, tk, tv, p, grid, st);
+  else r = fmt == 0 ? app_launch<32, true>(tq, tk, tv, p, grid, st) : app_launch<32, false>(tq, tk, tv, p, grid, st);
+  if (r != 0) return r;
+  prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
+  B200_LAUNCH_OK();
+  if (kAppProbes) {
+    static int printed = 0;
+    cudaStreamSynchronize(st);
+    if (printed++ % 8 == 3) {   // (a warm launch)
+      long long h[16 * 16];
+      cudaMemcpy(h, dbg_buf, sizeof h, cudaMemcpyDeviceToHost);
+      const long long t0 = h[8];
+      fprintf(stderr, "[app probes] hd %d Nq %d Nk %d | softmax w0 of the set: wait_s s_full pass1 bar pass2 wait_o o_full done | mma: s_begin q_full o_free | pv_begin p_full issued\n", d->hd, d->Nq, d->Nk);
+      for (int it = 0; it < 16; ++it) {
+        if (h[it * 16 + 8] == 0) break;
+        fprintf(stderr, "[app probes] tile %2d:", it);
+        for (int s2 = 0; s2 < 14; ++s2) fprintf(stderr, "%s %6lld", (s2 == 8 || s2 == 11) ? " |" : "", h[it * 16 + s2] ? h[it * 16 + s2] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace b200

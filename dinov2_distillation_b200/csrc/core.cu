@@ -51,6 +51,8 @@ static OptDef g_opts[OPT_COUNT] = {
     {"stat_attn_mma_bwd", "", 0},                    //   attention backward launches per path
     {"stat_attn_tc_fwd", "", 0},
     {"stat_attn_mma_fwd", "", 0},
+    {"attn_pp_fwd", "B200_ATTN_PP", 1},              // two-tile tcgen05 attention forward (Nk <= 256, head dims 16-64)
+    {"stat_attn_pp_fwd", "", 0},
 };
 static const bool g_opts_init = [] {
   for (auto& o : g_opts) {

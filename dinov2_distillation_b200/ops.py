@@ -248,15 +248,21 @@ def _attn_desc(q, k, v, o, lse, heads, scale):
     return d
 
 
-def attention_fwd(q, k, v, heads: int, scale: float):
-    """q [B,Nq,D], k/v [B,Nk,D] bf16 (last dim contiguous, any batch/token strides) -> o [B,Nq,D] bf16, lse [B,h,Nq]."""
+def attention_fwd(q, k, v, heads: int, scale: float, want_alt: bool = False):
+    """q [B,Nq,D], k/v [B,Nk,D] bf16 or fp16 (last dim contiguous, any batch/token strides) -> o [B,Nq,D] in the input
+    format, lse [B,h,Nq]. want_alt: also return a copy of o in the other 16-bit format (b200_attn_desc.o_alt)."""
     _need_cuda(q, k, v)
     B, Nq, Dm = q.shape
     o = torch.empty(B, Nq, Dm, device=q.device, dtype=q.dtype)
     lse = torch.empty(B, heads, Nq, device=q.device, dtype=torch.float32)
     d = _attn_desc(q, k, v, o, lse, heads, scale)
+    o_alt = None
+    if want_alt:
+        o_alt = torch.empty(B, Nq, Dm, device=q.device,
+                            dtype=torch.bfloat16 if q.dtype == torch.float16 else torch.float16)
+        d.o_alt = o_alt.data_ptr()
     L.check(L.load().b200_attention_fwd(C.byref(d), _stream()), "attention_fwd")
-    return o, lse
+    return (o, lse, o_alt) if want_alt else (o, lse)
 
 
 def set_option(name: str, value: int) -> None:

@@ -354,6 +354,64 @@ def test_attention_fp16_forward_bf16_grads(hd, heads, N):
     assert rel_err(dq, qr.grad) < 1e-2, rel_err(dq, qr.grad)
 
 
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("hd,heads,Nq,Nk,B", [(16, 24, 256, 256, 3), (24, 16, 256, 256, 3), (32, 24, 100, 77, 2),
+                                              (48, 16, 64, 200, 2), (64, 6, 256, 256, 5), (24, 16, 64, 64, 9),
+                                              (16, 24, 130, 16, 2), (64, 2, 300, 129, 2), (40, 3, 17, 5, 1),
+                                              (24, 16, 256, 256, 40)])
+def test_attention_pp_forward(dt, hd, heads, Nq, Nk, B):
+    """Two-tile tcgen05 forward (attention_pp.cu): every projector head dim (16 / 24 / 32 / 48 / 64, padded to 32 / 64 by
+    the TMA zero fill), fp16 and bf16, whole-grid and window-sized sequences, ragged query / key counts (partial tiles,
+    key counts that are not a multiple of 16, a single 128-column half), odd tile counts per CTA, more units than SMs,
+    both output formats and the log-sum-exp; the launch must have taken the new path."""
+    ops = _ops()
+    tdt = torch.float16 if dt == "fp16" else torch.bfloat16
+    D = hd * heads
+    scale = 5.0 / math.sqrt(hd)
+    q = (torch.randn(B, Nq, D, device="cuda") * 0.5).to(tdt)
+    k = (torch.randn(B, Nk, D, device="cuda") * 0.5).to(tdt)
+    v = torch.randn(B, Nk, D, device="cuda").to(tdt)
+    ops.set_option("stat_attn_pp_fwd", 0)
+    ops.set_option("attn_pp_fwd", 2)   # (also the window-sized shapes the dispatcher leaves to the flash-style kernel)
+    try:
+        o, lse, o_alt = ops.attention_fwd(q, k, v, heads, scale, want_alt=True)
+    finally:
+        ops.set_option("attn_pp_fwd", 1)
+    assert ops.get_option("stat_attn_pp_fwd") == 1
+    assert o.dtype == tdt and o_alt.dtype != tdt
+    ref = _attn_ref(q, k, v, heads, scale)
+    tol = 2e-3 if dt == "fp16" else 8e-3
+    assert rel_err(o, ref) < tol, rel_err(o, ref)
+    assert rel_err(o_alt, ref) < 8e-3, rel_err(o_alt, ref)
+    qh = q.float().reshape(B, Nq, heads, hd).transpose(1, 2)
+    kh = k.float().reshape(B, Nk, heads, hd).transpose(1, 2)
+    lse_ref = torch.logsumexp(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    assert (lse - lse_ref).abs().max().item() < 2e-3, (lse - lse_ref).abs().max().item()
+    # against the mma.sync kernel on the same inputs (same exp2-domain arithmetic): near bit-equal
+    ops.set_option("attn_pp_fwd", 0)
+    try:
+        o2, lse2 = ops.attention_fwd(q, k, v, heads, scale)
+    finally:
+        ops.set_option("attn_pp_fwd", 1)
+    assert rel_err(o, o2) < (1.5e-3 if dt == "fp16" else 6e-3)
+    assert (lse - lse2).abs().max().item() < 1e-4
+
+
+def test_attention_pp_batch_invariant_query_and_strided_kv():
+    """The self-query embedding (scalekd.py:232-234) is one [HW, D] tensor for the whole batch (batch stride 0); k / v are
+    column slices of the fused [k|v] projection output."""
+    ops = _ops()
+    B, N, heads, hd = 5, 256, 16, 24
+    D = heads * hd
+    kv = (torch.randn(B, N, 2 * D, device="cuda") * 0.5).half()
+    k, v = kv[..., :D], kv[..., D:]
+    qs = (torch.randn(1, N, D, device="cuda") * 0.5).half().expand(B, N, D)
+    ops.set_option("stat_attn_pp_fwd", 0)
+    o, lse = ops.attention_fwd(qs, k, v, heads, 3.0 / math.sqrt(hd))
+    assert ops.get_option("stat_attn_pp_fwd") == 1
+    assert rel_err(o, _attn_ref(qs, k, v, heads, 3.0 / math.sqrt(hd))) < 2e-3
+
+
 def test_attention_strided_qkv_and_shared_query():
     ops = _ops()
     B, N, heads, hd = 3, 70, 6, 64
