@@ -20,7 +20,7 @@ INCLUDE = PKG_DIR.parent / "include"
 BUILD_DIR = PKG_DIR / "build"
 LIB_PATH = PKG_DIR / "libb200distill.so"
 
-SOURCES = ["core.cu", "gemm_tcgen05.cu", "gemm_v2.cu", "attention.cu", "attention_tc.cu", "attention_pp.cu", "attention_bwd_tc.cu", "elementwise.cu", "kd_loss.cu", "optim.cu", "engine.cu"]
+SOURCES = ["core.cu", "gemm_tcgen05.cu", "gemm_v2.cu", "attention.cu", "attention_tc.cu", "attention_pp.cu", "attention_bwd_tc.cu", "elementwise.cu", "kd_loss.cu", "augment.cu", "optim.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -164,43 +164,75 @@ __global__ void __launch_bounds__(256) tokenize_split3_kernel(const float* __res
   }
 }
 
-// ------------------------------------------------------------------------------------------------ patch im2col
-__global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W,
-                                    int Kp) {
-  pdl_wait();   // PDL: launched through launch_pdl(); multi-wave grid, no early trigger
-  extern __shared__ float srow[];  // [3*14][W + 1]  (odd pitch: the column-segment reads below hit distinct banks)
-  const int Wp = W / 14, Hp = H / 14;
-  const int b = blockIdx.x / Hp, ph = blockIdx.x % Hp;
-  const int W2 = W >> 1;   // W % 14 == 0, so W is even: float2 loads stay aligned
-  const int WP = W + 1;
-#pragma unroll 6
-  for (int idx = threadIdx.x; idx < 42 * W2; idx += blockDim.x) {
-    const int rr = idx / W2, x2 = idx - rr * W2;
-    const int c = rr / 14, i = rr - c * 14;
-    const float2 v = __ldg(reinterpret_cast<const float2*>(img + (((long long)b * 3 + c) * H + (ph * 14 + i)) * W) + x2);
-    srow[rr * WP + 2 * x2] = v.x;
-    srow[rr * WP + 2 * x2 + 1] = v.y;
+// Same for channel counts that are a multiple of 4 (every student tap of the model zoo): 128 channels x 32 positions per
+// block, the tile kept position-major in shared memory so that a thread reads its four channels with one 16-byte load
+// and writes 8-byte words -- each warp store is a 256-byte run of one token row (the 64-channel version above moves 4
+// bytes per thread and store: 57-59 % of the copy bandwidth, measured with tools/hbm_bench.py).
+__global__ void __launch_bounds__(256) tokenize_split3_wide_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xt,
+                                                                  __nv_bfloat16* __restrict__ xt3, int C, int HW) {
+  pdl_wait();   // multi-wave grid: no early trigger
+  __shared__ __align__(16) float tile[32][132];   // [position][channel], pitch 132: 16-byte aligned rows
+  const int b = blockIdx.z, c0 = blockIdx.y * 128, p0 = blockIdx.x * 32;
+  const float* src = x + (long long)b * C * HW;
+  const int p = p0 + threadIdx.x;
+#pragma unroll 8
+  for (int j = threadIdx.y; j < 128; j += 8) {
+    const int c = c0 + j;
+    tile[threadIdx.x][j] = (c < C && p < HW) ? src[(long long)c * HW + p] : 0.f;
   }
   __syncthreads();
-  __nv_bfloat16* obase = out + ((long long)(b * Hp + ph) * Wp) * Kp;
-  // output column = c*196 + i*14 + j = (c*14 + i)*14 + j =: ci*14 + j. One warp writes one patch's row of the output
-  // (Kp bf16, contiguous): lanes take consecutive column pairs -> 128-byte coalesced stores, consecutive shared-memory
-  // reads (14 columns share a ci), and the only division is by the constant 14.
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int Kp2 = Kp >> 1;
-  for (int pw = warp; pw < Wp; pw += nwarp) {
-    uint32_t* dst = reinterpret_cast<uint32_t*>(obase + (long long)pw * Kp);
-    const float* src = srow + pw * 14;
-    for (int k2 = lane; k2 < Kp2; k2 += 32) {
-      const int col = 2 * k2;
-      uint32_t v = 0u;
-      if (col < 588) {   // 588 is even: a pair never straddles the padding
-        const int ci0 = col / 14, j0 = col - ci0 * 14;
-        const int ci1 = (col + 1) / 14, j1 = col + 1 - ci1 * 14;
-        v = pack_bf16(src[ci0 * WP + j0], src[ci1 * WP + j1]);
-      }
-      dst[k2] = v;
+  const int c = c0 + 4 * threadIdx.x;
+  if (c >= C) return;
+#pragma unroll
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int pp = p0 + j;
+    if (pp >= HW) continue;
+    const float4 v = *reinterpret_cast<const float4*>(&tile[j][4 * threadIdx.x]);
+    const long long row = (long long)b * HW + pp;
+    *reinterpret_cast<uint2*>(xt + row * C + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    const float h0 = __half2float(__float2half_rn(v.x)), h1 = __half2float(__float2half_rn(v.y));
+    const float h2 = __half2float(__float2half_rn(v.z)), h3 = __half2float(__float2half_rn(v.w));
+    const uint2 hi = make_uint2(pack16(h0, h1, 1), pack16(h2, h3, 1));
+    const uint2 lo = make_uint2(pack16(v.x - h0, v.y - h1, 1), pack16(v.z - h2, v.w - h3, 1));
+    __nv_bfloat16* o = xt3 + row * 3 * C + c;
+    *reinterpret_cast<uint2*>(o) = hi;
+    *reinterpret_cast<uint2*>(o + C) = hi;
+    *reinterpret_cast<uint2*>(o + 2 * C) = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ patch im2col
+// One block per (image, patch row, channel), no staging: every thread produces output column PAIRS -- one aligned 8-byte
+// load (two horizontally adjacent pixels; 14 is even, so a pair never leaves its patch row) and one 4-byte store. Lanes
+// run over consecutive pairs of one patch's 196-column run of the channel (coalesced 128-byte stores; the block of channel
+// 2 also writes the zero padding up to Kp); the loads of a warp touch ~5 image rows x 56 bytes whose sector remainders
+// belong to the neighbouring patches handled by the same block, so they hit in L1 and HBM sees each pixel once. All
+// loads of a thread are independent and there is no barrier: the earlier version staged the 3 x 14 x W strip in shared
+// memory (load phase, __syncthreads, store phase; 2 blocks per SM at 518 pixels) and measured 1.3-2.1 TB/s.
+__global__ void __launch_bounds__(256)
+patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W, int Kp) {
+  pdl_wait();   // PDL: launched through launch_pdl(); multi-wave grid, no early trigger
+  const int Wp = W / 14, Hp = H / 14;
+  const int c = blockIdx.x % 3;
+  const int bp = blockIdx.x / 3;
+  const int b = bp / Hp, ph = bp % Hp;
+  const float* base = img + (((long long)b * 3 + c) * H + ph * 14) * W;
+  uint2* obase = reinterpret_cast<uint2*>(out + ((long long)(b * Hp + ph) * Wp) * Kp + c * 196);
+  const int n4 = c == 2 ? (Kp - 392) >> 2 : 49;   // 4-column groups of this block per patch (channel 2: + the zero padding)
+  const int Kp4 = Kp >> 2;
+  const int total = Wp * n4;
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pw = idx / n4, k4 = idx - pw * n4;
+    uint2 v = make_uint2(0u, 0u);
+    if (k4 < 49) {   // two column pairs = two aligned 8-byte loads (a group of 4 may straddle two image rows: 14 = 3.5 x 4)
+      const int ka = 2 * k4, kb = 2 * k4 + 1;
+      const int ia = ka / 7, ja = ka - ia * 7, ib = kb / 7, jb = kb - ib * 7;
+      const float2 pa = __ldg(reinterpret_cast<const float2*>(base + (long long)ia * W + pw * 14) + ja);
+      const float2 pb = __ldg(reinterpret_cast<const float2*>(base + (long long)ib * W + pw * 14) + jb);
+      v = make_uint2(pack_bf16(pa.x, pa.y), pack_bf16(pb.x, pb.y));
     }
+    obase[(long long)pw * Kp4 + k4] = v;
   }
 }
 
@@ -424,6 +456,113 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       for (int k = 0; k < warps_per_block; ++k) so += red[(long long)k * D + c];
       atomicAdd(dx_colsum + c, so);
     }
+  }
+}
+
+// Accumulating backward for wide rows (D >= 768: NV >= 6). The register form above keeps 9 * NV accumulator registers plus a
+// double-buffered row per lane -- fine at NV = 3 (ViT-S), 1.2-2.4 KB of spills per thread at NV = 6 / 8 / 12 (measured:
+// 17 % of the copy bandwidth at D = 1024). Here the row is read twice (statistics, then outputs: the second read is an
+// L1 / L2 hit, HBM sees each byte once) so no row values live across the warp reduction, and the column partials live in
+// per-warp shared-memory strips [warp][dw | db | colsum][D] that each lane updates at its own columns (no conflicts, no
+// synchronisation until the final cross-warp reduction).
+template <int NV>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd_wide_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+                          float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dw,
+                          float* __restrict__ db, float* __restrict__ dx_colsum, int rows, int D) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float red[];   // [warps][K][D], K = 2 (dw, db) and / or 1 (colsum)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int K = (dw ? 2 : 0) + (dx_colsum ? 1 : 0);
+  const float inv_d = 1.0f / (float)D;
+  float4* s_w = reinterpret_cast<float4*>(red + (size_t)(wid * K) * D);
+  float4* s_b = reinterpret_cast<float4*>(red + (size_t)(wid * K + 1) * D);
+  float4* s_o = reinterpret_cast<float4*>(red + (size_t)(wid * K + (dw ? 2 : 0)) * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = i * 32 + lane;
+    if (c4 * 4 < D) {
+      if (dw) { s_w[c4] = make_float4(0, 0, 0, 0); s_b[c4] = make_float4(0, 0, 0, 0); }
+      if (dx_colsum) s_o[c4] = make_float4(0, 0, 0, 0);
+    }
+  }
+  const int r_step = gridDim.x * warps_per_block;
+  for (int r = blockIdx.x * warps_per_block + wid; r < rows; r += r_step) {
+    const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)r * D);
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)r * D);
+    const float mu = mean[r], rs = rstd[r];
+    // pass 1: the two row sums (all 2 * NV loads of the lane are issued before the first is consumed)
+    float s1 = 0.f, s2 = 0.f;
+    {
+      float4 d4[NV], x4[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c4 = i * 32 + lane;
+        if (c4 * 4 < D) { d4[i] = dyr[c4]; x4[i] = xr[c4]; }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c4 = i * 32 + lane;
+        if (c4 * 4 < D) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + c4);
+          const float gx = d4[i].x * w4.x, gy = d4[i].y * w4.y, gz = d4[i].z * w4.z, gw = d4[i].w * w4.w;
+          s1 += (gx + gy) + (gz + gw);
+          s2 += (gx * (x4[i].x - mu) + gy * (x4[i].y - mu)) + (gz * (x4[i].z - mu) + gw * (x4[i].w - mu));
+        }
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * rs * inv_d;
+    // pass 2: outputs and column partials (row re-read: cache hit)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 * 4 < D) {
+        const float4 d4 = dyr[c4], x4 = xr[c4];
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + c4);
+        const float4 xh = make_float4((x4.x - mu) * rs, (x4.y - mu) * rs, (x4.z - mu) * rs, (x4.w - mu) * rs);
+        float4 o;
+        o.x = rs * (d4.x * w4.x - s1 - xh.x * s2);
+        o.y = rs * (d4.y * w4.y - s1 - xh.y * s2);
+        o.z = rs * (d4.z * w4.z - s1 - xh.z * s2);
+        o.w = rs * (d4.w * w4.w - s1 - xh.w * s2);
+        if (dres) {
+          const float4 rr = reinterpret_cast<const float4*>(dres + (long long)r * D)[c4];
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        if (dw) {
+          float4 a = s_w[c4], bq = s_b[c4];
+          a.x += d4.x * xh.x; a.y += d4.y * xh.y; a.z += d4.z * xh.z; a.w += d4.w * xh.w;
+          bq.x += d4.x; bq.y += d4.y; bq.z += d4.z; bq.w += d4.w;
+          s_w[c4] = a; s_b[c4] = bq;
+        }
+        if (dx_colsum) {
+          float4 a = s_o[c4];
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+          s_o[c4] = a;
+        }
+        if (dx) reinterpret_cast<float4*>(dx + (long long)r * D)[c4] = o;
+        if (dx16) {
+          uint2 u;
+          u.x = pack_bf16(o.x, o.y);
+          u.y = pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(dx16 + (long long)r * D)[c4] = u;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sw = 0.f, sb = 0.f, so = 0.f;
+    for (int k = 0; k < warps_per_block; ++k) {
+      if (dw) { sw += red[(size_t)(k * K) * D + c]; sb += red[(size_t)(k * K + 1) * D + c]; }
+      if (dx_colsum) so += red[(size_t)(k * K + (dw ? 2 : 0)) * D + c];
+    }
+    if (dw) { atomicAdd(dw + c, sw); atomicAdd(db + c, sb); }
+    if (dx_colsum) atomicAdd(dx_colsum + c, so);
   }
 }
 
@@ -755,26 +894,40 @@ __global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ x12, __nv_bfloat
   }
 }
 
-__global__ void batch_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ o32,
-                                      __nv_bfloat16* __restrict__ o16, int B, long long n) {
+// Block (32, 8): lane x owns 4 consecutive elements, slice y sums the images b = y, y + 8, ... with up to eight 8-byte loads
+// in flight, the eight partial sums meet in shared memory. (One thread per 4 elements summing all B images alone -- the
+// earlier form -- has n / 4 = 24 576 threads at the cfg2 shape: too few bytes in flight, 0.75 TB/s under ncu.)
+__global__ void __launch_bounds__(256)
+batch_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ o32, __nv_bfloat16* __restrict__ o16, int B,
+                      long long n) {
   pdl_trigger();   // PDL (common.cuh): launched through launch_pdl()
   pdl_wait();
+  __shared__ float4 red[8][32];
   const long long n4 = n >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 a = make_float4(0, 0, 0, 0);
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  float4 a = make_float4(0, 0, 0, 0);
+  if (i < n4) {
 #pragma unroll 8
-    for (int b = 0; b < B; ++b) {   // (few threads -- n / 4 -- so each keeps eight images' loads in flight)
+    for (int b = threadIdx.y; b < B; b += 8) {
       const uint2 u = reinterpret_cast<const uint2*>(x + (long long)b * n)[i];
       const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
       a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
     }
-    if (o32) reinterpret_cast<float4*>(o32)[i] = a;
-    if (o16) {
-      uint2 u;
-      u.x = pack_bf16(a.x, a.y);
-      u.y = pack_bf16(a.z, a.w);
-      reinterpret_cast<uint2*>(o16)[i] = u;
-    }
+  }
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y != 0 || i >= n4) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    const float4 r = red[k][threadIdx.x];
+    a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+  }
+  if (o32) reinterpret_cast<float4*>(o32)[i] = a;
+  if (o16) {
+    uint2 u;
+    u.x = pack_bf16(a.x, a.y);
+    u.y = pack_bf16(a.z, a.w);
+    reinterpret_cast<uint2*>(o16)[i] = u;
   }
 }
 
@@ -831,6 +984,18 @@ static int launch_ln_bwd(const float* dy, const float* x, const float* w, const 
                          const float* dres, float* dx, void* dx16, float* dw, float* db, float* dx_colsum, int rows,
                          int D, cudaStream_t st) {
   const bool wg = dw != nullptr || dx_colsum != nullptr;
+  if (wg && NV >= 6) {   // wide rows: shared-memory column partials, two passes over the row
+    auto kern = layernorm_bwd_wide_kernel<NV>;
+    const size_t smem = size_t(8) * ((dw ? 2 : 0) + (dx_colsum ? 1 : 0)) * D * sizeof(float);
+    static bool set = false;
+    if (!set) { B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = true; }
+    const int bps = smem > 110 * 1024 ? 1 : 2;
+    const int grid = grid_for(rows, 32, bps);
+    B200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(256), smem, st, dy, x, w, mean, rstd, dres, dx,
+                            static_cast<__nv_bfloat16*>(dx16), dw, db, dx_colsum, rows, D));
+    B200_LAUNCH_OK();
+    return 0;
+  }
   auto kern = wg ? layernorm_bwd_kernel<NV, true> : layernorm_bwd_kernel<NV, false>;
   size_t smem = dw ? size_t(8) * 2 * D * sizeof(float) : (dx_colsum ? size_t(8) * D * sizeof(float) : 0);
   if (smem > 48 * 1024) {
@@ -1215,9 +1380,90 @@ extern "C" int b200_window_rows16(const void* src, void* dst, long long rows, in
 
 int b200::tokenize_split3(const float* x, void* xt_bf16, void* xt3_fp16, int B, int C, int HW, void* stream) {
   B200_CHECK_ARG(x && xt_bf16 && xt3_fp16 && B > 0 && C > 0 && HW > 0 && C % 2 == 0, "bad args");
+  const bool wide = C % 4 == 0 && (reinterpret_cast<uintptr_t>(xt_bf16) & 7) == 0 && (reinterpret_cast<uintptr_t>(xt3_fp16) & 7) == 0;
+  if (wide) {
+    dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(C, 128), (unsigned)B);
+    B200_CUDA_OK(launch_pdl(tokenize_split3_wide_kernel, grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream), x,
+                            static_cast<__nv_bfloat16*>(xt_bf16), static_cast<__nv_bfloat16*>(xt3_fp16), C, HW));
+    B200_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(C, 64), (unsigned)B);
   B200_CUDA_OK(launch_pdl(tokenize_split3_kernel, grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream), x,
                           static_cast<__nv_bfloat16*>(xt_bf16), static_cast<__nv_bfloat16*>(xt3_fp16), C, HW));
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ teacher-feature cache
+// the frozen teacher's output for a sample does not depend on the student, so a deterministic input pipeline
+// (no augmentation, or a fixed augmentation per sample id) can keep it in HBM -- 180 GB hold 0.9 M images of vits14 @224
+// in bf16 -- and skip models/backbones/dinov2.py:27-46 from the second epoch on. Rows of the pool are whole images
+// ([N, D] tokens, cls row included or not as the caller lays them out); slots[b] picks the row of batch item b.
+// One block per (image, 8 KB chunk): 16-byte loads, 8- or 16-byte stores.
+template <bool POOL_BF16>
+__global__ void __launch_bounds__(256)
+feature_cache_store_kernel(const float* __restrict__ feat, long long f_bs, long long f_ts, const long long* __restrict__ slots,
+                           void* __restrict__ pool, int N, int D) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const long long slot = slots[b];
+  if (slot < 0) return;
+  const int D4 = D >> 2;
+  const long long n4 = (long long)N * D4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / D4), c4 = (int)(i - (long long)t * D4);
+    const float4 v = reinterpret_cast<const float4*>(feat + (long long)b * f_bs + (long long)t * f_ts)[c4];
+    if (POOL_BF16) {
+      reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(pool) + slot * N * D)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    } else {
+      reinterpret_cast<float4*>(static_cast<float*>(pool) + slot * N * D)[i] = v;
+    }
+  }
+}
+template <bool POOL_BF16>
+__global__ void __launch_bounds__(256)
+feature_cache_load_kernel(const void* __restrict__ pool, const long long* __restrict__ slots, float* __restrict__ out, int N,
+                          int D) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const long long slot = slots[b];
+  if (slot < 0) return;
+  const long long n4 = (long long)N * D >> 2;
+  float4* o = reinterpret_cast<float4*>(out + (long long)b * N * D);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    if (POOL_BF16) {
+      const uint2 u = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(pool) + slot * N * D)[i];
+      const float2 a = unpack_bf16(u.x), c = unpack_bf16(u.y);
+      o[i] = make_float4(a.x, a.y, c.x, c.y);
+    } else {
+      o[i] = reinterpret_cast<const float4*>(static_cast<const float*>(pool) + slot * N * D)[i];
+    }
+  }
+}
+
+extern "C" int b200_feature_cache_store(const float* feat, long long f_bs, long long f_ts, const long long* slots, void* pool,
+                                        int pool_is_bf16, int B, int N, int D, void* stream) {
+  B200_CHECK_ARG(feat && slots && pool && B > 0 && N > 0 && D > 0 && D % 4 == 0, "bad args");
+  B200_CHECK_ARG(f_bs % 4 == 0 && f_ts % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(pool) & 15) == 0, "feature rows and the pool must be 16-byte aligned");
+  const long long n4 = (long long)N * D / 4;
+  dim3 grid((unsigned)(cdiv(n4, 2048) < 1 ? 1 : cdiv(n4, 2048)), (unsigned)B);
+  if (pool_is_bf16) B200_CUDA_OK(launch_pdl(feature_cache_store_kernel<true>, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), feat, f_bs, f_ts, slots, pool, N, D));
+  else B200_CUDA_OK(launch_pdl(feature_cache_store_kernel<false>, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), feat, f_bs, f_ts, slots, pool, N, D));
+  B200_LAUNCH_OK();
+  return 0;
+}
+extern "C" int b200_feature_cache_load(const void* pool, int pool_is_bf16, const long long* slots, float* out, int B, int N, int D,
+                                       void* stream) {
+  B200_CHECK_ARG(pool && slots && out && B > 0 && N > 0 && D > 0 && ((long long)N * D) % 4 == 0, "bad args");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(pool) & 15) == 0, "alignment");
+  const long long n4 = (long long)N * D / 4;
+  dim3 grid((unsigned)(cdiv(n4, 2048) < 1 ? 1 : cdiv(n4, 2048)), (unsigned)B);
+  if (pool_is_bf16) B200_CUDA_OK(launch_pdl(feature_cache_load_kernel<true>, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), pool, slots, out, N, D));
+  else B200_CUDA_OK(launch_pdl(feature_cache_load_kernel<false>, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), pool, slots, out, N, D));
   B200_LAUNCH_OK();
   return 0;
 }
@@ -1226,16 +1472,7 @@ extern "C" int b200_patch_im2col(const float* img, void* out, int B, int H, int 
   B200_CHECK_ARG(img && out && B > 0, "bad args");
   B200_CHECK_ARG(H % 14 == 0 && W % 14 == 0 && H > 0 && W > 0, "image size must be a multiple of the 14-pixel patch");
   B200_CHECK_ARG(Kp >= 588 && Kp % 8 == 0, "Kp must be >= 588 and a multiple of 8");
-  const size_t smem = size_t(42) * (W + 1) * sizeof(float);
-  B200_CHECK_ARG(smem <= 200 * 1024, "image too wide");
-  if (smem > 48 * 1024) {
-    static size_t set_to = 0;
-    if (set_to < smem) {
-      B200_CUDA_OK(cudaFuncSetAttribute(patch_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set_to = smem;
-    }
-  }
-  B200_CUDA_OK(launch_pdl(patch_im2col_kernel, dim3(B * (H / 14)), dim3(256), smem, static_cast<cudaStream_t>(stream), 
+  B200_CUDA_OK(launch_pdl(patch_im2col_kernel, dim3(B * (H / 14) * 3), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       img, static_cast<__nv_bfloat16*>(out), H, W, Kp));
   B200_LAUNCH_OK();
   return 0;
@@ -1407,7 +1644,7 @@ extern "C" int b200_swiglu(const void* x12, void* out, int rows, int H, void* st
 
 extern "C" int b200_batch_sum_bf16(const void* x, float* out_f32, void* out_bf16, int B, long long n, void* stream) {
   B200_CHECK_ARG(x && (out_f32 || out_bf16) && B > 0 && n > 0 && n % 4 == 0, "bad args");
-  B200_CUDA_OK(launch_pdl(batch_sum_bf16_kernel, dim3(grid_for(n / 4, 64, 16)), dim3(64), 0, static_cast<cudaStream_t>(stream), 
+  B200_CUDA_OK(launch_pdl(batch_sum_bf16_kernel, dim3((unsigned)cdiv(n / 4, 32)), dim3(32, 8), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), out_f32, static_cast<__nv_bfloat16*>(out_bf16), B, n));
   B200_LAUNCH_OK();
   return 0;

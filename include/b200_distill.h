@@ -249,6 +249,31 @@ int b200_kd_loss_bwd_split(const float* S, const float* T, int B, int HW, int D,
  * mean-subtraction identity (losses/scalekd.py:337-428). R = H = W <= 64. */
 int b200_dct_zero_dc_idct(const float* x, float* y, int B, int R, int D, long long x_bs, long long x_ts, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ input pipeline
+ * datasets/augmentations.py:24-78 without RandAugment -- RandomResizedCrop (PIL's antialiased bicubic over
+ * the crop box, restated integer for integer: bit-exact with the reference transforms) + horizontal flip + ToTensor +
+ * Normalize + RandomErasing(value 0). The random parameters are drawn on the host (torchvision's get_params: same
+ * distributions and draws as the reference) and passed in as device arrays.
+ * pixels: decoded uint8 RGB, HWC, images packed back to back (offsets[b] = first byte of image b; hw[b] = {H, W});
+ * crop[b] = {top, left, height, width} in the source; flip[b] != 0 mirrors the resized crop; erase[b] = {top, left,
+ * height, width} in the OUTPUT (height 0 = no erasing); mean / std: HOST float[3]. out: fp32 [B, 3, S, S].
+ * max_taps >= 2 * ceil(2 * max(largest crop side / S, 1)) + 1 (Pillow's ksize); ws: b200_augment_ws_bytes(). */
+size_t b200_augment_ws_bytes(int B, int S, int max_taps);
+int b200_augment_batch(const unsigned char* pixels, const long long* offsets, const int* hw, const int* crop,
+                       const int* flip, const int* erase, float* out, int B, int S, int max_taps, const float* mean,
+                       const float* std, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ teacher-feature cache
+ * SURVEY 8 f3. The frozen teacher's output (models/backbones/dinov2.py:27-46) depends only on the input image: with a
+ * deterministic input pipeline it can be kept in HBM per sample and the teacher forward skipped on later epochs.
+ * pool: [slots_total, N, D] bf16 (pool_is_bf16 = 1) or fp32; slots: device int64 [B], slot < 0 = skip this batch item.
+ * store: feat fp32 [B, N, D] with batch / token strides f_bs / f_ts in elements (the teacher's strided token view, cls row
+ * skipped by pointer offset, is passed as is). load: out fp32 [B, N, D] contiguous. */
+int b200_feature_cache_store(const float* feat, long long f_bs, long long f_ts, const long long* slots, void* pool,
+                             int pool_is_bf16, int B, int N, int D, void* stream);
+int b200_feature_cache_load(const void* pool, int pool_is_bf16, const long long* slots, float* out, int B, int N, int D,
+                            void* stream);
+
 /* ------------------------------------------------------------------------------------------------ teacher (DINOv2 ViT)
  * Weight tables are host arrays of device pointers, filled by the Python shell from the hub-format state_dict. */
 typedef struct b200_vit_block {

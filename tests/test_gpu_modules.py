@@ -681,3 +681,61 @@ def test_scalekd_odd_grid_37x37_long_sequence_paths(heads, raw):
     pairs = {n: (p.grad, sd_ref[n].grad) for n, p in m.named_parameters() if sd_ref[n].grad is not None}
     assert flat_rel(list(pairs.values())) <= GRAD_RTOL
     check_param_grads(pairs, tol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ teacher-feature cache (f3)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_feature_cache_round_trip_strided_rows(dtype):
+    """b200_feature_cache_store / load: the teacher's strided token view (cls row skipped) in, contiguous fp32 out;
+    exact in fp32, one bf16 rounding otherwise; rows already cached are not rewritten; slot -1 rows are skipped."""
+    from dinov2_distillation_b200.feature_cache import TeacherFeatureCache
+    B, HW, D = 5, 49, 64
+    full = torch.randn(B, HW + 1, D, device="cuda")
+    tok = full[:, 1:]                                   # strides ((HW+1)*D, D, 1)
+    cache = TeacherFeatureCache(capacity=4, tokens=HW, dim=D, dtype=dtype)
+    ids = [7, 3, 9, 3, 11]
+    assert cache.store(ids[:2], tok[:2]) == 2
+    assert cache.load(ids) is None                      # 9 and 11 unseen
+    assert cache.store(ids, tok) == 2                   # 9, 11 added (3 is already there); now full
+    got = cache.load([3, 9, 11, 7])
+    want = torch.stack([tok[1], tok[2], tok[4], tok[0]])
+    if dtype == torch.float32:
+        assert torch.equal(got, want)
+    else:
+        assert torch.equal(got, want.bfloat16().float())
+    assert cache.store([99], tok[:1]) == 0 and 99 not in cache   # pool full
+    # an id seen twice in one batch with different rows keeps the first row handed to the kernel for its slot
+    assert cache.hits == 1 and cache.misses == 1
+
+
+@pytest.mark.gpu
+def test_cached_teacher_skips_the_forward_and_keeps_the_reference_surface():
+    """CachedTeacher(ids=...) returns the teacher's feature map (bf16-rounded) without launching a single teacher kernel
+    on the second pass, keeps `.model.blocks`, and without ids is the plain reference call."""
+    from dinov2_distillation_b200 import ops
+    from dinov2_distillation_b200.feature_cache import CachedTeacher, TeacherFeatureCache
+    from dinov2_distillation_b200.teacher import DINOv2ViT
+    t = DINOv2ViT("dinov2_vits14", weights="synthetic").cuda().eval()
+    cache = TeacherFeatureCache(capacity=8, tokens=256, dim=384)
+    ct = CachedTeacher(t, cache)
+    assert ct.model.blocks is t.model.blocks and len(ct.model.blocks) == 12
+    x = torch.randn(3, 3, 224, 224, device="cuda")
+    ref = t(x)["feature_map"].clone()
+    first = ct(x, ids=[5, 6, 7])["feature_map"]
+    assert torch.equal(first, ref) and len(cache) == 3
+    torch.cuda.synchronize()
+    ops.reset_launch_count()
+    second = ct(x, ids=[5, 6, 7])["feature_map"]
+    torch.cuda.synchronize()
+    assert ops.launch_count() == 1                       # the cache load, nothing of the teacher
+    assert second.shape == ref.shape == (3, 384, 16, 16)
+    assert torch.equal(second, ref.bfloat16().float())
+    cos = torch.nn.functional.cosine_similarity(second.flatten(1), ref.flatten(1), dim=1)
+    assert cos.min().item() > 0.99999
+    # a different order / subset is served row by row
+    sub = ct(x[[2, 0]], ids=[7, 5])["feature_map"]
+    assert torch.equal(sub, ref[[2, 0]].bfloat16().float())
+    assert torch.equal(ct(x)["feature_map"], ref)        # no ids: the plain call
+    with pytest.raises(ValueError):
+        ct(x, ids=[1, 2])

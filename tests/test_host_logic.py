@@ -291,3 +291,21 @@ def test_compute_losses_dict_weights_and_gradients_with_stub_losses():
     (g4,) = torch.autograd.grad(out["scalekd_res4_frequency_loss"], [f4])
     (g4_ref,) = torch.autograd.grad(ref["scalekd_res4_frequency_loss"], [f4])
     assert torch.allclose(g4, g4_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_teacher_feature_cache_host_logic():
+    """slot hand-out, capacity, all-or-nothing lookups -- and no CPU pool (no CPU fallback)."""
+    from dinov2_distillation_b200._lib import B200Error
+    from dinov2_distillation_b200.feature_cache import TeacherFeatureCache
+    c = TeacherFeatureCache(capacity=3, tokens=4, dim=8, device="cpu")
+    assert c.slots_for([10, 11], allocate=False) == [-1, -1] and len(c) == 0
+    assert c.slots_for([10, 11, 10], allocate=True) == [0, 1, 0]
+    assert c.slots_for([12, 13], allocate=True) == [2, -1]          # full: 13 is not cached
+    assert len(c) == 3 and 12 in c and 13 not in c
+    assert c.all_cached([10, 12]) and not c.all_cached([10, 13])
+    with pytest.raises(B200Error):
+        c.load([10])
+    with pytest.raises(ValueError):
+        TeacherFeatureCache(capacity=1, tokens=4, dim=6, device="cpu")
+    with pytest.raises(ValueError):
+        TeacherFeatureCache(capacity=1, tokens=4, dim=8, device="cpu", dtype=torch.float16)

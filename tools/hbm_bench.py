@@ -93,12 +93,15 @@ for tag, B, R in (("cfg2 (64 x 224²)", 64, 224), ("cfg4 (32 x 518²)", 32, 518)
     del ni
     torch.cuda.empty_cache()
 
-for tag, B, C, HW in (("cfg2 res5 (64 x 1024 x 16²)", 64, 1024, 256), ("cfg4 res5 (32 x 768 x 37²)", 32, 768, 1369)):
-    n = max(2, int(400e6 // (B * C * HW * 4)) + 1)
-    ni = rot(lambda: torch.randn(B, C, HW, device="cuda"), n)
-    us = bench(lambda: ops.nchw_to_tokens(ni()))
-    report("nchw_to_tokens (student map -> bf16 tokens)", tag, us, B * C * HW * 6, "B·C·HW·(4 + 2)")
-    del ni
+from dinov2_distillation_b200.scalekd import ScaleKD  # noqa: E402
+for tag, B, C, g, D, heads in (("cfg2 res5 (64 x 1024 x 16²)", 64, 1024, 16, 384, 24), ("cfg4 res5 (32 x 768 x 37²)", 32, 768, 37, 1024, 16)):
+    m = ScaleKD(name="scalekd_res5", alpha=[0.08, 0.06], student_dims=C, teacher_dims=D, query_hw=[g, g], pos_hw=[g, g],
+                pos_dims=D, window_shapes=[1, 1], self_query=True, softmax_scale=[5.0, 5.0], num_heads=heads).cuda().train()
+    n = max(2, int(400e6 // (B * C * g * g * 4)) + 1)
+    ni = rot(lambda: torch.randn(B, C, g, g, device="cuda"), n)
+    us = bench(lambda: m.projector_0.tokenize(ni()))
+    report("tokenize_split3_kernel (student map -> bf16 tokens + 3-term fp16 split)", tag, us, B * C * g * g * 12, "B·C·HW·(4 + 2 + 6)")
+    del ni, m
     torch.cuda.empty_cache()
 
 print(f"# Bandwidth-bound kernels, timed alone (tools/hbm_bench.py)\n")
