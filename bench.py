@@ -316,6 +316,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the stock-eager-PyTorch-on-this-GPU baseline leg")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--dense-table", default="", help="write the per-shape table of the dense launches (roofline leg) here")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-student-tail", action="store_true",
@@ -538,9 +539,39 @@ def main():
             else:
                 hot_path(dev["img"], feats)
         torch.cuda.synchronize()
-        ms_c, fl_c, n_c = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
-        L.check(lib.b200_profile_read(3, ms_c, fl_c, n_c), "profile_read")
+        # per-launch records (launch order): per-category sums, and a table by (category, algorithmic flops) on request
+        cap = 4096 * nprof
+        r_ms, r_fl, r_cat = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_int * cap)()
+        n_rec = lib.b200_profile_read_records(cap, r_ms, r_fl, r_cat)
+        if n_rec < 0:
+            L.check(n_rec, "profile_read_records")
         lib.b200_profile_enable(0)
+        ms_c, fl_c, n_c = [0.0] * 3, [0.0] * 3, [0] * 3
+        table = {}
+        for i in range(n_rec):
+            c = r_cat[i]
+            if 0 <= c < 3:
+                ms_c[c] += r_ms[i]
+                fl_c[c] += r_fl[i]
+                n_c[c] += 1
+                e = table.setdefault((c, r_fl[i]), [0, 0.0])
+                e[0] += 1
+                e[1] += r_ms[i]
+        # what the event pair itself adds to each bracketed launch (measured live with a null kernel)
+        br, bb = C.c_float(), C.c_float()
+        L.check(lib.b200_profile_event_overhead(256, C.byref(br), C.byref(bb), torch.cuda.current_stream().cuda_stream),
+                "profile_event_overhead")
+        ev_over_us = max(0.0, br.value - bb.value)
+        if args.dense_table and rank == 0:
+            names = {0: "gemm", 1: "attention fwd", 2: "attention bwd"}
+            with open(args.dense_table, "w") as f:
+                f.write(f"# dense launches of one {args.workload} step, by (kind, algorithmic GFLOP): CUDA events around each launch, "
+                        f"eager, one stream, {nprof} steps; event-pair overhead {ev_over_us:.2f} us per launch NOT subtracted\n\n")
+                f.write("| kind | GFLOP / launch | launches / step | avg us | TFLOP/s | us / step | TFLOP/s net of event overhead |\n|---|---:|---:|---:|---:|---:|---:|\n")
+                for (c, fl), (cnt, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+                    us = ms * 1e3 / cnt
+                    f.write(f"| {names[c]} | {fl / 1e9:.2f} | {cnt / nprof:.1f} | {us:.1f} | {fl / us / 1e6:.0f} | {ms * 1e3 / nprof:.0f} | "
+                            f"{fl / max(us - ev_over_us, 1e-3) / 1e6:.0f} |\n")
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -557,8 +588,15 @@ def main():
             pass
         if n_c[0] > 0 and ms_c[0] > 0:
             ach = fl_c[0] / (ms_c[0] * 1e-3) / 1e12
+            net_ms = ms_c[0] - n_c[0] * ev_over_us * 1e-3
             roofline = {"bound": "tensor", "kernel": "gemm_v2_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r0*_gemm_v2_ncu_full.md)",
+                        "frac": ach / peak, "traffic": traffic,
+                        "event_overhead_us_per_launch": ev_over_us,
+                        "event_overhead_note": "a null kernel bracketed launch by launch like every record here, minus the "
+                                               "same kernel back to back (b200_profile_event_overhead, measured in this run); "
+                                               "`achieved` / `frac` keep it in (conservative), the *_net fields take it out",
+                        "achieved_net": fl_c[0] / (net_ms * 1e-3) / 1e12 if net_ms > 0 else None,
+                        "frac_net": fl_c[0] / (net_ms * 1e-3) / 1e12 / peak if net_ms > 0 else None, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r0*_gemm_v2_ncu_full.md)",
                         "peak_source": peak_src,
                         "peak_kind": "sustained (the kernel is timed inside a long step; the burst figure is for a kernel timed alone)",
                         "launches_per_step": n_c[0] / nprof, "avg_launch_us": ms_c[0] * 1e3 / n_c[0],

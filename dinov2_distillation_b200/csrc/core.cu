@@ -7,6 +7,7 @@
 #include <atomic>
 #include <mutex>
 #include <vector>
+#include <algorithm>
 
 namespace b200 {
 
@@ -117,6 +118,60 @@ extern "C" int b200_profile_read(int n_cat, double* ms, double* flops, long long
   }
   g_recs.clear();
   return 0;
+}
+
+// What bracketing ONE kernel with an event pair adds to its measured duration (no programmatic overlap with the
+// predecessor across the event, launch latency after the first event, timestamp granularity): a null kernel is timed
+// (a) bracketed launch by launch exactly like prof_begin / prof_end do, (b) back to back between one event pair;
+// *bracketed_us and *back_to_back_us are per-launch medians / means, their difference is the overhead.
+namespace b200 {
+__global__ void profile_null_kernel() {
+  pdl_trigger();
+  pdl_wait();
+}
+}  // namespace b200
+extern "C" int b200_profile_event_overhead(int reps, float* bracketed_us, float* back_to_back_us, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(reps >= 8 && reps <= 4096 && bracketed_us && back_to_back_us, "bad args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> ev(2 * reps + 2);
+  for (auto& e : ev) B200_CUDA_OK(cudaEventCreate(&e));
+  for (int i = 0; i < 8; ++i) B200_CUDA_OK(launch_pdl(profile_null_kernel, dim3(148), dim3(128), 0, st));
+  for (int i = 0; i < reps; ++i) {
+    B200_CUDA_OK(cudaEventRecord(ev[2 * i], st));
+    B200_CUDA_OK(launch_pdl(profile_null_kernel, dim3(148), dim3(128), 0, st));
+    B200_CUDA_OK(cudaEventRecord(ev[2 * i + 1], st));
+  }
+  B200_CUDA_OK(cudaEventRecord(ev[2 * reps], st));
+  for (int i = 0; i < reps; ++i) B200_CUDA_OK(launch_pdl(profile_null_kernel, dim3(148), dim3(128), 0, st));
+  B200_CUDA_OK(cudaEventRecord(ev[2 * reps + 1], st));
+  B200_CUDA_OK(cudaEventSynchronize(ev[2 * reps + 1]));
+  std::vector<float> t(reps);
+  for (int i = 0; i < reps; ++i) B200_CUDA_OK(cudaEventElapsedTime(&t[i], ev[2 * i], ev[2 * i + 1]));
+  std::sort(t.begin(), t.end());
+  float all = 0.f;
+  B200_CUDA_OK(cudaEventElapsedTime(&all, ev[2 * reps], ev[2 * reps + 1]));
+  *bracketed_us = t[reps / 2] * 1e3f;
+  *back_to_back_us = all * 1e3f / reps;
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+// per-launch records in launch order (ms, algorithmic flops, category); clears them like b200_profile_read
+extern "C" int b200_profile_read_records(int cap, float* ms, double* flops, int* cat) {
+  using namespace b200;
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  int n = 0;
+  for (auto& r : g_recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) { set_error("profile: event sync failed"); return -2; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (n < cap) { ms[n] = t; flops[n] = r.flops; cat[n] = r.cat; ++n; }
+    g_pool.push_back(r.a);
+    g_pool.push_back(r.b);
+  }
+  g_recs.clear();
+  return n;
 }
 
 extern "C" int b200_set_option(const char* name, int value) {
