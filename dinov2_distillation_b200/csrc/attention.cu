@@ -964,7 +964,7 @@ extern "C" int b200_attention_fwd(const b200_attn_desc* d, void* stream) {
     if (r == 0) bump_stat(STAT_ATTN_PP_FWD);
     if (r <= 0) return r;
   }
-  if (d->o_alt == nullptr) {   // (the tcgen05 kernel writes one output format)
+  {
     const int r = launch_attention_tc_fwd(d, st);
     if (r == 0) bump_stat(STAT_ATTN_TC_FWD);
     if (r <= 0) return r;

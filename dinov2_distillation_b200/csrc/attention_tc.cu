@@ -69,6 +69,9 @@ struct AttnTcParams {
   int nk_last, nkp_last;     // keys / padded keys of the last block (all other blocks hold 256)
   uint32_t idesc_qk_full;    // QK^T of a full 256-key block
   long long* dbg;            // B200_ATTN_DBG=1: per-phase clock64 stamps of CTA 0 ([item][16])
+  int fp16;                  // q / k / v / o are fp16 (ScaleKD projector forward precision); P is packed the same way
+  int has_alt;               // a second copy of o in the other 16-bit format goes out through tmOalt
+  int q_batched;             // 0: q is batch invariant (the self-query embedding)
 };
 
 __device__ __forceinline__ void atc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -125,7 +128,7 @@ template <bool MULTI>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                   const AttnTcParams p) {
+                   const __grid_constant__ CUtensorMap tmOalt, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_OFF_BAR);
@@ -147,6 +150,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
+    if (p.has_alt) tma_prefetch_desc(&tmOalt);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < 2; ++i) {
@@ -184,7 +188,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const int qb = qc & 1;
           mbar_wait(&q_empty[qb], ((qc >> 1) & 1) ^ 1);
           mbar_expect_tx(&q_full[qb], ATC_Q_BYTES);
-          tma_load_3d(smem + ATC_OFF_Q + qb * ATC_Q_BYTES, &tmQ, &q_full[qb], h * 64, qt * 128, b);
+          tma_load_3d(smem + ATC_OFF_Q + qb * ATC_Q_BYTES, &tmQ, &q_full[qb], h * 64, qt * 128, p.q_batched ? b : 0);
           for (int j = 0; j < p.nblk; ++j) {
             if (p.nblk == 1 && qt > 0) break;
             const int kb = kvc & 1;
@@ -453,7 +457,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const float e0 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j2]), p.scale_log2, -ms));
                 const float e1 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j2 + 1]), p.scale_log2, -ms));
                 sum += e0 + e1;
-                pk[j2] = pack_bf16(e0, e1);
+                pk[j2] = pack16(e0, e1, p.fp16);
               }
               atc_tmem_st_32x16(t_p + c * 16, pk);
               const bool last = (i == MAXC - 1) || (c + 2 >= n_chunks);
@@ -508,22 +512,30 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         if (ew == 0) ATC_STAMP(7);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int j2 = c * 8;
-          const uint32_t w0 = pack_bf16(o_acc[j2] * inv, o_acc[j2 + 1] * inv);
-          const uint32_t w1 = pack_bf16(o_acc[j2 + 2] * inv, o_acc[j2 + 3] * inv);
-          const uint32_t w2 = pack_bf16(o_acc[j2 + 4] * inv, o_acc[j2 + 5] * inv);
-          const uint32_t w3 = pack_bf16(o_acc[j2 + 6] * inv, o_acc[j2 + 7] * inv);
-          const uint32_t addr = stage + row_off + ((c ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
         const int row0 = qt * 128 + quad * 32;
-        if (lane == 0) {
-          atc_tma_store_3d(&tmO, stage, h * 64 + hf * 32, row0, b);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#pragma unroll 1
+        for (int fmt_pass = 0; fmt_pass < (p.has_alt ? 2 : 1); ++fmt_pass) {
+          const int f16 = fmt_pass == 0 ? p.fp16 : !p.fp16;
+          if (fmt_pass == 1) {   // the first copy must have left the staging tile
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j2 = c * 8;
+            const uint32_t w0 = pack16(o_acc[j2] * inv, o_acc[j2 + 1] * inv, f16);
+            const uint32_t w1 = pack16(o_acc[j2 + 2] * inv, o_acc[j2 + 3] * inv, f16);
+            const uint32_t w2 = pack16(o_acc[j2 + 4] * inv, o_acc[j2 + 5] * inv, f16);
+            const uint32_t w3 = pack16(o_acc[j2 + 6] * inv, o_acc[j2 + 7] * inv, f16);
+            const uint32_t addr = stage + row_off + ((c ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            atc_tma_store_3d(fmt_pass == 0 ? &tmO : &tmOalt, stage, h * 64 + hf * 32, row0, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
         if (hf == 0 && p.lse != nullptr && row0 + lane < p.Nq)
           p.lse[((long long)b * p.heads + h) * p.Nq + row0 + lane] = (m_run * p.scale_log2 + log2f(sum)) * 0.6931471805599453f;
@@ -542,10 +554,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // Returns 1 when the problem is outside this kernel's envelope (the caller falls back to the mma.sync kernel).
 int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   if (!option(OPT_ATTN_TC_FWD)) return 1;
-  if (d->hd != 64 || d->qkvo_is_fp16 || d->Nk < 33 || d->q_bs == 0) return 1;
+  if (d->hd != 64 || d->Nk < 33) return 1;
   if (d->Nk > ATC_NKP_MAX && !option(OPT_ATTN_TC_FWD_LONG)) return 1;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (!al16(d->q) || !al16(d->k) || !al16(d->v) || !al16(d->o)) return 1;
+  if (!al16(d->q) || !al16(d->k) || !al16(d->v) || !al16(d->o) || (d->o_alt != nullptr && !al16(d->o_alt))) return 1;
+  if (d->k_bs == 0 || d->v_bs == 0 || d->o_bs == 0) return 1;
   if (d->q_ts % 8 || d->k_ts % 8 || d->v_ts % 8 || d->o_ts % 8 || d->q_bs % 8 || d->k_bs % 8 || d->v_bs % 8 || d->o_bs % 8)
     return 1;
   AttnTcParams p{};
@@ -556,7 +569,12 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   p.nkp_last = (p.nk_last + 15) & ~15;
   p.nkp = p.nkp_last;
   const int rem = d->Nq % 128;
-  if (p.nblk == 1 && rem > 0 && rem <= ATC_TAIL_MAX) {
+  const int fmt = d->qkvo_is_fp16 ? 0 : 1;
+  p.fp16 = d->qkvo_is_fp16 ? 1 : 0;
+  p.has_alt = d->o_alt != nullptr ? 1 : 0;
+  p.q_batched = d->q_bs != 0 ? 1 : 0;
+  // (the tail-row warp reads bf16 q rows with a bf16 mma.sync and indexes q per batch item)
+  if (p.nblk == 1 && rem > 0 && rem <= ATC_TAIL_MAX && fmt == 1 && p.q_batched) {
     p.n_qt = d->Nq / 128; p.tail0 = p.n_qt * 128; p.tail_n = rem;
   } else {
     p.n_qt = (d->Nq + 127) / 128; p.tail0 = 0; p.tail_n = 0;
@@ -568,17 +586,21 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   p.o = static_cast<__nv_bfloat16*>(d->o); p.o_bs = d->o_bs; p.o_ts = d->o_ts;
   p.n1 = p.nkp_last > 256 ? 256 : p.nkp_last;
   p.n2 = p.nkp_last - p.n1;
-  p.idesc_qk1 = make_idesc_bf16(128, p.n1, false, false);
-  p.idesc_qk2 = p.n2 > 0 ? make_idesc_bf16(128, p.n2, false, false) : 0u;
-  p.idesc_qk_full = make_idesc_bf16(128, 256, false, false);
-  p.idesc_pv = make_idesc_bf16(128, 64, false, true);
+  p.idesc_qk1 = make_idesc_16(128, p.n1, false, false, fmt);
+  p.idesc_qk2 = p.n2 > 0 ? make_idesc_16(128, p.n2, false, false, fmt) : 0u;
+  p.idesc_qk_full = make_idesc_16(128, 256, false, false, fmt);
+  p.idesc_pv = make_idesc_16(128, 64, false, true, fmt);
 
   const uint64_t cols = (uint64_t)d->heads * 64;
-  CUtensorMap tq, tk, tv, to;
-  B200_TRY(make_tensor_map_3d(&tq, d->q, 2, cols, (uint64_t)d->Nq, (uint64_t)d->B, (uint64_t)d->q_ts, (uint64_t)d->q_bs, 64, 128, 1, 128));
+  CUtensorMap tq, tk, tv, to, toa;
+  B200_TRY(make_tensor_map_3d(&tq, d->q, 2, cols, (uint64_t)d->Nq, (uint64_t)(p.q_batched ? d->B : 1), (uint64_t)d->q_ts,
+                              (uint64_t)(p.q_batched ? d->q_bs : (long long)d->Nq * d->q_ts), 64, 128, 1, 128));
   B200_TRY(make_tensor_map_3d(&tk, d->k, 2, cols, (uint64_t)d->Nk, (uint64_t)d->B, (uint64_t)d->k_ts, (uint64_t)d->k_bs, 64, ATC_KV_BOX, 1, 128));
   B200_TRY(make_tensor_map_3d(&tv, d->v, 2, cols, (uint64_t)d->Nk, (uint64_t)d->B, (uint64_t)d->v_ts, (uint64_t)d->v_bs, 64, ATC_KV_BOX, 1, 128));
   B200_TRY(make_tensor_map_3d(&to, d->o, 2, cols, (uint64_t)d->Nq, (uint64_t)d->B, (uint64_t)d->o_ts, (uint64_t)d->o_bs, 32, 32, 1, 64));
+  toa = to;
+  if (p.has_alt)
+    B200_TRY(make_tensor_map_3d(&toa, d->o_alt, 2, cols, (uint64_t)d->Nq, (uint64_t)d->B, (uint64_t)d->o_ts, (uint64_t)d->o_bs, 32, 32, 1, 64));
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -594,8 +616,8 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   if (dbg_on && dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 9 * 16 * sizeof(long long)); }
   if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 9 * 16 * sizeof(long long), st);
   p.dbg = dbg_on ? dbg_buf : nullptr;
-  if (p.nblk > 1) B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, p));
-  else B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, p));
+  if (p.nblk > 1) B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, toa, p));
+  else B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, toa, p));
   prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
   B200_LAUNCH_OK();
   if (dbg_on) {

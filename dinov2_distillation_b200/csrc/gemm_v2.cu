@@ -875,7 +875,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             if (ln.mean) ln.mean[row] = mean;
             if (ln.rstd) ln.rstd[row] = rstd;
           }
-          const float nm = -mean * rstd;   // (x - mean) * rstd as one FMA: x * rstd + nm
           const uint32_t row_addr = (uint32_t)r * 128u;
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
@@ -883,8 +882,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             if (c < p.K) {
               uint32_t u0 = 0u, u1 = 0u;
               if (live) {
-                u0 = pack_bf16(fmaf(fmaf(vr[i].x, rstd, nm), g4[i].x, b4[i].x), fmaf(fmaf(vr[i].y, rstd, nm), g4[i].y, b4[i].y));
-                u1 = pack_bf16(fmaf(fmaf(vr[i].z, rstd, nm), g4[i].z, b4[i].z), fmaf(fmaf(vr[i].w, rstd, nm), g4[i].w, b4[i].w));
+                // (layernorm_fwd_kernel's expression, operation for operation: a batch whose row count sends it to the
+                // two-kernel path must produce the same bits -- test_cfg2_full_size_properties compares B = 64 with B = 8)
+                u0 = pack_bf16((vr[i].x - mean) * rstd * g4[i].x + b4[i].x, (vr[i].y - mean) * rstd * g4[i].y + b4[i].y);
+                u1 = pack_bf16((vr[i].z - mean) * rstd * g4[i].z + b4[i].z, (vr[i].w - mean) * rstd * g4[i].w + b4[i].w);
               }
               const uint32_t sw = EW % 8 == 0 ? (uint32_t)ew & 7u : (uint32_t)r & 7u;
               const uint32_t addr = col_addr[i] + row_addr + (((((uint32_t)c & 63u) >> 3) ^ sw) << 4);

@@ -334,6 +334,33 @@ def test_attention_tc_head64(B, heads, Nq, Nk):
     assert (lse - lse_ref).abs().max().item() < 2e-3, (lse - lse_ref).abs().max().item()
 
 
+@pytest.mark.parametrize("B,heads,Nq,Nk,shared_q", [(2, 16, 1369, 1369, False), (2, 16, 1369, 1369, True), (3, 4, 300, 273, True),
+                                                    (2, 2, 520, 1024, False)])
+def test_attention_tc_head64_fp16_both_formats_shared_query(B, heads, Nq, Nk, shared_q):
+    """The long-sequence tcgen05 forward (attention_tc.cu) on the ScaleKD projector's operands at 518 pixels: fp16 q / k / v,
+    both output formats, the batch-invariant self-query (batch stride 0), k / v sliced out of the fused [k|v] tensor."""
+    ops = _ops()
+    hd = 64
+    D = hd * heads
+    scale = 5.0 / math.sqrt(hd)
+    kv = (torch.randn(B, Nk, 2 * D, device="cuda") * 0.5).half()
+    k, v = kv[..., :D], kv[..., D:]
+    q = (torch.randn(1 if shared_q else B, Nq, D, device="cuda") * 0.5).half()
+    if shared_q:
+        q = q.expand(B, Nq, D)
+    ops.set_option("stat_attn_tc_fwd", 0)
+    o, lse, o_alt = ops.attention_fwd(q, k, v, heads, scale, want_alt=True)
+    assert ops.get_option("stat_attn_tc_fwd") == 1
+    assert o.dtype == torch.float16 and o_alt.dtype == torch.bfloat16
+    ref = _attn_ref(q, k, v, heads, scale)
+    assert rel_err(o, ref) < 2e-3, rel_err(o, ref)
+    assert rel_err(o_alt, ref) < 8e-3, rel_err(o_alt, ref)
+    qh = q.float().reshape(B, Nq, heads, hd).transpose(1, 2)
+    kh = k.float().reshape(B, Nk, heads, hd).transpose(1, 2)
+    lse_ref = torch.logsumexp(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    assert (lse - lse_ref).abs().max().item() < 2e-3
+
+
 @pytest.mark.parametrize("hd,heads,N", [(16, 24, 256), (24, 16, 256), (64, 4, 150), (96, 2, 70)])
 def test_attention_fp16_forward_bf16_grads(hd, heads, N):
     """ScaleKD projector precision policy: q/k/v/o fp16, gradients bf16."""
