@@ -532,6 +532,9 @@ def main():
             torch.cuda.synchronize()
             ms_one_stream = e0.elapsed_time(e1) / 10
         lib.b200_profile_enable(1)
+        stat_names = ("stat_attn_tc_fwd", "stat_attn_pp_fwd", "stat_attn_mma_fwd", "stat_attn_tc_bwd", "stat_attn_mma_bwd")
+        for nm in stat_names:
+            lib.b200_set_option(nm.encode(), 0)
         nprof = max(2, min(args.steps, 5))
         for _ in range(nprof):   # eager launches (events bracket each dense kernel); not part of `value`
             if graphed is not None:
@@ -606,6 +609,8 @@ def main():
                                       "timed alone); the timed `value` overlaps the spatial and frequency branches on two",
                         "ms_per_step_one_stream": ms_one_stream}
         step.two_streams = True
+        # which attention kernels the step launched (per step): tcgen05 (tc / pp) vs the mma.sync fallback
+        extra["attention_paths_per_step"] = {nm[5:]: lib.b200_get_option(nm.encode()) / nprof for nm in stat_names}
         for i, nm in ((1, "attention_fwd"), (2, "attention_bwd")):
             if n_c[i] > 0 and ms_c[i] > 0:
                 extra[nm] = {"tflops": fl_c[i] / (ms_c[i] * 1e-3) / 1e12, "ms_per_step": ms_c[i] / nprof,

@@ -124,7 +124,9 @@ __device__ __forceinline__ float atc_ex2(float x) {
 // MULTI = false: the whole key range is resident (one block of up to 272 keys per query tile, 5 S chunks per softmax warp,
 // the output is read once from TMEM). MULTI = true: key blocks of 256 with online softmax (4 chunks per warp plus the
 // running 32-column output accumulator in registers).
-template <bool MULTI>
+// FP16: q / k / v / o (and P) are fp16 and a bf16 copy of o leaves through tmOalt -- the ScaleKD projector's forward operands
+// (DESIGN.md section 3); otherwise bf16 in, bf16 out (the teacher).
+template <bool MULTI, bool FP16>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -150,7 +152,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
-    if (p.has_alt) tma_prefetch_desc(&tmOalt);
+    if (FP16) tma_prefetch_desc(&tmOalt);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < 2; ++i) {
@@ -457,7 +459,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const float e0 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j2]), p.scale_log2, -ms));
                 const float e1 = atc_ex2(fmaf(__uint_as_float(sv[i][2 * j2 + 1]), p.scale_log2, -ms));
                 sum += e0 + e1;
-                pk[j2] = pack16(e0, e1, p.fp16);
+                pk[j2] = FP16 ? pack16(e0, e1, 1) : pack_bf16(e0, e1);
               }
               atc_tmem_st_32x16(t_p + c * 16, pk);
               const bool last = (i == MAXC - 1) || (c + 2 >= n_chunks);
@@ -513,29 +515,29 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (ew == 0) ATC_STAMP(7);
         const int row0 = qt * 128 + quad * 32;
-#pragma unroll 1
-        for (int fmt_pass = 0; fmt_pass < (p.has_alt ? 2 : 1); ++fmt_pass) {
-          const int f16 = fmt_pass == 0 ? p.fp16 : !p.fp16;
-          if (fmt_pass == 1) {   // the first copy must have left the staging tile
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-          }
+        auto emit = [&](const bool f16, const CUtensorMap* tm) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int j2 = c * 8;
-            const uint32_t w0 = pack16(o_acc[j2] * inv, o_acc[j2 + 1] * inv, f16);
-            const uint32_t w1 = pack16(o_acc[j2 + 2] * inv, o_acc[j2 + 3] * inv, f16);
-            const uint32_t w2 = pack16(o_acc[j2 + 4] * inv, o_acc[j2 + 5] * inv, f16);
-            const uint32_t w3 = pack16(o_acc[j2 + 6] * inv, o_acc[j2 + 7] * inv, f16);
+            const uint32_t w0 = f16 ? pack16(o_acc[j2] * inv, o_acc[j2 + 1] * inv, 1) : pack_bf16(o_acc[j2] * inv, o_acc[j2 + 1] * inv);
+            const uint32_t w1 = f16 ? pack16(o_acc[j2 + 2] * inv, o_acc[j2 + 3] * inv, 1) : pack_bf16(o_acc[j2 + 2] * inv, o_acc[j2 + 3] * inv);
+            const uint32_t w2 = f16 ? pack16(o_acc[j2 + 4] * inv, o_acc[j2 + 5] * inv, 1) : pack_bf16(o_acc[j2 + 4] * inv, o_acc[j2 + 5] * inv);
+            const uint32_t w3 = f16 ? pack16(o_acc[j2 + 6] * inv, o_acc[j2 + 7] * inv, 1) : pack_bf16(o_acc[j2 + 6] * inv, o_acc[j2 + 7] * inv);
             const uint32_t addr = stage + row_off + ((c ^ sw) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            atc_tma_store_3d(fmt_pass == 0 ? &tmO : &tmOalt, stage, h * 64 + hf * 32, row0, b);
+            atc_tma_store_3d(tm, stage, h * 64 + hf * 32, row0, b);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+        };
+        emit(FP16, &tmO);
+        if constexpr (FP16) {   // second copy in the other 16-bit format: the first must have left the staging tile
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+          emit(!FP16, &tmOalt);
         }
         if (hf == 0 && p.lse != nullptr && row0 + lane < p.Nq)
           p.lse[((long long)b * p.heads + h) * p.Nq + row0 + lane] = (m_run * p.scale_log2 + log2f(sum)) * 0.6931471805599453f;
@@ -572,6 +574,7 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   const int fmt = d->qkvo_is_fp16 ? 0 : 1;
   p.fp16 = d->qkvo_is_fp16 ? 1 : 0;
   p.has_alt = d->o_alt != nullptr ? 1 : 0;
+  if (p.fp16 != p.has_alt) return 1;   // two variants are built: bf16 -> bf16 (teacher) and fp16 -> fp16 + bf16 copy (projector)
   p.q_batched = d->q_bs != 0 ? 1 : 0;
   // (the tail-row warp reads bf16 q rows with a bf16 mma.sync and indexes q per batch item)
   if (p.nblk == 1 && rem > 0 && rem <= ATC_TAIL_MAX && fmt == 1 && p.q_batched) {
@@ -604,8 +607,10 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
-    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
     attr_set = true;
   }
   const int units = d->B * d->heads;
@@ -616,8 +621,9 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   if (dbg_on && dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 9 * 16 * sizeof(long long)); }
   if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 9 * 16 * sizeof(long long), st);
   p.dbg = dbg_on ? dbg_buf : nullptr;
-  if (p.nblk > 1) B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, toa, p));
-  else B200_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, toa, p));
+  auto kern = p.nblk > 1 ? (p.fp16 ? attn_tc_fwd_kernel<true, true> : attn_tc_fwd_kernel<true, false>)
+                         : (p.fp16 ? attn_tc_fwd_kernel<false, true> : attn_tc_fwd_kernel<false, false>);
+  B200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, toa, p));
   prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
   B200_LAUNCH_OK();
   if (dbg_on) {

@@ -34,6 +34,12 @@ class _PosAttention(nn.Module):
         super().__init__()
         self.embed_dims, self.num_heads = embed_dims, num_heads
         self.head_dims = embed_dims // num_heads
+        # The reference accepts any divisor (losses/scalekd.py:273); the attention kernels here cover head dims that are
+        # multiples of 8 up to 96 (config.yaml's 16 / 24 heads on every teacher; NOT the reference default of 8 heads on
+        # vitl14 / vitg14 = 128 / 192). Refuse at construction, not at the first forward.
+        if embed_dims % num_heads == 0 and (self.head_dims % 8 != 0 or self.head_dims > 96):
+            raise ValueError(f"head_dim = teacher_dims / num_heads = {self.head_dims}: this library supports multiples of 8 "
+                             "up to 96 (use more heads, e.g. 16 or 24 as in the reference's config.yaml)")
         self.softmax_scale = softmax_scale
         self.window_shapes = window_shapes
         self.q = nn.Linear(pos_dims, embed_dims, bias=True)
