@@ -1,6 +1,8 @@
-// tcgen05 attention forward for head_dim 64 and short sequences (Nk <= 272: the 224-pixel teacher, N = 257, and the
-// re-used teacher blocks, N = 256).  (hub Attention.forward, reached through models/backbones/dinov2.py:32 and
-// train/distillation_module.py:177.)
+// tcgen05 attention forward for head_dim 64: the 224-pixel teacher (N = 257, whole key range resident) and every
+// 518-pixel sequence (N = 1 369 / 1 370, key blocks of 256 with online softmax) -- hub Attention.forward, reached through
+// models/backbones/dinov2.py:32 and train/distillation_module.py:177 (bf16), and the ScaleKD cross-attention at 518
+// pixels, losses/scalekd.py:299-314 (template FP16: fp16 operands, a bf16 copy of the output, batch-invariant query).
+// Key ranges of 128-256 tokens go to attention_pp.cu (two tiles in flight) first.
 //
 // With the whole key range resident, a 128-query tile needs ONE QK^T and ONE PV: no online-softmax rescaling.
 //   S[128, Nk] = Q K^T        tcgen05.mma  SS  (Q: smem K-major, K: smem K-major)   -> TMEM columns [0, 272)

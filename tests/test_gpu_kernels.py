@@ -239,7 +239,8 @@ def test_layernorm_drop_cls_rows():
 def test_ln_gemm_fused_prologue_and_fallback(M, K, N, act, pre):
     """b200_ln_gemm_bf16: LayerNorm fused in front of the GEMM as a shared-memory prologue (K <= 384: CTA-pair kernel,
     the panel is normalised once and stays resident; partial last pair / panel at M = 16448, 300, 1000) and the
-    LayerNorm + GEMM fallback (K = 768). Must equal the two-kernel path (same per-row arithmetic) and the fp32 reference."""
+    LayerNorm + GEMM fallback (K = 768). Must equal the two-kernel path (same per-row arithmetic, operation for operation:
+    small batches are dispatched to it) and the fp32 reference."""
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(M + K + N)
     x = torch.randn(M, K, device="cuda", generator=g) * 2.0 + 0.3
