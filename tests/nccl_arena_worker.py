@@ -69,8 +69,14 @@ def main():
     torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
     ref_opt = torch.optim.AdamW(ref_params, lr=1e-2, betas=(0.9, 0.999), weight_decay=0.01)
     ref_opt.step()
-    e2 = max(rel(p.detach() - q, r.detach() - q.cpu().double()) for p, q, r in zip(arena.params, p0, ref_params)
-             if (r.detach() - q.cpu().double()).norm() > 1e-12)
+    # the update of ALL parameters as one vector (per tensor it is ill conditioned where the gradient is exactly zero --
+    # the conv bias under BatchNorm: the update is lr * wd * p = 1e-4 |p|, a few fp32 ulps of p), and every new parameter
+    # value against the float64 reference to fp32 rounding of (|p| + lr)
+    upd = torch.cat([(p.detach() - q).flatten().cpu().double() for p, q in zip(arena.params, p0)])
+    upd_ref = torch.cat([(r.detach() - q.cpu().double()).flatten() for q, r in zip(p0, ref_params)])
+    e2 = ((upd - upd_ref).norm() / upd_ref.norm()).item()
+    e2b = max(((p.detach().cpu().double() - r.detach()).abs() / (r.detach().abs() + 1e-2)).max().item()
+              for p, r in zip(arena.params, ref_params))
 
     # (3) packed metrics
     met = D.reduce_metrics({"loss": out["loss"].detach(), "rank": torch.tensor(float(rank), device=dev)})
@@ -79,9 +85,9 @@ def main():
     e3 = abs(met["loss"].item() - torch.stack(losses).mean().item())
     e4 = abs(met["rank"].item() - (world - 1) / 2)
 
-    print(f"rank {rank}/{world}: arena vs host mean {e1:.2e}; AdamW update vs reference {e2:.2e}; metrics {e3:.2e} {e4:.2e}",
-          flush=True)
-    ok = e1 < 1e-6 and e2 < 1e-4 and e3 < 1e-6 and e4 < 1e-6
+    print(f"rank {rank}/{world}: arena vs host mean {e1:.2e}; AdamW update vs reference {e2:.2e} (worst element {e2b:.2e}); "
+          f"metrics {e3:.2e} {e4:.2e}", flush=True)
+    ok = e1 < 1e-6 and e2 < 1e-4 and e2b < 1e-5 and e3 < 1e-6 and e4 < 1e-6
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
