@@ -1196,7 +1196,6 @@ int launch_gemm_ln(const b200_gemm_desc* d, const float* x, long long ldx, const
   if (d->out_f32 || d->residual || d->col_scale || d->aux || d->out16_colsum || d->out16_pre_alt || d->out16_is_fp16) return 1;
   if (d->out_row_period > 0 || d->res_row_period > 0 || d->out_batch_period > 0) return 1;
   if (d->out_bf16 == nullptr || (d->act != B200_ACT_NONE && d->act != B200_ACT_GELU)) return 1;
-  if (d->act == B200_ACT_GELU && false) return 1;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(x) || ldx % 4 != 0 || !al16(ln_w) || !al16(ln_b) || !al16(d->B) || d->ldb % 8 != 0) return 1;
   if (!al16(d->out_bf16) || d->ldo16 % 8 != 0 || (d->bias && !al16(d->bias))) return 1;
