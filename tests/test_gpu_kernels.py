@@ -659,6 +659,28 @@ def test_gemm_epilogue_column_sums_of_16bit_output(M, N, K):
     assert rel_err(cs2, o2.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(16400, 1536, 384), (40000, 384, 256), (16384, 768, 128), (300, 192, 64)])
+@pytest.mark.parametrize("mode", ["drelu", "dgelu"])
+def test_gemm_aux_epilogue_shapes(M, N, K, mode):
+    """dgrad-through-activation GEMMs (x relu mask / x gelu' from a 16-bit aux tile fetched by TMA per 32 x 32 unit) at the
+    shapes of the step and around them: several tiles per CTA, a ragged last row tile, one tile per CTA, a single tile."""
+    ops = _ops()
+    a = bf(torch.randn(M, K, device="cuda"))
+    b = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    aux = torch.randn(M, N, device="cuda").to(torch.float16 if mode == "drelu" else torch.bfloat16)
+    plain = a.float() @ b.float().t()
+    xa = aux.float()
+    if mode == "drelu":
+        ref = plain * (xa > 0)
+    else:
+        ref = plain * (0.5 * (1 + torch.erf(xa / math.sqrt(2))) + xa * torch.exp(-0.5 * xa * xa) / math.sqrt(2 * math.pi))
+    out = ops.gemm(a, b, aux=aux, aux_mode=mode, out_dtype=torch.bfloat16)
+    assert rel_err(out, ref) < 6e-3, rel_err(out, ref)
+    # twice in a row on the same buffers: barrier phases start clean in every launch
+    out2 = ops.gemm(a, b, aux=aux, aux_mode=mode, out_dtype=torch.bfloat16)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("B,HW,D", [(16, 256, 384), (8, 1369, 256), (2, 49, 128)])
 def test_batchnorm_relu_pos_kernels_vs_autograd(B, HW, D):
     """proj_student's BatchNorm2d -> ReLU, + pos_embed (losses/scalekd.py:199-201, :238) on token-major data: forward
