@@ -739,3 +739,47 @@ def test_cached_teacher_skips_the_forward_and_keeps_the_reference_surface():
     assert torch.equal(ct(x)["feature_map"], ref)        # no ids: the plain call
     with pytest.raises(ValueError):
         ct(x, ids=[1, 2])
+
+
+@pytest.mark.gpu
+def test_distillation_step_with_cached_teacher_matches_uncached():
+    """f3 end to end: DistillationStep over a CachedTeacher (its .model.blocks are the wrapped teacher's, the feature map
+    comes from the HBM pool on the second pass) gives the uncached step's losses and gradients to the bf16 rounding of the
+    cached features (north-star gates)."""
+    _, teacher, distill = _mods()
+    from dinov2_distillation_b200.feature_cache import CachedTeacher, TeacherFeatureCache
+    t, cfg, _ = _teacher_pair("dinov2_vits14", seed=1)
+    common = dict(alpha=[0.08, 0.06], teacher_dims=384, query_hw=[16, 16], pos_hw=[16, 16], pos_dims=384, window_shapes=[1, 1],
+                  softmax_scale=[5.0, 5.0])
+    specs = [{"type": "scalekd", "weight": 1.0, "kwargs": dict(common, name="scalekd_res4", student_dims=96, self_query=True, num_heads=16)},
+             {"type": "scalekd", "weight": 1.0, "kwargs": dict(common, name="scalekd_res5", student_dims=128, self_query=False, num_heads=24)}]
+    torch.manual_seed(5)
+    step = distill.DistillationStep(None, t, specs).cuda().train()
+    ct = CachedTeacher(t, TeacherFeatureCache(capacity=8, tokens=256, dim=384))
+    gen = torch.Generator().manual_seed(6)
+    B = 4
+    img = torch.randn(B, 3, 224, 224, generator=gen).cuda()
+    feats = {"res4": torch.randn(B, 96, 16, 16, generator=gen).cuda(), "res5": torch.randn(B, 128, 16, 16, generator=gen).cuda()}
+    ids = [11, 12, 13, 14]
+
+    def run(T):
+        for p in step.losses.parameters():
+            p.grad = None
+        f = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+        out = step._compute_losses({"student": f, "teacher": T})
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        return out, {k: v.grad.clone() for k, v in f.items()}
+
+    ref_out, ref_g = run(t(img)["feature_map"])
+    ct(img, ids=ids)                                        # first pass: fills the pool
+    assert ct.cache.all_cached(ids)
+    out, g = run(ct(img, ids=ids)["feature_map"])           # second pass: served from the pool
+    assert ct.cache.hits == 1
+    for k, v in ref_out.items():
+        if k.endswith("similarity"):
+            assert abs(out[k].item() - v.item()) <= SIM_ATOL, (k, out[k].item(), v.item())
+        else:
+            assert abs(out[k].item() - v.item()) / abs(v.item()) <= LOSS_RTOL, (k, out[k].item(), v.item())
+    for k in ref_g:
+        assert rel(g[k], ref_g[k]) <= GRAD_RTOL, (k, rel(g[k], ref_g[k]))
