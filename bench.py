@@ -544,8 +544,8 @@ def main():
         torch.cuda.synchronize()
         # per-launch records (launch order): per-category sums, and a table by (category, algorithmic flops) on request
         cap = 4096 * nprof
-        r_ms, r_fl, r_cat = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_int * cap)()
-        n_rec = lib.b200_profile_read_records(cap, r_ms, r_fl, r_cat)
+        r_ms, r_fl, r_cat, r_by = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_int * cap)(), (C.c_double * cap)()
+        n_rec = lib.b200_profile_read_records(cap, r_ms, r_fl, r_cat, r_by)
         if n_rec < 0:
             L.check(n_rec, "profile_read_records")
         lib.b200_profile_enable(0)
@@ -557,7 +557,7 @@ def main():
                 ms_c[c] += r_ms[i]
                 fl_c[c] += r_fl[i]
                 n_c[c] += 1
-                e = table.setdefault((c, r_fl[i]), [0, 0.0])
+                e = table.setdefault((c, r_fl[i], r_by[i]), [0, 0.0])
                 e[0] += 1
                 e[1] += r_ms[i]
         # what the event pair itself adds to each bracketed launch (measured live with a null kernel)
@@ -565,16 +565,40 @@ def main():
         L.check(lib.b200_profile_event_overhead(256, C.byref(br), C.byref(bb), torch.cuda.current_stream().cuda_stream),
                 "profile_event_overhead")
         ev_over_us = max(0.0, br.value - bb.value)
+        # the roofline that binds each shape: tensor time (algorithmic FLOPs / sustained bf16 peak) against HBM time
+        # (algorithmic operand + result bytes / copy bandwidth); what fraction of that bound the launch achieves, net of the
+        # event overhead. Aggregate: sum of bounds / sum of net times over the GEMM launches.
+        try:
+            _pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            _pk = {}
+        pk_tf, pk_gb = float(_pk.get("bf16_tflops_sustained", 1400.0)), float(_pk.get("hbm_gbs", 6545.0))
+        bound_us_sum, net_us_sum = 0.0, 0.0
+        rows_tbl = []
+        for (c, fl, by), (cnt, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+            us = ms * 1e3 / cnt
+            t_tensor, t_hbm = fl / pk_tf * 1e-6, by / pk_gb * 1e-3
+            bound = max(t_tensor, t_hbm)
+            net = max(us - ev_over_us, 1e-3)
+            if c == 0:
+                bound_us_sum += bound * cnt
+                net_us_sum += net * cnt
+            rows_tbl.append((c, fl, by, cnt, us, ms, t_tensor, t_hbm, bound, net))
+        frac_of_bound = bound_us_sum / net_us_sum if net_us_sum > 0 else None
         if args.dense_table and rank == 0:
             names = {0: "gemm", 1: "attention fwd", 2: "attention bwd"}
             with open(args.dense_table, "w") as f:
-                f.write(f"# dense launches of one {args.workload} step, by (kind, algorithmic GFLOP): CUDA events around each launch, "
-                        f"eager, one stream, {nprof} steps; event-pair overhead {ev_over_us:.2f} us per launch NOT subtracted\n\n")
-                f.write("| kind | GFLOP / launch | launches / step | avg us | TFLOP/s | us / step | TFLOP/s net of event overhead |\n|---|---:|---:|---:|---:|---:|---:|\n")
-                for (c, fl), (cnt, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
-                    us = ms * 1e3 / cnt
-                    f.write(f"| {names[c]} | {fl / 1e9:.2f} | {cnt / nprof:.1f} | {us:.1f} | {fl / us / 1e6:.0f} | {ms * 1e3 / nprof:.0f} | "
-                            f"{fl / max(us - ev_over_us, 1e-3) / 1e6:.0f} |\n")
+                f.write(f"# dense launches of one {args.workload} step, by (kind, algorithmic GFLOP, algorithmic MB): CUDA events around each "
+                        f"launch, eager, one stream, {nprof} steps; event-pair overhead {ev_over_us:.2f} us per launch\n\n"
+                        f"Bound = max(FLOP / {pk_tf:.0f} TFLOP/s, bytes / {pk_gb:.0f} GB/s): the roofline that binds the shape "
+                        f"(`hbm` where the operand + result traffic takes longer than the math); `of bound` = bound / (measured - event "
+                        f"overhead). GEMM launches together: {frac_of_bound * 100 if frac_of_bound else 0:.0f} % of their bounds.\n\n")
+                f.write("| kind | GFLOP | MB | launches / step | avg us | TFLOP/s | us / step | tensor us | hbm us | binds | of bound |\n"
+                        "|---|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|\n")
+                for (c, fl, by, cnt, us, ms, t_tensor, t_hbm, bound, net) in rows_tbl:
+                    f.write(f"| {names[c]} | {fl / 1e9:.2f} | {by / 1e6:.1f} | {cnt / nprof:.1f} | {us:.1f} | {fl / us / 1e6:.0f} | "
+                            f"{ms * 1e3 / nprof:.0f} | {t_tensor:.1f} | {t_hbm:.1f} | {'hbm' if t_hbm > t_tensor else 'tensor'} | "
+                            f"{bound / net * 100:.0f} % |\n")
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -598,6 +622,10 @@ def main():
                         "event_overhead_note": "a null kernel bracketed launch by launch like every record here, minus the "
                                                "same kernel back to back (b200_profile_event_overhead, measured in this run); "
                                                "`achieved` / `frac` keep it in (conservative), the *_net fields take it out",
+                        "frac_of_binding_roofline_net": frac_of_bound,
+                        "frac_of_binding_roofline_note": "per GEMM shape the bound is max(FLOP / sustained bf16 peak, algorithmic operand + "
+                                                         "result bytes / copy bandwidth); sum of bounds / sum of (event time - event overhead): "
+                                                         "the K = 384 GEMMs with fp32 residual or saved activations are HBM-bound shapes",
                         "achieved_net": fl_c[0] / (net_ms * 1e-3) / 1e12 if net_ms > 0 else None,
                         "frac_net": fl_c[0] / (net_ms * 1e-3) / 1e12 / peak if net_ms > 0 else None, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r0*_gemm_v2_ncu_full.md)",
                         "peak_source": peak_src,

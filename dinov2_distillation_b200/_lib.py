@@ -131,7 +131,7 @@ SIGNATURES = {
     "b200_bilinear_tokens_bwd": (_i, [c_vp, c_vp, _i, _i, _i, _i, _i, _i, c_vp]),
     "b200_patch_im2col": (_i, [c_fp, c_vp, _i, _i, _i, _i, c_vp]),
     "b200_profile_event_overhead": (_i, [_i, C.POINTER(C.c_float), C.POINTER(C.c_float), c_vp]),
-    "b200_profile_read_records": (_i, [_i, c_vp, c_vp, c_vp]),
+    "b200_profile_read_records": (_i, [_i, c_vp, c_vp, c_vp, c_vp]),
     "b200_augment_ws_bytes": (_sz, [_i, _i, _i]),
     "b200_augment_batch": (_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_fp, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), c_vp, _sz, c_vp]),
     "b200_feature_cache_store": (_i, [c_fp, C.c_longlong, C.c_longlong, c_vp, c_vp, _i, _i, _i, _i, c_vp]),

@@ -683,7 +683,11 @@ int launch_attention_tc_bwd(const b200_attn_desc* d, cudaStream_t st) {
   if (hdp == 64) r = dual ? abt_launch<64, true>(tm, p, grid, st) : abt_launch<64, false>(tm, p, grid, st);
   else r = dual ? abt_launch<32, true>(tm, p, grid, st) : abt_launch<32, false>(tm, p, grid, st);
   if (r != 0) return r;
-  prof_end(prof, st, 8.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 2);
+  {
+    const double D = (double)d->heads * d->hd;   // q, dO read and dq written per query; k, v read and dk, dv written per key
+    prof_end(prof, st, 8.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 2,
+             2.0 * D * d->B * (3.0 * d->Nq + 4.0 * d->Nk) * (d->qkvo_is_fp16 ? 1.5 : 1.0));
+  }
   B200_LAUNCH_OK();
   if (stream) {
     dim3 g((unsigned)cdiv(d->Nq, ABT_FIN_ROWS), (unsigned)d->B);

@@ -491,7 +491,11 @@ int launch_attention_pp_fwd(const b200_attn_desc* d, cudaStream_t st) {
   if (hdp == 64) r = fmt == 0 ? app_launch<64, true>(tq, tk, tv, p, grid, st) : app_launch<64, false>(tq, tk, tv, p, grid, st);
   else r = fmt == 0 ? app_launch<32, true>(tq, tk, tv, p, grid, st) : app_launch<32, false>(tq, tk, tv, p, grid, st);
   if (r != 0) return r;
-  prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
+  {
+    const double D = (double)d->heads * d->hd;   // q (once when batch invariant), k, v read; o (and its copy) written
+    prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1,
+             2.0 * D * ((d->q_bs != 0 ? d->B : 1) * (double)d->Nq + 2.0 * d->B * d->Nk + d->B * (double)d->Nq * (d->o_alt ? 2.0 : 1.0)));
+  }
   B200_LAUNCH_OK();
   if (kAppProbes) {
     static int printed = 0;

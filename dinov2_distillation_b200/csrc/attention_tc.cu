@@ -626,7 +626,11 @@ int launch_attention_tc_fwd(const b200_attn_desc* d, cudaStream_t st) {
   auto kern = p.nblk > 1 ? (p.fp16 ? attn_tc_fwd_kernel<true, true> : attn_tc_fwd_kernel<true, false>)
                          : (p.fp16 ? attn_tc_fwd_kernel<false, true> : attn_tc_fwd_kernel<false, false>);
   B200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(ATC_THREADS), ATC_SMEM_BYTES, st, tq, tk, tv, to, toa, p));
-  prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1);
+  {
+    const double D = (double)d->heads * d->hd;   // q (once when batch invariant), k, v read; o (and its copy) written
+    prof_end(prof, st, 4.0 * d->B * d->heads * (double)d->Nq * d->Nk * d->hd, 1,
+             2.0 * D * ((d->q_bs != 0 ? d->B : 1) * (double)d->Nq + 2.0 * d->B * d->Nk + d->B * (double)d->Nq * (d->o_alt ? 2.0 : 1.0)));
+  }
   B200_LAUNCH_OK();
   if (dbg_on) {
     long long h[9 * 16];

@@ -20,7 +20,7 @@ int option(int id);
 void bump_stat(int id);
 // per-launch timing hooks (no-ops unless b200_profile_enable(1)); cat: 0 GEMM, 1 attention fwd, 2 attention bwd
 int prof_begin(cudaStream_t st);
-void prof_end(int idx, cudaStream_t st, double flops, int cat);
+void prof_end(int idx, cudaStream_t st, double flops, int cat, double bytes = 0.0);   // bytes: algorithmic operand + result traffic
 
 #define B200_CHECK_ARG(cond, msg)                                                      \
   do {                                                                                 \

@@ -68,7 +68,7 @@ void bump_stat(int id) { ++g_opts[id].value; }
 bool pdl_enabled() { return g_opts[OPT_PDL].value != 0; }
 
 // ---- optional per-launch timing of the dense kernels (bench.py's roofline leg): CUDA events on the launch stream
-struct ProfRec { cudaEvent_t a, b; double flops; int cat; };
+struct ProfRec { cudaEvent_t a, b; double flops; int cat; double bytes; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_pool;
@@ -85,18 +85,19 @@ int prof_begin(cudaStream_t st) {
   if (!g_prof_on) return -1;
   std::lock_guard<std::mutex> g(g_prof_mu);
   ProfRec r;
-  r.a = take_event(); r.b = take_event(); r.flops = 0; r.cat = 0;
+  r.a = take_event(); r.b = take_event(); r.flops = 0; r.cat = 0; r.bytes = 0;
   cudaEventRecord(r.a, st);
   g_recs.push_back(r);
   return (int)g_recs.size() - 1;
 }
 
-void prof_end(int idx, cudaStream_t st, double flops, int cat) {
+void prof_end(int idx, cudaStream_t st, double flops, int cat, double bytes) {
   if (idx < 0) return;
   std::lock_guard<std::mutex> g(g_prof_mu);
   if (idx >= (int)g_recs.size()) return;
   g_recs[idx].flops = flops;
   g_recs[idx].cat = cat;
+  g_recs[idx].bytes = bytes;
   cudaEventRecord(g_recs[idx].b, st);
 }
 
@@ -158,7 +159,7 @@ extern "C" int b200_profile_event_overhead(int reps, float* bracketed_us, float*
 }
 
 // per-launch records in launch order (ms, algorithmic flops, category); clears them like b200_profile_read
-extern "C" int b200_profile_read_records(int cap, float* ms, double* flops, int* cat) {
+extern "C" int b200_profile_read_records(int cap, float* ms, double* flops, int* cat, double* bytes) {
   using namespace b200;
   std::lock_guard<std::mutex> g(g_prof_mu);
   int n = 0;
@@ -166,7 +167,7 @@ extern "C" int b200_profile_read_records(int cap, float* ms, double* flops, int*
     if (cudaEventSynchronize(r.b) != cudaSuccess) { set_error("profile: event sync failed"); return -2; }
     float t = 0.f;
     cudaEventElapsedTime(&t, r.a, r.b);
-    if (n < cap) { ms[n] = t; flops[n] = r.flops; cat[n] = r.cat; ++n; }
+    if (n < cap) { ms[n] = t; flops[n] = r.flops; cat[n] = r.cat; if (bytes) bytes[n] = r.bytes; ++n; }
     g_pool.push_back(r.a);
     g_pool.push_back(r.b);
   }

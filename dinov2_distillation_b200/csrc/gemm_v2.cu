@@ -974,7 +974,15 @@ static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     return 0;
   }
   B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tx, p, use_x, reduce_out));
-  prof_end(prof, st, 2.0 * p.M * p.N * p.K * p.algo_scale, 0);
+  {
+    // algorithmic traffic: both operands once, the result once (a read-modify-write result twice), operand tiles of the
+    // epilogue (fp32 residual / 16-bit aux) once, the second 16-bit copy once
+    const double mn = (double)p.M * p.N;
+    double bytes = 2.0 * ((double)p.M * p.K + (double)p.N * p.K) * p.algo_scale;
+    if (EPI == 2) bytes += mn * 4.0 * ((reduce_out || p.split_k > 1) ? 2.0 : 1.0) + (use_x ? mn * 4.0 : 0.0);
+    else bytes += mn * 2.0 * (p.out_bf16_pre != nullptr ? 2.0 : 1.0) + (use_x ? mn * 2.0 : 0.0);
+    prof_end(prof, st, 2.0 * p.M * p.N * p.K * p.algo_scale, 0, bytes);
+  }
   B200_LAUNCH_OK();
   return 0;
 }
@@ -1171,7 +1179,8 @@ static int lng_launch(const CUtensorMap& tb, const CUtensorMap& to, const CUtens
     return 0;
   }
   B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tb, to, tx, p, ln));
-  prof_end(prof, st, 2.0 * p.M * p.N * p.K, 0);
+  prof_end(prof, st, 2.0 * p.M * p.N * p.K, 0,
+           4.0 * p.M * p.K + 2.0 * p.N * p.K + 2.0 * p.M * p.N * (p.out_bf16_pre != nullptr ? 2.0 : 1.0));
   B200_LAUNCH_OK();
   return 0;
 }

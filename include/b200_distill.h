@@ -41,8 +41,9 @@ int b200_profile_read(int n_cat, double* ms, double* flops, long long* launches)
 /* what an event pair around ONE launch adds to its measured duration: a null kernel timed bracketed launch by launch (as
  * the records above are) and back to back; per-launch microseconds, the difference is the overhead */
 int b200_profile_event_overhead(int reps, float* bracketed_us, float* back_to_back_us, void* stream);
-/* the same records one by one, in launch order (returns how many were written, at most cap; clears them) */
-int b200_profile_read_records(int cap, float* ms, double* flops, int* cat);
+/* the same records one by one, in launch order (returns how many were written, at most cap; clears them); bytes (may be
+ * NULL): the algorithmic operand + result traffic of the launch, for the roofline that binds each shape */
+int b200_profile_read_records(int cap, float* ms, double* flops, int* cat, double* bytes);
 /* Dispatch options (ints; defaults select the production kernels). The launchers read this table, never the
  * environment; tests and A/B tools flip entries. Names: "pdl", "attn_tc_fwd", "attn_tc_fwd_long", "attn_tc_bwd",
  * "attn_bwd_fused", "attn_tc_bwd_long", "gemm_ln". b200_set_option returns -1 for an unknown name; b200_get_option returns -1 likewise. */
