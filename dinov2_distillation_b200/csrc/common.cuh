@@ -15,7 +15,7 @@ int sm_count();
 // dispatch options (core.cu): read by the launchers, set through b200_set_option()
 enum { OPT_PDL = 0, OPT_ATTN_TC_FWD, OPT_ATTN_TC_FWD_LONG, OPT_ATTN_TC_BWD, OPT_ATTN_BWD_FUSED, OPT_ATTN_TC_BWD_LONG,
        OPT_GEMM_V2, OPT_GEMM_BN, OPT_GEMM_2CTA, OPT_GEMM_INPLACE_RED, OPT_GEMM_EW, OPT_GEMM_DBG, OPT_ATTN_PROBE_SKIP, OPT_GEMM_LN,
-       STAT_ATTN_TC_BWD, STAT_ATTN_MMA_BWD, STAT_ATTN_TC_FWD, STAT_ATTN_MMA_FWD, OPT_ATTN_PP_FWD, STAT_ATTN_PP_FWD, OPT_COUNT };
+       STAT_ATTN_TC_BWD, STAT_ATTN_MMA_BWD, STAT_ATTN_TC_FWD, STAT_ATTN_MMA_FWD, OPT_ATTN_PP_FWD, STAT_ATTN_PP_FWD, OPT_GEMM_AUX_DEEP, OPT_COUNT };
 int option(int id);
 void bump_stat(int id);
 // per-launch timing hooks (no-ops unless b200_profile_enable(1)); cat: 0 GEMM, 1 attention fwd, 2 attention bwd

@@ -54,6 +54,7 @@ static OptDef g_opts[OPT_COUNT] = {
     {"stat_attn_mma_fwd", "", 0},
     {"attn_pp_fwd", "B200_ATTN_PP", 1},              // two-tile tcgen05 attention forward (Nk <= 256, head dims 16-64)
     {"stat_attn_pp_fwd", "", 0},
+    {"gemm_aux_deep", "B200_GEMM_AUX_DEEP", 1},      // aux-epilogue GEMMs: aux tiles two units ahead, across tiles
 };
 static const bool g_opts_init = [] {
   for (auto& o : g_opts) {

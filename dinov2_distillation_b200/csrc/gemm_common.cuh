@@ -37,6 +37,7 @@ struct GemmParams {
   int out_bp;                // fp32 output batched along columns with this period (3-D output tensor map); 0 = plain 2-D
   int vec_ok;  // all leading dims / pointers allow 16-byte vector access
   int out16_fp16, aux_fp16;  // 16-bit output / aux element type: 0 = bf16, 1 = fp16
+  int aux_deep;              // gemm_v2: aux tiles requested two units ahead across tiles (option gemm_aux_deep)
   float* colsum;             // gemm_v2.cu: fp32 [N], += column sums of the 16-bit output as stored (or NULL)
   int pre_alt;               // 1: the second 16-bit output is the final value in the other format (gemm_v2.cu only)
   uint32_t idesc;            // tcgen05 instruction descriptor (operand formats, majors, tile shape)

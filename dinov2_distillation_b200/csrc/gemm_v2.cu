@@ -23,7 +23,7 @@ namespace b200 {
 // Epilogue warps per CTA (template EW): 8 warps with 8 KB of staging each (every path), or 16 warps with 4 KB each for
 // the epilogues that need no operand tile (no separate residual / aux / pre-activation copy): four warps per scheduler
 // instead of two hide the tcgen05.ld -> st.shared -> fence -> bulk-store latency chain that paces the K = 384 shapes.
-constexpr int V2_MAX_EPI_WARPS = 16;
+constexpr int V2_MAX_EPI_WARPS = 16;   // (also the number of operand-tile barriers: one per warp, or two per warp of an 8-warp epilogue)
 constexpr int V2_EPI_BYTES = 65536;
 
 template <int BN, bool PAIR>
@@ -187,12 +187,22 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
                                                  uint32_t taddr, int row0, int n0, uint32_t stage_smem, uint64_t* xbar,
                                                  uint32_t& xphase, int half, int lane, bool first_split, bool use_x_arg,
                                                  bool reduce_out, uint64_t* tempty, bool pair, uint32_t* out_toggle, uint32_t vec_smem,
-                                                 uint32_t bias_row_smem = 0) {
+                                                 uint32_t bias_row_smem = 0, bool deep_arg = false, int next_row0 = -1,
+                                                 int next_n0 = 0) {
   constexpr int NG = EW / 4;                             // warps per TMEM quadrant
   constexpr int UNITS = (BN / 32 + NG - 1) / NG;         // units per warp (the last may be absent: BN = 192, NG = 4)
   constexpr bool PREFETCH = EW == 8;                     // 8 warps: next unit's tcgen05.ld in flight during this one
   constexpr bool F32 = EPI == 2;
   const bool use_x = EW == 8 && use_x_arg;               // 16 warps: 4 KB of staging per warp, no operand tile
+  // Aux tiles two units ahead, across tiles (x relu mask / x gelu' of the dgrad-through-activation GEMMs; BN = 192: three
+  // units per warp and tile). Requested one unit ahead, the 32 x 32 tile arrived ~540 cycles late in every unit (wait
+  // cycles of a -DB200_GEMM_PROBES build: 2 600 cycles per unit against 1 600 without the aux operand). Two aux tiles
+  // rotate over this warp's unit sequence g = 3 * tile + unit: buffer / barrier g & 1 (staging bytes 4096.. and 6144..,
+  // the latter free because these GEMMs carry no bias vector; barriers xbar and xbar + 8), and the tile of unit g + 2 --
+  // unit 2 of this tile, or unit 0 / 1 of the warp's NEXT tile -- is requested as soon as unit g has been read.
+  // xphase: bit 0 / 1 = parity of the two barriers, bits 2.. = g.
+  constexpr bool DEEP_OK = EW == 8 && !F32 && BN == 192;
+  const bool deep = DEEP_OK && deep_arg && use_x;
   constexpr int ROWB = F32 ? 128 : 64;                   // staging row bytes (32 columns)
   constexpr int CHUNKS = ROWB / 16;
   constexpr uint32_t UNIT_BYTES = 32 * ROWB;
@@ -221,7 +231,7 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
   uint32_t raw[PREFETCH ? 2 : 1][32];
   // residual rows repeat with period res_row_period (pos_embed under the patch-embed GEMM): 32-row units never straddle
   const int xrow = (F32 && p.res_row_period > 0) ? row0 % p.res_row_period : row0;
-  if (use_x && lane == 0) {
+  if (use_x && !deep && lane == 0) {
     mbar_expect_tx(xbar, UNIT_BYTES);
     v2_tma_load_2d_s(buf_x, tmX, xbar, n0 + half * 32, xrow);
   }
@@ -310,9 +320,17 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
         if (use_x) {
-          mbar_wait(xbar, xphase);
-          xphase ^= 1;
-          const uint32_t bx = buf_x + row_off;
+          const uint32_t xb_i = deep ? ((xphase >> 2) & 1u) : 0u;          // buffer / barrier of this unit
+          uint64_t* xb = xbar + 8 * xb_i;
+          const uint32_t bx_tile = buf_x + 2048u * xb_i;
+          if (deep) {
+            mbar_wait(xb, (xphase >> xb_i) & 1u);
+            xphase = (xphase ^ (1u << xb_i)) + 4u;                         // flip the parity bit, g += 1
+          } else {
+            mbar_wait(xbar, xphase);
+            xphase ^= 1;
+          }
+          const uint32_t bx = bx_tile + row_off;
           float a[32];
 #pragma unroll
           for (int c = 0; c < CHUNKS; ++c) {
@@ -324,9 +342,19 @@ __device__ __forceinline__ void v2_epilogue_tile(const GemmParams& p, const CUte
             a[j + 4] = f2.x; a[j + 5] = f2.y; a[j + 6] = f3.x; a[j + 7] = f3.y;
           }
           __syncwarp();   // every lane has read the aux tile: it may be refilled
-          if (next_ok && lane == 0) {
-            mbar_expect_tx(xbar, UNIT_BYTES);
-            v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, xrow);
+          if (lane == 0) {
+            if (deep) {   // unit g + 2 into the tile just read: unit 2 of this tile, or unit i - 1 of the next
+              if (i == 0) {
+                mbar_expect_tx(xb, UNIT_BYTES);
+                v2_tma_load_2d_s(bx_tile, tmX, xb, n0 + (half + 2 * NG) * 32, row0);
+              } else if (next_row0 >= 0) {
+                mbar_expect_tx(xb, UNIT_BYTES);
+                v2_tma_load_2d_s(bx_tile, tmX, xb, next_n0 + (half + (i - 1) * NG) * 32, next_row0);
+              }
+            } else if (next_ok) {
+              mbar_expect_tx(xbar, UNIT_BYTES);
+              v2_tma_load_2d_s(buf_x, tmX, xbar, c0 + NG * 32, xrow);
+            }
           }
           if (p.aux_mode == B200_AUX_DGELU) {
 #pragma unroll
@@ -495,7 +523,7 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], (PAIR ? 2 : 1) * EW);
     }
-    for (int s = 0; s < EW; ++s) mbar_init(&x_bar[s], 1);
+    for (int s = 0; s < V2_MAX_EPI_WARPS; ++s) mbar_init(&x_bar[s], 1);   // (8-warp epilogues: [ew] and [ew + 8])
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -612,11 +640,35 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aphase = 0;
     long long w_tfull = 0;
     const long long t_begin = clock64();
+    // aux tiles two units ahead (v2_epilogue_tile): every column tile full (three live units per warp), no bias vector in the
+    // staging bytes the second aux tile uses, no split-K
+    const bool deep = EW == 8 && EPI != 2 && BN == 192 && !PAIR && use_x != 0 && p.bias == nullptr && p.out_bf16_pre == nullptr &&
+                      p.N % 192 == 0 && p.split_k == 1 && p.aux_deep != 0;
+    auto tile_origin = [&](int t, int& m0, int& n0) {
+      const int r = t % tiles_mn;
+      m0 = (r / p.n_tiles) * TILE_M + (int)rank * 128;
+      n0 = (r % p.n_tiles) * BN;
+    };
+    if (deep && worker < p.total_tiles && lane == 0) {   // units 0 and 1 of the first tile
+      int m0, n0;
+      tile_origin(worker, m0, n0);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        mbar_expect_tx(xbar + 8 * i, 2048u);
+        v2_tma_load_2d_s(stage_smem + 4096u + 2048u * i, &tmX, xbar + 8 * i, n0 + (half + 2 * i) * 32, m0 + quad * 32);
+      }
+    }
     for (int t = worker; t < p.total_tiles; t += workers) {
       const int ks = t / tiles_mn;
       const int r = t - ks * tiles_mn;
       const int m0 = (r / p.n_tiles) * TILE_M + (int)rank * 128;
       const int n0 = (r % p.n_tiles) * BN;
+      int next_row0 = -1, next_n0 = 0;
+      if (deep && t + workers < p.total_tiles) {
+        int nm0;
+        tile_origin(t + workers, nm0, next_n0);
+        next_row0 = nm0 + quad * 32;
+      }
       // per-column epilogue vectors (bias, LayerScale) of this warp's units -> its spare staging bytes, while the
       // accumulator is still being produced: first touch of a new column range is an L2 round trip per unit otherwise
       // (16-bit: bytes 6144.. are free; fp32: the residual tile's 4 KB when no residual is loaded)
@@ -641,7 +693,8 @@ gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::TMEM_STRIDE;
       v2_epilogue_tile<BN, EPI, EW>(p, &tmO, &tmX, taddr, m0 + quad * 32, n0, stage_smem, xbar, xphase, half, lane, ks == 0,
-                                use_x != 0, reduce_out != 0, &tempty_bar[as], PAIR, &out_toggle, vec_smem);
+                                use_x != 0, reduce_out != 0, &tempty_bar[as], PAIR, &out_toggle, vec_smem, 0u, deep, next_row0,
+                                next_n0);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     const long long t_loop = clock64() - t_begin;
@@ -1061,6 +1114,7 @@ int launch_gemm_v2(const b200_gemm_desc* d, GemmParams& p, cudaStream_t st) {
   if (d->col_scale && !al16(d->col_scale)) return 1;
   if (d->N % 32 != 0) return 1;   // ragged N: first-generation kernel (per-column tail handling)
   p.pre_alt = (d->out16_pre_alt && d->out_bf16_pre) ? 1 : 0;
+  p.aux_deep = option(OPT_GEMM_AUX_DEEP);
   p.colsum = (!f32 && p.split_k == 1) ? d->out16_colsum : nullptr;
   if (d->out16_colsum != nullptr && p.colsum == nullptr) return 1;
 
