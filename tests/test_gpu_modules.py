@@ -582,7 +582,7 @@ def test_scalekd_window_attention_golden(tag):
     check_param_grads(pairs, tol=2e-2)                          # per tensor: toy widths (D = 64, B = 3), see f1 test
 
 
-@pytest.mark.parametrize("win", [(2, 2), (4, 2), (1, 4)])
+@pytest.mark.parametrize("win", [(2, 2), (4, 2), (1, 4), (1, 2), (2, 1)])   # (1, 2) / (2, 1): 128-token windows, two-tile tcgen05 forward
 def test_scalekd_window_attention_vs_oracle(win):
     """Other window shapes (incl. non-square window counts) on a 16x16 grid with config.yaml-like widths, against the
     oracle port (itself pinned to the reference by the golden files above)."""
